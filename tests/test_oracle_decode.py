@@ -1,0 +1,129 @@
+"""CPU tests: the oracle's Parquet restatement (S1/S2) against pyarrow 24 — an independent implementation of the
+same format — and its filter / pruning / aggregation arithmetic against numpy."""
+import io
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pyarrow.parquet as pq
+import pytest
+
+from helpers import arrow_schema, record_batch
+from horaedb_b200 import sstgen
+from horaedb_b200.config import ColumnOptions, ParquetCompression, WriteConfig
+from horaedb_b200.types import StorageSchema
+from oracle import oracle
+
+
+def _random_batch(rng, n, null_frac):
+    sch = arrow_schema([("k1", "uint64"), ("k2", "int64"), ("a", "float64"), ("b", "uint32"), ("c", "int8"),
+                        ("d", "uint8"), ("e", "int32"), ("f", "float32"), ("g", "int16"), ("h", "uint16")])
+    k1 = np.sort(rng.integers(0, max(n // 7, 1), n).astype(np.uint64))
+    k2 = np.arange(n, dtype=np.int64) - n // 2
+    cols = [pa.array(k1), pa.array(k2)]
+    gens = [lambda: rng.standard_normal(n), lambda: rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32),
+            lambda: rng.integers(-128, 128, n).astype(np.int8), lambda: rng.integers(0, 256, n).astype(np.uint8),
+            lambda: rng.integers(-2**31, 2**31, n).astype(np.int32), lambda: rng.standard_normal(n).astype(np.float32),
+            lambda: rng.integers(-2**15, 2**15, n).astype(np.int16), lambda: rng.integers(0, 2**16, n).astype(np.uint16)]
+    for g in gens:
+        v = g()
+        mask = rng.random(n) < null_frac
+        cols.append(pa.array(v, mask=mask))
+    return sch, pa.RecordBatch.from_arrays(cols, schema=sch)
+
+
+@pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed])
+@pytest.mark.parametrize("n,null_frac,rg", [(0, 0.0, 8192), (1, 0.0, 8192), (5, 0.5, 2), (1000, 0.0, 8192), (20000, 0.3, 8192),
+                                            (20000, 1.0, 8192), (70000, 0.01, 8192), (9000, 0.9, 100)])
+def test_decode_matches_pyarrow(compression, n, null_frac, rg):
+    rng = np.random.default_rng(n + int(null_frac * 100))
+    user, batch = _random_batch(rng, n, null_frac)
+    schema = StorageSchema.try_new(user, 2)
+    data = sstgen.write_sst(schema, batch, seq=77, cfg=WriteConfig(compression=compression, max_row_group_size=rg),
+                            presorted=True)
+    got = oracle.decode_sst(data, schema.arrow_schema)
+    ref = pq.read_table(io.BytesIO(data)).cast(schema.arrow_schema)
+    assert got.num_rows == n
+    assert got.equals(ref)
+
+
+def test_decode_small_pages_and_v2():
+    """Multi-page chunks (tiny data_page_size) and DataPage V2 — page counts must come from headers (SURVEY §8 caveat)."""
+    rng = np.random.default_rng(3)
+    user, batch = _random_batch(rng, 30000, 0.2)
+    schema = StorageSchema.try_new(user, 2)
+    full = schema.fill_builtin_columns(batch, 5)
+    for version in ("1.0", "2.0"):
+        for comp in ("snappy", "none"):
+            sink = io.BytesIO()
+            pq.write_table(pa.Table.from_batches([full]), sink, row_group_size=8192, compression=comp, use_dictionary=False,
+                           data_page_size=3000, data_page_version=version)
+            data = sink.getvalue()
+            got = oracle.decode_sst(data, schema.arrow_schema)
+            assert got.equals(pq.read_table(io.BytesIO(data)).cast(schema.arrow_schema)), (version, comp)
+
+
+def test_filter_and_pruning_match_numpy():
+    schema = sstgen.metric_storage_schema()
+    data, n = sstgen.synth_sst(0, 32, 2000, 1000, seq=9)
+    tbl = pq.read_table(io.BytesIO(data))
+    t_lo, t_hi = sstgen.T0_MS + 500 * 1000, sstgen.T0_MS + 1500 * 1000
+    preds = [("tag", "eq", 3), ("ts", "ge", t_lo), ("ts", "lt", t_hi)]
+    mask = pc.and_(pc.and_(pc.equal(tbl["tag"], 3), pc.greater_equal(tbl["ts"], t_lo)), pc.less(tbl["ts"], t_hi))
+    expect = tbl.filter(mask).select(["series_id", "ts", "value", "tag"])
+    for prune in (False, True):
+        res = oracle.scan([data], schema.arrow_schema, 2, preds=preds, prune=prune)
+        got = pa.Table.from_batches(res.batches) if res.batches else expect.slice(0, 0)
+        assert got.equals(expect.cast(got.schema))
+        assert res.rows_in_files == n
+        assert (res.rows_decoded < n) == prune  # stats pruning drops row groups whose tag range excludes 3
+    for op, fn in (("ne", pc.not_equal), ("le", pc.less_equal), ("gt", pc.greater)):
+        res = oracle.scan([data], schema.arrow_schema, 2, preds=[("value", op, 0.5)])
+        assert sum(b.num_rows for b in res.batches) == pc.sum(fn(tbl["value"], 0.5)).as_py()
+
+
+def test_null_predicate_is_false():
+    user = arrow_schema([("pk", "int64"), ("v", "float64")])
+    schema = StorageSchema.try_new(user, 1)
+    b = pa.RecordBatch.from_arrays([pa.array([1, 2, 3, 4], pa.int64()), pa.array([1.0, None, 3.0, None])], schema=user)
+    data = sstgen.write_sst(schema, b, seq=1)
+    for op in ("eq", "ne", "lt", "ge"):
+        res = oracle.scan([data], schema.arrow_schema, 1, preds=[("v", op, 2.0)])
+        rows = pa.Table.from_batches(res.batches).to_pydict() if res.batches else {"pk": []}
+        assert all(p in (1, 3) for p in rows["pk"])  # NULL => false (arrow filter semantics, read.rs:467-469)
+
+
+def test_aggregate_sequential_sum_and_buckets():
+    schema = sstgen.metric_storage_schema()
+    ssts = [sstgen.synth_sst(lo, lo + 8, 300, 10_000, seq=20 + i)[0] for i, lo in enumerate((0, 8, 16))]
+    w = 60_000
+    res = oracle.scan_aggregate(ssts, schema.arrow_schema, 2, group_col=0, ts_col=1, window_ms=w, value_col=2)
+    tbl = pa.concat_tables([pq.read_table(io.BytesIO(s)) for s in ssts])
+    sid = tbl["series_id"].to_numpy(); ts = tbl["ts"].to_numpy(); v = tbl["value"].to_numpy()
+    bucket = ts // w * w
+    key_change = np.r_[True, (sid[1:] != sid[:-1]) | (bucket[1:] != bucket[:-1])]
+    starts = np.flatnonzero(key_change)
+    assert res.count.tolist() == np.diff(np.r_[starts, len(sid)]).tolist()
+    assert res.gkey.tolist() == sid[starts].tolist() and res.bucket.tolist() == bucket[starts].tolist()
+    ends = np.r_[starts[1:], len(sid)]
+    for g in range(0, len(starts), 37):
+        acc = 0.0
+        for x in v[starts[g]:ends[g]]:
+            acc += x  # sequential order
+        assert res.sum[g] == acc
+        assert res.min[g] == v[starts[g]:ends[g]].min() and res.max[g] == v[starts[g]:ends[g]].max()
+    assert int(res.count.sum()) == len(sid)
+
+
+def test_dedup_newest_seq_wins_across_files():
+    ssts = sstgen.synth_overlapping_ssts(6, series=40, points=50, delta_ms=1000, keep_frac=0.5)
+    schema = sstgen.metric_storage_schema()
+    res = oracle.scan([s[0] for s in ssts], schema.arrow_schema, 2, keep_builtin=True, batch_size=256)
+    out = pa.Table.from_batches(res.batches)
+    full = pa.concat_tables([pq.read_table(io.BytesIO(s[0])) for s in ssts])
+    exp = full.group_by(["series_id", "ts"]).aggregate([("__seq__", "max")]).sort_by([("series_id", "ascending"), ("ts", "ascending")])
+    assert out.num_rows == exp.num_rows
+    assert out["series_id"].to_pylist() == exp["series_id"].to_pylist()
+    assert out["ts"].to_pylist() == exp["ts"].to_pylist()
+    assert out["__seq__"].to_pylist() == exp["__seq___max"].to_pylist()
+    assert res.rows_merged == full.num_rows
