@@ -1,0 +1,244 @@
+"""ctypes binding of libhorae_gpu.so (include/horae_gpu.h).  Fails loudly when the CUDA library is missing:
+there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import pyarrow as pa
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libhorae_gpu.so")
+
+HG_TYPES = {pa.uint8(): 0, pa.int8(): 1, pa.uint16(): 2, pa.int16(): 3, pa.uint32(): 4, pa.int32(): 5,
+            pa.uint64(): 6, pa.int64(): 7, pa.float32(): 8, pa.float64(): 9}
+HG_OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
+HG_FLAG_NO_PRUNING = 1
+HG_FLAG_NO_FUSED = 2
+
+STATUS = {0: "OK", 1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "FORMAT", 5: "OOM", 6: "NOT_FOUND", 7: "INTERNAL"}
+
+
+class HgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"HG_ERR_{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class HgSchemaDesc(C.Structure):
+    _fields_ = [("num_columns", C.c_uint32), ("num_primary_keys", C.c_uint32), ("update_mode", C.c_uint32),
+                ("_pad", C.c_uint32), ("types", C.POINTER(C.c_uint32)), ("names", C.POINTER(C.c_char_p))]
+
+
+class HgConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("batch_size", C.c_uint32), ("hbm_budget_bytes", C.c_uint64),
+                ("flags", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class HgSstDesc(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("data", C.c_void_p), ("size", C.c_uint64), ("path", C.c_char_p),
+                ("num_rows", C.c_uint32), ("_pad", C.c_uint32), ("time_start", C.c_int64), ("time_end", C.c_int64),
+                ("max_sequence", C.c_uint64)]
+
+
+class HgPredicate(C.Structure):
+    _fields_ = [("column", C.c_uint32), ("op", C.c_uint32), ("i64", C.c_int64), ("u64", C.c_uint64), ("f64", C.c_double)]
+
+
+class HgAggSpec(C.Structure):
+    _fields_ = [("group_col", C.c_int32), ("ts_col", C.c_int32), ("window_ms", C.c_int64), ("value_col", C.c_int32),
+                ("_pad", C.c_uint32)]
+
+
+class HgScanStats(C.Structure):
+    _fields_ = [("rows_in_files", C.c_uint64), ("rows_decoded", C.c_uint64), ("rows_filtered", C.c_uint64),
+                ("rows_out", C.c_uint64), ("groups_out", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
+                ("kernel_launches", C.c_uint32), ("path", C.c_uint32), ("gpu_ms", C.c_float), ("_pad", C.c_float)]
+
+
+class HgAggDevice(C.Structure):
+    _fields_ = [("num_groups", C.c_uint64), ("d_gkey", C.c_void_p), ("d_bucket", C.c_void_p), ("d_count", C.c_void_p),
+                ("d_sum", C.c_void_p), ("d_min", C.c_void_p), ("d_max", C.c_void_p)]
+
+
+class ArrowArrayStream(C.Structure):
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_sst_load",
+           "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
+           "hg_scan_aggregate_device", "hg_last_stats"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(horaedb_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.hg_abi_version.restype = C.c_uint32
+        L.hg_last_error.restype = C.c_char_p
+        L.hg_engine_stream.restype = C.c_void_p
+        L.hg_engine_stream.argtypes = [C.c_void_p]
+        L.hg_engine_destroy.argtypes = [C.c_void_p]
+        L.hg_engine_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise HgError(rc, lib().hg_last_error().decode())
+
+
+@dataclass
+class SstInput:
+    """`SstFile` + `FileMeta` (sst.rs:51-53, 155-160) as passed across the ABI."""
+    id: int
+    data: Optional[object] = None   # bytes / numpy uint8 / None when resident
+    path: Optional[str] = None
+    num_rows: int = 0
+    time_start: int = 0
+    time_end: int = 0
+    max_sequence: int = 0
+    ptr: int = 0                    # raw host pointer (e.g. pinned memory) used instead of `data`
+    size: int = 0
+
+
+class SchemaHandle:
+    """Keeps the ctypes arrays behind an hg_schema_desc alive."""
+
+    def __init__(self, arrow_schema: pa.Schema, num_primary_keys: int, update_mode: int = 0):
+        n = len(arrow_schema)
+        self.types = (C.c_uint32 * n)(*[HG_TYPES[f.type] if f.type in HG_TYPES else 0xFFFF for f in arrow_schema])
+        self.names = (C.c_char_p * n)(*[f.name.encode() for f in arrow_schema])
+        self.desc = HgSchemaDesc(n, num_primary_keys, update_mode, 0, self.types, self.names)
+        self.arrow_schema = arrow_schema
+
+
+def _make_preds(arrow_schema: pa.Schema, preds: Sequence[tuple]):
+    arr = (HgPredicate * max(len(preds), 1))()
+    for k, (col, op, lit) in enumerate(preds):
+        idx = col if isinstance(col, int) else arrow_schema.get_field_index(col)
+        t = arrow_schema.field(idx).type
+        arr[k].column = idx
+        arr[k].op = HG_OPS[op]
+        if pa.types.is_floating(t):
+            arr[k].f64 = float(lit)
+        elif pa.types.is_signed_integer(t):
+            arr[k].i64 = int(lit)
+        else:
+            arr[k].u64 = int(lit)
+    return arr
+
+
+class Engine:
+    """One engine per GPU (per rank).  Thin object wrapper over the C ABI."""
+
+    def __init__(self, device: int = 0, batch_size: int = 8192, hbm_budget_bytes: int = 0, flags: int = 0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        cfg = HgConfig(device, batch_size, hbm_budget_bytes, flags, 0)
+        _check(self._L.hg_engine_create(C.byref(cfg), C.byref(self._h)))
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self._L.hg_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream_ptr(self) -> int:
+        return self._L.hg_engine_stream(self._h)
+
+    # -- residency
+    def _descs(self, ssts: Sequence[SstInput]):
+        arr = (HgSstDesc * max(len(ssts), 1))()
+        keep = []
+        for i, s in enumerate(ssts):
+            arr[i].id = s.id
+            if s.ptr:
+                arr[i].data = s.ptr
+                arr[i].size = s.size
+            elif s.data is not None:
+                buf = np.frombuffer(s.data, dtype=np.uint8) if not isinstance(s.data, np.ndarray) else s.data
+                keep.append(buf)
+                arr[i].data = buf.ctypes.data
+                arr[i].size = buf.nbytes
+            else:
+                arr[i].data = None
+                arr[i].size = 0
+            arr[i].path = s.path.encode() if s.path else None
+            arr[i].num_rows = s.num_rows
+            arr[i].time_start = s.time_start
+            arr[i].time_end = s.time_end
+            arr[i].max_sequence = s.max_sequence
+        return arr, keep
+
+    def load_sst(self, schema: SchemaHandle, sst: SstInput):
+        arr, keep = self._descs([sst])
+        _check(self._L.hg_sst_load(self._h, C.byref(schema.desc), C.byref(arr[0])))
+
+    def unload_sst(self, id: int):
+        _check(self._L.hg_sst_unload(self._h, C.c_uint64(id)))
+
+    def resident_bytes(self) -> int:
+        out = C.c_uint64()
+        _check(self._L.hg_sst_resident_bytes(self._h, C.byref(out)))
+        return out.value
+
+    # -- scan / compaction
+    def scan(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (),
+             projection: Optional[Sequence[int]] = None, keep_builtin: bool = False) -> pa.RecordBatchReader:
+        arr, keep = self._descs(ssts)
+        p = _make_preds(schema.arrow_schema, preds)
+        proj = (C.c_uint32 * max(len(projection), 1))(*projection) if projection is not None else None
+        stream = ArrowArrayStream()
+        _check(self._L.hg_scan_open(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p, C.c_size_t(len(preds)),
+                                    proj, C.c_size_t(len(projection) if projection is not None else 0), int(keep_builtin),
+                                    C.byref(stream)))
+        return pa.RecordBatchReader._import_from_c(C.addressof(stream))
+
+    def compact(self, schema: SchemaHandle, ssts: Sequence[SstInput]) -> pa.RecordBatchReader:
+        arr, keep = self._descs(ssts)
+        stream = ArrowArrayStream()
+        _check(self._L.hg_compact_open(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), C.byref(stream)))
+        return pa.RecordBatchReader._import_from_c(C.addressof(stream))
+
+    def scan_aggregate(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (), group_col: int = 0,
+                       ts_col: int = -1, window_ms: int = 0, value_col: int = -1) -> pa.Table:
+        arr, keep = self._descs(ssts)
+        p = _make_preds(schema.arrow_schema, preds)
+        spec = HgAggSpec(group_col, ts_col, window_ms, value_col, 0)
+        stream = ArrowArrayStream()
+        _check(self._L.hg_scan_aggregate(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p, C.c_size_t(len(preds)),
+                                         C.byref(spec), C.byref(stream)))
+        return pa.RecordBatchReader._import_from_c(C.addressof(stream)).read_all()
+
+    def scan_aggregate_device(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (),
+                              group_col: int = 0, ts_col: int = -1, window_ms: int = 0, value_col: int = -1) -> HgAggDevice:
+        arr, keep = self._descs(ssts)
+        p = _make_preds(schema.arrow_schema, preds)
+        spec = HgAggSpec(group_col, ts_col, window_ms, value_col, 0)
+        out = HgAggDevice()
+        _check(self._L.hg_scan_aggregate_device(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p,
+                                                C.c_size_t(len(preds)), C.byref(spec), C.byref(out)))
+        return out
+
+    def stats(self) -> dict:
+        st = HgScanStats()
+        _check(self._L.hg_last_stats(self._h, C.byref(st)))
+        return {f[0]: getattr(st, f[0]) for f in HgScanStats._fields_ if not f[0].startswith("_")}

@@ -1,0 +1,938 @@
+// engine.cu — host side of libhorae_gpu.so: SST residency, scan planning, pipeline orchestration, Arrow C export
+// and the C ABI declared in include/horae_gpu.h.
+//
+// The planner mirrors ParquetReader::build_df_plan (read.rs:429-494):
+//   ParquetExec (row-group pruning by chunk statistics)  -> FilterExec -> SortPreservingMergeExec -> MergeExec
+// but runs every data-touching step as CUDA kernels (kernels.cu / fused_scan.cu).  There is no CPU fallback: if the
+// device library cannot do something it returns HG_ERR_UNSUPPORTED.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "engine_internal.h"
+#include "fused_scan.h"
+
+static thread_local std::string g_last_error;
+int set_error(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* d) {
+  if (e->ssts.count(d->id)) return HG_OK;
+  std::vector<uint8_t> filebuf;
+  const uint8_t* data = d->data;
+  uint64_t size = d->size;
+  if (!data) {
+    if (!d->path) return set_error(HG_ERR_NOT_FOUND, "sst " + std::to_string(d->id) + " is not resident and no data/path given");
+    FILE* f = std::fopen(d->path, "rb");
+    if (!f) return set_error(HG_ERR_NOT_FOUND, std::string("cannot open ") + d->path);
+    std::fseek(f, 0, SEEK_END);
+    long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    filebuf.resize(size_t(n));
+    size_t got = std::fread(filebuf.data(), 1, size_t(n), f);
+    std::fclose(f);
+    if (got != size_t(n)) return set_error(HG_ERR_NOT_FOUND, std::string("short read on ") + d->path);
+    data = filebuf.data();
+    size = uint64_t(n);
+  }
+  auto r = std::make_unique<SstResident>();
+  r->id = d->id;
+  r->size = size;
+  std::string err;
+  if (!parse_parquet(data, size, &r->meta, &err)) return set_error(HG_ERR_FORMAT, "sst " + std::to_string(d->id) + ": " + err);
+  const FileMetaData& m = r->meta;
+  if (uint32_t(m.ncols) != schema->num_columns)
+    return set_error(HG_ERR_INVALID, "sst has " + std::to_string(m.ncols) + " columns, schema has " + std::to_string(schema->num_columns));
+  for (int c = 0; c < m.ncols; c++) {
+    if (m.phys_types[c] != expected_phys(schema->types[c]))
+      return set_error(HG_ERR_INVALID, "column " + std::to_string(c) + ": parquet physical type does not match the schema");
+    if (m.repetition[c] == 2) return set_error(HG_ERR_UNSUPPORTED, "repeated columns");
+  }
+  std::vector<PageDev> pages(m.pages.size());
+  for (size_t i = 0; i < pages.size(); i++) {
+    const PageMeta& pm = m.pages[i];
+    if (pm.encoding != ENC_PLAIN)
+      return set_error(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (only PLAIN is implemented)");
+    PageDev& pd = pages[i];
+    pd.payload_off = pm.payload_off;
+    pd.comp_size = pm.comp_size;
+    pd.uncomp_size = pm.uncomp_size;
+    pd.num_values = pm.num_values;
+    pd.v2_def_len = pm.v2_def_len;
+    pd.v2_rep_len = pm.v2_rep_len;
+    pd.page_type = pm.page_type;
+    pd.encoding = pm.encoding;
+    pd.v2_compressed = pm.v2_compressed;
+    pd._pad = 0;
+  }
+  std::vector<ChunkDev> chunks(m.rgs.size() * size_t(m.ncols));
+  for (size_t g = 0; g < m.rgs.size(); g++)
+    for (int c = 0; c < m.ncols; c++) {
+      const ChunkMeta& cm = m.rgs[g].cols[c];
+      if (cm.codec != CODEC_UNCOMPRESSED && cm.codec != CODEC_SNAPPY)
+        return set_error(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED and SNAPPY are implemented)");
+      if (cm.has_dict_page) return set_error(HG_ERR_UNSUPPORTED, "dictionary-encoded column chunk");
+      if (cm.scratch_bytes > 0xffffffffull) return set_error(HG_ERR_UNSUPPORTED, "column chunk larger than 4 GiB");
+      ChunkDev& cd = chunks[g * m.ncols + c];
+      cd.first_page = cm.first_page;
+      cd.num_pages = cm.num_pages;
+      cd.scratch_bytes = uint32_t(cm.scratch_bytes);
+      cd.phys = uint8_t(cm.phys_type);
+      cd.codec = uint8_t(cm.codec);
+      cd.optional = uint8_t(m.repetition[c] == 1);
+      cd._pad = 0;
+    }
+  uint64_t need = size + 64 + pages.size() * sizeof(PageDev) + chunks.size() * sizeof(ChunkDev);
+  if (e->budget && e->resident_bytes + need > e->budget)
+    return set_error(HG_ERR_OOM, "HBM budget exceeded while loading sst " + std::to_string(d->id));
+  CU_TRY(cudaMalloc(&r->d_bytes, size + 64));
+  CU_TRY(cudaMalloc(&r->d_pages, std::max<size_t>(pages.size(), 1) * sizeof(PageDev)));
+  CU_TRY(cudaMalloc(&r->d_chunks, std::max<size_t>(chunks.size(), 1) * sizeof(ChunkDev)));
+  CU_TRY(cudaMemcpyAsync(r->d_bytes, data, size, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(cudaMemsetAsync(r->d_bytes + size, 0, 64, e->stream));
+  if (!pages.empty()) CU_TRY(cudaMemcpyAsync(r->d_pages, pages.data(), pages.size() * sizeof(PageDev), cudaMemcpyHostToDevice, e->stream));
+  if (!chunks.empty()) CU_TRY(cudaMemcpyAsync(r->d_chunks, chunks.data(), chunks.size() * sizeof(ChunkDev), cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(cudaStreamSynchronize(e->stream));
+  r->device_bytes = need;
+  e->resident_bytes += need;
+  e->stats.bytes_h2d += need;
+  e->ssts[d->id] = std::move(r);
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------ scan planning
+struct ScanPlan {
+  std::vector<SstResident*> files;     // in decode order
+  std::vector<RgSel> sel;
+  std::vector<uint32_t> file_base;     // decoded-row base per file (k+1)
+  std::vector<uint32_t> piece_end;     // single-SST pass-through: reader batch boundaries (decoded rows)
+  uint64_t rows_in_files = 0, rows_decoded = 0, scratch_bytes = 0;
+  bool disjoint = false;               // concatenation in decode order is sorted by PK with no cross-file equal PKs
+  std::vector<bool> col_has_nulls;     // per schema column: may any selected chunk contain nulls?
+  bool all_single_plain_page = true;   // every selected chunk is one uncompressed V1 page (fused path precondition)
+};
+
+static bool rg_may_match(const RowGroupMeta& rg, const hg_schema_desc* schema, const hg_predicate* preds, size_t np) {
+  // DataFusion PruningPredicate (pinned by the plan text at read.rs:613):
+  //   CASE WHEN null_count = row_count THEN false ELSE <min/max rewrite of the comparison> END
+  for (size_t i = 0; i < np; i++) {
+    const ChunkMeta& cm = rg.cols[preds[i].column];
+    uint32_t t = schema->types[preds[i].column];
+    if (cm.stats.has_null_count && cm.stats.null_count == rg.num_rows) return false;
+    if (!cm.stats.has_min || !cm.stats.has_max) continue;
+    uint64_t mn = widen_stat(cm.stats.min, cm.phys_type, t), mx = widen_stat(cm.stats.max, cm.phys_type, t);
+    uint64_t lit = pred_literal(preds[i], t);
+    bool ok = true;
+    switch (preds[i].op) {
+      case HG_OP_EQ: ok = cmp_host(mn, lit, t) <= 0 && cmp_host(lit, mx, t) <= 0; break;
+      case HG_OP_NE: ok = cmp_host(mn, lit, t) != 0 || cmp_host(lit, mx, t) != 0; break;
+      case HG_OP_LT: ok = cmp_host(mn, lit, t) < 0; break;
+      case HG_OP_LE: ok = cmp_host(mn, lit, t) <= 0; break;
+      case HG_OP_GT: ok = cmp_host(mx, lit, t) > 0; break;
+      case HG_OP_GE: ok = cmp_host(mx, lit, t) >= 0; break;
+    }
+    if (!ok) return false;
+  }
+  return true;
+}
+
+static int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
+                      size_t np, const std::vector<uint32_t>& need_cols, ScanPlan* plan) {
+  const bool prune = !(e->flags & HG_FLAG_NO_PRUNING);
+  struct FileSel { SstResident* f; std::vector<uint32_t> rgs; bool has_range = false; uint64_t mn = 0, mx = 0; size_t given_idx; };
+  std::vector<FileSel> fs(n);
+  const uint32_t t0 = schema->types[0];
+  bool ranges_ok = true;
+  for (size_t i = 0; i < n; i++) {
+    auto it = e->ssts.find(ssts[i].id);
+    if (it == e->ssts.end()) return set_error(HG_ERR_INTERNAL, "sst not resident after load");
+    fs[i].f = it->second.get();
+    fs[i].given_idx = i;
+    const FileMetaData& m = fs[i].f->meta;
+    for (size_t g = 0; g < m.rgs.size(); g++) {
+      const RowGroupMeta& rg = m.rgs[g];
+      plan->rows_in_files += uint64_t(rg.num_rows);
+      if (rg.num_rows == 0) continue;
+      if (prune && np && !rg_may_match(rg, schema, preds, np)) continue;
+      fs[i].rgs.push_back(uint32_t(g));
+      const ChunkMeta& c0 = rg.cols[0];
+      if (c0.stats.has_min && c0.stats.has_max && (!c0.stats.has_null_count || c0.stats.null_count == 0)) {
+        uint64_t mn = widen_stat(c0.stats.min, c0.phys_type, t0), mx = widen_stat(c0.stats.max, c0.phys_type, t0);
+        if (!fs[i].has_range) { fs[i].mn = mn; fs[i].mx = mx; fs[i].has_range = true; }
+        else {
+          if (cmp_host(mn, fs[i].mn, t0) < 0) fs[i].mn = mn;
+          if (cmp_host(mx, fs[i].mx, t0) > 0) fs[i].mx = mx;
+        }
+      } else ranges_ok = false;
+    }
+  }
+  // PK-disjointness from pk0 chunk statistics: order files by min(pk0); require max_f < min_{f+1} strictly.
+  std::vector<size_t> order(n);
+  for (size_t i = 0; i < n; i++) order[i] = i;
+  plan->disjoint = false;
+  if (n <= 1) plan->disjoint = true;
+  else if (ranges_ok) {
+    std::vector<size_t> nonempty;
+    for (size_t i = 0; i < n; i++) if (!fs[i].rgs.empty()) nonempty.push_back(i);
+    std::stable_sort(nonempty.begin(), nonempty.end(), [&](size_t a, size_t b) { return cmp_host(fs[a].mn, fs[b].mn, t0) < 0; });
+    bool ok = true;
+    for (size_t j = 0; j + 1 < nonempty.size() && ok; j++)
+      ok = cmp_host(fs[nonempty[j]].mx, fs[nonempty[j + 1]].mn, t0) < 0;
+    if (ok) {
+      plan->disjoint = true;
+      order.clear();
+      for (size_t i : nonempty) order.push_back(i);
+      for (size_t i = 0; i < n; i++) if (fs[i].rgs.empty()) order.push_back(i);
+    }
+  }
+  plan->col_has_nulls.assign(schema->num_columns, false);
+  uint64_t row = 0, scratch = 0;
+  for (size_t oi = 0; oi < order.size(); oi++) {
+    FileSel& f = fs[order[oi]];
+    plan->files.push_back(f.f);
+    plan->file_base.push_back(uint32_t(row));
+    const FileMetaData& m = f.f->meta;
+    for (uint32_t g : f.rgs) {
+      const RowGroupMeta& rg = m.rgs[g];
+      RgSel s;
+      s.sst = uint32_t(oi);
+      s.rg = g;
+      s.out_row = uint32_t(row);
+      s.num_rows = uint32_t(rg.num_rows);
+      s.scratch_off = scratch;
+      for (uint32_t c : need_cols) {
+        const ChunkMeta& cm = rg.cols[c];
+        if (cm.codec == CODEC_SNAPPY) scratch += cm.scratch_bytes;
+        if (!(cm.stats.has_null_count && cm.stats.null_count == 0)) plan->col_has_nulls[c] = true;
+        if (cm.codec != CODEC_UNCOMPRESSED || cm.num_pages != 1 || m.pages[cm.first_page].page_type != PAGE_DATA)
+          plan->all_single_plain_page = false;
+      }
+      plan->sel.push_back(s);
+      if (n == 1) {
+        for (int64_t b = e->batch_size; b < rg.num_rows; b += e->batch_size) plan->piece_end.push_back(uint32_t(row + uint64_t(b)));
+        plan->piece_end.push_back(uint32_t(row + uint64_t(rg.num_rows)));
+      }
+      row += uint64_t(rg.num_rows);
+      if (row >= 0xfffffff0ull) return set_error(HG_ERR_UNSUPPORTED, "more than 2^32 rows in one scan call");
+    }
+  }
+  plan->file_base.push_back(uint32_t(row));
+  plan->rows_decoded = row;
+  plan->scratch_bytes = scratch;
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------- the general pipeline
+struct DecodedCol {
+  DevBuf vals, valid;
+  uint32_t type = 0, width = 0;
+  bool present = false;
+  ColView view() const { return ColView{vals.p, reinterpret_cast<const uint8_t*>(valid.p), type, width}; }
+};
+
+struct PipelineState {
+  ScanPlan plan;
+  std::vector<DecodedCol> cols;       // indexed by schema column
+  uint32_t N = 0;                     // decoded rows (capacity of every row-indexed buffer)
+  DevBuf d_ssts, d_sel, d_colsel, d_scratch, d_err, d_counters;   // counters: [0]=M survivors [1]=R outputs [2]=G groups
+  DevBuf alive, surv, keep, out_pos, out_rows, tmp, run_start, file_base, recA, recB, order, chunk_end, piece_end, bound;
+  uint32_t nchunks = 0;
+  const uint32_t* surv_ptr = nullptr;    // nullptr = identity
+  const uint32_t* d_m = nullptr;
+  const uint32_t* d_r = nullptr;
+  const uint32_t* d_g = nullptr;
+  uint32_t* counters() const { return d_counters.as<uint32_t>(); }
+};
+
+static int validate_schema(const hg_schema_desc* s) {
+  if (!s || !s->types) return set_error(HG_ERR_INVALID, "null schema");
+  if (s->num_primary_keys == 0) return set_error(HG_ERR_INVALID, "num_primary_keys should large than 0");  // types.rs:165
+  if (s->num_columns < s->num_primary_keys + 3 || s->num_columns > uint32_t(MAX_COLS))
+    return set_error(HG_ERR_INVALID, "schema needs pk columns, at least one value column and the two builtin columns");
+  if (s->num_primary_keys > uint32_t(MAX_PK)) return set_error(HG_ERR_UNSUPPORTED, "more than 4 primary key columns");
+  if (s->update_mode != HG_UPDATE_OVERWRITE)
+    return set_error(HG_ERR_UNSUPPORTED, "UpdateMode::Append (BytesMergeOperator) is not implemented on the GPU path");
+  uint32_t pk_bytes = 0;
+  for (uint32_t c = 0; c < s->num_columns; c++) if (s->types[c] > T_F64) return set_error(HG_ERR_INVALID, "bad column type");
+  for (uint32_t c = 0; c < s->num_primary_keys; c++) {
+    uint32_t t = s->types[c];
+    // primary_key_eq supports exactly these (read.rs:269-286); other types silently compare equal there — fenced off here
+    if (!(t == T_U8 || t == T_I8 || t == T_U32 || t == T_I32 || t == T_U64 || t == T_I64))
+      return set_error(HG_ERR_UNSUPPORTED, "primary key type not supported by the reference's primary_key_eq");
+    pk_bytes += type_width_host(t);
+  }
+  if (pk_bytes > 16) return set_error(HG_ERR_UNSUPPORTED, "primary key wider than 128 bits");
+  if (s->types[s->num_columns - 2] != T_U64 || s->types[s->num_columns - 1] != T_U64)
+    return set_error(HG_ERR_INVALID, "builtin columns must be UInt64");
+  return HG_OK;
+}
+
+static int validate_preds(const hg_schema_desc* s, const hg_predicate* preds, size_t np) {
+  if (np > size_t(MAX_PREDS)) return set_error(HG_ERR_UNSUPPORTED, "more than 8 predicates");
+  for (size_t i = 0; i < np; i++) {
+    if (preds[i].column >= s->num_columns) return set_error(HG_ERR_INVALID, "predicate column out of range");
+    if (preds[i].op > HG_OP_GE) return set_error(HG_ERR_UNSUPPORTED, "predicate operator");
+  }
+  return HG_OK;
+}
+
+// Runs decode -> filter -> merge -> dedup.  On return st->out_rows holds the surviving row ids in stream order,
+// counters()[0..1] = M, R (device), st->out_pos their merged positions.
+static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
+                        size_t np, std::vector<uint32_t> need_cols, bool want_batches, PipelineState* st) {
+  cudaStream_t s = e->stream;
+  Launch L = e->L();
+  // PKs are always needed (dedup); __seq__ whenever a real merge happens (decided after planning, so include it
+  // only if more than one SST is given).
+  for (uint32_t c = 0; c < schema->num_primary_keys; c++) need_cols.push_back(c);
+  for (size_t i = 0; i < np; i++) need_cols.push_back(preds[i].column);
+  std::sort(need_cols.begin(), need_cols.end());
+  need_cols.erase(std::unique(need_cols.begin(), need_cols.end()), need_cols.end());
+  const uint32_t seq_idx = schema->num_columns - 2;
+  {
+    std::vector<uint32_t> probe = need_cols;
+    ScanPlan trial;
+    // plan once without seq to learn disjointness, then add seq if a merge is required
+    int rc = build_plan(e, schema, ssts, n, preds, np, probe, &trial);
+    if (rc) return rc;
+    if (!trial.disjoint && std::find(need_cols.begin(), need_cols.end(), seq_idx) == need_cols.end()) {
+      need_cols.push_back(seq_idx);
+      std::sort(need_cols.begin(), need_cols.end());
+      ScanPlan again;
+      rc = build_plan(e, schema, ssts, n, preds, np, need_cols, &again);
+      if (rc) return rc;
+      st->plan = std::move(again);
+    } else st->plan = std::move(trial);
+  }
+  ScanPlan& plan = st->plan;
+  const uint32_t N = uint32_t(plan.rows_decoded);
+  st->N = N;
+  const int k = int(n);
+
+  CU_TRY(st->d_counters.alloc(8 * sizeof(uint32_t), s));
+  CU_TRY(cudaMemsetAsync(st->d_counters.p, 0, 8 * sizeof(uint32_t), s));
+  CU_TRY(st->d_err.alloc(sizeof(int), s));
+  CU_TRY(cudaMemsetAsync(st->d_err.p, 0, sizeof(int), s));
+  st->d_m = st->counters() + 0;
+  st->d_r = st->counters() + 1;
+  st->d_g = st->counters() + 2;
+
+  // --- S2: decode
+  st->cols.resize(schema->num_columns);
+  std::vector<ColSel> colsel;
+  for (uint32_t c : need_cols) {
+    DecodedCol& dc = st->cols[c];
+    dc.type = schema->types[c];
+    dc.width = type_width_host(dc.type);
+    dc.present = true;
+    CU_TRY(dc.vals.alloc(size_t(N) * dc.width + 16, s));
+    if (plan.col_has_nulls[c]) CU_TRY(dc.valid.alloc(size_t(N) + 16, s));
+    ColSel cs;
+    cs.col = c;
+    cs.type = dc.type;
+    cs.out_width = dc.width;
+    cs._pad = 0;
+    cs.out_vals = dc.vals.p;
+    cs.out_valid = reinterpret_cast<uint8_t*>(dc.valid.p);
+    colsel.push_back(cs);
+  }
+  if (N > 0) {
+    std::vector<SstDev> sd(plan.files.size());
+    for (size_t i = 0; i < plan.files.size(); i++) {
+      SstResident* f = plan.files[i];
+      sd[i] = SstDev{f->d_bytes, f->d_pages, f->d_chunks, uint32_t(f->meta.ncols), uint32_t(f->meta.rgs.size())};
+    }
+    CU_TRY(st->d_ssts.alloc(sd.size() * sizeof(SstDev), s));
+    CU_TRY(st->d_sel.alloc(plan.sel.size() * sizeof(RgSel), s));
+    CU_TRY(st->d_colsel.alloc(colsel.size() * sizeof(ColSel), s));
+    CU_TRY(cudaMemcpyAsync(st->d_ssts.p, sd.data(), sd.size() * sizeof(SstDev), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(st->d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(st->d_colsel.p, colsel.data(), colsel.size() * sizeof(ColSel), cudaMemcpyHostToDevice, s));
+    // the host vectors must outlive the async copies: pageable memcpy is staged synchronously by the runtime
+    if (plan.scratch_bytes) {
+      CU_TRY(st->d_scratch.alloc(plan.scratch_bytes + 64, s));
+      k::snappy_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
+                       int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
+    }
+    k::decode_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
+                     int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
+    st->d_scratch.reset();
+  }
+
+  // --- S3: filter (before the merge, read.rs:459-470)
+  CU_TRY(st->tmp.alloc(k::compact_tmp_elems(N) * sizeof(uint32_t), s));
+  if (np > 0 && N > 0) {
+    PredSet ps;
+    ps.n = int(np);
+    for (size_t i = 0; i < np; i++) {
+      ps.p[i].col = st->cols[preds[i].column].view();
+      ps.p[i].op = preds[i].op;
+      ps.p[i]._pad = 0;
+      ps.p[i].lit = pred_literal(preds[i], schema->types[preds[i].column]);
+    }
+    CU_TRY(st->alive.alloc(size_t(N) + 16, s));
+    CU_TRY(st->surv.alloc(size_t(N) * 4 + 16, s));
+    k::eval_predicates(L, ps, N, st->alive.as<uint8_t>());
+    k::compact_flags(L, st->alive.as<uint8_t>(), N, st->tmp.as<uint32_t>(), st->surv.as<uint32_t>(), st->counters() + 0);
+    st->alive.reset();
+    st->surv_ptr = st->surv.as<uint32_t>();
+  } else {
+    k::fill_u32(L, st->counters() + 0, N, 1);
+    st->surv_ptr = nullptr;
+  }
+
+  // --- S4: merge on (pk..., __seq__) when the inputs are not provably PK-disjoint
+  PkSet pk;
+  pk.n = int(schema->num_primary_keys);
+  for (int c = 0; c < pk.n; c++) {
+    pk.c[c] = st->cols[c].view();
+    if (plan.col_has_nulls[c]) return set_error(HG_ERR_UNSUPPORTED, "NULL primary keys are not supported on the GPU path");
+  }
+  const uint32_t* order = st->surv_ptr;
+  CU_TRY(st->keep.alloc(size_t(N) + 16, s));
+  if (!plan.disjoint && N > 0) {
+    CU_TRY(st->file_base.alloc((k + 1) * sizeof(uint32_t), s));
+    CU_TRY(st->run_start.alloc((k + 2) * sizeof(uint32_t), s));
+    CU_TRY(cudaMemcpyAsync(st->file_base.p, plan.file_base.data(), (k + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    k::survivor_run_starts(L, st->surv_ptr, st->d_m, st->file_base.as<uint32_t>(), k, st->run_start.as<uint32_t>());
+    CU_TRY(st->recA.alloc(size_t(N) * sizeof(SortRec) + 32, s));
+    CU_TRY(st->recB.alloc(size_t(N) * sizeof(SortRec) + 32, s));
+    k::build_records(L, pk, st->cols[seq_idx].view(), st->surv_ptr, st->d_m, N, st->recA.as<SortRec>());
+    SortRec* src = st->recA.as<SortRec>();
+    SortRec* dst = st->recB.as<SortRec>();
+    for (int level = 0; (1 << level) < k; level++) {
+      k::merge_pass(L, src, dst, st->run_start.as<uint32_t>(), k, level, st->d_m, N);
+      std::swap(src, dst);
+    }
+    CU_TRY(st->order.alloc(size_t(N) * 4 + 16, s));
+    k::records_to_rows(L, src, st->d_m, N, st->order.as<uint32_t>());
+    k::dedup_flags_recs(L, src, st->d_m, N, st->keep.as<uint8_t>());
+    order = st->order.as<uint32_t>();
+    st->recA.reset();
+    st->recB.reset();
+    st->surv.reset();
+    st->surv_ptr = nullptr;  // (no longer valid)
+  } else if (N > 0) {
+    k::dedup_flags_cols(L, pk, order, st->d_m, N, st->keep.as<uint8_t>());
+  }
+
+  // --- batch boundaries of MergeStream need the chunking of its INPUT (computed before surv is dropped)
+  if (want_batches && N > 0) {
+    if (k == 1) {
+      st->nchunks = uint32_t(plan.piece_end.size());
+      CU_TRY(st->piece_end.alloc(st->nchunks * sizeof(uint32_t) + 16, s));
+      CU_TRY(st->chunk_end.alloc(st->nchunks * sizeof(uint32_t) + 16, s));
+      CU_TRY(cudaMemcpyAsync(st->piece_end.p, plan.piece_end.data(), st->nchunks * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      k::chunk_ends_from_rows(L, order /* == surv or identity */, st->d_m, st->piece_end.as<uint32_t>(), st->nchunks,
+                              st->chunk_end.as<uint32_t>());
+    } else {
+      st->nchunks = (N + e->batch_size - 1) / e->batch_size;
+      CU_TRY(st->chunk_end.alloc(st->nchunks * sizeof(uint32_t) + 16, s));
+      k::uniform_chunk_ends(L, st->d_m, e->batch_size, st->nchunks, st->chunk_end.as<uint32_t>());
+    }
+  }
+
+  // --- S5/S6: keep the last row of every PK run
+  CU_TRY(st->out_pos.alloc(size_t(N) * 4 + 16, s));
+  CU_TRY(st->out_rows.alloc(size_t(N) * 4 + 16, s));
+  if (N > 0) {
+    // compaction over the first M flags only: flags beyond M are stale, so clear the tail by bounding n on device
+    k::clear_tail(L, st->keep.as<uint8_t>(), st->d_m, N);
+    k::compact_flags(L, st->keep.as<uint8_t>(), N, st->tmp.as<uint32_t>(), st->out_pos.as<uint32_t>(), st->counters() + 1);
+    k::gather_rows(L, order, st->out_pos.as<uint32_t>(), st->d_r, N, st->out_rows.as<uint32_t>());
+    if (want_batches && st->nchunks) {
+      CU_TRY(st->bound.alloc(st->nchunks * sizeof(uint32_t) + 16, s));
+      k::batch_bounds(L, st->out_pos.as<uint32_t>(), st->d_r, st->chunk_end.as<uint32_t>(), st->nchunks, st->bound.as<uint32_t>());
+    }
+  }
+  st->keep.reset();
+  st->order.reset();
+  st->surv.reset();
+  return HG_OK;
+}
+
+static int check_device_error(hg_engine* e, PipelineState* st) {
+  int herr = 0;
+  CU_TRY(cudaMemcpyAsync(&herr, st->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(cudaStreamSynchronize(e->stream));
+  if (herr) return set_error(HG_ERR_FORMAT, "device decode error code " + std::to_string(herr));
+  return HG_OK;
+}
+
+// --------------------------------------------------------------------------------------------- Arrow C stream export
+struct HostColumn {
+  std::string name;
+  uint32_t type = 0, width = 0;
+  void* vals = nullptr;          // pinned host
+  uint8_t* bitmap = nullptr;     // pinned host, nullptr = no nulls
+  int64_t null_count = 0;
+};
+struct StreamData {
+  std::vector<HostColumn> cols;
+  std::vector<uint32_t> batch_start;  // nb+1 row offsets
+  size_t next = 0;
+  std::string last_error;
+  ~StreamData() {
+    for (auto& c : cols) {
+      if (c.vals) cudaFreeHost(c.vals);
+      if (c.bitmap) cudaFreeHost(c.bitmap);
+    }
+  }
+};
+struct StreamPriv { std::shared_ptr<StreamData> data; };
+
+static void schema_release(struct ArrowSchema* s) {
+  if (!s || !s->release) return;
+  for (int64_t i = 0; i < s->n_children; i++) {
+    if (s->children[i]->release) s->children[i]->release(s->children[i]);
+    delete s->children[i];
+  }
+  delete[] s->children;
+  delete reinterpret_cast<std::string*>(s->private_data);
+  s->release = nullptr;
+}
+static void fill_schema(struct ArrowSchema* out, const std::shared_ptr<StreamData>& d) {
+  std::memset(out, 0, sizeof(*out));
+  out->format = "+s";
+  out->name = "";
+  out->n_children = int64_t(d->cols.size());
+  out->children = new ArrowSchema*[d->cols.size() ? d->cols.size() : 1];
+  for (size_t i = 0; i < d->cols.size(); i++) {
+    ArrowSchema* c = new ArrowSchema();
+    std::memset(c, 0, sizeof(*c));
+    std::string* nm = new std::string(d->cols[i].name);
+    c->format = arrow_format(d->cols[i].type);
+    c->name = nm->c_str();
+    c->flags = ARROW_FLAG_NULLABLE;
+    c->private_data = nm;
+    c->release = [](struct ArrowSchema* s) { delete reinterpret_cast<std::string*>(s->private_data); s->release = nullptr; };
+    out->children[i] = c;
+  }
+  out->private_data = nullptr;
+  out->release = schema_release;
+}
+struct ArrayPriv { std::shared_ptr<StreamData> keep; const void* bufs[2]; };
+static void child_release(struct ArrowArray* a) {
+  if (!a || !a->release) return;
+  delete reinterpret_cast<ArrayPriv*>(a->private_data);
+  a->release = nullptr;
+}
+static void batch_release(struct ArrowArray* a) {
+  if (!a || !a->release) return;
+  for (int64_t i = 0; i < a->n_children; i++) {
+    if (a->children[i]->release) a->children[i]->release(a->children[i]);
+    delete a->children[i];
+  }
+  delete[] a->children;
+  delete reinterpret_cast<ArrayPriv*>(a->private_data);
+  a->release = nullptr;
+}
+static int stream_get_schema(struct ArrowArrayStream* st, struct ArrowSchema* out) {
+  fill_schema(out, reinterpret_cast<StreamPriv*>(st->private_data)->data);
+  return 0;
+}
+static int stream_get_next(struct ArrowArrayStream* st, struct ArrowArray* out) {
+  auto d = reinterpret_cast<StreamPriv*>(st->private_data)->data;
+  std::memset(out, 0, sizeof(*out));
+  if (d->next + 1 >= d->batch_start.size()) { out->release = nullptr; return 0; }  // end of stream
+  uint32_t lo = d->batch_start[d->next], hi = d->batch_start[d->next + 1];
+  d->next++;
+  ArrayPriv* top = new ArrayPriv{d, {nullptr, nullptr}};
+  out->length = hi - lo;
+  out->null_count = 0;
+  out->offset = 0;
+  out->n_buffers = 1;
+  out->buffers = top->bufs;
+  out->n_children = int64_t(d->cols.size());
+  out->children = new ArrowArray*[d->cols.size() ? d->cols.size() : 1];
+  for (size_t i = 0; i < d->cols.size(); i++) {
+    ArrowArray* c = new ArrowArray();
+    std::memset(c, 0, sizeof(*c));
+    ArrayPriv* p = new ArrayPriv{d, {d->cols[i].bitmap, d->cols[i].vals}};
+    c->length = hi - lo;
+    c->offset = lo;
+    c->null_count = d->cols[i].bitmap ? -1 : 0;
+    c->n_buffers = 2;
+    c->buffers = p->bufs;
+    c->private_data = p;
+    c->release = child_release;
+    out->children[i] = c;
+  }
+  out->private_data = top;
+  out->release = batch_release;
+  return 0;
+}
+static const char* stream_last_error(struct ArrowArrayStream* st) {
+  auto d = reinterpret_cast<StreamPriv*>(st->private_data)->data;
+  return d->last_error.empty() ? nullptr : d->last_error.c_str();
+}
+static void stream_release(struct ArrowArrayStream* st) {
+  if (!st || !st->release) return;
+  delete reinterpret_cast<StreamPriv*>(st->private_data);
+  st->release = nullptr;
+}
+static void make_stream(struct ArrowArrayStream* out, std::shared_ptr<StreamData> d) {
+  out->get_schema = stream_get_schema;
+  out->get_next = stream_get_next;
+  out->get_last_error = stream_last_error;
+  out->release = stream_release;
+  out->private_data = new StreamPriv{std::move(d)};
+}
+
+static const char* col_name(const hg_schema_desc* s, uint32_t c, std::string* tmp) {
+  if (s->names && s->names[c]) return s->names[c];
+  *tmp = "c" + std::to_string(c);
+  return tmp->c_str();
+}
+
+// ------------------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+uint32_t hg_abi_version(void) { return HG_ABI_VERSION; }
+const char* hg_last_error(void) { return g_last_error.c_str(); }
+
+int hg_engine_create(const hg_config* cfg, hg_engine** out) {
+  if (!cfg || !out) return set_error(HG_ERR_INVALID, "null argument");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return set_error(HG_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return set_error(HG_ERR_INVALID, "device ordinal out of range");
+  CU_TRY(cudaSetDevice(cfg->device));
+  auto e = std::make_unique<hg_engine>();
+  e->device = cfg->device;
+  e->batch_size = cfg->batch_size ? cfg->batch_size : 8192;
+  e->flags = cfg->flags;
+  e->budget = cfg->hbm_budget_bytes;
+  CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreate(&e->ev0));
+  CU_TRY(cudaEventCreate(&e->ev1));
+  cudaMemPool_t pool;
+  CU_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+  uint64_t thresh = UINT64_MAX;
+  CU_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  *out = e.release();
+  return HG_OK;
+}
+
+void hg_engine_destroy(hg_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (void* p : e->agg_keep) cudaFree(p);
+  e->fused_ws.release();
+  e->ssts.clear();
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+void* hg_engine_stream(hg_engine* e) { return e ? reinterpret_cast<void*>(e->stream) : nullptr; }
+
+int hg_sst_load(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* sst) {
+  if (!e || !schema || !sst) return set_error(HG_ERR_INVALID, "null argument");
+  int rc = validate_schema(schema);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(e->mu);
+  CU_TRY(cudaSetDevice(e->device));
+  return load_sst_locked(e, schema, sst);
+}
+
+int hg_sst_unload(hg_engine* e, uint64_t id) {
+  if (!e) return set_error(HG_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> g(e->mu);
+  auto it = e->ssts.find(id);
+  if (it == e->ssts.end()) return set_error(HG_ERR_NOT_FOUND, "sst not resident");
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->resident_bytes -= it->second->device_bytes;
+  e->ssts.erase(it);
+  return HG_OK;
+}
+
+int hg_sst_resident_bytes(hg_engine* e, uint64_t* out) {
+  if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  *out = e->resident_bytes;
+  return HG_OK;
+}
+
+int hg_last_stats(hg_engine* e, hg_scan_stats* out) {
+  if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  *out = e->stats;
+  return HG_OK;
+}
+
+static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds, size_t np) {
+  int rc = validate_schema(schema);
+  if (rc) return rc;
+  rc = validate_preds(schema, preds, np);
+  if (rc) return rc;
+  if (n && !ssts) return set_error(HG_ERR_INVALID, "null sst list");
+  CU_TRY(cudaSetDevice(e->device));
+  std::memset(&e->stats, 0, sizeof(e->stats));
+  e->launches = 0;
+  for (size_t i = 0; i < n; i++) {
+    rc = load_sst_locked(e, schema, &ssts[i]);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaEventRecord(e->ev0, e->stream));
+  return HG_OK;
+}
+
+static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
+                     size_t np, const uint32_t* projection, size_t nproj, int keep_builtin, struct ArrowArrayStream* out) {
+  if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = begin_call(e, schema, ssts, n, preds, np);
+  if (rc) return rc;
+  cudaStream_t s = e->stream;
+  Launch L = e->L();
+  // output columns: all user columns (+ builtin when keep_builtin) or the projection (treated as a
+  // post-merge column selection over the user columns)
+  std::vector<uint32_t> out_cols;
+  const uint32_t user_cols = schema->num_columns - 2;
+  if (projection) {
+    for (size_t i = 0; i < nproj; i++) {
+      if (projection[i] >= schema->num_columns) return set_error(HG_ERR_INVALID, "projection index out of range");
+      out_cols.push_back(projection[i]);
+    }
+  } else {
+    for (uint32_t c = 0; c < (keep_builtin ? schema->num_columns : user_cols); c++) out_cols.push_back(c);
+  }
+  auto data = std::make_shared<StreamData>();
+  std::string tmpname;
+  for (uint32_t c : out_cols) {
+    HostColumn hc;
+    hc.name = col_name(schema, c, &tmpname);
+    hc.type = schema->types[c];
+    hc.width = type_width_host(hc.type);
+    data->cols.push_back(hc);
+  }
+  data->batch_start.push_back(0);
+  if (n == 0) { make_stream(out, data); return HG_OK; }   // EmptyRecordBatchStream (storage.rs:337-341)
+
+  PipelineState st;
+  rc = run_pipeline(e, schema, ssts, n, preds, np, out_cols, /*want_batches=*/true, &st);
+  if (rc) return rc;
+  const uint32_t N = st.N;
+  uint32_t hc[8] = {0};
+  CU_TRY(cudaMemcpyAsync(hc, st.d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  rc = check_device_error(e, &st);   // synchronises
+  if (rc) return rc;
+  const uint32_t M = hc[0], R = hc[1];
+  // gather + export
+  DevBuf d_null;
+  CU_TRY(d_null.alloc(sizeof(unsigned long long) * out_cols.size() + 16, s));
+  CU_TRY(cudaMemsetAsync(d_null.p, 0, sizeof(unsigned long long) * out_cols.size() + 16, s));
+  std::vector<DevBuf> gv(out_cols.size()), gb(out_cols.size()), gm(out_cols.size());
+  uint64_t d2h = 0;
+  for (size_t i = 0; i < out_cols.size() && R > 0; i++) {
+    DecodedCol& dc = st.cols[out_cols[i]];
+    HostColumn& hcx = data->cols[i];
+    CU_TRY(gv[i].alloc(size_t(R) * dc.width + 16, s));
+    bool nulls = dc.valid.p != nullptr;
+    if (nulls) { CU_TRY(gb[i].alloc(size_t(R) + 16, s)); CU_TRY(gm[i].alloc((size_t(R) + 7) / 8 + 16, s)); }
+    k::gather_column(L, dc.view(), st.out_rows.as<uint32_t>(), st.d_r, R, gv[i].p, gb[i].as<uint8_t>());
+    CU_TRY(cudaMallocHost(&hcx.vals, size_t(R) * dc.width + 16));
+    CU_TRY(cudaMemcpyAsync(hcx.vals, gv[i].p, size_t(R) * dc.width, cudaMemcpyDeviceToHost, s));
+    d2h += size_t(R) * dc.width;
+    if (nulls) {
+      k::pack_validity(L, gb[i].as<uint8_t>(), R, gm[i].as<uint8_t>(), d_null.as<unsigned long long>() + i);
+      CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&hcx.bitmap), (size_t(R) + 7) / 8 + 16));
+      CU_TRY(cudaMemcpyAsync(hcx.bitmap, gm[i].p, (size_t(R) + 7) / 8, cudaMemcpyDeviceToHost, s));
+      d2h += (size_t(R) + 7) / 8;
+    }
+  }
+  std::vector<uint32_t> bound(st.nchunks);
+  if (st.nchunks && N > 0) CU_TRY(cudaMemcpyAsync(bound.data(), st.bound.p, st.nchunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaEventRecord(e->ev1, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  // MergeStream batch boundaries (read.rs:289-343, 349-384): batch c = outputs [bound[c-1], bound[c]); final flush = the rest
+  uint32_t prev = 0;
+  for (uint32_t c = 0; c < st.nchunks; c++) {
+    uint32_t b = std::min(bound[c], R);
+    if (b > prev) { data->batch_start.push_back(b); prev = b; }
+  }
+  if (R > prev) data->batch_start.push_back(R);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.rows_in_files = st.plan.rows_in_files;
+  e->stats.rows_decoded = st.plan.rows_decoded;
+  e->stats.rows_filtered = M;
+  e->stats.rows_out = R;
+  e->stats.bytes_d2h = d2h;
+  e->stats.kernel_launches = e->launches;
+  e->stats.gpu_ms = ms;
+  e->stats.path = 0;
+  make_stream(out, data);
+  return HG_OK;
+}
+
+int hg_scan_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
+                 size_t n_preds, const uint32_t* projection, size_t n_projection, int keep_builtin, struct ArrowArrayStream* out) {
+  return scan_impl(e, schema, ssts, n_ssts, preds, n_preds, projection, n_projection, keep_builtin, out);
+}
+
+int hg_compact_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, struct ArrowArrayStream* out) {
+  // Executor::do_compaction builds the same plan with no predicate and keep_builtin = true (executor.rs:164-169)
+  return scan_impl(e, schema, ssts, n_ssts, nullptr, 0, nullptr, 0, 1, out);
+}
+
+
+static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
+                          size_t np, const hg_agg_spec* agg, AggBuffers* ab) {
+  cudaStream_t s = e->stream;
+  Launch L = e->L();
+  if (!agg) return set_error(HG_ERR_INVALID, "null aggregation spec");
+  auto col_ok = [&](int32_t c) { return c < 0 || uint32_t(c) < schema->num_columns; };
+  if (!col_ok(agg->group_col) || !col_ok(agg->ts_col) || !col_ok(agg->value_col)) return set_error(HG_ERR_INVALID, "aggregation column out of range");
+  const bool has_ts = agg->ts_col >= 0 && agg->window_ms > 0;
+  if (has_ts && type_is_float(schema->types[agg->ts_col])) return set_error(HG_ERR_INVALID, "time column must be an integer column");
+  if (agg->group_col >= 0) { ab->gtype = schema->types[agg->group_col]; ab->gwidth = type_width_host(ab->gtype); }
+  if (n == 0) { ab->G = 0; return HG_OK; }
+
+  // fused fast path: sorted PK-disjoint inputs, one uncompressed PLAIN page per chunk, group = pk0, time = pk1
+  if (!(e->flags & HG_FLAG_NO_FUSED)) {
+    int frc = fused::try_scan_aggregate(e, schema, ssts, n, preds, np, agg, ab);
+    if (frc != fused::NOT_APPLICABLE) return frc;
+  }
+
+  std::vector<uint32_t> need;
+  if (agg->group_col >= 0) need.push_back(uint32_t(agg->group_col));
+  if (has_ts) need.push_back(uint32_t(agg->ts_col));
+  if (agg->value_col >= 0) need.push_back(uint32_t(agg->value_col));
+  PipelineState st;
+  int rc = run_pipeline(e, schema, ssts, n, preds, np, need, /*want_batches=*/false, &st);
+  if (rc) return rc;
+  const uint32_t N = st.N;
+  AggSpecDev spec;
+  std::memset(&spec, 0, sizeof(spec));
+  spec.has_group = agg->group_col >= 0;
+  spec.has_ts = has_ts;
+  spec.has_value = agg->value_col >= 0;
+  spec.window_ms = has_ts ? agg->window_ms : 1;
+  if (spec.has_group) spec.group = st.cols[agg->group_col].view();
+  if (spec.has_ts) spec.ts = st.cols[agg->ts_col].view();
+  if (spec.has_value) spec.value = st.cols[agg->value_col].view();
+  DevBuf head, seg;
+  CU_TRY(head.alloc(size_t(N) + 16, s));
+  CU_TRY(seg.alloc(size_t(N) * 4 + 16, s));
+  uint32_t hc[8] = {0};
+  if (N > 0) {
+    k::group_flags(L, spec, st.out_rows.as<uint32_t>(), st.d_r, N, head.as<uint8_t>());
+    k::clear_tail(L, head.as<uint8_t>(), st.d_r, N);
+    k::compact_flags(L, head.as<uint8_t>(), N, st.tmp.as<uint32_t>(), seg.as<uint32_t>(), st.counters() + 2);
+  }
+  CU_TRY(cudaMemcpyAsync(hc, st.d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  rc = check_device_error(e, &st);
+  if (rc) return rc;
+  const uint32_t G = hc[2];
+  ab->G = G;
+  CU_TRY(ab->gkey.alloc(size_t(G) * 8 + 16, s));
+  CU_TRY(ab->bucket.alloc(size_t(G) * 8 + 16, s));
+  CU_TRY(ab->count.alloc(size_t(G) * 8 + 16, s));
+  CU_TRY(ab->sum.alloc(size_t(G) * 8 + 16, s));
+  CU_TRY(ab->mn.alloc(size_t(G) * 8 + 16, s));
+  CU_TRY(ab->mx.alloc(size_t(G) * 8 + 16, s));
+  AggOut ao{ab->gkey.p, ab->bucket.as<int64_t>(), ab->count.as<uint64_t>(), ab->sum.as<double>(), ab->mn.as<double>(), ab->mx.as<double>()};
+  if (G > 0) k::reduce_groups(L, spec, st.out_rows.as<uint32_t>(), st.d_r, seg.as<uint32_t>(), st.d_g, G, ao);
+  e->stats.rows_in_files = st.plan.rows_in_files;
+  e->stats.rows_decoded = st.plan.rows_decoded;
+  e->stats.rows_filtered = hc[0];
+  e->stats.rows_out = hc[1];
+  e->stats.groups_out = G;
+  e->stats.path = 0;
+  return HG_OK;
+}
+
+int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
+                             const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg, hg_agg_device* out) {
+  if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds);
+  if (rc) return rc;
+  for (void* p : e->agg_keep) cudaFreeAsync(p, e->stream);
+  e->agg_keep.clear();
+  AggBuffers ab;
+  rc = aggregate_core(e, schema, ssts, n_ssts, preds, n_preds, agg, &ab);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord(e->ev1, e->stream));
+  CU_TRY(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.gpu_ms = ms;
+  e->stats.kernel_launches = e->launches;
+  out->num_groups = ab.G;
+  out->d_gkey = ab.gkey.p;
+  out->d_bucket = ab.bucket.as<int64_t>();
+  out->d_count = ab.count.as<uint64_t>();
+  out->d_sum = ab.sum.as<double>();
+  out->d_min = ab.mn.as<double>();
+  out->d_max = ab.mx.as<double>();
+  for (DevBuf* b : {&ab.gkey, &ab.bucket, &ab.count, &ab.sum, &ab.mn, &ab.mx}) if (b->p) e->agg_keep.push_back(b->release());
+  return HG_OK;
+}
+
+int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
+                      size_t n_preds, const hg_agg_spec* agg, struct ArrowArrayStream* out) {
+  if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds);
+  if (rc) return rc;
+  cudaStream_t s = e->stream;
+  AggBuffers ab;
+  rc = aggregate_core(e, schema, ssts, n_ssts, preds, n_preds, agg, &ab);
+  if (rc) return rc;
+  const uint32_t G = ab.G;
+  auto data = std::make_shared<StreamData>();
+  std::string tmp;
+  struct Src { const char* name; uint32_t type; void* dev; uint32_t width; };
+  std::vector<Src> srcs;
+  if (agg->group_col >= 0) srcs.push_back({col_name(schema, uint32_t(agg->group_col), &tmp), ab.gtype, ab.gkey.p, ab.gwidth});
+  if (agg->ts_col >= 0 && agg->window_ms > 0) srcs.push_back({"bucket", T_I64, ab.bucket.p, 8});
+  srcs.push_back({"count", T_U64, ab.count.p, 8});
+  if (agg->value_col >= 0) {
+    srcs.push_back({"sum", T_F64, ab.sum.p, 8});
+    srcs.push_back({"min", T_F64, ab.mn.p, 8});
+    srcs.push_back({"max", T_F64, ab.mx.p, 8});
+  }
+  uint64_t d2h = 0;
+  for (auto& sc : srcs) {
+    HostColumn hc;
+    hc.name = sc.name;
+    hc.type = sc.type;
+    hc.width = sc.width;
+    if (G) {
+      CU_TRY(cudaMallocHost(&hc.vals, size_t(G) * sc.width + 16));
+      CU_TRY(cudaMemcpyAsync(hc.vals, sc.dev, size_t(G) * sc.width, cudaMemcpyDeviceToHost, s));
+      d2h += size_t(G) * sc.width;
+    }
+    data->cols.push_back(hc);
+  }
+  CU_TRY(cudaEventRecord(e->ev1, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.gpu_ms = ms;
+  e->stats.bytes_d2h = d2h;
+  e->stats.kernel_launches = e->launches;
+  data->batch_start.push_back(0);
+  if (G) data->batch_start.push_back(G);
+  make_stream(out, data);
+  return HG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// engine_internal.h — internals shared by engine.cu and fused_scan.cu (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/horae_gpu.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "parquet_meta.hpp"
+
+namespace horae {
+namespace fused { struct Workspace { void* p = nullptr; size_t bytes = 0; void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; } }; }
+}
+using namespace horae;
+
+// --------------------------------------------------------------------------------------------------- error plumbing
+int set_error(int code, const std::string& msg);   // defined in engine.cu (thread-local message)
+#define CU_TRY(expr)                                                                                         \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess)                                                                                   \
+      return set_error(HG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+  } while (0)
+
+inline uint32_t type_width_host(uint32_t t) {
+  switch (t) {
+    case T_U8: case T_I8: return 1;
+    case T_U16: case T_I16: return 2;
+    case T_U32: case T_I32: case T_F32: return 4;
+    default: return 8;
+  }
+}
+inline bool type_is_signed(uint32_t t) { return t == T_I8 || t == T_I16 || t == T_I32 || t == T_I64; }
+inline bool type_is_float(uint32_t t) { return t == T_F32 || t == T_F64; }
+inline int expected_phys(uint32_t t) {
+  switch (t) {
+    case T_U64: case T_I64: return PT_INT64;
+    case T_F32: return PT_FLOAT;
+    case T_F64: return PT_DOUBLE;
+    default: return PT_INT32;
+  }
+}
+inline const char* arrow_format(uint32_t t) {
+  static const char* f[] = {"C", "c", "S", "s", "I", "i", "L", "l", "f", "g"};
+  return f[t];
+}
+
+// widen a PLAIN-encoded statistics value to the comparison domain (i64 / u64 / f64 bits)
+inline uint64_t widen_stat(const uint8_t raw[8], int phys, uint32_t t) {
+  if (phys == PT_INT32) {
+    int32_t v;
+    std::memcpy(&v, raw, 4);
+    switch (t) {
+      case T_U8: return uint8_t(v);
+      case T_U16: return uint16_t(v);
+      case T_U32: return uint32_t(v);
+      default: return uint64_t(int64_t(v));
+    }
+  }
+  if (phys == PT_FLOAT) {
+    float f;
+    std::memcpy(&f, raw, 4);
+    double d = f;
+    uint64_t v;
+    std::memcpy(&v, &d, 8);
+    return v;
+  }
+  uint64_t v;
+  std::memcpy(&v, raw, 8);
+  return v;
+}
+inline int cmp_host(uint64_t a, uint64_t b, uint32_t t) {
+  if (type_is_float(t)) {
+    double x, y;
+    std::memcpy(&x, &a, 8);
+    std::memcpy(&y, &b, 8);
+    return x < y ? -1 : (x > y ? 1 : 0);
+  }
+  if (type_is_signed(t)) {
+    int64_t x = int64_t(a), y = int64_t(b);
+    return x < y ? -1 : (x > y ? 1 : 0);
+  }
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+inline uint64_t pred_literal(const hg_predicate& p, uint32_t t) {
+  if (type_is_float(t)) {
+    uint64_t v;
+    std::memcpy(&v, &p.f64, 8);
+    return v;
+  }
+  return type_is_signed(t) ? uint64_t(p.i64) : p.u64;
+}
+
+// ------------------------------------------------------------------------------------------------------ SST residency
+struct SstResident {
+  uint64_t id = 0, size = 0;
+  FileMetaData meta;
+  uint8_t* d_bytes = nullptr;
+  PageDev* d_pages = nullptr;
+  ChunkDev* d_chunks = nullptr;
+  uint64_t device_bytes = 0;
+  ~SstResident() {
+    if (d_bytes) cudaFree(d_bytes);
+    if (d_pages) cudaFree(d_pages);
+    if (d_chunks) cudaFree(d_chunks);
+  }
+};
+
+struct hg_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t batch_size = 8192;
+  uint32_t flags = 0;
+  uint64_t budget = 0;
+  std::mutex mu;
+  std::unordered_map<uint64_t, std::unique_ptr<SstResident>> ssts;
+  uint64_t resident_bytes = 0;
+  hg_scan_stats stats{};
+  uint32_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<void*> agg_keep;  // device buffers of the last hg_scan_aggregate_device result
+  fused::Workspace fused_ws;
+  Launch L() { return Launch{stream, &launches}; }
+};
+
+// stream-ordered device buffer
+struct DevBuf {
+  void* p = nullptr;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), s(o.s) { o.p = nullptr; }
+  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { reset(); p = o.p; s = o.s; o.p = nullptr; } return *this; }
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+  }
+  cudaError_t alloc(size_t bytes, cudaStream_t st) {
+    reset();
+    s = st;
+    return cudaMallocAsync(&p, bytes ? bytes : 16, st);
+  }
+  void* release() { void* q = p; p = nullptr; return q; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+
+struct AggBuffers {
+  DevBuf gkey, bucket, count, sum, mn, mx;
+  uint32_t G = 0;
+  uint32_t gwidth = 8, gtype = T_U64;
+};
+

@@ -1,0 +1,77 @@
+// kernels.h — host-callable launch wrappers of the sm_100a kernels (kernels.cu, fused_scan.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_types.h"
+
+namespace horae {
+
+struct Launch {
+  cudaStream_t stream;
+  uint32_t* counter;  // host-side count of kernels launched (reported as hg_scan_stats.kernel_launches)
+  void tick() const { if (counter) ++*counter; }
+};
+
+namespace k {
+
+// S2: page decompression + decode --------------------------------------------------------------------------------
+void snappy_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols,
+                   int ncolsel, uint8_t* scratch, int* err);
+void decode_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols,
+                   int ncolsel, const uint8_t* scratch, int* err);
+
+// S3: predicate -> alive bytes -----------------------------------------------------------------------------------
+void eval_predicates(const Launch& L, const PredSet& preds, uint32_t n, uint8_t* alive);
+
+// stream compaction: indices of non-zero flag bytes, in order.  tmp must hold (n/2048+2) uint32.  *d_total = count.
+void compact_flags(const Launch& L, const uint8_t* flags, uint32_t n, uint32_t* tmp, uint32_t* out_idx,
+                   uint32_t* d_total);
+size_t compact_tmp_elems(uint32_t n);
+
+// S4: k-way merge on (pk..., __seq__) ----------------------------------------------------------------------------
+// run_start[f] = first survivor index of file f (k+1 entries, device); derived from decoded-row file bases.
+void survivor_run_starts(const Launch& L, const uint32_t* surv, const uint32_t* d_m, const uint32_t* file_base,
+                         int k, uint32_t* run_start);
+void build_records(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* surv, const uint32_t* d_m,
+                   uint32_t cap, SortRec* rec);
+void merge_pass(const Launch& L, const SortRec* src, SortRec* dst, const uint32_t* run_start, int k, int level,
+                const uint32_t* d_m, uint32_t cap);
+void records_to_rows(const Launch& L, const SortRec* rec, const uint32_t* d_m, uint32_t cap, uint32_t* order);
+
+// S5/S6: PK-run boundaries, LastValue = keep the last row of each run ---------------------------------------------
+// order == nullptr means identity.  keep[j] = 1 iff row order[j] is the last of its PK run in the merged stream.
+void dedup_flags_cols(const Launch& L, const PkSet& pk, const uint32_t* order, const uint32_t* d_m, uint32_t cap,
+                      uint8_t* keep);
+void dedup_flags_recs(const Launch& L, const SortRec* rec, const uint32_t* d_m, uint32_t cap, uint8_t* keep);
+// out_rows[r] = order[out_pos[r]]
+void gather_rows(const Launch& L, const uint32_t* order, const uint32_t* out_pos, const uint32_t* d_r, uint32_t cap,
+                 uint32_t* out_rows);
+// bound[c] = #outputs whose merged position < chunk_end[c] - 1   (batch boundaries of MergeStream, read.rs:289-343)
+void batch_bounds(const Launch& L, const uint32_t* out_pos, const uint32_t* d_r, const uint32_t* chunk_end,
+                  uint32_t nchunks, uint32_t* bound);
+// chunk_end for the single-SST pass-through: #survivors before each reader-batch boundary row
+void chunk_ends_from_rows(const Launch& L, const uint32_t* surv, const uint32_t* d_m, const uint32_t* piece_end_row,
+                          uint32_t npieces, uint32_t* chunk_end);
+
+// output materialisation ------------------------------------------------------------------------------------------
+void gather_column(const Launch& L, ColView src, const uint32_t* rows, const uint32_t* d_r, uint32_t cap,
+                   void* dst_vals, uint8_t* dst_valid);
+void pack_validity(const Launch& L, const uint8_t* valid_bytes, uint32_t n, uint8_t* bitmap,
+                   unsigned long long* null_count);
+
+// A1/A2: time-bucket aggregation over the post-dedup stream -------------------------------------------------------
+void group_flags(const Launch& L, const AggSpecDev& spec, const uint32_t* rows, const uint32_t* d_r, uint32_t cap,
+                 uint8_t* head);
+void reduce_groups(const Launch& L, const AggSpecDev& spec, const uint32_t* rows, const uint32_t* d_r,
+                   const uint32_t* seg_start, const uint32_t* d_g, uint32_t cap, AggOut out);
+
+void fill_u32(const Launch& L, uint32_t* p, uint32_t v, uint32_t n);
+// chunk_end[c] = min((c+1)*batch, *d_m): SortPreservingMergeExec re-batches its output at batch_size rows
+void uniform_chunk_ends(const Launch& L, const uint32_t* d_m, uint32_t batch, uint32_t nchunks, uint32_t* chunk_end);
+// flags[i] = 0 for i in [*d_n, cap)
+void clear_tail(const Launch& L, uint8_t* flags, const uint32_t* d_n, uint32_t cap);
+
+}  // namespace k
+}  // namespace horae

@@ -1,0 +1,168 @@
+/*
+ * horae_gpu.h — C ABI of libhorae_gpu.so, the B200 (sm_100a) implementation of HoraeDB's columnar hot path.
+ *
+ * Every entry point replaces one seam of the reference (paths relative to apache/horaedb @ 9cec5636,
+ * src/columnar_storage/src/):
+ *
+ *   hg_scan_open         ParquetReader::build_df_plan(ssts, projection, predicates, keep_builtin=false)
+ *                        + execute_stream                      read.rs:429-494, storage.rs:350-369
+ *                        i.e. ParquetExec -> FilterExec -> SortPreservingMergeExec -> MergeExec(LastValue)
+ *   hg_compact_open      the same plan as built by Executor::do_compaction: no predicate, keep_builtin=true
+ *                                                              compaction/executor.rs:164-171
+ *   hg_scan_aggregate*   the time-bucket aggregation the metric engine is meant to run on top of the scan
+ *                        (absent in the reference: metric_engine/src/metric/mod.rs:37-49 is todo!();
+ *                        window arithmetic = Timestamp::truncate_by, types.rs:82-85)
+ *   hg_sst_load/unload   residency of immutable SST bytes in HBM, keyed by FileId (sst.rs:48, 193-205)
+ *   hg_schema_desc       StorageSchema (types.rs:143-157);   hg_sst_desc = SstFile + FileMeta (sst.rs:51-53,155-160)
+ *   hg_predicate         the lowered form of ScanRequest.predicate: Vec<Expr> (storage.rs:65-70) — a conjunction of
+ *                        `column <op> literal`; anything else must be rejected by the caller (no CPU fallback)
+ *
+ * Results travel as Arrow C streams (arrow_c_abi.h): the Rust shim wraps them with
+ * arrow::ffi_stream::ArrowArrayStreamReader and hands the batches to DataFusion.
+ *
+ * Conventions: plain C types only; every function returns an hg_status (0 = OK) and records a message readable with
+ * hg_last_error() on the calling thread; nothing throws or aborts across the boundary.  The engine handle is
+ * thread-safe (calls are serialised per engine); streams may be consumed from any thread.
+ */
+#ifndef HORAE_GPU_H
+#define HORAE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "arrow_c_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_ABI_VERSION 1u
+
+typedef struct hg_engine hg_engine;
+
+typedef enum {
+  HG_OK = 0,
+  HG_ERR_INVALID = 1,      /* bad argument / schema mismatch                       (ensure!, macros.rs:36-52) */
+  HG_ERR_UNSUPPORTED = 2,  /* encoding / codec / type / expression not implemented on the GPU path (never a CPU fallback) */
+  HG_ERR_CUDA = 3,
+  HG_ERR_FORMAT = 4,       /* malformed Parquet */
+  HG_ERR_OOM = 5,          /* HBM admission control (the analogue of Executor::pre_check, executor.rs:93-114) */
+  HG_ERR_NOT_FOUND = 6,
+  HG_ERR_INTERNAL = 7
+} hg_status;
+
+/* Arrow primitive types the reference's primary_key_eq / value columns use (read.rs:269-286) */
+typedef enum {
+  HG_U8 = 0, HG_I8 = 1, HG_U16 = 2, HG_I16 = 3, HG_U32 = 4, HG_I32 = 5, HG_U64 = 6, HG_I64 = 7, HG_F32 = 8, HG_F64 = 9
+} hg_type;
+
+typedef enum { HG_UPDATE_OVERWRITE = 0, HG_UPDATE_APPEND = 1 } hg_update_mode; /* config.rs:166-172 */
+
+typedef enum { HG_OP_EQ = 0, HG_OP_NE = 1, HG_OP_LT = 2, HG_OP_LE = 3, HG_OP_GT = 4, HG_OP_GE = 5 } hg_op;
+
+/* StorageSchema (types.rs:143-157): columns = pk0..pkN-1, values..., __seq__ (u64), __reserved__ (u64) */
+typedef struct {
+  uint32_t num_columns;       /* including the two builtin columns */
+  uint32_t num_primary_keys;
+  uint32_t update_mode;       /* hg_update_mode; only OVERWRITE (LastValueOperator, operator.rs:37-44) is implemented */
+  uint32_t _pad;
+  const uint32_t* types;      /* hg_type per column */
+  const char* const* names;   /* column names (for the exported Arrow schema) */
+} hg_schema_desc;
+
+typedef struct {
+  int32_t device;             /* CUDA ordinal (one engine per GPU / per rank) */
+  uint32_t batch_size;        /* DataFusion batch_size the merge re-batches at; 0 = 8192 */
+  uint64_t hbm_budget_bytes;  /* 0 = no admission limit */
+  uint32_t flags;             /* HG_FLAG_* */
+  uint32_t _pad;
+} hg_config;
+
+#define HG_FLAG_NO_PRUNING 1u   /* disable row-group pruning by chunk statistics (for A/B measurements) */
+#define HG_FLAG_NO_FUSED 2u     /* force the general (materialising) pipeline even when the fused fast path applies */
+
+/* SstFile + FileMeta (sst.rs:51-53, 155-160).  `data` may be NULL when the file is already resident (hg_sst_load). */
+typedef struct {
+  uint64_t id;
+  const uint8_t* data;        /* whole-file bytes in host memory, or NULL */
+  uint64_t size;
+  const char* path;           /* optional: "{root}/data/{id}.sst" (sst.rs:202-204), read when data == NULL and not resident */
+  uint32_t num_rows;
+  uint32_t _pad;
+  int64_t time_start, time_end;   /* [start, end) */
+  uint64_t max_sequence;
+} hg_sst_desc;
+
+typedef struct {
+  uint32_t column;            /* index into the storage schema */
+  uint32_t op;                /* hg_op */
+  int64_t i64;                /* literal for signed integer columns */
+  uint64_t u64;               /* literal for unsigned integer columns */
+  double f64;                 /* literal for float columns */
+} hg_predicate;
+
+/* GROUP BY (group column, time bucket) over the post-dedup scan output; groups come out in stream (key) order. */
+typedef struct {
+  int32_t group_col;          /* -1: one global group */
+  int32_t ts_col;             /* -1: no bucketing */
+  int64_t window_ms;          /* bucket = ts / window_ms * window_ms (truncating, types.rs:82-85) */
+  int32_t value_col;          /* -1: count(*) only */
+  uint32_t _pad;
+} hg_agg_spec;
+
+typedef struct {
+  uint64_t rows_in_files;     /* rows of the selected SSTs */
+  uint64_t rows_decoded;      /* after row-group pruning */
+  uint64_t rows_filtered;     /* after the predicate */
+  uint64_t rows_out;          /* after merge + dedup */
+  uint64_t groups_out;
+  uint64_t bytes_h2d, bytes_d2h;
+  uint32_t kernel_launches;   /* kernels launched by the last call */
+  uint32_t path;              /* 0 = general pipeline, 1 = fused fast path */
+  float gpu_ms;               /* device time of the last call's kernels (CUDA events on the engine stream) */
+  float _pad;
+} hg_scan_stats;
+
+/* Device-resident aggregate (for the NCCL combine and HBM-resident timing); valid until the next call on the engine. */
+typedef struct {
+  uint64_t num_groups;
+  const void* d_gkey;         /* group column values, native width */
+  const int64_t* d_bucket;
+  const uint64_t* d_count;
+  const double* d_sum;
+  const double* d_min;
+  const double* d_max;
+} hg_agg_device;
+
+uint32_t hg_abi_version(void);
+const char* hg_last_error(void);
+
+int hg_engine_create(const hg_config* cfg, hg_engine** out);
+void hg_engine_destroy(hg_engine* e);
+void* hg_engine_stream(hg_engine* e); /* the cudaStream_t every kernel of this engine is launched on */
+
+int hg_sst_load(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* sst);
+int hg_sst_unload(hg_engine* e, uint64_t id);
+int hg_sst_resident_bytes(hg_engine* e, uint64_t* out);
+
+int hg_scan_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
+                 const hg_predicate* preds, size_t n_preds, const uint32_t* projection, size_t n_projection,
+                 int keep_builtin, struct ArrowArrayStream* out);
+
+int hg_compact_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
+                    struct ArrowArrayStream* out);
+
+int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
+                      const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg,
+                      struct ArrowArrayStream* out);
+
+int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
+                             const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg,
+                             hg_agg_device* out);
+
+int hg_last_stats(hg_engine* e, hg_scan_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HORAE_GPU_H */

@@ -1,0 +1,294 @@
+"""GPU parity tests: every call goes through the C ABI (libhorae_gpu.so) and is compared with the CPU oracle and with
+the reference's own test vectors.  Integer / selection / ordering results must be bit-exact; f64 sums too (sequential
+order)."""
+import io
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+from helpers import arrow_schema, check_stream, record_batch
+from horaedb_b200 import sstgen
+from horaedb_b200._ffi import HG_FLAG_NO_FUSED, HG_FLAG_NO_PRUNING, Engine, HgError, SchemaHandle, SstInput
+from horaedb_b200.config import ParquetCompression, StorageConfig, WriteConfig
+from horaedb_b200.storage import ObjectBasedStorage, ScanRequest, Task, WriteRequest, col, lit
+from horaedb_b200.types import SEQ_COLUMN_NAME, StorageSchema, TimeRange, Timestamp
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+_ids = iter(range(10_000, 10_000_000))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(device=0)
+    yield e
+    e.close()
+
+
+def _inputs(datas):
+    return [SstInput(id=next(_ids), data=d) for d in datas]
+
+
+def _scan_both(eng, schema, datas, preds=(), keep_builtin=False, batch_size=8192):
+    handle = SchemaHandle(schema.arrow_schema, schema.num_primary_keys)
+    e = eng if batch_size == 8192 else Engine(device=0, batch_size=batch_size)
+    got = list(e.scan(handle, _inputs(datas), preds, None, keep_builtin))
+    exp = oracle.scan(datas, schema.arrow_schema, schema.num_primary_keys, preds, keep_builtin, batch_size).batches
+    if e is not eng:
+        e.close()
+    return got, exp
+
+
+# ------------------------------------------------------------------------------------------ reference golden vectors
+@pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed])
+def test_storage_write_and_scan(golden, tmp_path, eng, compression):  # storage.rs:391-491
+    g = golden["test_storage_write_and_scan"]
+    user = arrow_schema(g["schema"])
+    cfg = StorageConfig(write=WriteConfig(compression=compression))
+    storage = ObjectBasedStorage(str(tmp_path), g["segment_duration_ms"], user, g["num_primary_keys"], cfg, engine=eng)
+    for w in g["writes"]:
+        storage.write(WriteRequest(record_batch(user, w), TimeRange(*w["time_range"]), enable_check=True))
+    stream = storage.scan(ScanRequest(TimeRange.new(Timestamp(0), Timestamp.MAX), [], None))
+    check_stream(stream, [record_batch(user, e) for e in g["scan_all_expected"]])
+    stream = storage.scan(ScanRequest(TimeRange.new(Timestamp(0), Timestamp.MAX), [col("pk1").eq(lit(11))], None))
+    check_stream(stream, [record_batch(user, e) for e in g["scan_pk1_eq_11_expected"]])
+    # compaction: same plan with keep_builtin (executor.rs:164-169); afterwards one SST, same scan result
+    new = storage.compact()
+    assert len(new) == 1 and len(storage.manifest.all_ssts()) == 1 and new[0].meta().num_rows == 5
+    stream = storage.scan(ScanRequest(TimeRange.new(Timestamp(0), Timestamp.MAX), [], None))
+    rows = pa.Table.from_batches(list(stream))
+    exp = pa.Table.from_batches([record_batch(user, e) for e in g["scan_all_expected"]])
+    assert rows.equals(exp)
+
+
+def test_merge_stream_vectors_as_ssts(golden, eng):
+    """read.rs:512-573 — the same PK/seq stream (values as integers), fed as three SSTs; boundaries vs the oracle."""
+    g = golden["test_merge_stream"]
+    user = arrow_schema([("pk1", "uint8"), ("value", "int64")])
+    schema = StorageSchema.try_new(user, 1)
+    datas = []
+    for b in g["input_batches"]:
+        # one SST per distinct seq so that the merged (pk, seq) order equals the test's input order
+        for pk, v, seq in zip(b["pk1"], b["value"], b["__seq__"]):
+            datas.append(sstgen.write_sst(schema, record_batch(user, {"pk1": [pk], "value": [int(v)]}), seq=seq))
+    for bs in (2, 5, 8192):
+        got, exp = _scan_both(eng, schema, datas, batch_size=bs)
+        check_stream(got, exp)
+    got, _ = _scan_both(eng, schema, datas)
+    out = pa.Table.from_batches(got)
+    assert out["pk1"].to_pylist() == [11, 12, 13, 14] and out["value"].to_pylist() == [2, 4, 8, 9]
+
+
+# ------------------------------------------------------------------------------------------------- decode parity (S2)
+def _random_batch(rng, n, null_frac):
+    sch = arrow_schema([("k1", "uint64"), ("k2", "int64"), ("a", "float64"), ("b", "uint32"), ("c", "int8"),
+                        ("d", "uint8"), ("e", "int32"), ("f", "float32"), ("g", "int16"), ("h", "uint16")])
+    k1 = np.sort(rng.integers(0, max(n // 7, 1), n).astype(np.uint64))
+    k2 = np.arange(n, dtype=np.int64) - n // 2
+    cols = [pa.array(k1), pa.array(k2)]
+    gens = [lambda: rng.standard_normal(n), lambda: rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32),
+            lambda: rng.integers(-128, 128, n).astype(np.int8), lambda: rng.integers(0, 256, n).astype(np.uint8),
+            lambda: rng.integers(-2**31, 2**31, n).astype(np.int32), lambda: rng.standard_normal(n).astype(np.float32),
+            lambda: rng.integers(-2**15, 2**15, n).astype(np.int16), lambda: rng.integers(0, 2**16, n).astype(np.uint16)]
+    for g in gens:
+        cols.append(pa.array(g(), mask=rng.random(n) < null_frac))
+    return sch, pa.RecordBatch.from_arrays(cols, schema=sch)
+
+
+@pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed])
+@pytest.mark.parametrize("n,null_frac,rg", [(0, 0.0, 8192), (1, 0.0, 8192), (5, 0.5, 2), (1000, 0.0, 8192), (20000, 0.3, 8192),
+                                            (20000, 1.0, 8192), (70000, 0.01, 8192), (9000, 0.9, 100)])
+def test_decode_all_types_and_nulls(eng, compression, n, null_frac, rg):
+    rng = np.random.default_rng(n + int(null_frac * 100))
+    user, batch = _random_batch(rng, n, null_frac)
+    schema = StorageSchema.try_new(user, 2)
+    data = sstgen.write_sst(schema, batch, seq=77, cfg=WriteConfig(compression=compression, max_row_group_size=rg), presorted=True)
+    got, exp = _scan_both(eng, schema, [data], keep_builtin=True)
+    check_stream(got, exp)
+    if n:
+        ref = pq.read_table(io.BytesIO(data)).cast(schema.arrow_schema)
+        assert pa.Table.from_batches(got).equals(ref)      # unique PKs: scan output == file content
+
+
+def test_decode_small_pages_and_v2(eng):
+    rng = np.random.default_rng(3)
+    user, batch = _random_batch(rng, 30000, 0.2)
+    schema = StorageSchema.try_new(user, 2)
+    full = schema.fill_builtin_columns(batch, 5)
+    for version in ("1.0", "2.0"):
+        for comp in ("snappy", "none"):
+            sink = io.BytesIO()
+            pq.write_table(pa.Table.from_batches([full]), sink, row_group_size=8192, compression=comp, use_dictionary=False,
+                           data_page_size=3000, data_page_version=version)
+            data = sink.getvalue()
+            got, exp = _scan_both(eng, schema, [data], keep_builtin=True)
+            check_stream(got, exp)
+            assert pa.Table.from_batches(got).equals(pq.read_table(io.BytesIO(data)).cast(schema.arrow_schema)), (version, comp)
+
+
+# -------------------------------------------------------------------------------------------- filter / merge / dedup
+@pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed])
+def test_filter_predicates_and_pruning(eng, compression):
+    schema = sstgen.metric_storage_schema()
+    datas = [sstgen.synth_sst(lo, lo + 16, 2000, 1000, seq=9 + i, compression=compression)[0] for i, lo in enumerate((0, 16))]
+    t_lo, t_hi = sstgen.T0_MS + 500_000, sstgen.T0_MS + 1_500_000
+    cases = [[("tag", "eq", 3), ("ts", "ge", t_lo), ("ts", "lt", t_hi)], [("value", "gt", 0.75)], [("value", "le", 0.1), ("tag", "ne", 0)],
+             [("series_id", "ge", 30)], [("series_id", "eq", 10**9)], [("ts", "lt", 0)]]
+    for preds in cases:
+        got, exp = _scan_both(eng, schema, datas, preds)
+        check_stream(got, exp)
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    e2 = Engine(device=0, flags=HG_FLAG_NO_PRUNING)
+    a = e2.scan(handle, _inputs(datas), cases[0]).read_all()
+    assert e2.stats()["rows_decoded"] == 64000
+    b = eng.scan(handle, _inputs(datas), cases[0]).read_all()
+    assert eng.stats()["rows_decoded"] < 64000      # chunk statistics pruned row groups, same answer
+    assert a.equals(b)
+    e2.close()
+
+
+@pytest.mark.parametrize("k,bs", [(2, 8192), (3, 100), (6, 256), (9, 8192), (17, 1000)])
+def test_merge_dedup_overlapping_files(eng, k, bs):
+    ssts = sstgen.synth_overlapping_ssts(k, series=50, points=60, delta_ms=1000, keep_frac=0.5,
+                                         compression=ParquetCompression.Snappy if k % 2 else ParquetCompression.Uncompressed)
+    schema = sstgen.metric_storage_schema()
+    datas = [s[0] for s in ssts]
+    for keep_builtin in (False, True):
+        got, exp = _scan_both(eng, schema, datas, keep_builtin=keep_builtin, batch_size=bs)
+        check_stream(got, exp)
+    got, exp = _scan_both(eng, schema, datas, [("value", "lt", 0.5)], keep_builtin=True, batch_size=bs)
+    check_stream(got, exp)     # filter BEFORE dedup: an older version may surface (read.rs:459-480)
+    out = pa.Table.from_batches(got)
+    key = list(zip(out["series_id"].to_pylist(), out["ts"].to_pylist()))
+    assert key == sorted(set(key))
+
+
+def test_intra_file_duplicates_and_int_pk_types(eng):
+    """PK types of primary_key_eq (read.rs:269-286) incl. negative values; duplicate PKs across and inside files."""
+    rng = np.random.default_rng(11)
+    user = arrow_schema([("a", "int8"), ("b", "uint32"), ("c", "int32"), ("v", "int64")])
+    schema = StorageSchema.try_new(user, 3)
+    datas = []
+    for f in range(5):
+        n = 400
+        b = record_batch(user, {"a": rng.integers(-3, 3, n).tolist(), "b": rng.integers(0, 4, n).tolist(),
+                                "c": rng.integers(-2, 2, n).tolist(), "v": rng.integers(0, 10**9, n).tolist()})
+        tbl = pa.Table.from_batches([b]).group_by(["a", "b", "c"]).aggregate([("v", "max")])
+        b = pa.RecordBatch.from_arrays([tbl.column(0).combine_chunks(), tbl.column(1).combine_chunks(), tbl.column(2).combine_chunks(),
+                                        tbl.column(3).combine_chunks()], schema=user)
+        datas.append(sstgen.write_sst(schema, b, seq=500 + f, cfg=WriteConfig(max_row_group_size=32)))
+    for bs in (16, 8192):
+        got, exp = _scan_both(eng, schema, datas, keep_builtin=True, batch_size=bs)
+        check_stream(got, exp)
+
+
+# -------------------------------------------------------------------------------------------------- aggregation (A1-A3)
+def _agg_both(eng, schema, datas, preds, **kw):
+    handle = SchemaHandle(schema.arrow_schema, schema.num_primary_keys)
+    got = eng.scan_aggregate(handle, _inputs(datas), preds, **kw)
+    exp = oracle.scan_aggregate(datas, schema.arrow_schema, schema.num_primary_keys, preds, **kw)
+    return got, exp
+
+
+def _check_agg(got, exp, has_group=True, has_bucket=True, has_value=True):
+    assert got.num_rows == len(exp.count)
+    if has_group:
+        assert got.column(0).to_numpy().astype(np.uint64).tolist() == exp.gkey.tolist()
+    if has_bucket:
+        assert got["bucket"].to_numpy().tolist() == exp.bucket.tolist()
+    assert got["count"].to_numpy().tolist() == exp.count.tolist()
+    if has_value:
+        assert np.array_equal(got["sum"].to_numpy(), exp.sum), "f64 sums must be bit-exact (sequential order)"
+        assert np.array_equal(got["min"].to_numpy(), exp.min)
+        assert np.array_equal(got["max"].to_numpy(), exp.max)
+
+
+@pytest.mark.parametrize("flags", [0, HG_FLAG_NO_FUSED])
+@pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed])
+def test_aggregate_configs(compression, flags):
+    e = Engine(device=0, flags=flags)
+    schema = sstgen.metric_storage_schema()
+    datas = [sstgen.synth_sst(lo, lo + 24, 1500, 10_000, seq=20 + i, compression=compression)[0] for i, lo in enumerate((0, 24, 48))]
+    t_lo, t_hi = sstgen.T0_MS + 3_000_000, sstgen.T0_MS + 9_000_000
+    # config 1: full-scan count(*)
+    got, exp = _agg_both(e, schema, datas, [], group_col=-1, ts_col=-1, window_ms=0, value_col=-1)
+    _check_agg(got, exp, has_group=False, has_bucket=False, has_value=False)
+    assert got["count"].to_pylist() == [72 * 1500]
+    # config 2: time-range + tag predicate, sum(value) per series
+    preds = [("tag", "eq", 3), ("ts", "ge", t_lo), ("ts", "lt", t_hi)]
+    got, exp = _agg_both(e, schema, datas, preds, group_col=0, ts_col=-1, window_ms=0, value_col=2)
+    _check_agg(got, exp, has_bucket=False)
+    assert got.num_rows == 5   # series 3, 19, 35, 51, 67
+    # config 3: 1-minute downsample sum/min/max/count
+    got, exp = _agg_both(e, schema, datas, [], group_col=0, ts_col=1, window_ms=60_000, value_col=2)
+    _check_agg(got, exp)
+    got, exp = _agg_both(e, schema, datas, preds, group_col=0, ts_col=1, window_ms=60_000, value_col=2)
+    _check_agg(got, exp)
+    # empty result
+    got, exp = _agg_both(e, schema, datas, [("ts", "lt", 0)], group_col=0, ts_col=1, window_ms=60_000, value_col=2)
+    assert got.num_rows == 0 and len(exp.count) == 0
+    e.close()
+
+
+def test_aggregate_after_dedup_of_overlapping_files(eng):
+    ssts = sstgen.synth_overlapping_ssts(5, series=30, points=200, delta_ms=5000, keep_frac=0.6)
+    schema = sstgen.metric_storage_schema()
+    datas = [s[0] for s in ssts]
+    got, exp = _agg_both(eng, schema, datas, [("value", "ge", 0.2)], group_col=0, ts_col=1, window_ms=60_000, value_col=2)
+    _check_agg(got, exp)
+    assert int(got["count"].to_numpy().sum()) == exp.rows_out < exp.rows_filtered   # duplicates were removed first
+
+
+def test_aggregate_device_result(eng):
+    import torch
+    schema = sstgen.metric_storage_schema()
+    data, n = sstgen.synth_sst(0, 16, 1000, 1000, seq=5)
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    dev = eng.scan_aggregate_device(handle, _inputs([data]), [], group_col=0, ts_col=-1, window_ms=0, value_col=2)
+    assert dev.num_groups == 16
+    exp = oracle.scan_aggregate([data], schema.arrow_schema, 2, [], group_col=0, value_col=2)
+    import ctypes as C
+    host = np.empty(16, np.float64)
+    torch.cuda.synchronize()
+    rc = torch.cuda.cudart().cudaMemcpy(host.ctypes.data, dev.d_sum, 16 * 8, 2)
+    assert int(rc) == 0 and np.array_equal(host, exp.sum)
+    st = eng.stats()
+    assert st["rows_in_files"] == n and st["kernel_launches"] > 0 and st["gpu_ms"] > 0
+
+
+# ------------------------------------------------------------------------------------------------------- edge / errors
+def test_empty_inputs(eng):
+    schema = sstgen.metric_storage_schema()
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    assert eng.scan(handle, [], []).read_all().num_rows == 0       # EmptyRecordBatchStream (storage.rs:337-341)
+    empty = sstgen.write_sst(schema, pa.RecordBatch.from_arrays([pa.array([], f.type) for f in sstgen.METRIC_SCHEMA],
+                                                                schema=sstgen.METRIC_SCHEMA), seq=1)
+    data, n = sstgen.synth_sst(0, 4, 10, 1000, seq=2)
+    got, exp = _scan_both(eng, schema, [empty, data, empty])
+    check_stream(got, exp)
+    got, exp = _scan_both(eng, schema, [empty])
+    assert got == [] and exp == []
+
+
+def test_unsupported_is_an_error_not_a_fallback(eng):
+    schema = sstgen.metric_storage_schema()
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    data, _ = sstgen.synth_sst(0, 4, 10, 1000, seq=2, compression="zstd")
+    with pytest.raises(HgError) as ei:
+        eng.scan(handle, _inputs([data]), [])
+    assert ei.value.code == 2
+    append = SchemaHandle(schema.arrow_schema, 2, update_mode=1)
+    data, _ = sstgen.synth_sst(0, 4, 10, 1000, seq=2)
+    with pytest.raises(HgError) as ei:
+        eng.scan(append, _inputs([data]), [])
+    assert ei.value.code == 2
+    with pytest.raises(HgError) as ei:
+        eng.scan(handle, [SstInput(id=424242)], [])
+    assert ei.value.code == 6
+    with pytest.raises(HgError) as ei:
+        eng.scan(handle, _inputs([b"PAR1garbagePAR1"]), [])
+    assert ei.value.code == 4
