@@ -8,7 +8,7 @@ from horaedb_b200 import _ffi
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "horae_gpu.h")).read()
-    declared = set(re.findall(r"\b(hg_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"^(?:int|void\*?|uint32_t|const char\*)\s+(hg_[a-z_]+)\s*\(", hdr, flags=re.M))
     assert declared, "no declarations found"
     L = _ffi.lib()
     for sym in sorted(declared):
