@@ -56,7 +56,7 @@ class HgAggSpec(C.Structure):
 class HgScanStats(C.Structure):
     _fields_ = [("rows_in_files", C.c_uint64), ("rows_decoded", C.c_uint64), ("rows_filtered", C.c_uint64),
                 ("rows_out", C.c_uint64), ("groups_out", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
-                ("kernel_launches", C.c_uint32), ("path", C.c_uint32), ("gpu_ms", C.c_float), ("_pad", C.c_float)]
+                ("kernel_launches", C.c_uint32), ("path", C.c_uint32), ("gpu_ms", C.c_float), ("kernel_ms", C.c_float)]
 
 
 class HgAggDevice(C.Structure):
@@ -110,6 +110,13 @@ class SstInput:
     max_sequence: int = 0
     ptr: int = 0                    # raw host pointer (e.g. pinned memory) used instead of `data`
     size: int = 0
+
+
+class DeviceArray:
+    """Zero-copy view of an engine-owned device buffer (`__cuda_array_interface__`), e.g. for torch.as_tensor(...)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr or 0), False), "version": 2}
 
 
 class SchemaHandle:

@@ -111,17 +111,6 @@ static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_
 }
 
 // ------------------------------------------------------------------------------------------------------ scan planning
-struct ScanPlan {
-  std::vector<SstResident*> files;     // in decode order
-  std::vector<RgSel> sel;
-  std::vector<uint32_t> file_base;     // decoded-row base per file (k+1)
-  std::vector<uint32_t> piece_end;     // single-SST pass-through: reader batch boundaries (decoded rows)
-  uint64_t rows_in_files = 0, rows_decoded = 0, scratch_bytes = 0;
-  bool disjoint = false;               // concatenation in decode order is sorted by PK with no cross-file equal PKs
-  std::vector<bool> col_has_nulls;     // per schema column: may any selected chunk contain nulls?
-  bool all_single_plain_page = true;   // every selected chunk is one uncompressed V1 page (fused path precondition)
-};
-
 static bool rg_may_match(const RowGroupMeta& rg, const hg_schema_desc* schema, const hg_predicate* preds, size_t np) {
   // DataFusion PruningPredicate (pinned by the plan text at read.rs:613):
   //   CASE WHEN null_count = row_count THEN false ELSE <min/max rewrite of the comparison> END
@@ -146,7 +135,7 @@ static bool rg_may_match(const RowGroupMeta& rg, const hg_schema_desc* schema, c
   return true;
 }
 
-static int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
+int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
                       size_t np, const std::vector<uint32_t>& need_cols, ScanPlan* plan) {
   const bool prune = !(e->flags & HG_FLAG_NO_PRUNING);
   struct FileSel { SstResident* f; std::vector<uint32_t> rgs; bool has_range = false; uint64_t mn = 0, mx = 0; size_t given_idx; };
@@ -359,6 +348,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     CU_TRY(cudaMemcpyAsync(st->d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(st->d_colsel.p, colsel.data(), colsel.size() * sizeof(ColSel), cudaMemcpyHostToDevice, s));
     // the host vectors must outlive the async copies: pageable memcpy is staged synchronously by the runtime
+    CU_TRY(cudaEventRecord(e->evk0, s));
     if (plan.scratch_bytes) {
       CU_TRY(st->d_scratch.alloc(plan.scratch_bytes + 64, s));
       k::snappy_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
@@ -366,6 +356,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     }
     k::decode_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
                      int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
+    CU_TRY(cudaEventRecord(e->evk1, s));
     st->d_scratch.reset();
   }
 
@@ -617,6 +608,8 @@ int hg_engine_create(const hg_config* cfg, hg_engine** out) {
   CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CU_TRY(cudaEventCreate(&e->ev0));
   CU_TRY(cudaEventCreate(&e->ev1));
+  CU_TRY(cudaEventCreate(&e->evk0));
+  CU_TRY(cudaEventCreate(&e->evk1));
   cudaMemPool_t pool;
   CU_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
   uint64_t thresh = UINT64_MAX;
@@ -634,6 +627,8 @@ void hg_engine_destroy(hg_engine* e) {
   e->ssts.clear();
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
+  cudaEventDestroy(e->evk0);
+  cudaEventDestroy(e->evk1);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -777,6 +772,7 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
   e->stats.kernel_launches = e->launches;
   e->stats.gpu_ms = ms;
   e->stats.path = 0;
+  if (N > 0) { float kms = 0; cudaEventElapsedTime(&kms, e->evk0, e->evk1); e->stats.kernel_ms = kms; }
   make_stream(out, data);
   return HG_OK;
 }
@@ -855,6 +851,7 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
   e->stats.rows_out = hc[1];
   e->stats.groups_out = G;
   e->stats.path = 0;
+  if (N > 0) { float kms = 0; cudaEventElapsedTime(&kms, e->evk0, e->evk1); e->stats.kernel_ms = kms; }
   return HG_OK;
 }
 

@@ -123,7 +123,7 @@ struct hg_engine {
   uint64_t resident_bytes = 0;
   hg_scan_stats stats{};
   uint32_t launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;  // call / dominant-kernel brackets
   std::vector<void*> agg_keep;  // device buffers of the last hg_scan_aggregate_device result
   fused::Workspace fused_ws;
   Launch L() { return Launch{stream, &launches}; }
@@ -159,3 +159,19 @@ struct AggBuffers {
   uint32_t gwidth = 8, gtype = T_U64;
 };
 
+
+struct ScanPlan {
+  std::vector<SstResident*> files;     // in decode order
+  std::vector<RgSel> sel;
+  std::vector<uint32_t> file_base;     // decoded-row base per file (k+1)
+  std::vector<uint32_t> piece_end;     // single-SST pass-through: reader batch boundaries (decoded rows)
+  uint64_t rows_in_files = 0, rows_decoded = 0, scratch_bytes = 0;
+  bool disjoint = false;               // concatenation in decode order is sorted by PK with no cross-file equal PKs
+  std::vector<bool> col_has_nulls;     // per schema column: may any selected chunk contain nulls?
+  bool all_single_plain_page = true;   // every selected chunk is one uncompressed V1 page (fused path precondition)
+};
+
+
+// Row-group selection (statistics pruning), decode order, PK-disjointness.  Defined in engine.cu.
+int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
+               size_t np, const std::vector<uint32_t>& need_cols, ScanPlan* plan);

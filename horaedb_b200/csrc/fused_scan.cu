@@ -1,11 +1,534 @@
-// fused_scan.cu — single-pass decode+filter+aggregate fast path.  (placeholder: always defers to the general pipeline)
+// fused_scan.cu — single-pass scan for the common metric-engine case: PK-disjoint (or single) SSTs whose needed column
+// chunks are one uncompressed PLAIN page each.  One kernel reads the page payloads straight out of the resident SST
+// bytes and does S2 (def-level skip + PLAIN decode), S3 (predicate), S5/S6 (PK-run dedup, last row wins) and A1/A2
+// (group by pk0 [, time bucket of pk1]: count / sequential f64 sum / min / max) with no intermediate column ever
+// written to HBM: algorithmic traffic = the bytes of the columns the query touches (24-28 B/row).
+//
+// Work decomposition: every selected row group is split into kSplit sub-ranges; one warp owns one sub-range (taken
+// from an atomic ticket, so 148 SMs x resident warps stay busy until the stream is exhausted).  A group (key-run) is
+// owned by the sub-range in which it STARTS: the owner reads past the end of its sub-range until the key changes
+// ("overrun"), the next owner skips the rows of a run it does not own.  This keeps every group's f64 additions in
+// strict stream order (bit-exact with the oracle) without any cross-warp communication.  Group records are appended
+// unordered, tagged (item, local index), and a tiny scatter pass puts them in stream order.
 #include "fused_scan.h"
+
+#include <algorithm>
 
 namespace horae {
 namespace fused {
-int try_scan_aggregate(hg_engine*, const hg_schema_desc*, const hg_sst_desc*, size_t, const hg_predicate*, size_t,
-                       const hg_agg_spec*, AggBuffers*) {
-  return NOT_APPLICABLE;
+
+namespace {
+
+constexpr int MAXC = 8;
+constexpr int kSplit = 8;          // sub-ranges per row group
+constexpr int kWarpsPerCta = 8;
+
+struct alignas(16) FRec {
+  uint32_t item, local;
+  uint64_t gkey;
+  int64_t bucket;
+  uint64_t count;
+  double sum, mn, mx;
+  uint64_t _pad;
+};
+
+enum : uint32_t { K_RAW64 = 0, K_U32 = 1, K_I32 = 2, K_F32 = 3 };   // how a PLAIN slot widens to 64 bits
+enum : uint32_t { C_UNSIGNED = 0, C_SIGNED = 1, C_FLOAT = 2 };          // comparison class
+
+struct FParams {
+  const SstDev* ssts;
+  const RgSel* sel;
+  uint32_t nsel;
+  int nslots;
+  uint32_t col[MAXC], kind[MAXC], cls[MAXC];
+  int npk;                      // slots [0, npk) are the primary key columns in order
+  int has_group, has_ts, value_slot;
+  int npred;
+  int pslot[MAX_PREDS];
+  uint32_t pop[MAX_PREDS];
+  uint64_t plit[MAX_PREDS];
+  int64_t window_ms;
+  int global_mode;              // one global group, count only
+  FRec* rec;
+  uint32_t rec_cap;
+  uint32_t* item_cnt;
+  unsigned int* work;           // [0] item ticket, [1] record slots
+  unsigned long long* counters; // [0] rows passing the predicate, [1] rows kept after dedup (+ global count)
+  int* err;
+};
+
+__device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  uint32_t sh = uint32_t(a & 7) * 8;
+  const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+  uint64_t lo = __ldg(q);
+  if (sh == 0) return lo;
+  uint64_t hi = __ldg(q + 1);
+  return (lo >> sh) | (hi << (64 - sh));
 }
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  uint32_t sh = uint32_t(a & 3) * 8;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  uint32_t lo = __ldg(q);
+  if (sh == 0) return lo;
+  uint32_t hi = __ldg(q + 1);
+  return (lo >> sh) | (hi << (32 - sh));
+}
+
+// PLAIN value of `row`, widened: signed -> i64 bits, unsigned -> u64, floats -> f64 bits
+__device__ __forceinline__ uint64_t load_kind(const uint8_t* base, uint32_t kind, uint32_t row) {
+  if (kind == K_RAW64) return ld64u(base + size_t(row) * 8);
+  uint32_t r = ld32u(base + size_t(row) * 4);
+  if (kind == K_U32) return r;
+  if (kind == K_I32) return uint64_t(int64_t(int32_t(r)));
+  return uint64_t(__double_as_longlong(double(__uint_as_float(r))));
+}
+__device__ __forceinline__ bool pred_ok(uint64_t v, uint64_t lit, uint32_t cls, uint32_t op) {
+  int c;
+  if (cls == C_FLOAT) {
+    double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)lit);
+    c = x < y ? -1 : (x > y ? 1 : 0);
+  } else if (cls == C_SIGNED) {
+    int64_t x = int64_t(v), y = int64_t(lit);
+    c = x < y ? -1 : (x > y ? 1 : 0);
+  } else c = v < lit ? -1 : (v > lit ? 1 : 0);
+  switch (op) {
+    case OP_EQ: return c == 0;
+    case OP_NE: return c != 0;
+    case OP_LT: return c < 0;
+    case OP_LE: return c <= 0;
+    case OP_GT: return c > 0;
+    default: return c >= 0;
+  }
+}
+
+// Start of the PLAIN values of column slot `s` in selected row group `si` (pointer chase through the resident tables).
+__device__ __forceinline__ const uint8_t* slot_base(const FParams& P, uint32_t si, int s) {
+  RgSel rs = P.sel[si];
+  SstDev sst = P.ssts[rs.sst];
+  ChunkDev cd = sst.chunks[size_t(rs.rg) * sst.ncols + P.col[s]];
+  PageDev pg = sst.pages[cd.first_page];
+  const uint8_t* body = sst.bytes + pg.payload_off;
+  if (cd.optional) body += 4 + ld32u(body);      // [u32 len][RLE def levels] — all-valid pages only (planner)
+  return body;
+}
+// cold: one value addressed by (row group, slot, row)
+__device__ __noinline__ uint64_t fetch_val(const FParams& P, uint32_t si, int s, uint32_t row) {
+  return load_kind(slot_base(P, si, s), P.kind[s], row);
+}
+__device__ __forceinline__ int64_t bucket_of(const FParams& P, uint64_t ts) { int64_t t = int64_t(ts); return t / P.window_ms * P.window_ms; }
+
+// Rare path: row (si,row) has the same PK as the row after it (or is the last row of its row group).  It is dropped
+// iff some LATER row of the same PK run passes the predicate (the filter runs before merge/dedup: read.rs:459-480).
+__device__ __noinline__ bool later_alive_dup(const FParams& P, uint32_t si, uint32_t row, const uint64_t* pk) {
+  uint32_t nrows = P.sel[si].num_rows;
+  uint32_t r = row + 1;
+  for (;;) {
+    if (r >= nrows) {
+      si++;
+      if (si >= P.nsel) return false;
+      nrows = P.sel[si].num_rows;
+      r = 0;
+      if (nrows == 0) continue;
+    }
+    for (int k = 0; k < P.npk; k++)
+      if (fetch_val(P, si, k, r) != pk[k]) return false;
+    bool ok = true;
+    for (int p = 0; p < P.npred && ok; p++) ok = pred_ok(fetch_val(P, si, P.pslot[p], r), P.plit[p], P.cls[P.pslot[p]], P.pop[p]);
+    if (ok) return true;
+    r++;
+  }
+}
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, uint32_t(v), src);
+  uint32_t hi = __shfl_sync(0xffffffffu, uint32_t(v >> 32), src);
+  return (uint64_t(hi) << 32) | lo;
+}
+
+struct Acc {
+  bool open;
+  uint64_t g;
+  int64_t b;
+  uint64_t cnt;
+  double sum, mn, mx;
+};
+
+__device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item, uint32_t local) {
+  unsigned int slot = atomicAdd(&P.work[1], 1u);
+  if (slot < P.rec_cap) {
+    FRec r;
+    r.item = item; r.local = local; r.gkey = a.g; r.bucket = a.b; r.count = a.cnt; r.sum = a.sum; r.mn = a.mn; r.mx = a.mx; r._pad = 0;
+    P.rec[slot] = r;
+  } else atomicExch(P.err, 201);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) fused_scan_kernel(const __grid_constant__ FParams P) {
+  __shared__ const uint8_t* s_cur[kWarpsPerCta][MAXC];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint8_t* const* cur = s_cur[wid];
+  const uint32_t nitems = P.nsel * kSplit;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  auto set_cursor = [&](uint32_t si) {
+    __syncwarp();
+    if (lane < P.nslots) s_cur[wid][lane] = slot_base(P, si, lane);
+    __syncwarp();
+  };
+  auto val = [&](int slot, uint32_t row) -> uint64_t { return load_kind(cur[slot], P.kind[slot], row); };
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(&P.work[0], 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitems) return;
+    const uint32_t si = item / kSplit, w = item % kSplit;
+    uint32_t nrows = P.sel[si].num_rows;
+    const uint32_t n = nrows;
+    const uint32_t sr = (((n + kSplit - 1) / kSplit) + 31u) & ~31u;
+    const uint32_t a = w * sr;
+    uint32_t local = 0;
+    unsigned long long n_alive = 0, n_keep = 0;
+    if (a < n) {
+      set_cursor(si);
+      const uint32_t b = a + sr < n ? a + sr : n;
+      // key of the row just before this sub-range: rows that continue its run belong to an earlier owner
+      bool skipping = false;
+      uint64_t prev_g = 0;
+      int64_t prev_b = 0;
+      if (!P.global_mode) {
+        if (a > 0) {
+          skipping = true;
+          if (P.has_group) prev_g = val(0, a - 1);
+          if (P.has_ts) prev_b = bucket_of(P, val(1, a - 1));
+        } else if (si > 0) {
+          uint32_t pn = P.sel[si - 1].num_rows;      // the planner never selects empty row groups
+          skipping = true;
+          if (P.has_group) prev_g = fetch_val(P, si - 1, 0, pn - 1);
+          if (P.has_ts) prev_b = bucket_of(P, fetch_val(P, si - 1, 1, pn - 1));
+        }
+      }
+      Acc acc;
+      acc.open = false; acc.g = 0; acc.b = 0; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
+      bool overrun = false, done = false;
+      uint64_t tgt_g = 0;
+      int64_t tgt_b = 0;
+      uint32_t csi = si, row = a;
+      while (!done) {
+        if (!overrun && row >= b) {
+          // end of the owned sub-range: keep going only while rows continue the run of row b-1 (which we own)
+          if (P.global_mode || skipping) break;
+          overrun = true;
+          if (P.has_group) tgt_g = val(0, b - 1);
+          if (P.has_ts) tgt_b = bucket_of(P, val(1, b - 1));
+        }
+        if (row >= nrows) {
+          csi++;
+          if (csi >= P.nsel) break;
+          nrows = P.sel[csi].num_rows;
+          set_cursor(csi);
+          row = 0;
+          if (nrows == 0) continue;
+        }
+        const uint32_t i = row + lane;
+        const uint32_t lim = overrun ? nrows : b;
+        const bool inb = i < lim;
+        const uint64_t g = (inb && P.has_group) ? val(0, i) : 0;
+        uint64_t ts = 0;
+        int64_t bk = 0;
+        if (inb && P.has_ts) { ts = val(1, i); bk = bucket_of(P, ts); }
+        bool mine = inb;
+        const unsigned inb_mask = __ballot_sync(0xffffffffu, inb);
+        if (skipping) {
+          bool foreign = inb && g == prev_g && bk == prev_b;
+          unsigned fm = __ballot_sync(0xffffffffu, foreign);
+          if (fm != inb_mask) skipping = false;       // a new run starts inside this slice
+          mine = inb && !foreign;
+        }
+        if (overrun) {
+          bool match = inb && g == tgt_g && bk == tgt_b;
+          unsigned mm = __ballot_sync(0xffffffffu, match);
+          if (mm != inb_mask) done = true;            // the owned run ends inside this slice
+          mine = match;
+        }
+        bool alive = mine;
+        for (int p = 0; p < P.npred && alive; p++) {
+          int sl = P.pslot[p];
+          uint64_t v = (sl == 0 && P.has_group) ? g : ((sl == 1 && P.has_ts) ? ts : val(sl, i));
+          alive = pred_ok(v, P.plit[p], P.cls[sl], P.pop[p]);
+        }
+        // dedup: compare with the NEXT row of the stream (LastValue keeps the last row of a PK run)
+        bool keep = alive;
+        if (alive) {
+          bool same = true;
+          if (i + 1 < nrows) {
+            for (int k = 0; k < P.npk && same; k++) same = val(k, i + 1) == val(k, i);
+          }
+          if (same && (i + 1 < nrows || csi + 1 < P.nsel)) {
+            uint64_t pk[MAX_PK];
+            for (int k = 0; k < MAX_PK; k++) pk[k] = k < P.npk ? val(k, i) : 0;
+            keep = !later_alive_dup(P, csi, i, pk);
+          }
+        }
+        const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+        unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
+        n_alive += __popc(alive_mask);
+        n_keep += __popc(keep_mask);
+        if (!P.global_mode && keep_mask) {
+          uint64_t vbits = 0;
+          if (keep && P.value_slot >= 0) {
+            uint64_t wv = val(P.value_slot, i);
+            uint32_t vc = P.cls[P.value_slot];
+            double d = vc == C_FLOAT ? __longlong_as_double((long long)wv) : (vc == C_SIGNED ? double(int64_t(wv)) : double(wv));
+            vbits = uint64_t(__double_as_longlong(d));
+          }
+          // strictly sequential walk over the kept rows of this slice (stream order => bit-exact f64 sums)
+          while (keep_mask) {
+            int l = __ffs(keep_mask) - 1;
+            keep_mask &= keep_mask - 1;
+            uint64_t kg = P.has_group ? shfl64(g, l) : 0;
+            int64_t kb = P.has_ts ? int64_t(shfl64(uint64_t(bk), l)) : 0;
+            if (!acc.open || kg != acc.g || kb != acc.b) {
+              if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
+              acc.open = true; acc.g = kg; acc.b = kb; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
+            }
+            acc.cnt++;
+            if (P.value_slot >= 0) {
+              double v = __longlong_as_double((long long)shfl64(vbits, l));
+              acc.sum += v;
+              if (acc.cnt == 1 || v < acc.mn) acc.mn = v;
+              if (acc.cnt == 1 || v > acc.mx) acc.mx = v;
+            }
+          }
+        }
+        row += 32;
+      }
+      if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
+    }
+    if (lane == 0) {
+      P.item_cnt[item] = local;
+      if (n_alive) atomicAdd(&P.counters[0], n_alive);
+      if (n_keep) atomicAdd(&P.counters[1], n_keep);
+    }
+  }
+}
+
+// exclusive scan of per-item record counts (single block; items <= a few hundred thousand)
+__global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, uint32_t n, uint32_t* total) {
+  __shared__ uint32_t s_w[33];
+  __shared__ uint32_t s_carry;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < n ? cnt[i] : 0, inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t x = s_w[lane], xi = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+      s_w[lane] = xi - x;
+      if (lane == 31) s_w[32] = xi;
+    }
+    __syncthreads();
+    uint32_t carry = s_carry;
+    if (i < n) cnt[i] = carry + s_w[w] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + s_w[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void scatter_records_kernel(const FRec* __restrict__ rec, const unsigned int* nrec, const uint32_t* __restrict__ item_off,
+                                       uint32_t gwidth, AggOut out) {
+  uint32_t n = *nrec;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    FRec x = rec[r];
+    uint32_t pos = item_off[x.item] + x.local;
+    switch (gwidth) {
+      case 1: reinterpret_cast<uint8_t*>(out.gkey)[pos] = uint8_t(x.gkey); break;
+      case 4: reinterpret_cast<uint32_t*>(out.gkey)[pos] = uint32_t(x.gkey); break;
+      default: reinterpret_cast<uint64_t*>(out.gkey)[pos] = x.gkey;
+    }
+    out.bucket[pos] = x.bucket;
+    out.count[pos] = x.count;
+    out.sum[pos] = x.sum;
+    out.min[pos] = x.mn;
+    out.max[pos] = x.mx;
+  }
+}
+
+__global__ void global_count_kernel(const unsigned long long* counters, AggOut out) {
+  out.bucket[0] = 0;
+  out.count[0] = counters[1];
+  out.sum[0] = 0.0;
+  out.min[0] = __longlong_as_double(0x7ff0000000000000LL);
+  out.max[0] = -__longlong_as_double(0x7ff0000000000000LL);
+}
+
+bool is_int_type(uint32_t t) { return t != T_F32 && t != T_F64; }
+
+}  // namespace
+
+int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
+                       size_t np, const hg_agg_spec* agg, AggBuffers* out) {
+  // ---- shape preconditions
+  const bool has_group = agg->group_col >= 0;
+  const bool has_ts = agg->ts_col >= 0 && agg->window_ms > 0;
+  const bool global_mode = !has_group && !has_ts;
+  if (has_group && agg->group_col != 0) return NOT_APPLICABLE;                 // groups must be runs of the sort order
+  if (has_ts && !(has_group && agg->ts_col == 1 && schema->num_primary_keys >= 2)) return NOT_APPLICABLE;
+  if (global_mode && agg->value_col >= 0) return NOT_APPLICABLE;               // a global f64 sum is one serial chain
+  if (has_ts && schema->types[1] != T_I64 && schema->types[1] != T_U64 && schema->types[1] != T_I32 && schema->types[1] != T_U32)
+    return NOT_APPLICABLE;
+  // ---- column slots: PKs first, then predicate / value columns
+  std::vector<uint32_t> slots;
+  for (uint32_t c = 0; c < schema->num_primary_keys; c++) slots.push_back(c);
+  auto slot_of = [&](uint32_t c) {
+    for (size_t i = 0; i < slots.size(); i++) if (slots[i] == c) return int(i);
+    slots.push_back(c);
+    return int(slots.size() - 1);
+  };
+  int pslot[MAX_PREDS];
+  for (size_t i = 0; i < np; i++) pslot[i] = slot_of(preds[i].column);
+  int value_slot = agg->value_col >= 0 ? slot_of(uint32_t(agg->value_col)) : -1;
+  if (slots.size() > size_t(MAXC)) return NOT_APPLICABLE;
+
+  ScanPlan plan;
+  int rc = build_plan(e, schema, ssts, n, preds, np, slots, &plan);
+  if (rc) return rc;
+  if (!plan.disjoint || !plan.all_single_plain_page) return NOT_APPLICABLE;
+  for (uint32_t c : slots) if (plan.col_has_nulls[c]) return NOT_APPLICABLE;
+  const uint32_t nsel = uint32_t(plan.sel.size());
+
+  // ---- upper bound on the number of groups from chunk statistics (sizes the unordered record buffer)
+  uint64_t bound = 1;
+  if (!global_mode) {
+    if (!is_int_type(schema->types[0])) return NOT_APPLICABLE;
+    bound = 0;
+    for (const RgSel& s : plan.sel) {
+      const RowGroupMeta& rg = plan.files[s.sst]->meta.rgs[s.rg];
+      const ChunkMeta& c0 = rg.cols[0];
+      if (!c0.stats.has_min || !c0.stats.has_max) return NOT_APPLICABLE;
+      uint64_t mn = widen_stat(c0.stats.min, c0.phys_type, schema->types[0]), mx = widen_stat(c0.stats.max, c0.phys_type, schema->types[0]);
+      uint64_t span = mx - mn + 1;                       // distinct pk0 values possible in this row group
+      uint64_t per = 1;
+      if (has_ts) {
+        const ChunkMeta& c1 = rg.cols[1];
+        if (!c1.stats.has_min || !c1.stats.has_max) return NOT_APPLICABLE;
+        int64_t tmn = int64_t(widen_stat(c1.stats.min, c1.phys_type, schema->types[1])), tmx = int64_t(widen_stat(c1.stats.max, c1.phys_type, schema->types[1]));
+        per = uint64_t((tmx - tmn) / agg->window_ms) + 2;
+      }
+      uint64_t g = span > (1ull << 32) || per > (1ull << 32) ? uint64_t(rg.num_rows) : span * per;
+      bound += std::min<uint64_t>(g, uint64_t(rg.num_rows)) + 1;
+    }
+    if (bound > plan.rows_decoded / 4 + 1024) return NOT_APPLICABLE;     // groups ~ rows: not this kernel's regime
+  }
+  if (bound >= 0xfffffff0ull) return NOT_APPLICABLE;
+
+  cudaStream_t s = e->stream;
+  Launch L = e->L();
+  const uint32_t nitems = nsel * kSplit;
+  DevBuf d_ssts, d_sel, d_rec, d_item, d_work, d_counters, d_err;
+  CU_TRY(d_work.alloc(64, s));
+  CU_TRY(cudaMemsetAsync(d_work.p, 0, 64, s));
+  CU_TRY(d_counters.alloc(64, s));
+  CU_TRY(cudaMemsetAsync(d_counters.p, 0, 64, s));
+  CU_TRY(d_err.alloc(sizeof(int), s));
+  CU_TRY(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+  CU_TRY(d_rec.alloc(size_t(bound) * sizeof(FRec) + 64, s));
+  CU_TRY(d_item.alloc(size_t(nitems + 1) * sizeof(uint32_t) + 64, s));
+  out->gtype = has_group ? schema->types[0] : uint32_t(T_U64);
+  out->gwidth = has_group ? type_width_host(out->gtype) : 8;
+  CU_TRY(out->gkey.alloc(size_t(bound) * 8 + 16, s));
+  CU_TRY(out->bucket.alloc(size_t(bound) * 8 + 16, s));
+  CU_TRY(out->count.alloc(size_t(bound) * 8 + 16, s));
+  CU_TRY(out->sum.alloc(size_t(bound) * 8 + 16, s));
+  CU_TRY(out->mn.alloc(size_t(bound) * 8 + 16, s));
+  CU_TRY(out->mx.alloc(size_t(bound) * 8 + 16, s));
+  AggOut ao{out->gkey.p, out->bucket.as<int64_t>(), out->count.as<uint64_t>(), out->sum.as<double>(), out->mn.as<double>(), out->mx.as<double>()};
+
+  uint32_t hw[2] = {0, 0};
+  unsigned long long hc[2] = {0, 0};
+  int herr = 0;
+  if (nsel > 0) {
+    std::vector<SstDev> sd(plan.files.size());
+    for (size_t i = 0; i < plan.files.size(); i++) {
+      SstResident* f = plan.files[i];
+      sd[i] = SstDev{f->d_bytes, f->d_pages, f->d_chunks, uint32_t(f->meta.ncols), uint32_t(f->meta.rgs.size())};
+    }
+    CU_TRY(d_ssts.alloc(sd.size() * sizeof(SstDev), s));
+    CU_TRY(d_sel.alloc(plan.sel.size() * sizeof(RgSel), s));
+    CU_TRY(cudaMemcpyAsync(d_ssts.p, sd.data(), sd.size() * sizeof(SstDev), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), cudaMemcpyHostToDevice, s));
+
+    FParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.ssts = d_ssts.as<SstDev>();
+    P.sel = d_sel.as<RgSel>();
+    P.nsel = nsel;
+    P.nslots = int(slots.size());
+    for (size_t i = 0; i < slots.size(); i++) {
+      uint32_t t = schema->types[slots[i]];
+      P.col[i] = slots[i];
+      P.kind[i] = (t == T_U64 || t == T_I64 || t == T_F64) ? K_RAW64 : (t == T_F32 ? K_F32 : ((t == T_I8 || t == T_I16 || t == T_I32) ? K_I32 : K_U32));
+      P.cls[i] = type_is_float(t) ? C_FLOAT : (type_is_signed(t) ? C_SIGNED : C_UNSIGNED);
+    }
+    P.npk = int(schema->num_primary_keys);
+    P.has_group = has_group;
+    P.has_ts = has_ts;
+    P.value_slot = value_slot;
+    P.npred = int(np);
+    for (size_t i = 0; i < np; i++) {
+      P.pslot[i] = pslot[i];
+      P.pop[i] = preds[i].op;
+      P.plit[i] = pred_literal(preds[i], schema->types[preds[i].column]);
+    }
+    P.window_ms = has_ts ? agg->window_ms : 1;
+    P.global_mode = global_mode;
+    P.rec = d_rec.as<FRec>();
+    P.rec_cap = uint32_t(bound);
+    P.item_cnt = d_item.as<uint32_t>();
+    P.work = d_work.as<unsigned int>();
+    P.counters = d_counters.as<unsigned long long>();
+    P.err = d_err.as<int>();
+
+    int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
+    CU_TRY(cudaEventRecord(e->evk0, s));
+    fused_scan_kernel<<<ctas, kWarpsPerCta * 32, 0, s>>>(P);
+    L.tick();
+    CU_TRY(cudaEventRecord(e->evk1, s));
+    if (global_mode) {
+      global_count_kernel<<<1, 1, 0, s>>>(d_counters.as<unsigned long long>(), ao);
+      L.tick();
+    } else {
+      item_scan_kernel<<<1, 1024, 0, s>>>(d_item.as<uint32_t>(), nitems, d_work.as<uint32_t>() + 2);
+      L.tick();
+      scatter_records_kernel<<<148 * 4, 256, 0, s>>>(d_rec.as<FRec>(), d_work.as<unsigned int>() + 1, d_item.as<uint32_t>(), out->gwidth, ao);
+      L.tick();
+    }
+    CU_TRY(cudaMemcpyAsync(hw, d_work.as<uint32_t>() + 1, sizeof(hw), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(hc, d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&herr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (herr) return set_error(HG_ERR_INTERNAL, "fused scan: device error " + std::to_string(herr));
+    float kms = 0;
+    cudaEventElapsedTime(&kms, e->evk0, e->evk1);
+    e->stats.kernel_ms = kms;
+  }
+  out->G = global_mode ? (hc[1] > 0 ? 1u : 0u) : hw[0];   // like GROUP BY: no surviving rows, no group
+  e->stats.rows_in_files = plan.rows_in_files;
+  e->stats.rows_decoded = plan.rows_decoded;
+  e->stats.rows_filtered = hc[0];
+  e->stats.rows_out = hc[1];
+  e->stats.groups_out = out->G;
+  e->stats.path = 1;
+  return HG_OK;
+}
+
 }  // namespace fused
 }  // namespace horae

@@ -119,8 +119,8 @@ typedef struct {
   uint64_t bytes_h2d, bytes_d2h;
   uint32_t kernel_launches;   /* kernels launched by the last call */
   uint32_t path;              /* 0 = general pipeline, 1 = fused fast path */
-  float gpu_ms;               /* device time of the last call's kernels (CUDA events on the engine stream) */
-  float _pad;
+  float gpu_ms;               /* device time of the last call, first kernel to last (CUDA events on the engine stream) */
+  float kernel_ms;            /* device time of the call's dominant kernel alone (fused scan / page decode) */
 } hg_scan_stats;
 
 /* Device-resident aggregate (for the NCCL combine and HBM-resident timing); valid until the next call on the engine. */

@@ -251,11 +251,11 @@ def test_aggregate_device_result(eng):
     dev = eng.scan_aggregate_device(handle, _inputs([data]), [], group_col=0, ts_col=-1, window_ms=0, value_col=2)
     assert dev.num_groups == 16
     exp = oracle.scan_aggregate([data], schema.arrow_schema, 2, [], group_col=0, value_col=2)
-    import ctypes as C
-    host = np.empty(16, np.float64)
-    torch.cuda.synchronize()
-    rc = torch.cuda.cudart().cudaMemcpy(host.ctypes.data, dev.d_sum, 16 * 8, 2)
-    assert int(rc) == 0 and np.array_equal(host, exp.sum)
+    from horaedb_b200._ffi import DeviceArray
+    dsum = torch.as_tensor(DeviceArray(dev.d_sum, 16, "<f8"), device="cuda")
+    dcnt = torch.as_tensor(DeviceArray(dev.d_count, 16, "<i8"), device="cuda")
+    assert np.array_equal(dsum.cpu().numpy(), exp.sum)
+    assert dcnt.cpu().numpy().astype(np.uint64).tolist() == exp.count.tolist()
     st = eng.stats()
     assert st["rows_in_files"] == n and st["kernel_launches"] > 0 and st["gpu_ms"] > 0
 
