@@ -4,7 +4,7 @@
 // (group by pk0 [, time bucket of pk1]: count / sequential f64 sum / min / max) with no intermediate column ever
 // written to HBM: algorithmic traffic = the bytes of the columns the query touches (24-28 B/row).
 //
-// Work decomposition: every selected row group is split into kSplit sub-ranges; one warp owns one sub-range (taken
+// Work decomposition: every selected row group is split into `split` (1..8) sub-ranges; one warp owns one sub-range (taken
 // from an atomic ticket, so 148 SMs x resident warps stay busy until the stream is exhausted).  A group (key-run) is
 // owned by the sub-range in which it STARTS: the owner reads past the end of its sub-range until the key changes
 // ("overrun"), the next owner skips the rows of a run it does not own.  This keeps every group's f64 additions in
@@ -13,6 +13,7 @@
 #include "fused_scan.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace horae {
 namespace fused {
@@ -20,7 +21,6 @@ namespace fused {
 namespace {
 
 constexpr int MAXC = 8;
-constexpr int kSplit = 8;          // sub-ranges per row group
 constexpr int kWarpsPerCta = 8;
 
 struct alignas(16) FRec {
@@ -34,55 +34,57 @@ struct alignas(16) FRec {
 
 enum : uint32_t { K_RAW64 = 0, K_U32 = 1, K_I32 = 2, K_F32 = 3 };   // how a PLAIN slot widens to 64 bits
 enum : uint32_t { C_UNSIGNED = 0, C_SIGNED = 1, C_FLOAT = 2 };          // comparison class
+constexpr int kHot = 4;
 
 struct FParams {
   const SstDev* ssts;
   const RgSel* sel;
-  uint32_t nsel;
+  uint32_t nsel, split;         // split = sub-ranges (work items) per row group
   int nslots;
   uint32_t col[MAXC], kind[MAXC], cls[MAXC];
   int npk;                      // slots [0, npk) are the primary key columns in order
-  int has_group, has_ts, value_slot;
+  int has_group, has_ts, value_slot, global_mode;
+  // hot columns (position 0 = pk0, 1 = pk1, then predicate columns): loaded for every row.  The conjunction of all
+  // predicates on one column is pre-compiled into ONE interval test in an order-preserving unsigned domain:
+  //   key = (raw & mask) ^ flip ;  pass  <=>  key - lo <= span
+  int hot_slot[kHot];
+  uint64_t hot_mask[kHot], hot_flip[kHot], hot_lo[kHot], hot_span[kHot];
+  // the same predicates in generic form, for the cold dedup look-ahead
   int npred;
   int pslot[MAX_PREDS];
   uint32_t pop[MAX_PREDS];
   uint64_t plit[MAX_PREDS];
   int64_t window_ms;
-  int global_mode;              // one global group, count only
   FRec* rec;
   uint32_t rec_cap;
   uint32_t* item_cnt;
   unsigned int* work;           // [0] item ticket, [1] record slots
-  unsigned long long* counters; // [0] rows passing the predicate, [1] rows kept after dedup (+ global count)
+  unsigned long long* counters; // [0] rows passing the predicate, [1] rows kept after dedup
   int* err;
 };
 
-__device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {
+// 8 bytes at ANY byte alignment, branch-free (two aligned 8-byte loads + funnel shift), so that the compiler can issue
+// every load of a block back to back.  Buffers are padded: reading one aligned word past the value is always legal.
+__device__ __forceinline__ uint64_t ld_bytes8(const uint8_t* p) {
   uintptr_t a = reinterpret_cast<uintptr_t>(p);
   uint32_t sh = uint32_t(a & 7) * 8;
   const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
-  uint64_t lo = __ldg(q);
-  if (sh == 0) return lo;
-  uint64_t hi = __ldg(q + 1);
-  return (lo >> sh) | (hi << (64 - sh));
+  uint64_t lo = __ldg(q), hi = __ldg(q + 1);
+  return (lo >> sh) | ((hi << 1) << (63 - sh));
 }
-__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
-  uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  uint32_t sh = uint32_t(a & 3) * 8;
-  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-  uint32_t lo = __ldg(q);
-  if (sh == 0) return lo;
-  uint32_t hi = __ldg(q + 1);
-  return (lo >> sh) | (hi << (32 - sh));
-}
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) { return uint32_t(ld_bytes8(p)); }
 
-// PLAIN value of `row`, widened: signed -> i64 bits, unsigned -> u64, floats -> f64 bits
+// widen the raw little-endian bytes of a PLAIN value: signed -> i64 bits, unsigned -> u64, floats -> f64 bits
+__device__ __forceinline__ uint64_t widen_kind(uint64_t raw, uint32_t kind) {
+  uint32_t r = uint32_t(raw);
+  uint64_t v = raw;
+  v = kind == K_U32 ? uint64_t(r) : v;
+  v = kind == K_I32 ? uint64_t(int64_t(int32_t(r))) : v;
+  v = kind == K_F32 ? uint64_t(__double_as_longlong(double(__uint_as_float(r)))) : v;
+  return v;
+}
 __device__ __forceinline__ uint64_t load_kind(const uint8_t* base, uint32_t kind, uint32_t row) {
-  if (kind == K_RAW64) return ld64u(base + size_t(row) * 8);
-  uint32_t r = ld32u(base + size_t(row) * 4);
-  if (kind == K_U32) return r;
-  if (kind == K_I32) return uint64_t(int64_t(int32_t(r)));
-  return uint64_t(__double_as_longlong(double(__uint_as_float(r))));
+  return widen_kind(ld_bytes8(base + size_t(row) * (kind == K_RAW64 ? 8u : 4u)), kind);
 }
 __device__ __forceinline__ bool pred_ok(uint64_t v, uint64_t lit, uint32_t cls, uint32_t op) {
   int c;
@@ -113,15 +115,28 @@ __device__ __forceinline__ const uint8_t* slot_base(const FParams& P, uint32_t s
   if (cd.optional) body += 4 + ld32u(body);      // [u32 len][RLE def levels] — all-valid pages only (planner)
   return body;
 }
-// cold: one value addressed by (row group, slot, row)
+// cold: one widened value addressed by (row group, slot, row)
 __device__ __noinline__ uint64_t fetch_val(const FParams& P, uint32_t si, int s, uint32_t row) {
   return load_kind(slot_base(P, si, s), P.kind[s], row);
 }
-__device__ __forceinline__ int64_t bucket_of(const FParams& P, uint64_t ts) { int64_t t = int64_t(ts); return t / P.window_ms * P.window_ms; }
+
+// Time bucket of ts as the closed range [lo, hi] of timestamps that truncate to the same bucket start
+// (bucket = ts / w * w with TRUNCATING division, types.rs:82-85: bucket 0 spans (-w, w)).
+struct Bucket { int64_t start, lo, hi; };
+__device__ __noinline__ Bucket bucket_range(int64_t ts, int64_t w) {
+  Bucket b;
+  b.start = ts / w * w;
+  if (b.start > 0) { b.lo = b.start; b.hi = b.start + (w - 1); }
+  else if (b.start < 0) { b.lo = b.start - (w - 1); b.hi = b.start; }
+  else { b.lo = -(w - 1); b.hi = w - 1; }
+  return b;
+}
 
 // Rare path: row (si,row) has the same PK as the row after it (or is the last row of its row group).  It is dropped
 // iff some LATER row of the same PK run passes the predicate (the filter runs before merge/dedup: read.rs:459-480).
-__device__ __noinline__ bool later_alive_dup(const FParams& P, uint32_t si, uint32_t row, const uint64_t* pk) {
+__device__ __noinline__ bool later_alive_dup(const FParams& P, uint32_t si, uint32_t row) {
+  uint64_t pk[MAX_PK];
+  for (int k = 0; k < P.npk; k++) pk[k] = fetch_val(P, si, k, row);
   uint32_t nrows = P.sel[si].num_rows;
   uint32_t r = row + 1;
   for (;;) {
@@ -146,11 +161,17 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
   uint32_t hi = __shfl_sync(0xffffffffu, uint32_t(v >> 32), src);
   return (uint64_t(hi) << 32) | lo;
 }
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+  uint64_t b = uint64_t(__double_as_longlong(v));
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, uint32_t(b), m);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, uint32_t(b >> 32), m);
+  return __longlong_as_double((long long)((uint64_t(hi) << 32) | lo));
+}
 
 struct Acc {
   bool open;
   uint64_t g;
-  int64_t b;
+  int64_t bstart, blo, bhi;
   uint64_t cnt;
   double sum, mn, mx;
 };
@@ -159,16 +180,187 @@ __device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item,
   unsigned int slot = atomicAdd(&P.work[1], 1u);
   if (slot < P.rec_cap) {
     FRec r;
-    r.item = item; r.local = local; r.gkey = a.g; r.bucket = a.b; r.count = a.cnt; r.sum = a.sum; r.mn = a.mn; r.mx = a.mx; r._pad = 0;
+    r.item = item; r.local = local; r.gkey = a.g; r.bucket = a.bstart; r.count = a.cnt; r.sum = a.sum; r.mn = a.mn; r.mx = a.mx; r._pad = 0;
     P.rec[slot] = r;
   } else atomicExch(P.err, 201);
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) fused_scan_kernel(const __grid_constant__ FParams P) {
+// Per-warp state of one work item (a sub-range of a row group) while it walks the stream.
+struct WState {
+  Acc acc;
+  bool skipping, overrun, done;
+  uint64_t prev_g, tgt_g;
+  int64_t prev_lo, prev_hi, tgt_lo, tgt_hi;     // bucket ranges of the previous row / of the owned run
+  uint32_t local;
+  uint32_t n_alive, n_keep;
+};
+
+// Survivors of one slice, in stream order.  Fast path: they all extend the open group -> count by popc, min/max by a
+// warp butterfly (order-free), only the f64 sum is a sequential chain.  Otherwise the general walk with group breaks.
+template <bool HAS_TS>
+__device__ __noinline__ void walk_slice(const FParams& P, WState& ws, uint32_t item, unsigned keep_mask, bool keep, uint64_t g, int64_t ts,
+                                        double v, int lane) {
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  Acc& acc = ws.acc;
+  const bool has_val = P.value_slot >= 0;
+  bool ext = keep && acc.open && (!P.has_group || g == acc.g) && (!HAS_TS || (ts >= acc.blo && ts <= acc.bhi));
+  if (__ballot_sync(0xffffffffu, ext) == keep_mask) {
+    acc.cnt += __popc(keep_mask);
+    if (has_val) {
+      double mn = keep ? v : kInf, mx = keep ? v : -kInf;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        double a = shfl_xor_d(mn, m), b = shfl_xor_d(mx, m);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+      }
+      acc.mn = mn < acc.mn ? mn : acc.mn;
+      acc.mx = mx > acc.mx ? mx : acc.mx;
+      uint64_t vb = uint64_t(__double_as_longlong(v));
+      double sum = acc.sum;
+      while (keep_mask) {                       // strictly sequential f64 additions in stream order
+        int l = __ffs(keep_mask) - 1;
+        keep_mask &= keep_mask - 1;
+        sum += __longlong_as_double((long long)shfl64(vb, l));
+      }
+      acc.sum = sum;
+    }
+    return;
+  }
+  uint64_t vb = uint64_t(__double_as_longlong(v));
+  while (keep_mask) {
+    int l = __ffs(keep_mask) - 1;
+    keep_mask &= keep_mask - 1;
+    uint64_t kg = P.has_group ? shfl64(g, l) : 0;
+    int64_t kt = HAS_TS ? int64_t(shfl64(uint64_t(ts), l)) : 0;
+    if (!acc.open || kg != acc.g || (HAS_TS && (kt < acc.blo || kt > acc.bhi))) {
+      if (acc.open) { if (lane == 0) emit(P, acc, item, ws.local); ws.local++; }
+      acc.open = true; acc.g = kg; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
+      if (HAS_TS) { Bucket b = bucket_range(kt, P.window_ms); acc.bstart = b.start; acc.blo = b.lo; acc.bhi = b.hi; }
+      else { acc.bstart = 0; acc.blo = 0; acc.bhi = 0; }
+    }
+    acc.cnt++;
+    if (has_val) {
+      double x = __longlong_as_double((long long)shfl64(vb, l));
+      acc.sum += x;
+      if (acc.cnt == 1 || x < acc.mn) acc.mn = x;
+      if (acc.cnt == 1 || x > acc.mx) acc.mx = x;
+    }
+  }
+}
+
+__device__ __forceinline__ double to_double_kind(uint64_t raw, uint32_t kind, uint32_t cls) {
+  uint64_t wv = widen_kind(raw, kind);
+  return cls == C_FLOAT ? __longlong_as_double((long long)wv) : (cls == C_SIGNED ? double(int64_t(wv)) : double(wv));
+}
+
+// One block = kU slices of 32 rows.  Phase 1 issues every load of the block as straight-line code (clamped indices,
+// NH hot columns known at compile time, no branches): kU*NH*2 loads per lane in flight.  Phase 2 walks the slices in
+// stream order; everything beyond the interval tests runs only when a slice has survivors.
+template <int kU, int NH, bool HAS_TS, bool DENSE>
+__device__ __forceinline__ uint32_t process_block(const FParams& P, const uint8_t* const* cur, WState& ws, uint32_t item, uint32_t csi,
+                                                  uint32_t row, uint32_t lim, uint32_t nrows, int lane) {
+  uint64_t hv[kU][NH];
+  uint64_t vv[kU];
+  uint64_t halo[2];
+  const uint32_t last = nrows - 1;
+  const uint8_t* hb[NH];
+  uint32_t hw[NH];
+#pragma unroll
+  for (int h = 0; h < NH; h++) {
+    hb[h] = cur[P.hot_slot[h]];
+    hw[h] = P.kind[P.hot_slot[h]] == K_RAW64 ? 8u : 4u;
+  }
+#pragma unroll
+  for (int u = 0; u < kU; u++) {
+    uint32_t i = row + u * 32 + lane;
+    i = i < last ? i : last;
+#pragma unroll
+    for (int h = 0; h < NH; h++) hv[u][h] = ld_bytes8(hb[h] + size_t(i) * hw[h]) & P.hot_mask[h];
+  }
+  {
+    uint32_t i = row + kU * 32;
+    i = i < last ? i : last;
+    halo[0] = ld_bytes8(hb[0] + size_t(i) * hw[0]) & P.hot_mask[0];
+    halo[1] = ld_bytes8(hb[1] + size_t(i) * hw[1]) & P.hot_mask[1];
+  }
+  if (DENSE) {
+    const uint8_t* vb = cur[P.value_slot];
+    const uint32_t vw = P.kind[P.value_slot] == K_RAW64 ? 8u : 4u;
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      uint32_t i = row + u * 32 + lane;
+      i = i < last ? i : last;
+      vv[u] = ld_bytes8(vb + size_t(i) * vw);
+    }
+  }
+  uint32_t kept_in_block = 0;
+#pragma unroll
+  for (int u = 0; u < kU; u++) {
+    const uint32_t i = row + u * 32 + lane;
+    const bool inb = i < lim;
+    const unsigned inb_mask = __ballot_sync(0xffffffffu, inb);
+    if (inb_mask == 0 || ws.done) continue;
+    const uint64_t g = hv[u][0];
+    const int64_t ts = int64_t(hv[u][1]);
+    bool mine = inb;
+    if (ws.skipping) {
+      bool foreign = inb && (!P.has_group || g == ws.prev_g) && (!HAS_TS || (ts >= ws.prev_lo && ts <= ws.prev_hi));
+      unsigned fm = __ballot_sync(0xffffffffu, foreign);
+      if (fm != inb_mask) ws.skipping = false;       // a new run starts inside this slice
+      mine = inb && !foreign;
+    }
+    if (ws.overrun) {
+      bool match = inb && (!P.has_group || g == ws.tgt_g) && (!HAS_TS || (ts >= ws.tgt_lo && ts <= ws.tgt_hi));
+      unsigned mm = __ballot_sync(0xffffffffu, match);
+      if (mm != inb_mask) ws.done = true;            // the owned run ends inside this slice
+      mine = match;
+    }
+    bool alive = mine;
+#pragma unroll
+    for (int h = 0; h < NH; h++) alive = alive && ((hv[u][h] ^ P.hot_flip[h]) - P.hot_lo[h] <= P.hot_span[h]);
+    unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+    if (alive_mask == 0) continue;
+    // dedup: compare with the NEXT row of the stream (LastValue keeps the last row of a PK run).  The next row's
+    // pk0 / pk1 come from the neighbouring lane (or the next slice / the halo row), not from memory.
+    uint64_t n0 = shfl64(hv[u][0], (lane + 1) & 31), n1 = shfl64(hv[u][1], (lane + 1) & 31);
+    {
+      uint64_t f0 = u + 1 < kU ? shfl64(hv[u + 1 < kU ? u + 1 : u][0], 0) : halo[0];
+      uint64_t f1 = u + 1 < kU ? shfl64(hv[u + 1 < kU ? u + 1 : u][1], 0) : halo[1];
+      if (lane == 31) { n0 = f0; n1 = f1; }
+    }
+    bool keep = alive;
+    if (alive) {
+      bool same = true;
+      if (i + 1 < nrows) {
+        same = n0 == hv[u][0] && n1 == hv[u][1];
+        for (int k = 2; k < P.npk && same; k++) same = load_kind(cur[k], P.kind[k], i + 1) == load_kind(cur[k], P.kind[k], i);
+      }
+      if (same && (i + 1 < nrows || csi + 1 < P.nsel)) keep = !later_alive_dup(P, csi, i);
+    }
+    const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
+    ws.n_alive += __popc(alive_mask);
+    ws.n_keep += __popc(keep_mask);
+    kept_in_block += __popc(keep_mask);
+    if (!P.global_mode && keep_mask) {
+      double v = 0.0;
+      if (keep && P.value_slot >= 0) {
+        uint64_t raw = DENSE ? vv[u] : ld_bytes8(cur[P.value_slot] + size_t(i) * (P.kind[P.value_slot] == K_RAW64 ? 8u : 4u));
+        v = to_double_kind(raw, P.kind[P.value_slot], P.cls[P.value_slot]);
+      }
+      walk_slice<HAS_TS>(P, ws, item, keep_mask, keep, g, ts, v, lane);
+    }
+  }
+  return kept_in_block;
+}
+
+// kU = slices whose loads are issued together; NH = hot columns (pk0, pk1, + predicate columns) loaded for every row
+template <int kU, int kMinBlocks, int NH, bool HAS_TS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P) {
   __shared__ const uint8_t* s_cur[kWarpsPerCta][MAXC];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint8_t* const* cur = s_cur[wid];
-  const uint32_t nitems = P.nsel * kSplit;
+  const uint32_t nitems = P.nsel * P.split;
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   auto set_cursor = [&](uint32_t si) {
     __syncwarp();
@@ -181,45 +373,45 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) fused_scan_kernel(const 
     if (lane == 0) item = atomicAdd(&P.work[0], 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nitems) return;
-    const uint32_t si = item / kSplit, w = item % kSplit;
+    const uint32_t si = item / P.split, w = item % P.split;
     uint32_t nrows = P.sel[si].num_rows;
     const uint32_t n = nrows;
-    const uint32_t sr = (((n + kSplit - 1) / kSplit) + 31u) & ~31u;
+    const uint32_t sr = (((n + P.split - 1) / P.split) + 31u) & ~31u;
     const uint32_t a = w * sr;
-    uint32_t local = 0;
-    unsigned long long n_alive = 0, n_keep = 0;
+    WState ws;
+    ws.local = 0; ws.n_alive = 0; ws.n_keep = 0;
     if (a < n) {
       set_cursor(si);
       const uint32_t b = a + sr < n ? a + sr : n;
       // key of the row just before this sub-range: rows that continue its run belong to an earlier owner
-      bool skipping = false;
-      uint64_t prev_g = 0;
-      int64_t prev_b = 0;
+      ws.skipping = false; ws.prev_g = 0; ws.prev_lo = 0; ws.prev_hi = 0;
       if (!P.global_mode) {
+        uint64_t pts = 0;
         if (a > 0) {
-          skipping = true;
-          if (P.has_group) prev_g = val(0, a - 1);
-          if (P.has_ts) prev_b = bucket_of(P, val(1, a - 1));
+          ws.skipping = true;
+          ws.prev_g = val(0, a - 1) & P.hot_mask[0];
+          if (HAS_TS) pts = val(1, a - 1);
         } else if (si > 0) {
           uint32_t pn = P.sel[si - 1].num_rows;      // the planner never selects empty row groups
-          skipping = true;
-          if (P.has_group) prev_g = fetch_val(P, si - 1, 0, pn - 1);
-          if (P.has_ts) prev_b = bucket_of(P, fetch_val(P, si - 1, 1, pn - 1));
+          ws.skipping = true;
+          ws.prev_g = fetch_val(P, si - 1, 0, pn - 1) & P.hot_mask[0];
+          if (HAS_TS) pts = fetch_val(P, si - 1, 1, pn - 1);
         }
+        if (HAS_TS && ws.skipping) { Bucket pb = bucket_range(int64_t(pts), P.window_ms); ws.prev_lo = pb.lo; ws.prev_hi = pb.hi; }
       }
-      Acc acc;
-      acc.open = false; acc.g = 0; acc.b = 0; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
-      bool overrun = false, done = false;
-      uint64_t tgt_g = 0;
-      int64_t tgt_b = 0;
+      ws.acc.open = false; ws.acc.g = 0; ws.acc.bstart = 0; ws.acc.blo = 0; ws.acc.bhi = 0; ws.acc.cnt = 0;
+      ws.acc.sum = 0.0; ws.acc.mn = kInf; ws.acc.mx = -kInf;
+      ws.overrun = false; ws.done = false; ws.tgt_g = 0; ws.tgt_lo = 0; ws.tgt_hi = 0;
+      bool dense = false;                 // most rows survive: load the value column with the block, not per survivor
       uint32_t csi = si, row = a;
-      while (!done) {
-        if (!overrun && row >= b) {
+      while (!ws.done) {
+        if (!ws.overrun && row >= b) {
           // end of the owned sub-range: keep going only while rows continue the run of row b-1 (which we own)
-          if (P.global_mode || skipping) break;
-          overrun = true;
-          if (P.has_group) tgt_g = val(0, b - 1);
-          if (P.has_ts) tgt_b = bucket_of(P, val(1, b - 1));
+          if (P.global_mode || ws.skipping) break;
+          ws.overrun = true;
+          row = b;
+          ws.tgt_g = val(0, b - 1) & P.hot_mask[0];
+          if (HAS_TS) { Bucket tb = bucket_range(int64_t(val(1, b - 1)), P.window_ms); ws.tgt_lo = tb.lo; ws.tgt_hi = tb.hi; }
         }
         if (row >= nrows) {
           csi++;
@@ -229,87 +421,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) fused_scan_kernel(const 
           row = 0;
           if (nrows == 0) continue;
         }
-        const uint32_t i = row + lane;
-        const uint32_t lim = overrun ? nrows : b;
-        const bool inb = i < lim;
-        const uint64_t g = (inb && P.has_group) ? val(0, i) : 0;
-        uint64_t ts = 0;
-        int64_t bk = 0;
-        if (inb && P.has_ts) { ts = val(1, i); bk = bucket_of(P, ts); }
-        bool mine = inb;
-        const unsigned inb_mask = __ballot_sync(0xffffffffu, inb);
-        if (skipping) {
-          bool foreign = inb && g == prev_g && bk == prev_b;
-          unsigned fm = __ballot_sync(0xffffffffu, foreign);
-          if (fm != inb_mask) skipping = false;       // a new run starts inside this slice
-          mine = inb && !foreign;
-        }
-        if (overrun) {
-          bool match = inb && g == tgt_g && bk == tgt_b;
-          unsigned mm = __ballot_sync(0xffffffffu, match);
-          if (mm != inb_mask) done = true;            // the owned run ends inside this slice
-          mine = match;
-        }
-        bool alive = mine;
-        for (int p = 0; p < P.npred && alive; p++) {
-          int sl = P.pslot[p];
-          uint64_t v = (sl == 0 && P.has_group) ? g : ((sl == 1 && P.has_ts) ? ts : val(sl, i));
-          alive = pred_ok(v, P.plit[p], P.cls[sl], P.pop[p]);
-        }
-        // dedup: compare with the NEXT row of the stream (LastValue keeps the last row of a PK run)
-        bool keep = alive;
-        if (alive) {
-          bool same = true;
-          if (i + 1 < nrows) {
-            for (int k = 0; k < P.npk && same; k++) same = val(k, i + 1) == val(k, i);
-          }
-          if (same && (i + 1 < nrows || csi + 1 < P.nsel)) {
-            uint64_t pk[MAX_PK];
-            for (int k = 0; k < MAX_PK; k++) pk[k] = k < P.npk ? val(k, i) : 0;
-            keep = !later_alive_dup(P, csi, i, pk);
-          }
-        }
-        const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
-        unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
-        n_alive += __popc(alive_mask);
-        n_keep += __popc(keep_mask);
-        if (!P.global_mode && keep_mask) {
-          uint64_t vbits = 0;
-          if (keep && P.value_slot >= 0) {
-            uint64_t wv = val(P.value_slot, i);
-            uint32_t vc = P.cls[P.value_slot];
-            double d = vc == C_FLOAT ? __longlong_as_double((long long)wv) : (vc == C_SIGNED ? double(int64_t(wv)) : double(wv));
-            vbits = uint64_t(__double_as_longlong(d));
-          }
-          // strictly sequential walk over the kept rows of this slice (stream order => bit-exact f64 sums)
-          while (keep_mask) {
-            int l = __ffs(keep_mask) - 1;
-            keep_mask &= keep_mask - 1;
-            uint64_t kg = P.has_group ? shfl64(g, l) : 0;
-            int64_t kb = P.has_ts ? int64_t(shfl64(uint64_t(bk), l)) : 0;
-            if (!acc.open || kg != acc.g || kb != acc.b) {
-              if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
-              acc.open = true; acc.g = kg; acc.b = kb; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
-            }
-            acc.cnt++;
-            if (P.value_slot >= 0) {
-              double v = __longlong_as_double((long long)shfl64(vbits, l));
-              acc.sum += v;
-              if (acc.cnt == 1 || v < acc.mn) acc.mn = v;
-              if (acc.cnt == 1 || v > acc.mx) acc.mx = v;
-            }
-          }
-        }
-        row += 32;
+        const uint32_t lim = ws.overrun ? nrows : b;
+        uint32_t kept = dense ? process_block<kU, NH, HAS_TS, true>(P, cur, ws, item, csi, row, lim, nrows, lane)
+                              : process_block<kU, NH, HAS_TS, false>(P, cur, ws, item, csi, row, lim, nrows, lane);
+        dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
+        row += 32 * kU;
+        if (!ws.overrun && row > b) row = b;
       }
-      if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
+      if (ws.acc.open) { if (lane == 0) emit(P, ws.acc, item, ws.local); ws.local++; }
     }
     if (lane == 0) {
-      P.item_cnt[item] = local;
-      if (n_alive) atomicAdd(&P.counters[0], n_alive);
-      if (n_keep) atomicAdd(&P.counters[1], n_keep);
+      P.item_cnt[item] = ws.local;
+      if (ws.n_alive) atomicAdd(&P.counters[0], (unsigned long long)ws.n_alive);
+      if (ws.n_keep) atomicAdd(&P.counters[1], (unsigned long long)ws.n_keep);
     }
   }
+}
+
+template <int kU, int kMinBlocks>
+void launch_fused(int nhot, bool has_ts, int ctas, cudaStream_t s, const FParams& P) {
+#define HG_LAUNCH(NH)                                                                                           \
+  if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P);                \
+  else fused_scan_kernel<kU, kMinBlocks, NH, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P)
+  switch (nhot) {
+    case 2: HG_LAUNCH(2); break;
+    case 3: HG_LAUNCH(3); break;
+    default: HG_LAUNCH(4);
+  }
+#undef HG_LAUNCH
 }
 
 // exclusive scan of per-item record counts (single block; items <= a few hundred thousand)
@@ -383,8 +522,8 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   if (has_group && agg->group_col != 0) return NOT_APPLICABLE;                 // groups must be runs of the sort order
   if (has_ts && !(has_group && agg->ts_col == 1 && schema->num_primary_keys >= 2)) return NOT_APPLICABLE;
   if (global_mode && agg->value_col >= 0) return NOT_APPLICABLE;               // a global f64 sum is one serial chain
-  if (has_ts && schema->types[1] != T_I64 && schema->types[1] != T_U64 && schema->types[1] != T_I32 && schema->types[1] != T_U32)
-    return NOT_APPLICABLE;
+  if (schema->num_primary_keys < 2) return NOT_APPLICABLE;                     // the kernel keeps pk0 and pk1 in registers
+  if (has_ts && schema->types[1] != T_I64) return NOT_APPLICABLE;
   // ---- column slots: PKs first, then predicate / value columns
   std::vector<uint32_t> slots;
   for (uint32_t c = 0; c < schema->num_primary_keys; c++) slots.push_back(c);
@@ -397,6 +536,35 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   for (size_t i = 0; i < np; i++) pslot[i] = slot_of(preds[i].column);
   int value_slot = agg->value_col >= 0 ? slot_of(uint32_t(agg->value_col)) : -1;
   if (slots.size() > size_t(MAXC)) return NOT_APPLICABLE;
+  // ---- hot positions: [0] = pk0 (group key), [1] = pk1 (time), [2..3] = up to two further predicate columns.
+  // All predicates on one column fold into one interval [lo, hi] of an order-preserving unsigned key:
+  //   unsigned ints: key = value          signed ints: key = value ^ sign bit (of the 64-bit widened value)
+  int hot_slot[kHot] = {0, 1, 0, 0};
+  int nhot = 2;
+  uint64_t klo[kHot], khi[kHot];
+  for (int h = 0; h < kHot; h++) { klo[h] = 0; khi[h] = ~0ull; }
+  bool empty_interval = false;
+  for (size_t i = 0; i < np; i++) {
+    const uint32_t t = schema->types[preds[i].column];
+    if (type_is_float(t) || preds[i].op == HG_OP_NE) return NOT_APPLICABLE;    // general pipeline handles these
+    int h = -1;
+    for (int j = 0; j < nhot; j++) if (hot_slot[j] == pslot[i]) h = j;
+    if (h < 0) {
+      if (nhot == kHot) return NOT_APPLICABLE;                                 // more than two non-PK predicate columns
+      h = nhot++;
+      hot_slot[h] = pslot[i];
+    }
+    // literal in the key domain (64-bit widened, sign bit flipped for signed types)
+    uint64_t key = pred_literal(preds[i], t) ^ (type_is_signed(t) ? (1ull << 63) : 0ull);
+    switch (preds[i].op) {
+      case HG_OP_EQ: klo[h] = std::max(klo[h], key); khi[h] = std::min(khi[h], key); break;
+      case HG_OP_LT: if (key == 0) empty_interval = true; else khi[h] = std::min(khi[h], key - 1); break;
+      case HG_OP_LE: khi[h] = std::min(khi[h], key); break;
+      case HG_OP_GT: if (key == ~0ull) empty_interval = true; else klo[h] = std::max(klo[h], key + 1); break;
+      default: klo[h] = std::max(klo[h], key); break;
+    }
+  }
+  for (int h = 0; h < kHot; h++) if (klo[h] > khi[h]) empty_interval = true;
 
   ScanPlan plan;
   int rc = build_plan(e, schema, ssts, n, preds, np, slots, &plan);
@@ -432,7 +600,11 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
 
   cudaStream_t s = e->stream;
   Launch L = e->L();
-  const uint32_t nitems = nsel * kSplit;
+  // split row groups into enough work items to keep ~4 items per resident warp, but no finer: every item boundary
+  // costs an overrun of about half a group
+  uint32_t split = 1;
+  while (split < 8 && uint64_t(nsel) * split < 148ull * 32 * 4) split *= 2;
+  const uint32_t nitems = nsel * split;
   DevBuf d_ssts, d_sel, d_rec, d_item, d_work, d_counters, d_err;
   CU_TRY(d_work.alloc(64, s));
   CU_TRY(cudaMemsetAsync(d_work.p, 0, 64, s));
@@ -471,6 +643,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.ssts = d_ssts.as<SstDev>();
     P.sel = d_sel.as<RgSel>();
     P.nsel = nsel;
+    P.split = split;
     P.nslots = int(slots.size());
     for (size_t i = 0; i < slots.size(); i++) {
       uint32_t t = schema->types[slots[i]];
@@ -482,6 +655,34 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.has_group = has_group;
     P.has_ts = has_ts;
     P.value_slot = value_slot;
+    P.global_mode = global_mode;
+    for (int h = 0; h < kHot; h++) {
+      const int sl = h < nhot ? hot_slot[h] : 0;
+      const uint32_t t = schema->types[slots[sl]];
+      const bool w8 = (t == T_U64 || t == T_I64 || t == T_F64);
+      P.hot_slot[h] = sl;
+      // raw bytes -> key: 8-byte columns: raw ^ signflip.  4-byte columns hold the value in the low 32 bits; the widened
+      // 64-bit key of a signed 32-bit value v is (sext(v) ^ 2^63), which for comparison purposes equals comparing
+      // (v ^ 2^31) as unsigned 32-bit: use mask 0xffffffff, flip 2^31 and rebase the interval into that domain.
+      P.hot_mask[h] = w8 ? ~0ull : 0xffffffffull;
+      uint64_t lo = klo[h], hi = khi[h];
+      if (w8) P.hot_flip[h] = type_is_signed(t) ? (1ull << 63) : 0ull;
+      else if (type_is_signed(t)) {
+        P.hot_flip[h] = 1ull << 31;
+        // widened key k = sext(v) ^ 2^63 ranges over [2^63 - 2^31, 2^63 + 2^31); 32-bit key = k - (2^63 - 2^31)
+        const uint64_t base = (1ull << 63) - (1ull << 31), top = (1ull << 63) + (1ull << 31) - 1;
+        if (hi < base || lo > top) empty_interval = true;
+        lo = lo < base ? 0 : lo - base;
+        hi = hi > top ? 0xffffffffull : hi - base;
+      } else {
+        P.hot_flip[h] = 0;
+        if (lo > 0xffffffffull) empty_interval = true;
+        hi = std::min<uint64_t>(hi, 0xffffffffull);
+      }
+      P.hot_lo[h] = lo;
+      P.hot_span[h] = hi >= lo ? hi - lo : 0;
+    }
+    if (empty_interval) { P.hot_lo[0] = 1; P.hot_span[0] = 0; P.hot_mask[0] = P.hot_mask[0]; P.hot_flip[0] = 0; }
     P.npred = int(np);
     for (size_t i = 0; i < np; i++) {
       P.pslot[i] = pslot[i];
@@ -489,7 +690,6 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       P.plit[i] = pred_literal(preds[i], schema->types[preds[i].column]);
     }
     P.window_ms = has_ts ? agg->window_ms : 1;
-    P.global_mode = global_mode;
     P.rec = d_rec.as<FRec>();
     P.rec_cap = uint32_t(bound);
     P.item_cnt = d_item.as<uint32_t>();
@@ -498,8 +698,16 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.err = d_err.as<int>();
 
     int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("HORAE_FUSED_VARIANT"); variant = v ? atoi(v) : 0; }
     CU_TRY(cudaEventRecord(e->evk0, s));
-    fused_scan_kernel<<<ctas, kWarpsPerCta * 32, 0, s>>>(P);
+    switch (variant) {
+      case 1: launch_fused<4, 3>(nhot, has_ts, ctas, s, P); break;
+      case 2: launch_fused<2, 4>(nhot, has_ts, ctas, s, P); break;
+      case 3: launch_fused<2, 3>(nhot, has_ts, ctas, s, P); break;
+      case 4: launch_fused<1, 4>(nhot, has_ts, ctas, s, P); break;
+      default: launch_fused<4, 2>(nhot, has_ts, ctas, s, P);
+    }
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
     if (global_mode) {
