@@ -46,9 +46,10 @@ struct FParams {
   int has_group, has_ts, value_slot, global_mode;
   // hot columns (position 0 = pk0, 1 = pk1, then predicate columns): loaded for every row.  The conjunction of all
   // predicates on one column is pre-compiled into ONE interval test in an order-preserving unsigned domain:
-  //   key = (raw & mask) ^ flip ;  pass  <=>  key - lo <= span
+  //   key = value ^ flip ;  pass  <=>  key - lo <= span     (32-bit arithmetic for 4-byte columns)
   int hot_slot[kHot];
-  uint64_t hot_mask[kHot], hot_flip[kHot], hot_lo[kHot], hot_span[kHot];
+  uint64_t hot_flip[kHot], hot_lo[kHot], hot_span[kHot];
+  int hot_haspred[kHot];
   // the same predicates in generic form, for the cold dedup look-ahead
   int npred;
   int pslot[MAX_PREDS];
@@ -185,23 +186,12 @@ __device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item,
   } else atomicExch(P.err, 201);
 }
 
-// Per-warp state of one work item (a sub-range of a row group) while it walks the stream.
-struct WState {
-  Acc acc;
-  bool skipping, overrun, done;
-  uint64_t prev_g, tgt_g;
-  int64_t prev_lo, prev_hi, tgt_lo, tgt_hi;     // bucket ranges of the previous row / of the owned run
-  uint32_t local;
-  uint32_t n_alive, n_keep;
-};
-
 // Survivors of one slice, in stream order.  Fast path: they all extend the open group -> count by popc, min/max by a
 // warp butterfly (order-free), only the f64 sum is a sequential chain.  Otherwise the general walk with group breaks.
 template <bool HAS_TS>
-__device__ __noinline__ void walk_slice(const FParams& P, WState& ws, uint32_t item, unsigned keep_mask, bool keep, uint64_t g, int64_t ts,
-                                        double v, int lane) {
+__device__ __noinline__ void walk_slice(const FParams& P, Acc& acc, uint32_t& local, uint32_t item, unsigned keep_mask, bool keep, uint64_t g,
+                                        int64_t ts, double v, int lane) {
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-  Acc& acc = ws.acc;
   const bool has_val = P.value_slot >= 0;
   bool ext = keep && acc.open && (!P.has_group || g == acc.g) && (!HAS_TS || (ts >= acc.blo && ts <= acc.bhi));
   if (__ballot_sync(0xffffffffu, ext) == keep_mask) {
@@ -234,7 +224,7 @@ __device__ __noinline__ void walk_slice(const FParams& P, WState& ws, uint32_t i
     uint64_t kg = P.has_group ? shfl64(g, l) : 0;
     int64_t kt = HAS_TS ? int64_t(shfl64(uint64_t(ts), l)) : 0;
     if (!acc.open || kg != acc.g || (HAS_TS && (kt < acc.blo || kt > acc.bhi))) {
-      if (acc.open) { if (lane == 0) emit(P, acc, item, ws.local); ws.local++; }
+      if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
       acc.open = true; acc.g = kg; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
       if (HAS_TS) { Bucket b = bucket_range(kt, P.window_ms); acc.bstart = b.start; acc.blo = b.lo; acc.bhi = b.hi; }
       else { acc.bstart = 0; acc.blo = 0; acc.bhi = 0; }
@@ -255,119 +245,172 @@ __device__ __forceinline__ double to_double_kind(uint64_t raw, uint32_t kind, ui
 }
 
 // One block = kU slices of 32 rows.  Phase 1 issues every load of the block as straight-line code (clamped indices,
-// NH hot columns known at compile time, no branches): kU*NH*2 loads per lane in flight.  Phase 2 walks the slices in
+// hot columns and their widths known at compile time): kU*NH*2 loads per lane in flight.  Phase 2 walks the slices in
 // stream order; everything beyond the interval tests runs only when a slice has survivors.
-template <int kU, int NH, bool HAS_TS, bool DENSE>
-__device__ __forceinline__ uint32_t process_block(const FParams& P, const uint8_t* const* cur, WState& ws, uint32_t item, uint32_t csi,
-                                                  uint32_t row, uint32_t lim, uint32_t nrows, int lane) {
+//   X     bit k set => extra hot column 2+k is a 4-byte column (pk0 / pk1 are always 8-byte here)
+//   EDGE  false => steady state: the whole block lies inside the owned sub-range, no skip / overrun bookkeeping
+struct Cur {                       // per-warp view of the current row group (shared memory)
+  const uint8_t* q[MAXC];          // value base rounded down to the column's word size
+  uint32_t sh[MAXC];               // bit shift of the values inside their aligned words (uniform per column chunk)
+};
+
+__device__ __forceinline__ uint64_t ld8(const uint8_t* q, uint32_t sh, uint32_t i) {
+  const uint64_t* p = reinterpret_cast<const uint64_t*>(q) + i;
+  uint64_t lo = __ldg(p), hi = __ldg(p + 1);
+  uint32_t w0 = uint32_t(lo), w1 = uint32_t(lo >> 32), w2 = uint32_t(hi), w3 = uint32_t(hi >> 32);
+  const bool up = (sh & 32u) != 0;
+  const uint32_t s = sh & 31u;
+  uint32_t a = up ? w1 : w0, b = up ? w2 : w1, c = up ? w3 : w2;
+  return (uint64_t(__funnelshift_r(b, c, s)) << 32) | __funnelshift_r(a, b, s);
+}
+__device__ __forceinline__ uint32_t ld4(const uint8_t* q, uint32_t sh, uint32_t i) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(q) + i;
+  uint32_t lo = __ldg(p), hi = __ldg(p + 1);
+  return __funnelshift_r(lo, hi, sh);
+}
+
+struct Flags { bool skipping, overrun, done; };
+struct Edge {
+  uint64_t prev_g, tgt_g;
+  int64_t prev_lo, prev_hi, tgt_lo, tgt_hi;     // bucket ranges of the previous row / of the owned run
+};
+
+template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool EDGE>
+__device__ __forceinline__ uint32_t process_block(const FParams& P, const Cur& cur, Acc& acc, Flags& fl, const Edge& ed, uint32_t& local,
+                                                  uint32_t& n_alive, uint32_t& n_keep, uint32_t item, uint32_t csi, uint32_t row,
+                                                  uint32_t lim, uint32_t nrows, int lane) {
   uint64_t hv[kU][NH];
   uint64_t vv[kU];
-  uint64_t halo[2];
+  uint64_t halo[2] = {0, 0};
   const uint32_t last = nrows - 1;
-  const uint8_t* hb[NH];
-  uint32_t hw[NH];
+  const uint8_t* hq[NH];
+  uint32_t hs[NH];
 #pragma unroll
-  for (int h = 0; h < NH; h++) {
-    hb[h] = cur[P.hot_slot[h]];
-    hw[h] = P.kind[P.hot_slot[h]] == K_RAW64 ? 8u : 4u;
-  }
+  for (int h = 0; h < NH; h++) { hq[h] = cur.q[P.hot_slot[h]]; hs[h] = cur.sh[P.hot_slot[h]]; }
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     uint32_t i = row + u * 32 + lane;
-    i = i < last ? i : last;
+    if (EDGE) i = i < last ? i : last;
 #pragma unroll
-    for (int h = 0; h < NH; h++) hv[u][h] = ld_bytes8(hb[h] + size_t(i) * hw[h]) & P.hot_mask[h];
-  }
-  {
-    uint32_t i = row + kU * 32;
-    i = i < last ? i : last;
-    halo[0] = ld_bytes8(hb[0] + size_t(i) * hw[0]) & P.hot_mask[0];
-    halo[1] = ld_bytes8(hb[1] + size_t(i) * hw[1]) & P.hot_mask[1];
+    for (int h = 0; h < NH; h++) {
+      const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
+      hv[u][h] = w4 ? uint64_t(ld4(hq[h], hs[h], i)) : ld8(hq[h], hs[h], i);
+    }
   }
   if (DENSE) {
-    const uint8_t* vb = cur[P.value_slot];
-    const uint32_t vw = P.kind[P.value_slot] == K_RAW64 ? 8u : 4u;
+    uint32_t i = row + kU * 32;
+    i = i < last ? i : last;
+    halo[0] = ld8(hq[0], hs[0], i);
+    halo[1] = ld8(hq[1], hs[1], i);
+    const uint8_t* vq = cur.q[P.value_slot];
+    const uint32_t vs = cur.sh[P.value_slot];
+    const bool v8 = P.kind[P.value_slot] == K_RAW64;
 #pragma unroll
     for (int u = 0; u < kU; u++) {
-      uint32_t i = row + u * 32 + lane;
-      i = i < last ? i : last;
-      vv[u] = ld_bytes8(vb + size_t(i) * vw);
+      uint32_t i2 = row + u * 32 + lane;
+      if (EDGE) i2 = i2 < last ? i2 : last;
+      vv[u] = v8 ? ld8(vq, vs, i2) : uint64_t(ld4(vq, vs, i2));
     }
   }
   uint32_t kept_in_block = 0;
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     const uint32_t i = row + u * 32 + lane;
-    const bool inb = i < lim;
-    const unsigned inb_mask = __ballot_sync(0xffffffffu, inb);
-    if (inb_mask == 0 || ws.done) continue;
+    bool mine = true;
     const uint64_t g = hv[u][0];
     const int64_t ts = int64_t(hv[u][1]);
-    bool mine = inb;
-    if (ws.skipping) {
-      bool foreign = inb && (!P.has_group || g == ws.prev_g) && (!HAS_TS || (ts >= ws.prev_lo && ts <= ws.prev_hi));
-      unsigned fm = __ballot_sync(0xffffffffu, foreign);
-      if (fm != inb_mask) ws.skipping = false;       // a new run starts inside this slice
-      mine = inb && !foreign;
-    }
-    if (ws.overrun) {
-      bool match = inb && (!P.has_group || g == ws.tgt_g) && (!HAS_TS || (ts >= ws.tgt_lo && ts <= ws.tgt_hi));
-      unsigned mm = __ballot_sync(0xffffffffu, match);
-      if (mm != inb_mask) ws.done = true;            // the owned run ends inside this slice
-      mine = match;
+    if (EDGE) {
+      const bool inb = i < lim;
+      const unsigned inb_mask = __ballot_sync(0xffffffffu, inb);
+      if (inb_mask == 0 || fl.done) continue;
+      mine = inb;
+      if (fl.skipping) {
+        bool foreign = inb && (!P.has_group || g == ed.prev_g) && (!HAS_TS || (ts >= ed.prev_lo && ts <= ed.prev_hi));
+        unsigned fm = __ballot_sync(0xffffffffu, foreign);
+        if (fm != inb_mask) fl.skipping = false;       // a new run starts inside this slice
+        mine = inb && !foreign;
+      }
+      if (fl.overrun) {
+        bool match = inb && (!P.has_group || g == ed.tgt_g) && (!HAS_TS || (ts >= ed.tgt_lo && ts <= ed.tgt_hi));
+        unsigned mm = __ballot_sync(0xffffffffu, match);
+        if (mm != inb_mask) fl.done = true;            // the owned run ends inside this slice
+        mine = match;
+      }
     }
     bool alive = mine;
 #pragma unroll
-    for (int h = 0; h < NH; h++) alive = alive && ((hv[u][h] ^ P.hot_flip[h]) - P.hot_lo[h] <= P.hot_span[h]);
-    unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+    for (int h = 0; h < NH; h++) {
+      const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
+      if (P.hot_haspred[h]) {                          // uniform
+        if (w4) alive = alive && ((uint32_t(hv[u][h]) ^ uint32_t(P.hot_flip[h])) - uint32_t(P.hot_lo[h]) <= uint32_t(P.hot_span[h]));
+        else alive = alive && ((hv[u][h] ^ P.hot_flip[h]) - P.hot_lo[h] <= P.hot_span[h]);
+      }
+    }
+    const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
     if (alive_mask == 0) continue;
     // dedup: compare with the NEXT row of the stream (LastValue keeps the last row of a PK run).  The next row's
     // pk0 / pk1 come from the neighbouring lane (or the next slice / the halo row), not from memory.
     uint64_t n0 = shfl64(hv[u][0], (lane + 1) & 31), n1 = shfl64(hv[u][1], (lane + 1) & 31);
-    {
-      uint64_t f0 = u + 1 < kU ? shfl64(hv[u + 1 < kU ? u + 1 : u][0], 0) : halo[0];
-      uint64_t f1 = u + 1 < kU ? shfl64(hv[u + 1 < kU ? u + 1 : u][1], 0) : halo[1];
+    if (u + 1 < kU) {
+      uint64_t f0 = shfl64(hv[u + 1 < kU ? u + 1 : u][0], 0), f1 = shfl64(hv[u + 1 < kU ? u + 1 : u][1], 0);
       if (lane == 31) { n0 = f0; n1 = f1; }
+    } else {
+      if (!DENSE && (alive_mask >> 31)) {              // sparse blocks fetch the halo row only when lane 31 survives
+        uint32_t ih = row + kU * 32;
+        ih = ih < last ? ih : last;
+        halo[0] = ld8(hq[0], hs[0], ih);
+        halo[1] = ld8(hq[1], hs[1], ih);
+      }
+      if (lane == 31) { n0 = halo[0]; n1 = halo[1]; }
     }
     bool keep = alive;
     if (alive) {
       bool same = true;
       if (i + 1 < nrows) {
         same = n0 == hv[u][0] && n1 == hv[u][1];
-        for (int k = 2; k < P.npk && same; k++) same = load_kind(cur[k], P.kind[k], i + 1) == load_kind(cur[k], P.kind[k], i);
+        for (int k = 2; k < P.npk && same; k++) same = fetch_val(P, csi, k, i + 1) == fetch_val(P, csi, k, i);
       }
       if (same && (i + 1 < nrows || csi + 1 < P.nsel)) keep = !later_alive_dup(P, csi, i);
     }
     const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
-    ws.n_alive += __popc(alive_mask);
-    ws.n_keep += __popc(keep_mask);
+    n_alive += __popc(alive_mask);
+    n_keep += __popc(keep_mask);
     kept_in_block += __popc(keep_mask);
     if (!P.global_mode && keep_mask) {
       double v = 0.0;
       if (keep && P.value_slot >= 0) {
-        uint64_t raw = DENSE ? vv[u] : ld_bytes8(cur[P.value_slot] + size_t(i) * (P.kind[P.value_slot] == K_RAW64 ? 8u : 4u));
+        const bool v8 = P.kind[P.value_slot] == K_RAW64;
+        uint64_t raw = DENSE ? vv[u] : (v8 ? ld8(cur.q[P.value_slot], cur.sh[P.value_slot], i) : uint64_t(ld4(cur.q[P.value_slot], cur.sh[P.value_slot], i)));
         v = to_double_kind(raw, P.kind[P.value_slot], P.cls[P.value_slot]);
       }
-      walk_slice<HAS_TS>(P, ws, item, keep_mask, keep, g, ts, v, lane);
+      walk_slice<HAS_TS>(P, acc, local, item, keep_mask, keep, g, ts, v, lane);
     }
   }
   return kept_in_block;
 }
 
 // kU = slices whose loads are issued together; NH = hot columns (pk0, pk1, + predicate columns) loaded for every row
-template <int kU, int kMinBlocks, int NH, bool HAS_TS>
+template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P) {
-  __shared__ const uint8_t* s_cur[kWarpsPerCta][MAXC];
+  __shared__ Cur s_cur[kWarpsPerCta];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint8_t* const* cur = s_cur[wid];
+  const Cur& cur = s_cur[wid];
   const uint32_t nitems = P.nsel * P.split;
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   auto set_cursor = [&](uint32_t si) {
     __syncwarp();
-    if (lane < P.nslots) s_cur[wid][lane] = slot_base(P, si, lane);
+    if (lane < P.nslots) {
+      const uint8_t* base = slot_base(P, si, lane);
+      const uintptr_t a = reinterpret_cast<uintptr_t>(base);
+      const uintptr_t m = P.kind[lane] == K_RAW64 ? 7 : 3;
+      s_cur[wid].q[lane] = reinterpret_cast<const uint8_t*>(a & ~m);
+      s_cur[wid].sh[lane] = uint32_t(a & m) * 8;
+    }
     __syncwarp();
   };
-  auto val = [&](int slot, uint32_t row) -> uint64_t { return load_kind(cur[slot], P.kind[slot], row); };
+  auto val = [&](int slot, uint32_t row) -> uint64_t {
+    return P.kind[slot] == K_RAW64 ? ld8(cur.q[slot], cur.sh[slot], row) : widen_kind(ld4(cur.q[slot], cur.sh[slot], row), P.kind[slot]);
+  };
   for (;;) {
     uint32_t item = 0;
     if (lane == 0) item = atomicAdd(&P.work[0], 1u);
@@ -378,40 +421,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
     const uint32_t n = nrows;
     const uint32_t sr = (((n + P.split - 1) / P.split) + 31u) & ~31u;
     const uint32_t a = w * sr;
-    WState ws;
-    ws.local = 0; ws.n_alive = 0; ws.n_keep = 0;
+    uint32_t local = 0, n_alive = 0, n_keep = 0;
     if (a < n) {
       set_cursor(si);
       const uint32_t b = a + sr < n ? a + sr : n;
       // key of the row just before this sub-range: rows that continue its run belong to an earlier owner
-      ws.skipping = false; ws.prev_g = 0; ws.prev_lo = 0; ws.prev_hi = 0;
+      Flags fl;
+      Edge ed;
+      fl.skipping = false; fl.overrun = false; fl.done = false;
+      ed.prev_g = 0; ed.prev_lo = 0; ed.prev_hi = 0; ed.tgt_g = 0; ed.tgt_lo = 0; ed.tgt_hi = 0;
       if (!P.global_mode) {
         uint64_t pts = 0;
         if (a > 0) {
-          ws.skipping = true;
-          ws.prev_g = val(0, a - 1) & P.hot_mask[0];
+          fl.skipping = true;
+          ed.prev_g = val(0, a - 1);
           if (HAS_TS) pts = val(1, a - 1);
         } else if (si > 0) {
           uint32_t pn = P.sel[si - 1].num_rows;      // the planner never selects empty row groups
-          ws.skipping = true;
-          ws.prev_g = fetch_val(P, si - 1, 0, pn - 1) & P.hot_mask[0];
+          fl.skipping = true;
+          ed.prev_g = fetch_val(P, si - 1, 0, pn - 1);
           if (HAS_TS) pts = fetch_val(P, si - 1, 1, pn - 1);
         }
-        if (HAS_TS && ws.skipping) { Bucket pb = bucket_range(int64_t(pts), P.window_ms); ws.prev_lo = pb.lo; ws.prev_hi = pb.hi; }
+        if (HAS_TS && fl.skipping) { Bucket pb = bucket_range(int64_t(pts), P.window_ms); ed.prev_lo = pb.lo; ed.prev_hi = pb.hi; }
       }
-      ws.acc.open = false; ws.acc.g = 0; ws.acc.bstart = 0; ws.acc.blo = 0; ws.acc.bhi = 0; ws.acc.cnt = 0;
-      ws.acc.sum = 0.0; ws.acc.mn = kInf; ws.acc.mx = -kInf;
-      ws.overrun = false; ws.done = false; ws.tgt_g = 0; ws.tgt_lo = 0; ws.tgt_hi = 0;
+      Acc acc;
+      acc.open = false; acc.g = 0; acc.bstart = 0; acc.blo = 0; acc.bhi = 0; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
       bool dense = false;                 // most rows survive: load the value column with the block, not per survivor
       uint32_t csi = si, row = a;
-      while (!ws.done) {
-        if (!ws.overrun && row >= b) {
+      while (!fl.done) {
+        if (!fl.overrun && row >= b) {
           // end of the owned sub-range: keep going only while rows continue the run of row b-1 (which we own)
-          if (P.global_mode || ws.skipping) break;
-          ws.overrun = true;
+          if (P.global_mode || fl.skipping) break;
+          fl.overrun = true;
           row = b;
-          ws.tgt_g = val(0, b - 1) & P.hot_mask[0];
-          if (HAS_TS) { Bucket tb = bucket_range(int64_t(val(1, b - 1)), P.window_ms); ws.tgt_lo = tb.lo; ws.tgt_hi = tb.hi; }
+          ed.tgt_g = val(0, b - 1);
+          if (HAS_TS) { Bucket tb = bucket_range(int64_t(val(1, b - 1)), P.window_ms); ed.tgt_lo = tb.lo; ed.tgt_hi = tb.hi; }
         }
         if (row >= nrows) {
           csi++;
@@ -421,32 +465,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
           row = 0;
           if (nrows == 0) continue;
         }
-        const uint32_t lim = ws.overrun ? nrows : b;
-        uint32_t kept = dense ? process_block<kU, NH, HAS_TS, true>(P, cur, ws, item, csi, row, lim, nrows, lane)
-                              : process_block<kU, NH, HAS_TS, false>(P, cur, ws, item, csi, row, lim, nrows, lane);
+        const uint32_t lim = fl.overrun ? nrows : b;
+        const bool steady = !fl.skipping && !fl.overrun && row + 32u * kU < b;   // (< b: the halo row stays inside too)
+        uint32_t kept;
+        if (steady) {
+          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane)
+                       : process_block<kU, NH, X, HAS_TS, false, false>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane);
+        } else {
+          kept = dense ? process_block<kU, NH, X, HAS_TS, true, true>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane)
+                       : process_block<kU, NH, X, HAS_TS, false, true>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane);
+        }
         dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
         row += 32 * kU;
-        if (!ws.overrun && row > b) row = b;
+        if (!fl.overrun && row > b) row = b;
       }
-      if (ws.acc.open) { if (lane == 0) emit(P, ws.acc, item, ws.local); ws.local++; }
+      if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
     }
     if (lane == 0) {
-      P.item_cnt[item] = ws.local;
-      if (ws.n_alive) atomicAdd(&P.counters[0], (unsigned long long)ws.n_alive);
-      if (ws.n_keep) atomicAdd(&P.counters[1], (unsigned long long)ws.n_keep);
+      P.item_cnt[item] = local;
+      if (n_alive) atomicAdd(&P.counters[0], (unsigned long long)n_alive);
+      if (n_keep) atomicAdd(&P.counters[1], (unsigned long long)n_keep);
     }
   }
 }
 
 template <int kU, int kMinBlocks>
-void launch_fused(int nhot, bool has_ts, int ctas, cudaStream_t s, const FParams& P) {
-#define HG_LAUNCH(NH)                                                                                           \
-  if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P);                \
-  else fused_scan_kernel<kU, kMinBlocks, NH, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P)
-  switch (nhot) {
-    case 2: HG_LAUNCH(2); break;
-    case 3: HG_LAUNCH(3); break;
-    default: HG_LAUNCH(4);
+void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, const FParams& P) {
+#define HG_LAUNCH(NH, XM)                                                                                           \
+  do {                                                                                                              \
+    if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, XM, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P);              \
+    else fused_scan_kernel<kU, kMinBlocks, NH, XM, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P);                    \
+  } while (0)
+  if (nhot == 2) HG_LAUNCH(2, 0);
+  else if (nhot == 3) { if (xmask & 1) HG_LAUNCH(3, 1); else HG_LAUNCH(3, 0); }
+  else {
+    switch (xmask & 3) {
+      case 0: HG_LAUNCH(4, 0); break;
+      case 1: HG_LAUNCH(4, 1); break;
+      case 2: HG_LAUNCH(4, 2); break;
+      default: HG_LAUNCH(4, 3);
+    }
   }
 #undef HG_LAUNCH
 }
@@ -524,6 +582,8 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   if (global_mode && agg->value_col >= 0) return NOT_APPLICABLE;               // a global f64 sum is one serial chain
   if (schema->num_primary_keys < 2) return NOT_APPLICABLE;                     // the kernel keeps pk0 and pk1 in registers
   if (has_ts && schema->types[1] != T_I64) return NOT_APPLICABLE;
+  for (int k = 0; k < 2; k++)
+    if (schema->types[k] != T_U64 && schema->types[k] != T_I64) return NOT_APPLICABLE;   // pk0 / pk1 are read as 8-byte words
   // ---- column slots: PKs first, then predicate / value columns
   std::vector<uint32_t> slots;
   for (uint32_t c = 0; c < schema->num_primary_keys; c++) slots.push_back(c);
@@ -656,20 +716,19 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.has_ts = has_ts;
     P.value_slot = value_slot;
     P.global_mode = global_mode;
+    int xmask = 0;
     for (int h = 0; h < kHot; h++) {
       const int sl = h < nhot ? hot_slot[h] : 0;
       const uint32_t t = schema->types[slots[sl]];
       const bool w8 = (t == T_U64 || t == T_I64 || t == T_F64);
       P.hot_slot[h] = sl;
-      // raw bytes -> key: 8-byte columns: raw ^ signflip.  4-byte columns hold the value in the low 32 bits; the widened
-      // 64-bit key of a signed 32-bit value v is (sext(v) ^ 2^63), which for comparison purposes equals comparing
-      // (v ^ 2^31) as unsigned 32-bit: use mask 0xffffffff, flip 2^31 and rebase the interval into that domain.
-      P.hot_mask[h] = w8 ? ~0ull : 0xffffffffull;
+      P.hot_haspred[h] = (h < nhot && (klo[h] != 0 || khi[h] != ~0ull)) ? 1 : 0;
+      // 8-byte columns: key = raw ^ signflip.  4-byte columns are tested in 32-bit arithmetic: the widened key of a signed
+      // value v is sext(v) ^ 2^63, ordered like (v ^ 2^31) as unsigned 32-bit; rebase the interval into that domain.
       uint64_t lo = klo[h], hi = khi[h];
       if (w8) P.hot_flip[h] = type_is_signed(t) ? (1ull << 63) : 0ull;
       else if (type_is_signed(t)) {
         P.hot_flip[h] = 1ull << 31;
-        // widened key k = sext(v) ^ 2^63 ranges over [2^63 - 2^31, 2^63 + 2^31); 32-bit key = k - (2^63 - 2^31)
         const uint64_t base = (1ull << 63) - (1ull << 31), top = (1ull << 63) + (1ull << 31) - 1;
         if (hi < base || lo > top) empty_interval = true;
         lo = lo < base ? 0 : lo - base;
@@ -681,8 +740,9 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       }
       P.hot_lo[h] = lo;
       P.hot_span[h] = hi >= lo ? hi - lo : 0;
+      if (h >= 2 && h < nhot && !w8) xmask |= 1 << (h - 2);
     }
-    if (empty_interval) { P.hot_lo[0] = 1; P.hot_span[0] = 0; P.hot_mask[0] = P.hot_mask[0]; P.hot_flip[0] = 0; }
+    if (empty_interval) { P.hot_haspred[0] = 1; P.hot_flip[0] = 0; P.hot_lo[0] = 1; P.hot_span[0] = 0; P.hot_lo[0] = ~0ull; }   // nothing passes
     P.npred = int(np);
     for (size_t i = 0; i < np; i++) {
       P.pslot[i] = pslot[i];
@@ -702,11 +762,11 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     if (variant < 0) { const char* v = getenv("HORAE_FUSED_VARIANT"); variant = v ? atoi(v) : 0; }
     CU_TRY(cudaEventRecord(e->evk0, s));
     switch (variant) {
-      case 1: launch_fused<4, 3>(nhot, has_ts, ctas, s, P); break;
-      case 2: launch_fused<2, 4>(nhot, has_ts, ctas, s, P); break;
-      case 3: launch_fused<2, 3>(nhot, has_ts, ctas, s, P); break;
-      case 4: launch_fused<1, 4>(nhot, has_ts, ctas, s, P); break;
-      default: launch_fused<4, 2>(nhot, has_ts, ctas, s, P);
+      case 1: launch_fused<4, 3>(nhot, xmask, has_ts, ctas, s, P); break;
+      case 2: launch_fused<2, 4>(nhot, xmask, has_ts, ctas, s, P); break;
+      case 3: launch_fused<2, 3>(nhot, xmask, has_ts, ctas, s, P); break;
+      case 4: launch_fused<1, 4>(nhot, xmask, has_ts, ctas, s, P); break;
+      default: launch_fused<4, 2>(nhot, xmask, has_ts, ctas, s, P);
     }
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
