@@ -186,11 +186,101 @@ __device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item,
   } else atomicExch(P.err, 201);
 }
 
-// Survivors of one slice, in stream order.  Fast path: they all extend the open group -> count by popc, min/max by a
-// warp butterfly (order-free), only the f64 sum is a sequential chain.  Otherwise the general walk with group breaks.
+// ------------------------------------------------------------------------------------------------ item boundaries
+// Work items are sub-ranges of row groups.  A group (key-run) must be summed by ONE warp in stream order, so every
+// nominal boundary is moved forward to the next row that starts a new key-run: item j = [adj[j], adj[j+1]).
+// One warp per boundary; the run end is located by 32-way probing (keys are sorted, so "differs from the key at the
+// boundary" is monotone along the stream): 3 rounds cover a 8192-row group.
+struct KeyRef { uint64_t g; int64_t lo, hi; };
+
+template <bool HAS_TS>
+__device__ __forceinline__ bool key_differs(const FParams& P, const KeyRef& k, uint32_t si, uint32_t row) {
+  if (P.has_group && fetch_val(P, si, 0, row) != k.g) return true;
+  if (HAS_TS) { int64_t ts = int64_t(fetch_val(P, si, 1, row)); if (ts < k.lo || ts > k.hi) return true; }
+  return false;
+}
+
+__device__ __forceinline__ uint64_t pack_pos(uint32_t si, uint32_t row) { return (uint64_t(si) << 32) | row; }
+
+template <bool HAS_TS>
+__global__ void __launch_bounds__(256) item_bounds_kernel(const __grid_constant__ FParams P, uint64_t* __restrict__ adj) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nitems = P.nsel * P.split;
+  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j > nitems) return;
+  if (j == nitems) { if (lane == 0) adj[j] = pack_pos(P.nsel, 0); return; }
+  uint32_t si = j / P.split, w = j % P.split;
+  uint32_t n = P.sel[si].num_rows;
+  const uint32_t sr = (((n + P.split - 1) / P.split) + 31u) & ~31u;
+  uint32_t row = w * sr;
+  if (row >= n) { si++; row = 0; }                        // empty sub-range: same boundary as the next row group
+  if (si >= P.nsel) { if (lane == 0) adj[j] = pack_pos(P.nsel, 0); return; }
+  if (P.global_mode || (si == 0 && row == 0)) { if (lane == 0) adj[j] = pack_pos(si, row); return; }
+  // key of the row just before the nominal boundary
+  uint32_t psi = si, prow = row;
+  if (prow == 0) { psi--; prow = P.sel[psi].num_rows - 1; } else prow--;
+  KeyRef k;
+  k.g = P.has_group ? fetch_val(P, psi, 0, prow) : 0;
+  k.lo = 0; k.hi = 0;
+  if (HAS_TS) { Bucket b = bucket_range(int64_t(fetch_val(P, psi, 1, prow)), P.window_ms); k.lo = b.lo; k.hi = b.hi; }
+  // L = a position known to continue the run (start: the previous row); find the first later position that differs
+  for (;;) {
+    n = P.sel[si].num_rows;
+    uint32_t L = row, H = n;                              // candidates [L, H) in this row group
+    bool found = false;
+    uint32_t ans = H;
+    // invariant: every position < L (in this group) continues the run
+    while (L < H) {
+      uint32_t span = H - L;
+      uint32_t step = (span + 31) / 32;
+      uint32_t p = L + (uint32_t(lane) + 1) * step - 1;    // last position of lane's chunk
+      if (p >= H) p = H - 1;
+      bool ne = key_differs<HAS_TS>(P, k, si, p);
+      unsigned m = __ballot_sync(0xffffffffu, ne);
+      if (m == 0) { L = H; break; }                       // the whole window continues the run
+      int f = __ffs(m) - 1;
+      uint32_t pf = L + (uint32_t(f) + 1) * step - 1;
+      if (pf >= H) pf = H - 1;
+      uint32_t newL = L + uint32_t(f) * step;             // chunk f holds the first differing row
+      found = true;
+      ans = pf;
+      if (step == 1) break;
+      L = newL;
+      H = pf;                                             // rows [newL, pf) still unknown; pf differs
+      if (L >= H) break;
+    }
+    if (found) { if (lane == 0) adj[j] = pack_pos(si, ans); return; }
+    si++;                                                 // the run covers the rest of this row group
+    row = 0;
+    if (si >= P.nsel) { if (lane == 0) adj[j] = pack_pos(P.nsel, 0); return; }
+  }
+}
+
+// Survivors of one slice, fast path: they all extend the open group.  count by popc, min/max by a warp butterfly
+// (order-free); the f64 sum is a strictly sequential chain in stream order.  With many survivors the values go through
+// shared memory (non-survivors contribute +0.0, which is exact because the running sum starts at +0.0 and can never
+// be -0.0): 32 x (LDS + DADD) straight-line instead of a 12-instruction loop per survivor.
+__device__ __forceinline__ double seq_sum_slice(double sum, unsigned keep_mask, bool keep, double v, double* s_vals, int lane) {
+  if (__popc(keep_mask) >= 8) {
+    __syncwarp();
+    s_vals[lane] = keep ? v : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 32; l++) sum += s_vals[l];
+    return sum;
+  }
+  uint64_t vb = uint64_t(__double_as_longlong(v));
+  while (keep_mask) {
+    int l = __ffs(keep_mask) - 1;
+    keep_mask &= keep_mask - 1;
+    sum += __longlong_as_double((long long)shfl64(vb, l));
+  }
+  return sum;
+}
+
 template <bool HAS_TS>
 __device__ __noinline__ void walk_slice(const FParams& P, Acc& acc, uint32_t& local, uint32_t item, unsigned keep_mask, bool keep, uint64_t g,
-                                        int64_t ts, double v, int lane) {
+                                        int64_t ts, double v, double* s_vals, int lane) {
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   const bool has_val = P.value_slot >= 0;
   bool ext = keep && acc.open && (!P.has_group || g == acc.g) && (!HAS_TS || (ts >= acc.blo && ts <= acc.bhi));
@@ -206,14 +296,7 @@ __device__ __noinline__ void walk_slice(const FParams& P, Acc& acc, uint32_t& lo
       }
       acc.mn = mn < acc.mn ? mn : acc.mn;
       acc.mx = mx > acc.mx ? mx : acc.mx;
-      uint64_t vb = uint64_t(__double_as_longlong(v));
-      double sum = acc.sum;
-      while (keep_mask) {                       // strictly sequential f64 additions in stream order
-        int l = __ffs(keep_mask) - 1;
-        keep_mask &= keep_mask - 1;
-        sum += __longlong_as_double((long long)shfl64(vb, l));
-      }
-      acc.sum = sum;
+      acc.sum = seq_sum_slice(acc.sum, keep_mask, keep, v, s_vals, lane);
     }
     return;
   }
@@ -244,16 +327,6 @@ __device__ __forceinline__ double to_double_kind(uint64_t raw, uint32_t kind, ui
   return cls == C_FLOAT ? __longlong_as_double((long long)wv) : (cls == C_SIGNED ? double(int64_t(wv)) : double(wv));
 }
 
-// One block = kU slices of 32 rows.  Phase 1 issues every load of the block as straight-line code (clamped indices,
-// hot columns and their widths known at compile time): kU*NH*2 loads per lane in flight.  Phase 2 walks the slices in
-// stream order; everything beyond the interval tests runs only when a slice has survivors.
-//   X     bit k set => extra hot column 2+k is a 4-byte column (pk0 / pk1 are always 8-byte here)
-//   EDGE  false => steady state: the whole block lies inside the owned sub-range, no skip / overrun bookkeeping
-struct Cur {                       // per-warp view of the current row group (shared memory)
-  const uint8_t* q[MAXC];          // value base rounded down to the column's word size
-  uint32_t sh[MAXC];               // bit shift of the values inside their aligned words (uniform per column chunk)
-};
-
 __device__ __forceinline__ uint64_t ld8(const uint8_t* q, uint32_t sh, uint32_t i) {
   const uint64_t* p = reinterpret_cast<const uint64_t*>(q) + i;
   uint64_t lo = __ldg(p), hi = __ldg(p + 1);
@@ -269,46 +342,48 @@ __device__ __forceinline__ uint32_t ld4(const uint8_t* q, uint32_t sh, uint32_t 
   return __funnelshift_r(lo, hi, sh);
 }
 
-struct Flags { bool skipping, overrun, done; };
-struct Edge {
-  uint64_t prev_g, tgt_g;
-  int64_t prev_lo, prev_hi, tgt_lo, tgt_hi;     // bucket ranges of the previous row / of the owned run
+// Per-column constants of the hot columns, held in registers across the whole item.
+template <int NH>
+struct Hot {
+  const uint8_t* q[NH];      // value base rounded down to the column's word size (changes with the row group)
+  uint32_t sh[NH];           // bit shift of the values inside their aligned words
+  uint64_t flip[NH], lo[NH], span[NH];
+  bool haspred[NH];
 };
 
-template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool EDGE>
-__device__ __forceinline__ uint32_t process_block(const FParams& P, const Cur& cur, Acc& acc, Flags& fl, const Edge& ed, uint32_t& local,
+// One block = kU slices of 32 rows.  Phase 1 issues every load of the block as straight-line code: kU*NH*2 loads per
+// lane in flight.  Phase 2 walks the slices in stream order; everything beyond the interval tests runs only when a
+// slice has survivors.
+//   X        bit k set => extra hot column 2+k is a 4-byte column (pk0 / pk1 are always 8-byte here)
+//   PARTIAL  the block may extend past `lim` (end of the item or of the row group): indices clamped, lanes masked
+template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool PARTIAL>
+__device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH>& H, const uint8_t* vq, uint32_t vs, Acc& acc, uint32_t& local,
                                                   uint32_t& n_alive, uint32_t& n_keep, uint32_t item, uint32_t csi, uint32_t row,
-                                                  uint32_t lim, uint32_t nrows, int lane) {
+                                                  uint32_t lim, uint32_t nrows, double* s_vals, int lane) {
   uint64_t hv[kU][NH];
   uint64_t vv[kU];
   uint64_t halo[2] = {0, 0};
   const uint32_t last = nrows - 1;
-  const uint8_t* hq[NH];
-  uint32_t hs[NH];
-#pragma unroll
-  for (int h = 0; h < NH; h++) { hq[h] = cur.q[P.hot_slot[h]]; hs[h] = cur.sh[P.hot_slot[h]]; }
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     uint32_t i = row + u * 32 + lane;
-    if (EDGE) i = i < last ? i : last;
+    if (PARTIAL) i = i < last ? i : last;
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
-      hv[u][h] = w4 ? uint64_t(ld4(hq[h], hs[h], i)) : ld8(hq[h], hs[h], i);
+      hv[u][h] = w4 ? uint64_t(ld4(H.q[h], H.sh[h], i)) : ld8(H.q[h], H.sh[h], i);
     }
   }
   if (DENSE) {
     uint32_t i = row + kU * 32;
     i = i < last ? i : last;
-    halo[0] = ld8(hq[0], hs[0], i);
-    halo[1] = ld8(hq[1], hs[1], i);
-    const uint8_t* vq = cur.q[P.value_slot];
-    const uint32_t vs = cur.sh[P.value_slot];
+    halo[0] = ld8(H.q[0], H.sh[0], i);
+    halo[1] = ld8(H.q[1], H.sh[1], i);
     const bool v8 = P.kind[P.value_slot] == K_RAW64;
 #pragma unroll
     for (int u = 0; u < kU; u++) {
       uint32_t i2 = row + u * 32 + lane;
-      if (EDGE) i2 = i2 < last ? i2 : last;
+      if (PARTIAL) i2 = i2 < last ? i2 : last;
       vv[u] = v8 ? ld8(vq, vs, i2) : uint64_t(ld4(vq, vs, i2));
     }
   }
@@ -316,34 +391,17 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Cur& c
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     const uint32_t i = row + u * 32 + lane;
-    bool mine = true;
-    const uint64_t g = hv[u][0];
-    const int64_t ts = int64_t(hv[u][1]);
-    if (EDGE) {
-      const bool inb = i < lim;
-      const unsigned inb_mask = __ballot_sync(0xffffffffu, inb);
-      if (inb_mask == 0 || fl.done) continue;
-      mine = inb;
-      if (fl.skipping) {
-        bool foreign = inb && (!P.has_group || g == ed.prev_g) && (!HAS_TS || (ts >= ed.prev_lo && ts <= ed.prev_hi));
-        unsigned fm = __ballot_sync(0xffffffffu, foreign);
-        if (fm != inb_mask) fl.skipping = false;       // a new run starts inside this slice
-        mine = inb && !foreign;
-      }
-      if (fl.overrun) {
-        bool match = inb && (!P.has_group || g == ed.tgt_g) && (!HAS_TS || (ts >= ed.tgt_lo && ts <= ed.tgt_hi));
-        unsigned mm = __ballot_sync(0xffffffffu, match);
-        if (mm != inb_mask) fl.done = true;            // the owned run ends inside this slice
-        mine = match;
-      }
+    bool alive = true;
+    if (PARTIAL) {
+      alive = i < lim;
+      if (__ballot_sync(0xffffffffu, alive) == 0) continue;
     }
-    bool alive = mine;
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
-      if (P.hot_haspred[h]) {                          // uniform
-        if (w4) alive = alive && ((uint32_t(hv[u][h]) ^ uint32_t(P.hot_flip[h])) - uint32_t(P.hot_lo[h]) <= uint32_t(P.hot_span[h]));
-        else alive = alive && ((hv[u][h] ^ P.hot_flip[h]) - P.hot_lo[h] <= P.hot_span[h]);
+      if (H.haspred[h]) {                              // uniform
+        if (w4) alive = alive && ((uint32_t(hv[u][h]) ^ uint32_t(H.flip[h])) - uint32_t(H.lo[h]) <= uint32_t(H.span[h]));
+        else alive = alive && ((hv[u][h] ^ H.flip[h]) - H.lo[h] <= H.span[h]);
       }
     }
     const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
@@ -358,8 +416,8 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Cur& c
       if (!DENSE && (alive_mask >> 31)) {              // sparse blocks fetch the halo row only when lane 31 survives
         uint32_t ih = row + kU * 32;
         ih = ih < last ? ih : last;
-        halo[0] = ld8(hq[0], hs[0], ih);
-        halo[1] = ld8(hq[1], hs[1], ih);
+        halo[0] = ld8(H.q[0], H.sh[0], ih);
+        halo[1] = ld8(H.q[1], H.sh[1], ih);
       }
       if (lane == 31) { n0 = halo[0]; n1 = halo[1]; }
     }
@@ -380,10 +438,10 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Cur& c
       double v = 0.0;
       if (keep && P.value_slot >= 0) {
         const bool v8 = P.kind[P.value_slot] == K_RAW64;
-        uint64_t raw = DENSE ? vv[u] : (v8 ? ld8(cur.q[P.value_slot], cur.sh[P.value_slot], i) : uint64_t(ld4(cur.q[P.value_slot], cur.sh[P.value_slot], i)));
+        uint64_t raw = DENSE ? vv[u] : (v8 ? ld8(vq, vs, i) : uint64_t(ld4(vq, vs, i)));
         v = to_double_kind(raw, P.kind[P.value_slot], P.cls[P.value_slot]);
       }
-      walk_slice<HAS_TS>(P, acc, local, item, keep_mask, keep, g, ts, v, lane);
+      walk_slice<HAS_TS>(P, acc, local, item, keep_mask, keep, hv[u][0], int64_t(hv[u][1]), v, s_vals, lane);
     }
   }
   return kept_in_block;
@@ -391,93 +449,72 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Cur& c
 
 // kU = slices whose loads are issued together; NH = hot columns (pk0, pk1, + predicate columns) loaded for every row
 template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P) {
-  __shared__ Cur s_cur[kWarpsPerCta];
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P,
+                                                                                    const uint64_t* __restrict__ adj) {
+  __shared__ double s_vals_all[kWarpsPerCta][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const Cur& cur = s_cur[wid];
+  double* s_vals = s_vals_all[wid];
   const uint32_t nitems = P.nsel * P.split;
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  Hot<NH> H;
+#pragma unroll
+  for (int h = 0; h < NH; h++) {
+    H.flip[h] = P.hot_flip[h]; H.lo[h] = P.hot_lo[h]; H.span[h] = P.hot_span[h]; H.haspred[h] = P.hot_haspred[h] != 0;
+    H.q[h] = nullptr; H.sh[h] = 0;
+  }
+  const uint8_t* vq = nullptr;
+  uint32_t vs = 0;
   auto set_cursor = [&](uint32_t si) {
-    __syncwarp();
-    if (lane < P.nslots) {
-      const uint8_t* base = slot_base(P, si, lane);
-      const uintptr_t a = reinterpret_cast<uintptr_t>(base);
-      const uintptr_t m = P.kind[lane] == K_RAW64 ? 7 : 3;
-      s_cur[wid].q[lane] = reinterpret_cast<const uint8_t*>(a & ~m);
-      s_cur[wid].sh[lane] = uint32_t(a & m) * 8;
+    // every lane derives the same pointers (loads broadcast); keeps them in registers until the next row group
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(slot_base(P, si, P.hot_slot[h]));
+      const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
+      const uintptr_t m = w4 ? 3 : 7;
+      H.q[h] = reinterpret_cast<const uint8_t*>(a & ~m);
+      H.sh[h] = uint32_t(a & m) * 8;
     }
-    __syncwarp();
-  };
-  auto val = [&](int slot, uint32_t row) -> uint64_t {
-    return P.kind[slot] == K_RAW64 ? ld8(cur.q[slot], cur.sh[slot], row) : widen_kind(ld4(cur.q[slot], cur.sh[slot], row), P.kind[slot]);
+    if (P.value_slot >= 0) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(slot_base(P, si, P.value_slot));
+      const uintptr_t m = P.kind[P.value_slot] == K_RAW64 ? 7 : 3;
+      vq = reinterpret_cast<const uint8_t*>(a & ~m);
+      vs = uint32_t(a & m) * 8;
+    }
   };
   for (;;) {
     uint32_t item = 0;
     if (lane == 0) item = atomicAdd(&P.work[0], 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nitems) return;
-    const uint32_t si = item / P.split, w = item % P.split;
-    uint32_t nrows = P.sel[si].num_rows;
-    const uint32_t n = nrows;
-    const uint32_t sr = (((n + P.split - 1) / P.split) + 31u) & ~31u;
-    const uint32_t a = w * sr;
+    const uint64_t beg = adj[item], end = adj[item + 1];
+    uint32_t csi = uint32_t(beg >> 32), row = uint32_t(beg);
+    const uint32_t esi = uint32_t(end >> 32), erow = uint32_t(end);
     uint32_t local = 0, n_alive = 0, n_keep = 0;
-    if (a < n) {
-      set_cursor(si);
-      const uint32_t b = a + sr < n ? a + sr : n;
-      // key of the row just before this sub-range: rows that continue its run belong to an earlier owner
-      Flags fl;
-      Edge ed;
-      fl.skipping = false; fl.overrun = false; fl.done = false;
-      ed.prev_g = 0; ed.prev_lo = 0; ed.prev_hi = 0; ed.tgt_g = 0; ed.tgt_lo = 0; ed.tgt_hi = 0;
-      if (!P.global_mode) {
-        uint64_t pts = 0;
-        if (a > 0) {
-          fl.skipping = true;
-          ed.prev_g = val(0, a - 1);
-          if (HAS_TS) pts = val(1, a - 1);
-        } else if (si > 0) {
-          uint32_t pn = P.sel[si - 1].num_rows;      // the planner never selects empty row groups
-          fl.skipping = true;
-          ed.prev_g = fetch_val(P, si - 1, 0, pn - 1);
-          if (HAS_TS) pts = fetch_val(P, si - 1, 1, pn - 1);
-        }
-        if (HAS_TS && fl.skipping) { Bucket pb = bucket_range(int64_t(pts), P.window_ms); ed.prev_lo = pb.lo; ed.prev_hi = pb.hi; }
-      }
+    if (beg < end) {
       Acc acc;
       acc.open = false; acc.g = 0; acc.bstart = 0; acc.blo = 0; acc.bhi = 0; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
       bool dense = false;                 // most rows survive: load the value column with the block, not per survivor
-      uint32_t csi = si, row = a;
-      while (!fl.done) {
-        if (!fl.overrun && row >= b) {
-          // end of the owned sub-range: keep going only while rows continue the run of row b-1 (which we own)
-          if (P.global_mode || fl.skipping) break;
-          fl.overrun = true;
-          row = b;
-          ed.tgt_g = val(0, b - 1);
-          if (HAS_TS) { Bucket tb = bucket_range(int64_t(val(1, b - 1)), P.window_ms); ed.tgt_lo = tb.lo; ed.tgt_hi = tb.hi; }
-        }
+      uint32_t nrows = P.sel[csi].num_rows;
+      set_cursor(csi);
+      for (;;) {
         if (row >= nrows) {
           csi++;
-          if (csi >= P.nsel) break;
+          row = 0;
+          if (csi > esi || (csi == esi && erow == 0) || csi >= P.nsel) break;
           nrows = P.sel[csi].num_rows;
           set_cursor(csi);
-          row = 0;
-          if (nrows == 0) continue;
         }
-        const uint32_t lim = fl.overrun ? nrows : b;
-        const bool steady = !fl.skipping && !fl.overrun && row + 32u * kU < b;   // (< b: the halo row stays inside too)
+        const uint32_t lim = csi == esi ? erow : nrows;
+        if (row >= lim) break;
         uint32_t kept;
-        if (steady) {
-          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane)
-                       : process_block<kU, NH, X, HAS_TS, false, false>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane);
+        if (row + 32u * kU < lim) {       // (< lim: the halo row is inside the row group as well)
+          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane)
+                       : process_block<kU, NH, X, HAS_TS, false, false>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
         } else {
-          kept = dense ? process_block<kU, NH, X, HAS_TS, true, true>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane)
-                       : process_block<kU, NH, X, HAS_TS, false, true>(P, cur, acc, fl, ed, local, n_alive, n_keep, item, csi, row, lim, nrows, lane);
+          kept = process_block<kU, NH, X, HAS_TS, false, true>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
         }
         dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
         row += 32 * kU;
-        if (!fl.overrun && row > b) row = b;
       }
       if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
     }
@@ -490,11 +527,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
 }
 
 template <int kU, int kMinBlocks>
-void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, const FParams& P) {
-#define HG_LAUNCH(NH, XM)                                                                                           \
-  do {                                                                                                              \
-    if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, XM, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P);              \
-    else fused_scan_kernel<kU, kMinBlocks, NH, XM, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P);                    \
+void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, const FParams& P, const uint64_t* adj) {
+#define HG_LAUNCH(NH, XM)                                                                                                \
+  do {                                                                                                                   \
+    if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, XM, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);              \
+    else fused_scan_kernel<kU, kMinBlocks, NH, XM, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);                    \
   } while (0)
   if (nhot == 2) HG_LAUNCH(2, 0);
   else if (nhot == 3) { if (xmask & 1) HG_LAUNCH(3, 1); else HG_LAUNCH(3, 0); }
@@ -660,12 +697,12 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
 
   cudaStream_t s = e->stream;
   Launch L = e->L();
-  // split row groups into enough work items to keep ~4 items per resident warp, but no finer: every item boundary
-  // costs an overrun of about half a group
+  // split row groups into enough work items for ~8 items per resident warp (dynamic ticket => good balance);
+  // boundaries are then aligned to key-run starts by item_bounds_kernel
   uint32_t split = 1;
-  while (split < 8 && uint64_t(nsel) * split < 148ull * 32 * 4) split *= 2;
+  while (split < 8 && uint64_t(nsel) * split < 148ull * 32 * 8) split *= 2;
   const uint32_t nitems = nsel * split;
-  DevBuf d_ssts, d_sel, d_rec, d_item, d_work, d_counters, d_err;
+  DevBuf d_ssts, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj;
   CU_TRY(d_work.alloc(64, s));
   CU_TRY(cudaMemsetAsync(d_work.p, 0, 64, s));
   CU_TRY(d_counters.alloc(64, s));
@@ -674,6 +711,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   CU_TRY(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
   CU_TRY(d_rec.alloc(size_t(bound) * sizeof(FRec) + 64, s));
   CU_TRY(d_item.alloc(size_t(nitems + 1) * sizeof(uint32_t) + 64, s));
+  CU_TRY(d_adj.alloc(size_t(nitems + 2) * sizeof(uint64_t), s));
   out->gtype = has_group ? schema->types[0] : uint32_t(T_U64);
   out->gwidth = has_group ? type_width_host(out->gtype) : 8;
   CU_TRY(out->gkey.alloc(size_t(bound) * 8 + 16, s));
@@ -760,13 +798,20 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
     static int variant = -1;
     if (variant < 0) { const char* v = getenv("HORAE_FUSED_VARIANT"); variant = v ? atoi(v) : 0; }
+    {
+      const uint32_t nb = nitems + 1;
+      const int bctas = int((uint64_t(nb) * 32 + 255) / 256);
+      if (has_ts) item_bounds_kernel<true><<<bctas, 256, 0, s>>>(P, d_adj.as<uint64_t>());
+      else item_bounds_kernel<false><<<bctas, 256, 0, s>>>(P, d_adj.as<uint64_t>());
+      L.tick();
+    }
     CU_TRY(cudaEventRecord(e->evk0, s));
     switch (variant) {
-      case 1: launch_fused<4, 3>(nhot, xmask, has_ts, ctas, s, P); break;
-      case 2: launch_fused<2, 4>(nhot, xmask, has_ts, ctas, s, P); break;
-      case 3: launch_fused<2, 3>(nhot, xmask, has_ts, ctas, s, P); break;
-      case 4: launch_fused<1, 4>(nhot, xmask, has_ts, ctas, s, P); break;
-      default: launch_fused<4, 2>(nhot, xmask, has_ts, ctas, s, P);
+      case 1: launch_fused<4, 3>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      case 2: launch_fused<2, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      case 3: launch_fused<2, 3>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      case 4: launch_fused<1, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      default: launch_fused<4, 2>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>());
     }
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
