@@ -126,7 +126,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        nsample = min(args.files, 4)
+        nsample = args.files
         ssts = gen_ssts(0, "snappy", nsample, min(ncores, nsample))   # WriteConfig::default = Snappy (config.rs:120-133)
         rps, rows, dt, _ = cpu_reference(ssts, ncores, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": "scanned rows/s", "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
@@ -264,8 +264,14 @@ def main():
         st = main_r["stats"]
         alg_bytes = st["rows_decoded"] * ALG_BYTES_PER_ROW         # rows the dominant kernel actually processed
         achieved = alg_bytes / (main_r["kernel_ms"] / 1e3) / 1e9
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get("fused_scan_kernel" if st["path"] == 1 else "snappy_chunks_kernel")
+        except Exception:
+            pass
         # CPU oracle on a bounded sample of the same workload (same predicate, same files)
-        nsample = min(len(main_r["ssts"]), 2)
+        nsample = len(main_r["ssts"])
         cpu_rps, cpu_rows, cpu_dt, cpu_res = cpu_reference(main_r["ssts"][:nsample], ncores)
         line = {
             "metric": "scanned rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -276,7 +282,7 @@ def main():
                        "path": "fused" if st["path"] == 1 else "general", "rows_decoded_per_gpu": st["rows_decoded"],
                        "rows_filtered_per_gpu": st["rows_filtered"], "groups": main_r["groups"],
                        "decoded_GBps": rows_all * ALG_BYTES_PER_ROW / (main_r["ms_per_step"] / 1e3) / 1e9},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "fused_scan_kernel" if st["path"] == 1 else "snappy_chunks+decode_chunks",
                          "kernel_ms": main_r["kernel_ms"], "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src},
             "cpu_baseline": {"value": cpu_rps, "unit": "rows/s", "cores": ncores, "kind": "port",

@@ -92,6 +92,26 @@ static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_
       cd.optional = uint8_t(m.repetition[c] == 1);
       cd._pad = 0;
     }
+  r->rgcol.resize(m.rgs.size() * size_t(m.ncols));
+  r->rg_rows.resize(m.rgs.size());
+  for (size_t g = 0; g < m.rgs.size(); g++) {
+    r->rg_rows[g] = uint32_t(m.rgs[g].num_rows);
+    for (int c = 0; c < m.ncols; c++) {
+      const ChunkMeta& cm = m.rgs[g].cols[c];
+      RgCol& rc = r->rgcol[g * m.ncols + c];
+      const uint32_t t = schema->types[c];
+      if (cm.stats.has_min && cm.stats.has_max) {
+        rc.has_minmax = 1;
+        rc.mn = widen_stat(cm.stats.min, cm.phys_type, t);
+        rc.mx = widen_stat(cm.stats.max, cm.phys_type, t);
+      }
+      rc.null_all = cm.stats.has_null_count && cm.stats.null_count == m.rgs[g].num_rows;
+      rc.null_none = cm.stats.has_null_count && cm.stats.null_count == 0;
+      rc.snappy = cm.codec == CODEC_SNAPPY;
+      rc.scratch = uint32_t(cm.scratch_bytes);
+      rc.simple_page = cm.codec == CODEC_UNCOMPRESSED && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA;
+    }
+  }
   uint64_t need = size + 64 + pages.size() * sizeof(PageDev) + chunks.size() * sizeof(ChunkDev);
   if (e->budget && e->resident_bytes + need > e->budget)
     return set_error(HG_ERR_OOM, "HBM budget exceeded while loading sst " + std::to_string(d->id));
@@ -111,16 +131,15 @@ static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_
 }
 
 // ------------------------------------------------------------------------------------------------------ scan planning
-static bool rg_may_match(const RowGroupMeta& rg, const hg_schema_desc* schema, const hg_predicate* preds, size_t np) {
+static bool rg_may_match(const RgCol* rc, uint32_t num_rows, const hg_schema_desc* schema, const hg_predicate* preds, const uint64_t* lits, size_t np) {
   // DataFusion PruningPredicate (pinned by the plan text at read.rs:613):
   //   CASE WHEN null_count = row_count THEN false ELSE <min/max rewrite of the comparison> END
   for (size_t i = 0; i < np; i++) {
-    const ChunkMeta& cm = rg.cols[preds[i].column];
-    uint32_t t = schema->types[preds[i].column];
-    if (cm.stats.has_null_count && cm.stats.null_count == rg.num_rows) return false;
-    if (!cm.stats.has_min || !cm.stats.has_max) continue;
-    uint64_t mn = widen_stat(cm.stats.min, cm.phys_type, t), mx = widen_stat(cm.stats.max, cm.phys_type, t);
-    uint64_t lit = pred_literal(preds[i], t);
+    const RgCol& c = rc[preds[i].column];
+    const uint32_t t = schema->types[preds[i].column];
+    if (c.null_all) return false;
+    if (!c.has_minmax) continue;
+    const uint64_t mn = c.mn, mx = c.mx, lit = lits[i];
     bool ok = true;
     switch (preds[i].op) {
       case HG_OP_EQ: ok = cmp_host(mn, lit, t) <= 0 && cmp_host(lit, mx, t) <= 0; break;
@@ -135,35 +154,60 @@ static bool rg_may_match(const RowGroupMeta& rg, const hg_schema_desc* schema, c
   return true;
 }
 
+int stage_upload(hg_engine* e, void* dst, const void* src, size_t bytes, size_t* stage_off) {
+  size_t off = (*stage_off + 255) & ~size_t(255);
+  if (off + bytes > e->h_stage_bytes) {
+    // grow (rare): everything staged so far in this call must reach the device first
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    size_t nb = std::max<size_t>((off + bytes) * 2, 1 << 20);
+    void* p = nullptr;
+    CU_TRY(cudaMallocHost(&p, nb));
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    e->h_stage = p;
+    e->h_stage_bytes = nb;
+    off = 0;
+  }
+  std::memcpy(static_cast<char*>(e->h_stage) + off, src, bytes);
+  CU_TRY(cudaMemcpyAsync(dst, static_cast<char*>(e->h_stage) + off, bytes, cudaMemcpyHostToDevice, e->stream));
+  *stage_off = off + bytes;
+  return HG_OK;
+}
+
 int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
                       size_t np, const std::vector<uint32_t>& need_cols, ScanPlan* plan) {
   const bool prune = !(e->flags & HG_FLAG_NO_PRUNING);
   struct FileSel { SstResident* f; std::vector<uint32_t> rgs; bool has_range = false; uint64_t mn = 0, mx = 0; size_t given_idx; };
   std::vector<FileSel> fs(n);
   const uint32_t t0 = schema->types[0];
+  uint64_t lits[MAX_PREDS];
+  for (size_t i = 0; i < np; i++) lits[i] = pred_literal(preds[i], schema->types[preds[i].column]);
   bool ranges_ok = true;
+  size_t total_rgs = 0;
   for (size_t i = 0; i < n; i++) {
     auto it = e->ssts.find(ssts[i].id);
     if (it == e->ssts.end()) return set_error(HG_ERR_INTERNAL, "sst not resident after load");
     fs[i].f = it->second.get();
     fs[i].given_idx = i;
-    const FileMetaData& m = fs[i].f->meta;
-    for (size_t g = 0; g < m.rgs.size(); g++) {
-      const RowGroupMeta& rg = m.rgs[g];
-      plan->rows_in_files += uint64_t(rg.num_rows);
-      if (rg.num_rows == 0) continue;
-      if (prune && np && !rg_may_match(rg, schema, preds, np)) continue;
+    const SstResident& f = *fs[i].f;
+    const size_t ncols = size_t(f.meta.ncols), nrg = f.rg_rows.size();
+    fs[i].rgs.reserve(nrg);
+    for (size_t g = 0; g < nrg; g++) {
+      const uint32_t rows = f.rg_rows[g];
+      plan->rows_in_files += rows;
+      if (rows == 0) continue;
+      const RgCol* rc = &f.rgcol[g * ncols];
+      if (prune && np && !rg_may_match(rc, rows, schema, preds, lits, np)) continue;
       fs[i].rgs.push_back(uint32_t(g));
-      const ChunkMeta& c0 = rg.cols[0];
-      if (c0.stats.has_min && c0.stats.has_max && (!c0.stats.has_null_count || c0.stats.null_count == 0)) {
-        uint64_t mn = widen_stat(c0.stats.min, c0.phys_type, t0), mx = widen_stat(c0.stats.max, c0.phys_type, t0);
-        if (!fs[i].has_range) { fs[i].mn = mn; fs[i].mx = mx; fs[i].has_range = true; }
+      const RgCol& c0 = rc[0];
+      if (c0.has_minmax && c0.null_none) {
+        if (!fs[i].has_range) { fs[i].mn = c0.mn; fs[i].mx = c0.mx; fs[i].has_range = true; }
         else {
-          if (cmp_host(mn, fs[i].mn, t0) < 0) fs[i].mn = mn;
-          if (cmp_host(mx, fs[i].mx, t0) > 0) fs[i].mx = mx;
+          if (cmp_host(c0.mn, fs[i].mn, t0) < 0) fs[i].mn = c0.mn;
+          if (cmp_host(c0.mx, fs[i].mx, t0) > 0) fs[i].mx = c0.mx;
         }
       } else ranges_ok = false;
     }
+    total_rgs += fs[i].rgs.size();
   }
   // PK-disjointness from pk0 chunk statistics: order files by min(pk0); require max_f < min_{f+1} strictly.
   std::vector<size_t> order(n);
@@ -185,36 +229,39 @@ int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ss
     }
   }
   plan->col_has_nulls.assign(schema->num_columns, false);
+  plan->sel.reserve(total_rgs);
+  std::vector<uint8_t> has_nulls(schema->num_columns, 0);
   uint64_t row = 0, scratch = 0;
   for (size_t oi = 0; oi < order.size(); oi++) {
     FileSel& f = fs[order[oi]];
     plan->files.push_back(f.f);
     plan->file_base.push_back(uint32_t(row));
-    const FileMetaData& m = f.f->meta;
+    const size_t ncols = size_t(f.f->meta.ncols);
     for (uint32_t g : f.rgs) {
-      const RowGroupMeta& rg = m.rgs[g];
+      const uint32_t rows = f.f->rg_rows[g];
+      const RgCol* rc = &f.f->rgcol[size_t(g) * ncols];
       RgSel s;
       s.sst = uint32_t(oi);
       s.rg = g;
       s.out_row = uint32_t(row);
-      s.num_rows = uint32_t(rg.num_rows);
+      s.num_rows = rows;
       s.scratch_off = scratch;
       for (uint32_t c : need_cols) {
-        const ChunkMeta& cm = rg.cols[c];
-        if (cm.codec == CODEC_SNAPPY) scratch += cm.scratch_bytes;
-        if (!(cm.stats.has_null_count && cm.stats.null_count == 0)) plan->col_has_nulls[c] = true;
-        if (cm.codec != CODEC_UNCOMPRESSED || cm.num_pages != 1 || m.pages[cm.first_page].page_type != PAGE_DATA)
-          plan->all_single_plain_page = false;
+        const RgCol& cc = rc[c];
+        if (cc.snappy) scratch += cc.scratch;
+        if (!cc.null_none) has_nulls[c] = 1;
+        if (!cc.simple_page) plan->all_single_plain_page = false;
       }
       plan->sel.push_back(s);
       if (n == 1) {
-        for (int64_t b = e->batch_size; b < rg.num_rows; b += e->batch_size) plan->piece_end.push_back(uint32_t(row + uint64_t(b)));
-        plan->piece_end.push_back(uint32_t(row + uint64_t(rg.num_rows)));
+        for (uint64_t b = e->batch_size; b < rows; b += e->batch_size) plan->piece_end.push_back(uint32_t(row + b));
+        plan->piece_end.push_back(uint32_t(row + rows));
       }
-      row += uint64_t(rg.num_rows);
+      row += rows;
       if (row >= 0xfffffff0ull) return set_error(HG_ERR_UNSUPPORTED, "more than 2^32 rows in one scan call");
     }
   }
+  for (uint32_t c = 0; c < schema->num_columns; c++) plan->col_has_nulls[c] = has_nulls[c] != 0;
   plan->file_base.push_back(uint32_t(row));
   plan->rows_decoded = row;
   plan->scratch_bytes = scratch;
@@ -344,9 +391,11 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     CU_TRY(st->d_ssts.alloc(sd.size() * sizeof(SstDev), s));
     CU_TRY(st->d_sel.alloc(plan.sel.size() * sizeof(RgSel), s));
     CU_TRY(st->d_colsel.alloc(colsel.size() * sizeof(ColSel), s));
-    CU_TRY(cudaMemcpyAsync(st->d_ssts.p, sd.data(), sd.size() * sizeof(SstDev), cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(st->d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(st->d_colsel.p, colsel.data(), colsel.size() * sizeof(ColSel), cudaMemcpyHostToDevice, s));
+    size_t stage_off = 0;
+    int urc = stage_upload(e, st->d_ssts.p, sd.data(), sd.size() * sizeof(SstDev), &stage_off);
+    if (!urc) urc = stage_upload(e, st->d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), &stage_off);
+    if (!urc) urc = stage_upload(e, st->d_colsel.p, colsel.data(), colsel.size() * sizeof(ColSel), &stage_off);
+    if (urc) return urc;
     // the host vectors must outlive the async copies: pageable memcpy is staged synchronously by the runtime
     CU_TRY(cudaEventRecord(e->evk0, s));
     if (plan.scratch_bytes) {
@@ -623,6 +672,7 @@ void hg_engine_destroy(hg_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (void* p : e->agg_keep) cudaFree(p);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
   e->fused_ws.release();
   e->ssts.clear();
   cudaEventDestroy(e->ev0);

@@ -98,9 +98,19 @@ inline uint64_t pred_literal(const hg_predicate& p, uint32_t t) {
 }
 
 // ------------------------------------------------------------------------------------------------------ SST residency
+// Per (row group, column) planning facts, precomputed at load time: statistics widened to the comparison domain
+// (i64 / u64 / f64 bits) so that planning a scan is a tight loop over plain arrays.
+struct RgCol {
+  uint64_t mn = 0, mx = 0;
+  uint32_t scratch = 0;      // decompression scratch of the chunk
+  uint8_t has_minmax = 0, null_all = 0, null_none = 0, snappy = 0, simple_page = 0;   // simple = 1 uncompressed V1 page
+};
+
 struct SstResident {
   uint64_t id = 0, size = 0;
   FileMetaData meta;
+  std::vector<RgCol> rgcol;      // [rg * ncols + col]
+  std::vector<uint32_t> rg_rows;
   uint8_t* d_bytes = nullptr;
   PageDev* d_pages = nullptr;
   ChunkDev* d_chunks = nullptr;
@@ -124,6 +134,8 @@ struct hg_engine {
   hg_scan_stats stats{};
   uint32_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;  // call / dominant-kernel brackets
+  void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
+  size_t h_stage_bytes = 0;
   std::vector<void*> agg_keep;  // device buffers of the last hg_scan_aggregate_device result
   fused::Workspace fused_ws;
   Launch L() { return Launch{stream, &launches}; }
@@ -175,3 +187,7 @@ struct ScanPlan {
 // Row-group selection (statistics pruning), decode order, PK-disjointness.  Defined in engine.cu.
 int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
                size_t np, const std::vector<uint32_t>& need_cols, ScanPlan* plan);
+
+// Copies `bytes` of host data to the device through the engine's pinned staging area (async on the engine stream;
+// the staging area is reused by the next call, which is safe because every call ends with a stream synchronise).
+int stage_upload(hg_engine* e, void* dst, const void* src, size_t bytes, size_t* stage_off);

@@ -13,6 +13,7 @@
 #include "fused_scan.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 
 namespace horae {
@@ -194,9 +195,9 @@ __device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item,
 struct KeyRef { uint64_t g; int64_t lo, hi; };
 
 template <bool HAS_TS>
-__device__ __forceinline__ bool key_differs(const FParams& P, const KeyRef& k, uint32_t si, uint32_t row) {
-  if (P.has_group && fetch_val(P, si, 0, row) != k.g) return true;
-  if (HAS_TS) { int64_t ts = int64_t(fetch_val(P, si, 1, row)); if (ts < k.lo || ts > k.hi) return true; }
+__device__ __forceinline__ bool key_differs(const FParams& P, const KeyRef& k, const uint8_t* b0, const uint8_t* b1, uint32_t row) {
+  if (P.has_group && load_kind(b0, P.kind[0], row) != k.g) return true;
+  if (HAS_TS) { int64_t ts = int64_t(load_kind(b1, P.kind[1], row)); if (ts < k.lo || ts > k.hi) return true; }
   return false;
 }
 
@@ -226,6 +227,8 @@ __global__ void __launch_bounds__(256) item_bounds_kernel(const __grid_constant_
   // L = a position known to continue the run (start: the previous row); find the first later position that differs
   for (;;) {
     n = P.sel[si].num_rows;
+    const uint8_t* b0 = P.has_group ? slot_base(P, si, 0) : nullptr;
+    const uint8_t* b1 = HAS_TS ? slot_base(P, si, 1) : nullptr;
     uint32_t L = row, H = n;                              // candidates [L, H) in this row group
     bool found = false;
     uint32_t ans = H;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(256) item_bounds_kernel(const __grid_constant_
       uint32_t step = (span + 31) / 32;
       uint32_t p = L + (uint32_t(lane) + 1) * step - 1;    // last position of lane's chunk
       if (p >= H) p = H - 1;
-      bool ne = key_differs<HAS_TS>(P, k, si, p);
+      bool ne = key_differs<HAS_TS>(P, k, b0, b1, p);
       unsigned m = __ballot_sync(0xffffffffu, ne);
       if (m == 0) { L = H; break; }                       // the whole window continues the run
       int f = __ffs(m) - 1;
@@ -546,35 +549,30 @@ void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, co
 #undef HG_LAUNCH
 }
 
-// exclusive scan of per-item record counts (single block; items <= a few hundred thousand)
+// exclusive scan of per-item record counts (single block: each thread owns a contiguous chunk, one block-wide scan)
 __global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, uint32_t n, uint32_t* total) {
   __shared__ uint32_t s_w[33];
-  __shared__ uint32_t s_carry;
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t per = (n + 1023) / 1024;
+  const uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += cnt[i];
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) s_w[w] = inc;
   __syncthreads();
-  for (uint32_t base = 0; base < n; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < n ? cnt[i] : 0, inc = v;
+  if (w == 0) {
+    uint32_t x = s_w[lane], xi = x;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) s_w[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t x = s_w[lane], xi = x;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
-      s_w[lane] = xi - x;
-      if (lane == 31) s_w[32] = xi;
-    }
-    __syncthreads();
-    uint32_t carry = s_carry;
-    if (i < n) cnt[i] = carry + s_w[w] + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry = carry + s_w[32];
-    __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+    s_w[lane] = xi - x;
+    if (lane == 31) s_w[32] = xi;
   }
-  if (threadIdx.x == 0) *total = s_carry;
+  __syncthreads();
+  uint32_t run = s_w[w] + inc - sum;
+  for (uint32_t i = lo; i < hi; i++) { uint32_t c = cnt[i]; cnt[i] = run; run += c; }
+  if (threadIdx.x == 0) *total = s_w[32];
 }
 
 __global__ void scatter_records_kernel(const FRec* __restrict__ rec, const unsigned int* nrec, const uint32_t* __restrict__ item_off,
@@ -663,8 +661,13 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   }
   for (int h = 0; h < kHot; h++) if (klo[h] > khi[h]) empty_interval = true;
 
+  static const bool trace = getenv("HORAE_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  auto t0 = now();
   ScanPlan plan;
   int rc = build_plan(e, schema, ssts, n, preds, np, slots, &plan);
+  auto t1 = now();
   if (rc) return rc;
   if (!plan.disjoint || !plan.all_single_plain_page) return NOT_APPLICABLE;
   for (uint32_t c : slots) if (plan.col_has_nulls[c]) return NOT_APPLICABLE;
@@ -676,20 +679,17 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     if (!is_int_type(schema->types[0])) return NOT_APPLICABLE;
     bound = 0;
     for (const RgSel& s : plan.sel) {
-      const RowGroupMeta& rg = plan.files[s.sst]->meta.rgs[s.rg];
-      const ChunkMeta& c0 = rg.cols[0];
-      if (!c0.stats.has_min || !c0.stats.has_max) return NOT_APPLICABLE;
-      uint64_t mn = widen_stat(c0.stats.min, c0.phys_type, schema->types[0]), mx = widen_stat(c0.stats.max, c0.phys_type, schema->types[0]);
-      uint64_t span = mx - mn + 1;                       // distinct pk0 values possible in this row group
+      const SstResident* fr = plan.files[s.sst];
+      const RgCol* rc = &fr->rgcol[size_t(s.rg) * size_t(fr->meta.ncols)];
+      if (!rc[0].has_minmax) return NOT_APPLICABLE;
+      uint64_t span = rc[0].mx - rc[0].mn + 1;            // distinct pk0 values possible in this row group
       uint64_t per = 1;
       if (has_ts) {
-        const ChunkMeta& c1 = rg.cols[1];
-        if (!c1.stats.has_min || !c1.stats.has_max) return NOT_APPLICABLE;
-        int64_t tmn = int64_t(widen_stat(c1.stats.min, c1.phys_type, schema->types[1])), tmx = int64_t(widen_stat(c1.stats.max, c1.phys_type, schema->types[1]));
-        per = uint64_t((tmx - tmn) / agg->window_ms) + 2;
+        if (!rc[1].has_minmax) return NOT_APPLICABLE;
+        per = uint64_t((int64_t(rc[1].mx) - int64_t(rc[1].mn)) / agg->window_ms) + 2;
       }
-      uint64_t g = span > (1ull << 32) || per > (1ull << 32) ? uint64_t(rg.num_rows) : span * per;
-      bound += std::min<uint64_t>(g, uint64_t(rg.num_rows)) + 1;
+      uint64_t g = span > (1ull << 32) || per > (1ull << 32) ? uint64_t(s.num_rows) : span * per;
+      bound += std::min<uint64_t>(g, uint64_t(s.num_rows)) + 1;
     }
     if (bound > plan.rows_decoded / 4 + 1024) return NOT_APPLICABLE;     // groups ~ rows: not this kernel's regime
   }
@@ -722,6 +722,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   CU_TRY(out->mx.alloc(size_t(bound) * 8 + 16, s));
   AggOut ao{out->gkey.p, out->bucket.as<int64_t>(), out->count.as<uint64_t>(), out->sum.as<double>(), out->mn.as<double>(), out->mx.as<double>()};
 
+  auto t2 = now();
   uint32_t hw[2] = {0, 0};
   unsigned long long hc[2] = {0, 0};
   int herr = 0;
@@ -733,8 +734,10 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     }
     CU_TRY(d_ssts.alloc(sd.size() * sizeof(SstDev), s));
     CU_TRY(d_sel.alloc(plan.sel.size() * sizeof(RgSel), s));
-    CU_TRY(cudaMemcpyAsync(d_ssts.p, sd.data(), sd.size() * sizeof(SstDev), cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), cudaMemcpyHostToDevice, s));
+    size_t stage_off = 0;
+    int urc = stage_upload(e, d_ssts.p, sd.data(), sd.size() * sizeof(SstDev), &stage_off);
+    if (!urc) urc = stage_upload(e, d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), &stage_off);
+    if (urc) return urc;
 
     FParams P;
     std::memset(&P, 0, sizeof(P));
@@ -806,12 +809,10 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       L.tick();
     }
     CU_TRY(cudaEventRecord(e->evk0, s));
-    switch (variant) {
-      case 1: launch_fused<4, 3>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      case 2: launch_fused<2, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      case 3: launch_fused<2, 3>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      case 4: launch_fused<1, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      default: launch_fused<4, 2>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>());
+    switch (variant) {            // developer override (HORAE_FUSED_VARIANT); default = 2 slices per block, 4 CTAs/SM
+      case 1: launch_fused<4, 2>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      case 2: launch_fused<1, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      default: launch_fused<2, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>());
     }
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
@@ -824,10 +825,13 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       scatter_records_kernel<<<148 * 4, 256, 0, s>>>(d_rec.as<FRec>(), d_work.as<unsigned int>() + 1, d_item.as<uint32_t>(), out->gwidth, ao);
       L.tick();
     }
+    auto t3 = now();
     CU_TRY(cudaMemcpyAsync(hw, d_work.as<uint32_t>() + 1, sizeof(hw), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(hc, d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(&herr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
+    auto t4 = now();
+    if (trace) fprintf(stderr, "[fused] plan %.0f us, bound+alloc %.0f us, upload+launch %.0f us, wait %.0f us (nsel %u items %u)\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), nsel, nitems);
     if (herr) return set_error(HG_ERR_INTERNAL, "fused scan: device error " + std::to_string(herr));
     float kms = 0;
     cudaEventElapsedTime(&kms, e->evk0, e->evk1);
