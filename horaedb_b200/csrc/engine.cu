@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -20,6 +21,7 @@
 #include "engine_internal.h"
 #include "fused_scan.h"
 
+thread_local Arena* g_arena = nullptr;
 static thread_local std::string g_last_error;
 int set_error(int code, const std::string& msg) {
   g_last_error = msg;
@@ -350,6 +352,10 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
       st->plan = std::move(again);
     } else st->plan = std::move(trial);
   }
+  static const bool trace = getenv("HORAE_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  auto tp0 = now();
   ScanPlan& plan = st->plan;
   const uint32_t N = uint32_t(plan.rows_decoded);
   st->N = N;
@@ -397,6 +403,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     if (!urc) urc = stage_upload(e, st->d_colsel.p, colsel.data(), colsel.size() * sizeof(ColSel), &stage_off);
     if (urc) return urc;
     // the host vectors must outlive the async copies: pageable memcpy is staged synchronously by the runtime
+    auto tp1 = now();
     CU_TRY(cudaEventRecord(e->evk0, s));
     if (plan.scratch_bytes) {
       CU_TRY(st->d_scratch.alloc(plan.scratch_bytes + 64, s));
@@ -407,6 +414,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
                      int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
     CU_TRY(cudaEventRecord(e->evk1, s));
     st->d_scratch.reset();
+    if (trace) fprintf(stderr, "[general] col alloc+upload %.0f us, scratch alloc (%.1f MB) + decode launches %.0f us\n", us(tp0, tp1), plan.scratch_bytes / 1e6, us(tp1, now()));
   }
 
   // --- S3: filter (before the merge, read.rs:459-470)
@@ -671,9 +679,9 @@ void hg_engine_destroy(hg_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  for (void* p : e->agg_keep) cudaFree(p);
+  g_arena = nullptr;
+  e->arena.destroy();
   if (e->h_stage) cudaFreeHost(e->h_stage);
-  e->fused_ws.release();
   e->ssts.clear();
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
@@ -729,6 +737,8 @@ static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   CU_TRY(cudaSetDevice(e->device));
   std::memset(&e->stats, 0, sizeof(e->stats));
   e->launches = 0;
+  e->arena.reset();
+  g_arena = &e->arena;
   for (size_t i = 0; i < n; i++) {
     rc = load_sst_locked(e, schema, &ssts[i]);
     if (rc) return rc;
@@ -911,8 +921,6 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
   std::lock_guard<std::mutex> g(e->mu);
   int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds);
   if (rc) return rc;
-  for (void* p : e->agg_keep) cudaFreeAsync(p, e->stream);
-  e->agg_keep.clear();
   AggBuffers ab;
   rc = aggregate_core(e, schema, ssts, n_ssts, preds, n_preds, agg, &ab);
   if (rc) return rc;
@@ -929,7 +937,7 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
   out->d_sum = ab.sum.as<double>();
   out->d_min = ab.mn.as<double>();
   out->d_max = ab.mx.as<double>();
-  for (DevBuf* b : {&ab.gkey, &ab.bucket, &ab.count, &ab.sum, &ab.mn, &ab.mx}) if (b->p) e->agg_keep.push_back(b->release());
+  for (DevBuf* b : {&ab.gkey, &ab.bucket, &ab.count, &ab.sum, &ab.mn, &ab.mx}) b->release();   // arena memory: valid until the next call
   return HG_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -14,9 +15,6 @@
 #include "kernels.h"
 #include "parquet_meta.hpp"
 
-namespace horae {
-namespace fused { struct Workspace { void* p = nullptr; size_t bytes = 0; void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; } }; }
-}
 using namespace horae;
 
 // --------------------------------------------------------------------------------------------------- error plumbing
@@ -122,6 +120,76 @@ struct SstResident {
   }
 };
 
+// Device workspace of one engine: a grow-only arena.  Every per-call temporary is a bump allocation; the most recent
+// allocation can be popped (LIFO) so large short-lived scratch does not raise the peak; the arena is reset at the start
+// of the next call (results handed out as device pointers stay valid until then).  Steady state = no cudaMalloc at all.
+struct Arena {
+  struct Chunk { char* base; size_t cap, used; };
+  std::vector<Chunk> chunks;
+  size_t high_water = 0, in_call = 0;
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (chunks.empty() || chunks.back().used + bytes > chunks.back().cap) {
+      size_t cap = std::max<size_t>(bytes, chunks.empty() ? (size_t(64) << 20) : chunks.back().cap * 2);
+      void* p = nullptr;
+      if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+      chunks.push_back(Chunk{static_cast<char*>(p), cap, 0});
+    }
+    Chunk& c = chunks.back();
+    void* p = c.base + c.used;
+    c.used += bytes;
+    in_call += bytes;
+    if (in_call > high_water) high_water = in_call;
+    return p;
+  }
+  void free_if_top(void* p, size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (chunks.empty()) return;
+    Chunk& c = chunks.back();
+    if (c.used >= bytes && c.base + c.used - bytes == static_cast<char*>(p)) { c.used -= bytes; in_call -= bytes; }
+  }
+  // start of a call (stream idle): one chunk big enough for everything seen so far
+  void reset() {
+    in_call = 0;
+    if (chunks.size() > 1) {
+      size_t total = 0;
+      for (auto& c : chunks) { total += c.cap; cudaFree(c.base); }
+      chunks.clear();
+      void* p = nullptr;
+      if (cudaMalloc(&p, total) == cudaSuccess) chunks.push_back(Chunk{static_cast<char*>(p), total, 0});
+    } else if (!chunks.empty()) chunks[0].used = 0;
+  }
+  void destroy() {
+    for (auto& c : chunks) cudaFree(c.base);
+    chunks.clear();
+  }
+};
+extern thread_local Arena* g_arena;   // arena of the engine whose call is running on this thread (engine.cu)
+
+// per-call device buffer (arena-backed)
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; }
+  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { reset(); p = o.p; bytes = o.bytes; o.p = nullptr; } return *this; }
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p && g_arena) g_arena->free_if_top(p, bytes);
+    p = nullptr;
+  }
+  cudaError_t alloc(size_t nbytes, cudaStream_t) {
+    reset();
+    bytes = nbytes ? nbytes : 16;
+    p = g_arena ? g_arena->alloc(bytes) : nullptr;
+    return p ? cudaSuccess : cudaErrorMemoryAllocation;
+  }
+  void* release() { void* q = p; p = nullptr; return q; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct hg_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -136,33 +204,10 @@ struct hg_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;  // call / dominant-kernel brackets
   void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
   size_t h_stage_bytes = 0;
-  std::vector<void*> agg_keep;  // device buffers of the last hg_scan_aggregate_device result
-  fused::Workspace fused_ws;
+  Arena arena;
   Launch L() { return Launch{stream, &launches}; }
 };
 
-// stream-ordered device buffer
-struct DevBuf {
-  void* p = nullptr;
-  cudaStream_t s = nullptr;
-  DevBuf() = default;
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), s(o.s) { o.p = nullptr; }
-  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { reset(); p = o.p; s = o.s; o.p = nullptr; } return *this; }
-  ~DevBuf() { reset(); }
-  void reset() {
-    if (p) cudaFreeAsync(p, s);
-    p = nullptr;
-  }
-  cudaError_t alloc(size_t bytes, cudaStream_t st) {
-    reset();
-    s = st;
-    return cudaMallocAsync(&p, bytes ? bytes : 16, st);
-  }
-  void* release() { void* q = p; p = nullptr; return q; }
-  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
 
 
 struct AggBuffers {

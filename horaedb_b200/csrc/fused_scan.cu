@@ -359,7 +359,7 @@ struct Hot {
 // slice has survivors.
 //   X        bit k set => extra hot column 2+k is a 4-byte column (pk0 / pk1 are always 8-byte here)
 //   PARTIAL  the block may extend past `lim` (end of the item or of the row group): indices clamped, lanes masked
-template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool PARTIAL>
+template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool PARTIAL, int kPF>
 __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH>& H, const uint8_t* vq, uint32_t vs, Acc& acc, uint32_t& local,
                                                   uint32_t& n_alive, uint32_t& n_keep, uint32_t item, uint32_t csi, uint32_t row,
                                                   uint32_t lim, uint32_t nrows, double* s_vals, int lane) {
@@ -367,6 +367,18 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
   uint64_t vv[kU];
   uint64_t halo[2] = {0, 0};
   const uint32_t last = nrows - 1;
+  if (kPF > 0 && !PARTIAL) {
+    // pull the hot columns of the block kPF blocks ahead into L2: one 128-byte line per lane
+    const uint32_t prow = row + kPF * 32 * kU;
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+      const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
+      const uint32_t per_line = w4 ? 32u : 16u;                 // rows per 128-byte line
+      const uint32_t r = prow + uint32_t(lane) * per_line;
+      if (uint32_t(lane) <= (32u * kU) / per_line && r < nrows)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(H.q[h] + size_t(r) * (w4 ? 4 : 8)));
+    }
+  }
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     uint32_t i = row + u * 32 + lane;
@@ -451,7 +463,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
 }
 
 // kU = slices whose loads are issued together; NH = hot columns (pk0, pk1, + predicate columns) loaded for every row
-template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS>
+template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS, int kPF>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P,
                                                                                     const uint64_t* __restrict__ adj) {
   __shared__ double s_vals_all[kWarpsPerCta][32];
@@ -511,10 +523,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
         if (row >= lim) break;
         uint32_t kept;
         if (row + 32u * kU < lim) {       // (< lim: the halo row is inside the row group as well)
-          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane)
-                       : process_block<kU, NH, X, HAS_TS, false, false>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
+          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane)
+                       : process_block<kU, NH, X, HAS_TS, false, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
         } else {
-          kept = process_block<kU, NH, X, HAS_TS, false, true>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
+          kept = process_block<kU, NH, X, HAS_TS, false, true, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
         }
         dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
         row += 32 * kU;
@@ -529,12 +541,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
   }
 }
 
-template <int kU, int kMinBlocks>
+template <int kU, int kMinBlocks, int kPF>
 void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, const FParams& P, const uint64_t* adj) {
 #define HG_LAUNCH(NH, XM)                                                                                                \
   do {                                                                                                                   \
-    if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, XM, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);              \
-    else fused_scan_kernel<kU, kMinBlocks, NH, XM, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);                    \
+    if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, XM, true, kPF><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);              \
+    else fused_scan_kernel<kU, kMinBlocks, NH, XM, false, kPF><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);                    \
   } while (0)
   if (nhot == 2) HG_LAUNCH(2, 0);
   else if (nhot == 3) { if (xmask & 1) HG_LAUNCH(3, 1); else HG_LAUNCH(3, 0); }
@@ -809,10 +821,11 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       L.tick();
     }
     CU_TRY(cudaEventRecord(e->evk0, s));
-    switch (variant) {            // developer override (HORAE_FUSED_VARIANT); default = 2 slices per block, 4 CTAs/SM
-      case 1: launch_fused<4, 2>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      case 2: launch_fused<1, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      default: launch_fused<2, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>());
+    switch (variant) {            // developer override (HORAE_FUSED_VARIANT); default: 2 slices/block, 4 CTAs/SM, L2 prefetch 2 blocks ahead
+      case 1: launch_fused<2, 4, 0>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      case 2: launch_fused<2, 4, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      case 3: launch_fused<2, 4, 3>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
+      default: launch_fused<2, 4, 2>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>());
     }
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
