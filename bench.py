@@ -175,21 +175,17 @@ def main():
         torch.cuda.synchronize()
 
     def combine(dev):
-        """Cross-GPU combine of the per-GPU partial aggregates (groups are disjoint per rank: all-gather over NCCL)."""
-        if world == 1:
-            return int(dev.num_groups)
+        """Cross-GPU combine of the per-GPU partial aggregates: ONE NCCL all-gather (horaedb_b200/parallel.py)."""
         g = int(dev.num_groups)
-        cap = torch.tensor([g], device="cuda", dtype=torch.int64)
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-        cap = int(cap.item())
-        part = torch.zeros(3, max(cap, 1), device="cuda", dtype=torch.float64)
-        if g:
-            part[0, :g] = torch.as_tensor(DeviceArray(dev.d_gkey, g, "<i8"), device="cuda").to(torch.float64)
-            part[1, :g] = torch.as_tensor(DeviceArray(dev.d_count, g, "<i8"), device="cuda").to(torch.float64)
-            part[2, :g] = torch.as_tensor(DeviceArray(dev.d_sum, g, "<f8"), device="cuda")
-        allp = torch.empty(world, 3, max(cap, 1), device="cuda", dtype=torch.float64)
-        dist.all_gather_into_tensor(allp, part)
-        return int((allp[:, 1, :] > 0).sum().item())
+        if world == 1:
+            return g
+        from horaedb_b200.parallel import combine_partials
+
+        def view(ptr, ts):
+            return torch.as_tensor(DeviceArray(ptr, g, ts), device="cuda") if g else torch.zeros(0, device="cuda", dtype=torch.int64 if ts == "<i8" else torch.float64)
+        res = combine_partials(view(dev.d_gkey, "<i8"), view(dev.d_bucket, "<i8"), view(dev.d_count, "<i8"), view(dev.d_sum, "<f8"),
+                               view(dev.d_min, "<f8"), view(dev.d_max, "<f8"))
+        return int(res[0].numel())
 
     def measure(codec, steps, warmup, e2e_steps):
         ssts = gen[codec]
