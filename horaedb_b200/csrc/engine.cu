@@ -114,12 +114,43 @@ static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_
       rc.simple_page = cm.codec == CODEC_UNCOMPRESSED && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA;
     }
   }
-  uint64_t need = size + 64 + pages.size() * sizeof(PageDev) + chunks.size() * sizeof(ChunkDev);
+  {
+    const uint32_t t0 = schema->types[0];
+    for (int c = 0; c < m.ncols && c < MAX_COLS; c++) { r->col_all_simple[c] = true; r->col_null_none[c] = true; r->col_has_minmax[c] = true; }
+    bool first = true;
+    r->pk0_range_ok = true;
+    for (size_t g = 0; g < m.rgs.size(); g++) {
+      const uint32_t rows = r->rg_rows[g];
+      r->rows_total += rows;
+      if (rows == 0) continue;
+      const RgCol* rc = &r->rgcol[g * m.ncols];
+      for (int c = 0; c < m.ncols && c < MAX_COLS; c++) {
+        if (!rc[c].simple_page) r->col_all_simple[c] = false;
+        if (!rc[c].null_none) r->col_null_none[c] = false;
+        if (!rc[c].has_minmax) r->col_has_minmax[c] = false;
+      }
+      if (rc[0].has_minmax && rc[0].null_none) {
+        if (first) { r->pk0_min = rc[0].mn; r->pk0_max = rc[0].mx; first = false; }
+        else {
+          if (cmp_host(rc[0].mn, r->pk0_min, t0) < 0) r->pk0_min = rc[0].mn;
+          if (cmp_host(rc[0].mx, r->pk0_max, t0) > 0) r->pk0_max = rc[0].mx;
+        }
+        uint64_t span = rc[0].mx - rc[0].mn + 1;
+        r->group_bound += std::min<uint64_t>(span == 0 ? rows : span, rows) + 1;
+      } else { r->pk0_range_ok = false; r->group_bound += uint64_t(rows) + 1; }
+    }
+  }
+  uint64_t need = size + 64 + pages.size() * sizeof(PageDev) + chunks.size() * sizeof(ChunkDev) + r->rgcol.size() * sizeof(RgCol) +
+                  r->rg_rows.size() * sizeof(uint32_t);
   if (e->budget && e->resident_bytes + need > e->budget)
     return set_error(HG_ERR_OOM, "HBM budget exceeded while loading sst " + std::to_string(d->id));
   CU_TRY(cudaMalloc(&r->d_bytes, size + 64));
   CU_TRY(cudaMalloc(&r->d_pages, std::max<size_t>(pages.size(), 1) * sizeof(PageDev)));
   CU_TRY(cudaMalloc(&r->d_chunks, std::max<size_t>(chunks.size(), 1) * sizeof(ChunkDev)));
+  CU_TRY(cudaMalloc(&r->d_rgcol, std::max<size_t>(r->rgcol.size(), 1) * sizeof(RgCol)));
+  CU_TRY(cudaMalloc(&r->d_rg_rows, std::max<size_t>(r->rg_rows.size(), 1) * sizeof(uint32_t)));
+  if (!r->rgcol.empty()) CU_TRY(cudaMemcpyAsync(r->d_rgcol, r->rgcol.data(), r->rgcol.size() * sizeof(RgCol), cudaMemcpyHostToDevice, e->stream));
+  if (!r->rg_rows.empty()) CU_TRY(cudaMemcpyAsync(r->d_rg_rows, r->rg_rows.data(), r->rg_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
   CU_TRY(cudaMemcpyAsync(r->d_bytes, data, size, cudaMemcpyHostToDevice, e->stream));
   CU_TRY(cudaMemsetAsync(r->d_bytes + size, 0, 64, e->stream));
   if (!pages.empty()) CU_TRY(cudaMemcpyAsync(r->d_pages, pages.data(), pages.size() * sizeof(PageDev), cudaMemcpyHostToDevice, e->stream));

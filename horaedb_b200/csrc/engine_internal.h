@@ -109,6 +109,14 @@ struct SstResident {
   FileMetaData meta;
   std::vector<RgCol> rgcol;      // [rg * ncols + col]
   std::vector<uint32_t> rg_rows;
+  RgCol* d_rgcol = nullptr;      // the same two tables in HBM (device-side pruning of the fused path)
+  uint32_t* d_rg_rows = nullptr;
+  // per-file planning facts (over ALL row groups of the file)
+  uint64_t rows_total = 0;
+  bool col_all_simple[MAX_COLS] = {false}, col_null_none[MAX_COLS] = {false}, col_has_minmax[MAX_COLS] = {false};
+  uint64_t pk0_min = 0, pk0_max = 0;
+  bool pk0_range_ok = false;
+  uint64_t group_bound = 0;      // sum over row groups of min(#distinct pk0 possible, rows) + 1
   uint8_t* d_bytes = nullptr;
   PageDev* d_pages = nullptr;
   ChunkDev* d_chunks = nullptr;
@@ -117,6 +125,8 @@ struct SstResident {
     if (d_bytes) cudaFree(d_bytes);
     if (d_pages) cudaFree(d_pages);
     if (d_chunks) cudaFree(d_chunks);
+    if (d_rgcol) cudaFree(d_rgcol);
+    if (d_rg_rows) cudaFree(d_rg_rows);
   }
 };
 

@@ -39,8 +39,10 @@ constexpr int kHot = 4;
 
 struct FParams {
   const SstDev* ssts;
-  const RgSel* sel;
-  uint32_t nsel, split;         // split = sub-ranges (work items) per row group
+  const RgSel* sel;             // selected row groups in stream order, built on the device by select_rgs_kernel
+  const uint32_t* d_nsel;       // their count
+  uint32_t split;               // sub-ranges (work items) per row group
+  uint32_t pcol[MAX_PREDS], pcls[MAX_PREDS];   // schema column / comparison class of every predicate (statistics pruning)
   int nslots;
   uint32_t col[MAXC], kind[MAXC], cls[MAXC];
   int npk;                      // slots [0, npk) are the primary key columns in order
@@ -144,7 +146,7 @@ __device__ __noinline__ bool later_alive_dup(const FParams& P, uint32_t si, uint
   for (;;) {
     if (r >= nrows) {
       si++;
-      if (si >= P.nsel) return false;
+      if (si >= *P.d_nsel) return false;
       nrows = P.sel[si].num_rows;
       r = 0;
       if (nrows == 0) continue;
@@ -187,6 +189,92 @@ __device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item,
   } else atomicExch(P.err, 201);
 }
 
+// ------------------------------------------------------------------------------------------- row-group selection
+// Statistics pruning on the device (DataFusion PruningPredicate, read.rs:613: CASE WHEN null_count = row_count THEN
+// false ELSE <min/max rewrite> END) over the per-SST tables that live next to the SST bytes.  One block walks the row
+// groups of all files in stream order and writes the compacted RgSel list — the host touches only per-FILE facts.
+struct FileDev {
+  const RgCol* rgcol;
+  const uint32_t* rg_rows;
+  uint32_t rg_base, nrg, ncols, _pad;
+};
+
+__device__ __forceinline__ int cmp3(uint64_t a, uint64_t b, uint32_t cls) {
+  if (cls == C_FLOAT) {
+    double x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b);
+    return x < y ? -1 : (x > y ? 1 : 0);
+  }
+  if (cls == C_SIGNED) { int64_t x = int64_t(a), y = int64_t(b); return x < y ? -1 : (x > y ? 1 : 0); }
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(1024) select_rgs_kernel(const __grid_constant__ FParams P, const FileDev* __restrict__ files, int nfiles,
+                                                          uint32_t total_rgs, int prune, RgSel* __restrict__ sel, uint32_t* d_nsel,
+                                                          unsigned long long* counters) {
+  __shared__ uint32_t s_w[33];
+  __shared__ uint32_t s_carry;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  unsigned long long rows_sel = 0;
+  for (uint32_t base = 0; base < total_rgs; base += 1024) {
+    const uint32_t idx = base + threadIdx.x;
+    uint32_t keep = 0, f = 0, rg = 0, rows = 0;
+    if (idx < total_rgs) {
+      while (f + 1 < uint32_t(nfiles) && idx >= files[f + 1].rg_base) f++;
+      const FileDev fd = files[f];
+      rg = idx - fd.rg_base;
+      rows = fd.rg_rows[rg];
+      keep = rows > 0;
+      if (keep && prune) {
+        const RgCol* rc = fd.rgcol + size_t(rg) * fd.ncols;
+        for (int p = 0; p < P.npred && keep; p++) {
+          const RgCol c = rc[P.pcol[p]];
+          if (c.null_all) { keep = 0; break; }
+          if (!c.has_minmax) continue;
+          const uint64_t lit = P.plit[p];
+          const uint32_t cls = P.pcls[p];
+          bool ok = true;
+          switch (P.pop[p]) {
+            case OP_EQ: ok = cmp3(c.mn, lit, cls) <= 0 && cmp3(lit, c.mx, cls) <= 0; break;
+            case OP_NE: ok = cmp3(c.mn, lit, cls) != 0 || cmp3(lit, c.mx, cls) != 0; break;
+            case OP_LT: ok = cmp3(c.mn, lit, cls) < 0; break;
+            case OP_LE: ok = cmp3(c.mn, lit, cls) <= 0; break;
+            case OP_GT: ok = cmp3(c.mx, lit, cls) > 0; break;
+            default: ok = cmp3(c.mx, lit, cls) >= 0;
+          }
+          if (!ok) keep = 0;
+        }
+      }
+    }
+    uint32_t inc = keep;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t x = s_w[lane], xi = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+      s_w[lane] = xi - x;
+      if (lane == 31) s_w[32] = xi;
+    }
+    __syncthreads();
+    if (keep) {
+      RgSel r;
+      r.sst = f; r.rg = rg; r.out_row = 0; r.num_rows = rows; r.scratch_off = 0;
+      sel[s_carry + s_w[w] + inc - 1] = r;
+      rows_sel += rows;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += s_w[32];
+    __syncthreads();
+  }
+  for (int d = 16; d > 0; d >>= 1) rows_sel += __shfl_down_sync(0xffffffffu, rows_sel, d);
+  if (lane == 0 && rows_sel) atomicAdd(&counters[2], rows_sel);
+  if (threadIdx.x == 0) *d_nsel = s_carry;
+}
+
 // ------------------------------------------------------------------------------------------------ item boundaries
 // Work items are sub-ranges of row groups.  A group (key-run) must be summed by ONE warp in stream order, so every
 // nominal boundary is moved forward to the next row that starts a new key-run: item j = [adj[j], adj[j+1]).
@@ -206,16 +294,17 @@ __device__ __forceinline__ uint64_t pack_pos(uint32_t si, uint32_t row) { return
 template <bool HAS_TS>
 __global__ void __launch_bounds__(256) item_bounds_kernel(const __grid_constant__ FParams P, uint64_t* __restrict__ adj) {
   const int lane = threadIdx.x & 31;
-  const uint32_t nitems = P.nsel * P.split;
+  const uint32_t nsel = *P.d_nsel;
+  const uint32_t nitems = nsel * P.split;
   const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (j > nitems) return;
-  if (j == nitems) { if (lane == 0) adj[j] = pack_pos(P.nsel, 0); return; }
+  if (j == nitems) { if (lane == 0) adj[j] = pack_pos(nsel, 0); return; }
   uint32_t si = j / P.split, w = j % P.split;
   uint32_t n = P.sel[si].num_rows;
   const uint32_t sr = (((n + P.split - 1) / P.split) + 31u) & ~31u;
   uint32_t row = w * sr;
   if (row >= n) { si++; row = 0; }                        // empty sub-range: same boundary as the next row group
-  if (si >= P.nsel) { if (lane == 0) adj[j] = pack_pos(P.nsel, 0); return; }
+  if (si >= nsel) { if (lane == 0) adj[j] = pack_pos(nsel, 0); return; }
   if (P.global_mode || (si == 0 && row == 0)) { if (lane == 0) adj[j] = pack_pos(si, row); return; }
   // key of the row just before the nominal boundary
   uint32_t psi = si, prow = row;
@@ -255,7 +344,7 @@ __global__ void __launch_bounds__(256) item_bounds_kernel(const __grid_constant_
     if (found) { if (lane == 0) adj[j] = pack_pos(si, ans); return; }
     si++;                                                 // the run covers the rest of this row group
     row = 0;
-    if (si >= P.nsel) { if (lane == 0) adj[j] = pack_pos(P.nsel, 0); return; }
+    if (si >= nsel) { if (lane == 0) adj[j] = pack_pos(nsel, 0); return; }
   }
 }
 
@@ -443,7 +532,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
         same = n0 == hv[u][0] && n1 == hv[u][1];
         for (int k = 2; k < P.npk && same; k++) same = fetch_val(P, csi, k, i + 1) == fetch_val(P, csi, k, i);
       }
-      if (same && (i + 1 < nrows || csi + 1 < P.nsel)) keep = !later_alive_dup(P, csi, i);
+      if (same && (i + 1 < nrows || csi + 1 < *P.d_nsel)) keep = !later_alive_dup(P, csi, i);
     }
     const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
     n_alive += __popc(alive_mask);
@@ -469,7 +558,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
   __shared__ double s_vals_all[kWarpsPerCta][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* s_vals = s_vals_all[wid];
-  const uint32_t nitems = P.nsel * P.split;
+  const uint32_t nsel = *P.d_nsel;
+  const uint32_t nitems = nsel * P.split;
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   Hot<NH> H;
 #pragma unroll
@@ -515,7 +605,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
         if (row >= nrows) {
           csi++;
           row = 0;
-          if (csi > esi || (csi == esi && erow == 0) || csi >= P.nsel) break;
+          if (csi > esi || (csi == esi && erow == 0) || csi >= nsel) break;
           nrows = P.sel[csi].num_rows;
           set_cursor(csi);
         }
@@ -562,7 +652,8 @@ void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, co
 }
 
 // exclusive scan of per-item record counts (single block: each thread owns a contiguous chunk, one block-wide scan)
-__global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, uint32_t n, uint32_t* total) {
+__global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, const uint32_t* d_nsel, uint32_t split, uint32_t* total) {
+  const uint32_t n = *d_nsel * split;
   __shared__ uint32_t s_w[33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t per = (n + 1023) / 1024;
@@ -677,44 +768,64 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
   auto t0 = now();
-  ScanPlan plan;
-  int rc = build_plan(e, schema, ssts, n, preds, np, slots, &plan);
+  // ---- per-FILE planning only: residency, layout preconditions, PK-disjointness, stream order (row groups are pruned
+  //      and listed on the device)
+  std::vector<SstResident*> files;
+  uint64_t rows_in_files = 0;
+  const uint32_t t0type = schema->types[0];
+  for (size_t i = 0; i < n; i++) {
+    auto it = e->ssts.find(ssts[i].id);
+    if (it == e->ssts.end()) return set_error(HG_ERR_INTERNAL, "sst not resident after load");
+    SstResident* f = it->second.get();
+    rows_in_files += f->rows_total;
+    if (f->rows_total == 0) continue;
+    for (uint32_t c : slots)
+      if (!f->col_all_simple[c] || !f->col_null_none[c]) return NOT_APPLICABLE;
+    if (!global_mode && (!f->col_has_minmax[0] || (has_ts && !f->col_has_minmax[1]))) return NOT_APPLICABLE;
+    files.push_back(f);
+  }
+  if (files.size() > 1) {
+    for (SstResident* f : files) if (!f->pk0_range_ok) return NOT_APPLICABLE;
+    std::stable_sort(files.begin(), files.end(), [&](SstResident* a, SstResident* b) { return cmp_host(a->pk0_min, b->pk0_min, t0type) < 0; });
+    for (size_t j = 0; j + 1 < files.size(); j++)
+      if (cmp_host(files[j]->pk0_max, files[j + 1]->pk0_min, t0type) >= 0) return NOT_APPLICABLE;   // not provably PK-disjoint
+  }
+  uint32_t total_rgs = 0;
+  for (SstResident* f : files) total_rgs += uint32_t(f->rg_rows.size());
   auto t1 = now();
-  if (rc) return rc;
-  if (!plan.disjoint || !plan.all_single_plain_page) return NOT_APPLICABLE;
-  for (uint32_t c : slots) if (plan.col_has_nulls[c]) return NOT_APPLICABLE;
-  const uint32_t nsel = uint32_t(plan.sel.size());
 
   // ---- upper bound on the number of groups from chunk statistics (sizes the unordered record buffer)
   uint64_t bound = 1;
   if (!global_mode) {
     if (!is_int_type(schema->types[0])) return NOT_APPLICABLE;
     bound = 0;
-    for (const RgSel& s : plan.sel) {
-      const SstResident* fr = plan.files[s.sst];
-      const RgCol* rc = &fr->rgcol[size_t(s.rg) * size_t(fr->meta.ncols)];
-      if (!rc[0].has_minmax) return NOT_APPLICABLE;
-      uint64_t span = rc[0].mx - rc[0].mn + 1;            // distinct pk0 values possible in this row group
-      uint64_t per = 1;
-      if (has_ts) {
-        if (!rc[1].has_minmax) return NOT_APPLICABLE;
-        per = uint64_t((int64_t(rc[1].mx) - int64_t(rc[1].mn)) / agg->window_ms) + 2;
+    if (!has_ts) {
+      for (SstResident* f : files) bound += f->group_bound;
+    } else {
+      for (SstResident* f : files) {
+        const size_t ncols = size_t(f->meta.ncols);
+        for (size_t g = 0; g < f->rg_rows.size(); g++) {
+          const RgCol* rc = &f->rgcol[g * ncols];
+          const uint64_t rows = f->rg_rows[g];
+          uint64_t span = rc[0].mx - rc[0].mn + 1;
+          uint64_t per = uint64_t((int64_t(rc[1].mx) - int64_t(rc[1].mn)) / agg->window_ms) + 2;
+          uint64_t gcount = (span == 0 || span > (1ull << 32) || per > (1ull << 32)) ? rows : span * per;
+          bound += std::min<uint64_t>(gcount, rows) + 1;
+        }
       }
-      uint64_t g = span > (1ull << 32) || per > (1ull << 32) ? uint64_t(s.num_rows) : span * per;
-      bound += std::min<uint64_t>(g, uint64_t(s.num_rows)) + 1;
     }
-    if (bound > plan.rows_decoded / 4 + 1024) return NOT_APPLICABLE;     // groups ~ rows: not this kernel's regime
+    if (bound > rows_in_files / 4 + 1024) return NOT_APPLICABLE;     // groups ~ rows: not this kernel's regime
   }
-  if (bound >= 0xfffffff0ull) return NOT_APPLICABLE;
+  if (bound >= 0xfffffff0ull || rows_in_files >= 0xfffffff0ull) return NOT_APPLICABLE;
 
   cudaStream_t s = e->stream;
   Launch L = e->L();
   // split row groups into enough work items for ~8 items per resident warp (dynamic ticket => good balance);
   // boundaries are then aligned to key-run starts by item_bounds_kernel
   uint32_t split = 1;
-  while (split < 8 && uint64_t(nsel) * split < 148ull * 32 * 8) split *= 2;
-  const uint32_t nitems = nsel * split;
-  DevBuf d_ssts, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj;
+  while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * 8) split *= 2;
+  const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
+  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj;
   CU_TRY(d_work.alloc(64, s));
   CU_TRY(cudaMemsetAsync(d_work.p, 0, 64, s));
   CU_TRY(d_counters.alloc(64, s));
@@ -724,6 +835,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   CU_TRY(d_rec.alloc(size_t(bound) * sizeof(FRec) + 64, s));
   CU_TRY(d_item.alloc(size_t(nitems + 1) * sizeof(uint32_t) + 64, s));
   CU_TRY(d_adj.alloc(size_t(nitems + 2) * sizeof(uint64_t), s));
+  CU_TRY(d_sel.alloc(size_t(total_rgs + 1) * sizeof(RgSel), s));
   out->gtype = has_group ? schema->types[0] : uint32_t(T_U64);
   out->gwidth = has_group ? type_width_host(out->gtype) : 8;
   CU_TRY(out->gkey.alloc(size_t(bound) * 8 + 16, s));
@@ -735,27 +847,31 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   AggOut ao{out->gkey.p, out->bucket.as<int64_t>(), out->count.as<uint64_t>(), out->sum.as<double>(), out->mn.as<double>(), out->mx.as<double>()};
 
   auto t2 = now();
-  uint32_t hw[2] = {0, 0};
-  unsigned long long hc[2] = {0, 0};
+  unsigned long long hc[3] = {0, 0, 0};
   int herr = 0;
-  if (nsel > 0) {
-    std::vector<SstDev> sd(plan.files.size());
-    for (size_t i = 0; i < plan.files.size(); i++) {
-      SstResident* f = plan.files[i];
+  uint32_t hw[2] = {0, 0};
+  if (total_rgs > 0) {
+    std::vector<SstDev> sd(files.size());
+    std::vector<FileDev> fdv(files.size());
+    uint32_t rgb = 0;
+    for (size_t i = 0; i < files.size(); i++) {
+      SstResident* f = files[i];
       sd[i] = SstDev{f->d_bytes, f->d_pages, f->d_chunks, uint32_t(f->meta.ncols), uint32_t(f->meta.rgs.size())};
+      fdv[i] = FileDev{f->d_rgcol, f->d_rg_rows, rgb, uint32_t(f->rg_rows.size()), uint32_t(f->meta.ncols), 0};
+      rgb += uint32_t(f->rg_rows.size());
     }
     CU_TRY(d_ssts.alloc(sd.size() * sizeof(SstDev), s));
-    CU_TRY(d_sel.alloc(plan.sel.size() * sizeof(RgSel), s));
+    CU_TRY(d_files.alloc(fdv.size() * sizeof(FileDev), s));
     size_t stage_off = 0;
     int urc = stage_upload(e, d_ssts.p, sd.data(), sd.size() * sizeof(SstDev), &stage_off);
-    if (!urc) urc = stage_upload(e, d_sel.p, plan.sel.data(), plan.sel.size() * sizeof(RgSel), &stage_off);
+    if (!urc) urc = stage_upload(e, d_files.p, fdv.data(), fdv.size() * sizeof(FileDev), &stage_off);
     if (urc) return urc;
 
     FParams P;
     std::memset(&P, 0, sizeof(P));
     P.ssts = d_ssts.as<SstDev>();
     P.sel = d_sel.as<RgSel>();
-    P.nsel = nsel;
+    P.d_nsel = d_work.as<uint32_t>() + 3;
     P.split = split;
     P.nslots = int(slots.size());
     for (size_t i = 0; i < slots.size(); i++) {
@@ -801,6 +917,8 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       P.pslot[i] = pslot[i];
       P.pop[i] = preds[i].op;
       P.plit[i] = pred_literal(preds[i], schema->types[preds[i].column]);
+      P.pcol[i] = preds[i].column;
+      P.pcls[i] = type_is_float(schema->types[preds[i].column]) ? C_FLOAT : (type_is_signed(schema->types[preds[i].column]) ? C_SIGNED : C_UNSIGNED);
     }
     P.window_ms = has_ts ? agg->window_ms : 1;
     P.rec = d_rec.as<FRec>();
@@ -813,6 +931,9 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
     static int variant = -1;
     if (variant < 0) { const char* v = getenv("HORAE_FUSED_VARIANT"); variant = v ? atoi(v) : 0; }
+    select_rgs_kernel<<<1, 1024, 0, s>>>(P, d_files.as<FileDev>(), int(files.size()), total_rgs, (e->flags & HG_FLAG_NO_PRUNING) ? 0 : 1,
+                                         d_sel.as<RgSel>(), d_work.as<uint32_t>() + 3, d_counters.as<unsigned long long>());
+    L.tick();
     {
       const uint32_t nb = nitems + 1;
       const int bctas = int((uint64_t(nb) * 32 + 255) / 256);
@@ -833,7 +954,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       global_count_kernel<<<1, 1, 0, s>>>(d_counters.as<unsigned long long>(), ao);
       L.tick();
     } else {
-      item_scan_kernel<<<1, 1024, 0, s>>>(d_item.as<uint32_t>(), nitems, d_work.as<uint32_t>() + 2);
+      item_scan_kernel<<<1, 1024, 0, s>>>(d_item.as<uint32_t>(), d_work.as<uint32_t>() + 3, split, d_work.as<uint32_t>() + 2);
       L.tick();
       scatter_records_kernel<<<148 * 4, 256, 0, s>>>(d_rec.as<FRec>(), d_work.as<unsigned int>() + 1, d_item.as<uint32_t>(), out->gwidth, ao);
       L.tick();
@@ -844,15 +965,15 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     CU_TRY(cudaMemcpyAsync(&herr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     auto t4 = now();
-    if (trace) fprintf(stderr, "[fused] plan %.0f us, bound+alloc %.0f us, upload+launch %.0f us, wait %.0f us (nsel %u items %u)\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), nsel, nitems);
+    if (trace) fprintf(stderr, "[fused] plan %.0f us, bound+alloc %.0f us, upload+launch %.0f us, wait %.0f us (row groups %u, max items %u)\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), total_rgs, nitems);
     if (herr) return set_error(HG_ERR_INTERNAL, "fused scan: device error " + std::to_string(herr));
     float kms = 0;
     cudaEventElapsedTime(&kms, e->evk0, e->evk1);
     e->stats.kernel_ms = kms;
   }
   out->G = global_mode ? (hc[1] > 0 ? 1u : 0u) : hw[0];   // like GROUP BY: no surviving rows, no group
-  e->stats.rows_in_files = plan.rows_in_files;
-  e->stats.rows_decoded = plan.rows_decoded;
+  e->stats.rows_in_files = rows_in_files;
+  e->stats.rows_decoded = hc[2];
   e->stats.rows_filtered = hc[0];
   e->stats.rows_out = hc[1];
   e->stats.groups_out = out->G;
