@@ -438,8 +438,13 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     CU_TRY(cudaEventRecord(e->evk0, s));
     if (plan.scratch_bytes) {
       CU_TRY(st->d_scratch.alloc(plan.scratch_bytes + 64, s));
-      k::snappy_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
-                       int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
+      static const bool snappy_v1 = getenv("HORAE_SNAPPY_V1") != nullptr;   // developer A/B switch
+      if (snappy_v1)
+        k::snappy_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
+                         int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
+      else
+        k::snappy_chunks_v2(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
+                            int(colsel.size()), st->d_scratch.as<uint8_t>(), st->counters() + 4, st->d_err.as<int>());
     }
     k::decode_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
                      int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
@@ -479,6 +484,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
   }
   const uint32_t* order = st->surv_ptr;
   CU_TRY(st->keep.alloc(size_t(N) + 16, s));
+  CU_TRY(cudaEventRecord(e->evm0, s));
   if (!plan.disjoint && N > 0) {
     CU_TRY(st->file_base.alloc((k + 1) * sizeof(uint32_t), s));
     CU_TRY(st->run_start.alloc((k + 2) * sizeof(uint32_t), s));
@@ -534,6 +540,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
       k::batch_bounds(L, st->out_pos.as<uint32_t>(), st->d_r, st->chunk_end.as<uint32_t>(), st->nchunks, st->bound.as<uint32_t>());
     }
   }
+  CU_TRY(cudaEventRecord(e->evm1, s));
   st->keep.reset();
   st->order.reset();
   st->surv.reset();
@@ -698,6 +705,8 @@ int hg_engine_create(const hg_config* cfg, hg_engine** out) {
   CU_TRY(cudaEventCreate(&e->ev1));
   CU_TRY(cudaEventCreate(&e->evk0));
   CU_TRY(cudaEventCreate(&e->evk1));
+  CU_TRY(cudaEventCreate(&e->evm0));
+  CU_TRY(cudaEventCreate(&e->evm1));
   cudaMemPool_t pool;
   CU_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
   uint64_t thresh = UINT64_MAX;
@@ -718,6 +727,8 @@ void hg_engine_destroy(hg_engine* e) {
   cudaEventDestroy(e->ev1);
   cudaEventDestroy(e->evk0);
   cudaEventDestroy(e->evk1);
+  cudaEventDestroy(e->evm0);
+  cudaEventDestroy(e->evm1);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -863,7 +874,7 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
   e->stats.kernel_launches = e->launches;
   e->stats.gpu_ms = ms;
   e->stats.path = 0;
-  if (N > 0) { float kms = 0; cudaEventElapsedTime(&kms, e->evk0, e->evk1); e->stats.kernel_ms = kms; }
+  if (N > 0) { float kms = 0; cudaEventElapsedTime(&kms, e->evk0, e->evk1); e->stats.kernel_ms = kms; cudaEventElapsedTime(&kms, e->evm0, e->evm1); e->stats.merge_ms = kms; }
   make_stream(out, data);
   return HG_OK;
 }

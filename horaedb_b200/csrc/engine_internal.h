@@ -211,7 +211,7 @@ struct hg_engine {
   uint64_t resident_bytes = 0;
   hg_scan_stats stats{};
   uint32_t launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;  // call / dominant-kernel brackets
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evm0 = nullptr, evm1 = nullptr;  // call / dominant-kernel / merge brackets
   void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
   size_t h_stage_bytes = 0;
   Arena arena;

@@ -19,6 +19,9 @@ namespace k {
 // S2: page decompression + decode --------------------------------------------------------------------------------
 void snappy_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols,
                    int ncolsel, uint8_t* scratch, int* err);
+// v2: parallel tag parse + pointer-jumping resolve (snappy.cu); `ticket` is a zeroed device counter
+void snappy_chunks_v2(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols, int ncolsel,
+                      uint8_t* scratch, unsigned int* ticket, int* err);
 void decode_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols,
                    int ncolsel, const uint8_t* scratch, int* err);
 

@@ -121,6 +121,8 @@ typedef struct {
   uint32_t path;              /* 0 = general pipeline, 1 = fused fast path */
   float gpu_ms;               /* device time of the last call, first kernel to last (CUDA events on the engine stream) */
   float kernel_ms;            /* device time of the call's dominant kernel alone (fused scan / page decode) */
+  float merge_ms;             /* device time of S4-S6 (sort records, merge passes, dedup, compaction of survivors) */
+  float _pad2;
 } hg_scan_stats;
 
 /* Device-resident aggregate (for the NCCL combine and HBM-resident timing); valid until the next call on the engine. */

@@ -23,7 +23,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.HgSstDesc) == 64
     assert C.sizeof(_ffi.HgSchemaDesc) == 32
     assert C.sizeof(_ffi.HgAggSpec) == 24
-    assert C.sizeof(_ffi.HgScanStats) == 72
+    assert C.sizeof(_ffi.HgScanStats) == 80
     assert C.sizeof(_ffi.ArrowArrayStream) == 40
 
 

@@ -130,6 +130,35 @@ def test_decode_small_pages_and_v2(eng):
             assert pa.Table.from_batches(got).equals(pq.read_table(io.BytesIO(data)).cast(schema.arrow_schema)), (version, comp)
 
 
+def test_snappy_adversarial_patterns(eng):
+    """Element-dense and run-length-like Snappy streams: constant runs (offset-1 copies), short periods, sawtooth deltas,
+    long incompressible literals, and mixtures — every path of the page decompressor (snappy.cu)."""
+    rng = np.random.default_rng(5)
+    n = 50_000
+    pk = np.arange(n, dtype=np.int64)
+    cols = {
+        "pk": pk, "ts": pk * 1000 + rng.integers(0, 500, n),
+        "const": np.full(n, 7, np.int64),
+        "period3": np.tile(np.array([1, 2, 3], np.int64), n // 3 + 1)[:n],
+        "saw": (pk % 17) * 1_000_003,
+        "rand": rng.integers(-2**62, 2**62, n),
+        "small": rng.integers(0, 4, n).astype(np.int64),
+        "runs": np.repeat(rng.integers(0, 1000, n // 100 + 1), 100)[:n].astype(np.int64),
+        "mix": np.where(pk % 2000 < 1000, 5, rng.integers(0, 2**40, n)).astype(np.int64),
+        "bytes": rng.integers(0, 2, n).astype(np.uint8),
+        "f": np.round(rng.standard_normal(n), 1),
+    }
+    user = pa.schema([pa.field(k, pa.from_numpy_dtype(v.dtype), True) for k, v in cols.items()])
+    schema = StorageSchema.try_new(user, 2)
+    batch = pa.RecordBatch.from_arrays([pa.array(v) for v in cols.values()], schema=user)
+    for rg in (8192, 1000, 50_000):
+        data = sstgen.write_sst(schema, batch, seq=3, cfg=WriteConfig(compression=ParquetCompression.Snappy, max_row_group_size=rg), presorted=True)
+        handle = SchemaHandle(schema.arrow_schema, 2)
+        got = eng.scan(handle, _inputs([data]), [], None, True).read_all()
+        ref = pq.read_table(io.BytesIO(data)).cast(schema.arrow_schema)
+        assert got.equals(ref), rg
+
+
 # -------------------------------------------------------------------------------------------- filter / merge / dedup
 @pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed])
 def test_filter_predicates_and_pruning(eng, compression):
