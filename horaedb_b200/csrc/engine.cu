@@ -15,6 +15,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -28,43 +29,28 @@ int set_error(int code, const std::string& msg) {
   return code;
 }
 
-static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* d) {
-  if (e->ssts.count(d->id)) return HG_OK;
-  std::vector<uint8_t> filebuf;
-  const uint8_t* data = d->data;
-  uint64_t size = d->size;
-  if (!data) {
-    if (!d->path) return set_error(HG_ERR_NOT_FOUND, "sst " + std::to_string(d->id) + " is not resident and no data/path given");
-    FILE* f = std::fopen(d->path, "rb");
-    if (!f) return set_error(HG_ERR_NOT_FOUND, std::string("cannot open ") + d->path);
-    std::fseek(f, 0, SEEK_END);
-    long n = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    filebuf.resize(size_t(n));
-    size_t got = std::fread(filebuf.data(), 1, size_t(n), f);
-    std::fclose(f);
-    if (got != size_t(n)) return set_error(HG_ERR_NOT_FOUND, std::string("short read on ") + d->path);
-    data = filebuf.data();
-    size = uint64_t(n);
-  }
-  auto r = std::make_unique<SstResident>();
-  r->id = d->id;
+// Host-only, thread-safe: footer + page walk, validation against the schema, device tables, planning facts.
+static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t* data, uint64_t size, SstResident* r,
+                       std::vector<PageDev>* pages_out, std::vector<ChunkDev>* chunks_out, std::string* errmsg) {
+  auto fail = [&](int code, const std::string& msg) { *errmsg = msg; return code; };
+  r->id = id;
   r->size = size;
   std::string err;
-  if (!parse_parquet(data, size, &r->meta, &err)) return set_error(HG_ERR_FORMAT, "sst " + std::to_string(d->id) + ": " + err);
+  if (!parse_parquet(data, size, &r->meta, &err)) return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": " + err);
   const FileMetaData& m = r->meta;
   if (uint32_t(m.ncols) != schema->num_columns)
-    return set_error(HG_ERR_INVALID, "sst has " + std::to_string(m.ncols) + " columns, schema has " + std::to_string(schema->num_columns));
+    return fail(HG_ERR_INVALID, "sst has " + std::to_string(m.ncols) + " columns, schema has " + std::to_string(schema->num_columns));
   for (int c = 0; c < m.ncols; c++) {
     if (m.phys_types[c] != expected_phys(schema->types[c]))
-      return set_error(HG_ERR_INVALID, "column " + std::to_string(c) + ": parquet physical type does not match the schema");
-    if (m.repetition[c] == 2) return set_error(HG_ERR_UNSUPPORTED, "repeated columns");
+      return fail(HG_ERR_INVALID, "column " + std::to_string(c) + ": parquet physical type does not match the schema");
+    if (m.repetition[c] == 2) return fail(HG_ERR_UNSUPPORTED, "repeated columns");
   }
-  std::vector<PageDev> pages(m.pages.size());
+  std::vector<PageDev>& pages = *pages_out;
+  pages.assign(m.pages.size(), PageDev());
   for (size_t i = 0; i < pages.size(); i++) {
     const PageMeta& pm = m.pages[i];
     if (pm.encoding != ENC_PLAIN)
-      return set_error(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (only PLAIN is implemented)");
+      return fail(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (only PLAIN is implemented)");
     PageDev& pd = pages[i];
     pd.payload_off = pm.payload_off;
     pd.comp_size = pm.comp_size;
@@ -77,14 +63,15 @@ static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_
     pd.v2_compressed = pm.v2_compressed;
     pd._pad = 0;
   }
-  std::vector<ChunkDev> chunks(m.rgs.size() * size_t(m.ncols));
+  std::vector<ChunkDev>& chunks = *chunks_out;
+  chunks.assign(m.rgs.size() * size_t(m.ncols), ChunkDev());
   for (size_t g = 0; g < m.rgs.size(); g++)
     for (int c = 0; c < m.ncols; c++) {
       const ChunkMeta& cm = m.rgs[g].cols[c];
       if (cm.codec != CODEC_UNCOMPRESSED && cm.codec != CODEC_SNAPPY)
-        return set_error(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED and SNAPPY are implemented)");
-      if (cm.has_dict_page) return set_error(HG_ERR_UNSUPPORTED, "dictionary-encoded column chunk");
-      if (cm.scratch_bytes > 0xffffffffull) return set_error(HG_ERR_UNSUPPORTED, "column chunk larger than 4 GiB");
+        return fail(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED and SNAPPY are implemented)");
+      if (cm.has_dict_page) return fail(HG_ERR_UNSUPPORTED, "dictionary-encoded column chunk");
+      if (cm.scratch_bytes > 0xffffffffull) return fail(HG_ERR_UNSUPPORTED, "column chunk larger than 4 GiB");
       ChunkDev& cd = chunks[g * m.ncols + c];
       cd.first_page = cm.first_page;
       cd.num_pages = cm.num_pages;
@@ -140,6 +127,41 @@ static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_
       } else { r->pk0_range_ok = false; r->group_bound += uint64_t(rows) + 1; }
     }
   }
+  return HG_OK;
+}
+
+static int read_whole_file(const char* path, std::vector<uint8_t>* buf) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return set_error(HG_ERR_NOT_FOUND, std::string("cannot open ") + path);
+  std::fseek(f, 0, SEEK_END);
+  long n = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  buf->resize(size_t(n));
+  size_t got = std::fread(buf->data(), 1, size_t(n), f);
+  std::fclose(f);
+  if (got != size_t(n)) return set_error(HG_ERR_NOT_FOUND, std::string("short read on ") + path);
+  return HG_OK;
+}
+
+// hg_sst_load: the whole file becomes resident (cudaMalloc'd, cached until hg_sst_unload).
+static int load_sst_locked(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* d) {
+  if (e->ssts.count(d->id)) return HG_OK;
+  std::vector<uint8_t> filebuf;
+  const uint8_t* data = d->data;
+  uint64_t size = d->size;
+  if (!data) {
+    if (!d->path) return set_error(HG_ERR_NOT_FOUND, "sst " + std::to_string(d->id) + " is not resident and no data/path given");
+    int rc = read_whole_file(d->path, &filebuf);
+    if (rc) return rc;
+    data = filebuf.data();
+    size = filebuf.size();
+  }
+  auto r = std::make_unique<SstResident>();
+  std::vector<PageDev> pages;
+  std::vector<ChunkDev> chunks;
+  std::string err;
+  int prc = prepare_sst(schema, d->id, data, size, r.get(), &pages, &chunks, &err);
+  if (prc) return set_error(prc, err);
   uint64_t need = size + 64 + pages.size() * sizeof(PageDev) + chunks.size() * sizeof(ChunkDev) + r->rgcol.size() * sizeof(RgCol) +
                   r->rg_rows.size() * sizeof(uint32_t);
   if (e->budget && e->resident_bytes + need > e->budget)
@@ -203,6 +225,163 @@ int stage_upload(hg_engine* e, void* dst, const void* src, size_t bytes, size_t*
   std::memcpy(static_cast<char*>(e->h_stage) + off, src, bytes);
   CU_TRY(cudaMemcpyAsync(dst, static_cast<char*>(e->h_stage) + off, bytes, cudaMemcpyHostToDevice, e->stream));
   *stage_off = off + bytes;
+  return HG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------- transient, selective SST loads
+// A scan called with host bytes for SSTs that are not resident does not cache them: it copies ONLY the byte ranges the
+// query can touch — column chunks of the needed columns in row groups that survive statistics pruning — into arena
+// memory laid out at the file's own offsets (so the page table stays valid), uploads the page tables, and forgets
+// everything at the end of the call.  Footers are parsed on a small thread pool.  With pinned host buffers the ranges
+// are fetched by one gather kernel reading host memory over PCIe (no per-range API call).
+struct CopyRange { const uint8_t* src; uint8_t* dst; uint64_t bytes; };
+
+__global__ void __launch_bounds__(256) gather_ranges_kernel(const CopyRange* __restrict__ ranges, uint32_t nranges) {
+  for (uint32_t r = blockIdx.x; r < nranges; r += gridDim.x) {
+    const CopyRange cr = ranges[r];
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(cr.src), da = reinterpret_cast<uintptr_t>(cr.dst);
+    if (((sa ^ da) & 15) == 0) {
+      uint64_t head = (16 - (sa & 15)) & 15;
+      if (head > cr.bytes) head = cr.bytes;
+      for (uint64_t i = threadIdx.x; i < head; i += 256) cr.dst[i] = cr.src[i];
+      const uint64_t nvec = (cr.bytes - head) >> 4;
+      const uint4* s = reinterpret_cast<const uint4*>(cr.src + head);
+      uint4* d = reinterpret_cast<uint4*>(cr.dst + head);
+      for (uint64_t i = threadIdx.x; i < nvec; i += 256) d[i] = s[i];
+      for (uint64_t i = head + (nvec << 4) + threadIdx.x; i < cr.bytes; i += 256) cr.dst[i] = cr.src[i];
+    } else {
+      for (uint64_t i = threadIdx.x; i < cr.bytes; i += 256) cr.dst[i] = cr.src[i];
+    }
+  }
+}
+
+static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, const std::vector<size_t>& pending,
+                          const hg_predicate* preds, size_t np, std::vector<uint32_t> need_cols, bool seq_if_overlap,
+                          const std::vector<size_t>& resident_idx) {
+  const size_t k = pending.size();
+  std::vector<std::unique_ptr<SstResident>> rs(k);
+  std::vector<std::vector<PageDev>> pages(k);
+  std::vector<std::vector<ChunkDev>> chunks(k);
+  std::vector<std::vector<uint8_t>> filebufs(k);
+  std::vector<const uint8_t*> datas(k);
+  std::vector<uint64_t> sizes(k);
+  for (size_t j = 0; j < k; j++) {
+    const hg_sst_desc& d = ssts[pending[j]];
+    datas[j] = d.data;
+    sizes[j] = d.size;
+    if (!d.data) {
+      if (!d.path) return set_error(HG_ERR_NOT_FOUND, "sst " + std::to_string(d.id) + " is not resident and no data/path given");
+      int rc = read_whole_file(d.path, &filebufs[j]);
+      if (rc) return rc;
+      datas[j] = filebufs[j].data();
+      sizes[j] = filebufs[j].size();
+    }
+    rs[j] = std::make_unique<SstResident>();
+    rs[j]->owned = false;
+  }
+  // ---- parse in parallel
+  std::vector<int> codes(k, 0);
+  std::vector<std::string> errs(k);
+  {
+    const unsigned nthreads = unsigned(std::min<size_t>(k, 16));
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+      for (;;) {
+        size_t j = next.fetch_add(1);
+        if (j >= k) break;
+        codes[j] = prepare_sst(schema, ssts[pending[j]].id, datas[j], sizes[j], rs[j].get(), &pages[j], &chunks[j], &errs[j]);
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  for (size_t j = 0; j < k; j++) if (codes[j]) return set_error(codes[j], errs[j]);
+  // ---- __seq__ is only needed when the inputs are not provably PK-disjoint (a real merge will run)
+  if (seq_if_overlap) {
+    std::vector<const SstResident*> all;
+    for (auto& r : rs) if (r->rows_total) all.push_back(r.get());
+    for (size_t i : resident_idx) { auto it = e->ssts.find(ssts[i].id); if (it != e->ssts.end() && it->second->rows_total) all.push_back(it->second.get()); }
+    bool disjoint = true;
+    const uint32_t t0 = schema->types[0];
+    if (all.size() > 1) {
+      for (auto* f : all) if (!f->pk0_range_ok) disjoint = false;
+      if (disjoint) {
+        std::stable_sort(all.begin(), all.end(), [&](const SstResident* a, const SstResident* b) { return cmp_host(a->pk0_min, b->pk0_min, t0) < 0; });
+        for (size_t j = 0; j + 1 < all.size() && disjoint; j++) disjoint = cmp_host(all[j]->pk0_max, all[j + 1]->pk0_min, t0) < 0;
+      }
+    }
+    if (!disjoint) need_cols.push_back(schema->num_columns - 2);
+  }
+  std::sort(need_cols.begin(), need_cols.end());
+  need_cols.erase(std::unique(need_cols.begin(), need_cols.end()), need_cols.end());
+  // ---- arena allocations + byte ranges
+  const bool prune = !(e->flags & HG_FLAG_NO_PRUNING);
+  uint64_t lits[MAX_PREDS];
+  for (size_t i = 0; i < np; i++) lits[i] = pred_literal(preds[i], schema->types[preds[i].column]);
+  std::vector<CopyRange> ranges;
+  size_t stage_off = 0;
+  uint64_t copied = 0;
+  for (size_t j = 0; j < k; j++) {
+    SstResident& r = *rs[j];
+    const FileMetaData& m = r.meta;
+    r.d_bytes = static_cast<uint8_t*>(g_arena->alloc(r.size + 64));
+    r.d_pages = static_cast<PageDev*>(g_arena->alloc(std::max<size_t>(pages[j].size(), 1) * sizeof(PageDev)));
+    r.d_chunks = static_cast<ChunkDev*>(g_arena->alloc(std::max<size_t>(chunks[j].size(), 1) * sizeof(ChunkDev)));
+    r.d_rgcol = static_cast<RgCol*>(g_arena->alloc(std::max<size_t>(r.rgcol.size(), 1) * sizeof(RgCol)));
+    r.d_rg_rows = static_cast<uint32_t*>(g_arena->alloc(std::max<size_t>(r.rg_rows.size(), 1) * sizeof(uint32_t)));
+    if (!r.d_bytes || !r.d_pages || !r.d_chunks || !r.d_rgcol || !r.d_rg_rows) return set_error(HG_ERR_OOM, "out of device memory for transient SST");
+    int rc = 0;
+    if (!pages[j].empty()) rc = stage_upload(e, r.d_pages, pages[j].data(), pages[j].size() * sizeof(PageDev), &stage_off);
+    if (!rc && !chunks[j].empty()) rc = stage_upload(e, r.d_chunks, chunks[j].data(), chunks[j].size() * sizeof(ChunkDev), &stage_off);
+    if (!rc && !r.rgcol.empty()) rc = stage_upload(e, r.d_rgcol, r.rgcol.data(), r.rgcol.size() * sizeof(RgCol), &stage_off);
+    if (!rc && !r.rg_rows.empty()) rc = stage_upload(e, r.d_rg_rows, r.rg_rows.data(), r.rg_rows.size() * sizeof(uint32_t), &stage_off);
+    if (rc) return rc;
+    copied += pages[j].size() * sizeof(PageDev) + chunks[j].size() * sizeof(ChunkDev) + r.rgcol.size() * sizeof(RgCol);
+    const size_t ncols = size_t(m.ncols);
+    for (size_t g = 0; g < m.rgs.size(); g++) {
+      if (r.rg_rows[g] == 0) continue;
+      if (prune && np && !rg_may_match(&r.rgcol[g * ncols], r.rg_rows[g], schema, preds, lits, np)) continue;
+      for (uint32_t c : need_cols) {
+        const ChunkMeta& cm = m.rgs[g].cols[c];
+        uint64_t lo = uint64_t(cm.data_page_offset), hi = lo + uint64_t(cm.total_compressed);
+        if (hi > r.size) hi = r.size;
+        hi = std::min<uint64_t>(r.size, hi + 16);               // the unaligned 8-byte loads may touch one word past the values
+        if (!ranges.empty() && ranges.back().src + ranges.back().bytes >= datas[j] + lo && ranges.back().src <= datas[j] + lo &&
+            ranges.back().dst == r.d_bytes + (ranges.back().src - datas[j])) {
+          uint64_t end = std::max<uint64_t>(uint64_t(ranges.back().src - datas[j]) + ranges.back().bytes, hi);
+          ranges.back().bytes = end - uint64_t(ranges.back().src - datas[j]);
+        } else ranges.push_back(CopyRange{datas[j] + lo, r.d_bytes + lo, hi - lo});
+      }
+    }
+  }
+  for (auto& cr : ranges) copied += cr.bytes;
+  // ---- move the bytes
+  bool all_pinned = !ranges.empty();
+  for (size_t j = 0; j < k && all_pinned; j++) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, datas[j]) != cudaSuccess || at.type != cudaMemoryTypeHost) { all_pinned = false; cudaGetLastError(); }
+  }
+  if (all_pinned) {
+    CopyRange* d_ranges = static_cast<CopyRange*>(g_arena->alloc(ranges.size() * sizeof(CopyRange)));
+    if (!d_ranges) return set_error(HG_ERR_OOM, "out of device memory");
+    int rc = stage_upload(e, d_ranges, ranges.data(), ranges.size() * sizeof(CopyRange), &stage_off);
+    if (rc) return rc;
+    gather_ranges_kernel<<<int(std::min<size_t>(ranges.size(), 148 * 8)), 256, 0, e->stream>>>(d_ranges, uint32_t(ranges.size()));
+    e->launches++;
+  } else {
+    for (auto& cr : ranges) CU_TRY(cudaMemcpyAsync(cr.dst, cr.src, cr.bytes, cudaMemcpyHostToDevice, e->stream));
+  }
+  e->stats.bytes_h2d += copied;
+  for (size_t j = 0; j < k; j++) {
+    e->transient_ids.push_back(rs[j]->id);
+    e->ssts[rs[j]->id] = std::move(rs[j]);
+  }
+  // host buffers read from files must outlive the async copies
+  if (!all_pinned || std::any_of(filebufs.begin(), filebufs.end(), [](const std::vector<uint8_t>& b) { return !b.empty(); }))
+    CU_TRY(cudaStreamSynchronize(e->stream));
   return HG_OK;
 }
 
@@ -770,7 +949,15 @@ int hg_last_stats(hg_engine* e, hg_scan_stats* out) {
   return HG_OK;
 }
 
-static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds, size_t np) {
+static void end_call(hg_engine* e) {
+  for (uint64_t id : e->transient_ids) e->ssts.erase(id);     // transient SSTs live in the arena: nothing to free
+  e->transient_ids.clear();
+}
+struct CallGuard { hg_engine* e; ~CallGuard() { end_call(e); } };
+
+// need_cols: the columns this call can touch (only used to select the byte ranges of non-resident SSTs)
+static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds, size_t np,
+                      std::vector<uint32_t> need_cols, bool seq_if_overlap) {
   int rc = validate_schema(schema);
   if (rc) return rc;
   rc = validate_preds(schema, preds, np);
@@ -781,11 +968,18 @@ static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   e->launches = 0;
   e->arena.reset();
   g_arena = &e->arena;
-  for (size_t i = 0; i < n; i++) {
-    rc = load_sst_locked(e, schema, &ssts[i]);
-    if (rc) return rc;
-  }
   CU_TRY(cudaEventRecord(e->ev0, e->stream));
+  std::vector<size_t> pending, resident;
+  for (size_t i = 0; i < n; i++) {
+    if (e->ssts.count(ssts[i].id)) resident.push_back(i);
+    else if (std::find_if(pending.begin(), pending.end(), [&](size_t j) { return ssts[j].id == ssts[i].id; }) == pending.end()) pending.push_back(i);
+  }
+  if (!pending.empty()) {
+    for (uint32_t c = 0; c < schema->num_primary_keys; c++) need_cols.push_back(c);
+    for (size_t i = 0; i < np; i++) need_cols.push_back(preds[i].column);
+    rc = load_transient(e, schema, ssts, pending, preds, np, need_cols, seq_if_overlap && n > 1, resident);
+    if (rc) { end_call(e); return rc; }
+  }
   return HG_OK;
 }
 
@@ -793,8 +987,12 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
                      size_t np, const uint32_t* projection, size_t nproj, int keep_builtin, struct ArrowArrayStream* out) {
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
-  int rc = begin_call(e, schema, ssts, n, preds, np);
+  std::vector<uint32_t> touch;
+  if (projection) for (size_t i = 0; i < nproj; i++) { if (projection[i] < schema->num_columns) touch.push_back(projection[i]); }
+  else for (uint32_t c = 0; c < (keep_builtin ? schema->num_columns : schema->num_columns - 2); c++) touch.push_back(c);
+  int rc = begin_call(e, schema, ssts, n, preds, np, touch, true);
   if (rc) return rc;
+  CallGuard guard{e};
   cudaStream_t s = e->stream;
   Launch L = e->L();
   // output columns: all user columns (+ builtin when keep_builtin) or the projection (treated as a
@@ -961,8 +1159,11 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
                              const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg, hg_agg_device* out) {
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
-  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds);
+  std::vector<uint32_t> touch;
+  if (agg) for (int32_t c : {agg->group_col, agg->ts_col, agg->value_col}) if (c >= 0 && uint32_t(c) < (schema ? schema->num_columns : 0)) touch.push_back(uint32_t(c));
+  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds, touch, true);
   if (rc) return rc;
+  CallGuard guard{e};
   AggBuffers ab;
   rc = aggregate_core(e, schema, ssts, n_ssts, preds, n_preds, agg, &ab);
   if (rc) return rc;
@@ -987,8 +1188,11 @@ int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
                       size_t n_preds, const hg_agg_spec* agg, struct ArrowArrayStream* out) {
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
-  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds);
+  std::vector<uint32_t> touch;
+  if (agg) for (int32_t c : {agg->group_col, agg->ts_col, agg->value_col}) if (c >= 0 && uint32_t(c) < (schema ? schema->num_columns : 0)) touch.push_back(uint32_t(c));
+  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds, touch, true);
   if (rc) return rc;
+  CallGuard guard{e};
   cudaStream_t s = e->stream;
   AggBuffers ab;
   rc = aggregate_core(e, schema, ssts, n_ssts, preds, n_preds, agg, &ab);

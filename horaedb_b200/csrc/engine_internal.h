@@ -121,7 +121,9 @@ struct SstResident {
   PageDev* d_pages = nullptr;
   ChunkDev* d_chunks = nullptr;
   uint64_t device_bytes = 0;
+  bool owned = true;             // false: transient copy living in the engine arena
   ~SstResident() {
+    if (!owned) return;
     if (d_bytes) cudaFree(d_bytes);
     if (d_pages) cudaFree(d_pages);
     if (d_chunks) cudaFree(d_chunks);
@@ -215,6 +217,7 @@ struct hg_engine {
   void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
   size_t h_stage_bytes = 0;
   Arena arena;
+  std::vector<uint64_t> transient_ids;   // SSTs loaded only for the running call
   Launch L() { return Launch{stream, &launches}; }
 };
 

