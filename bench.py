@@ -202,6 +202,7 @@ def main():
         # ---- e2e: host buffers in, host result out, every step (SSTs are evicted between steps)
         e2e_t = []
         d2h = 0
+        h2d = 0
         for it in range(e2e_steps + 1):
             for sid, _, _ in ssts:
                 try:
@@ -214,6 +215,7 @@ def main():
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             d2h = eng.stats()["bytes_d2h"]
+            h2d = eng.stats()["bytes_h2d"]
             if it > 0:
                 e2e_t.append(dt)
         if world > 1:
@@ -223,7 +225,9 @@ def main():
         else:
             e2e_dt = float(np.median(e2e_t))
         groups_local = tbl.num_rows
-        # ---- HBM-resident steps
+        # ---- HBM-resident steps: make the SSTs resident once (untimed), then every step is one scan call
+        for inp in inputs_host:
+            eng.load_sst(handle, inp)
         for _ in range(warmup):
             dev = eng.scan_aggregate_device(handle, resident, P, group_col=0, ts_col=-1, window_ms=0, value_col=2)
             combine(dev)
@@ -257,7 +261,7 @@ def main():
             ms = float(tt.item())
         st = eng.stats()
         return {"rows": rows, "file_bytes": file_bytes, "ms_total": ms, "ms_per_step": ms / steps, "kernel_ms": float(np.mean(kernel_ms)),
-                "call_ms": float(np.mean(call_ms)), "launches": launches, "e2e_s": e2e_dt, "d2h": d2h, "stats": st,
+                "call_ms": float(np.mean(call_ms)), "launches": launches, "e2e_s": e2e_dt, "d2h": d2h, "h2d": h2d, "stats": st,
                 "groups": total_groups, "groups_local": groups_local,
                 "clocks": sampler.summary() if rank == 0 else None, "ssts": ssts}
 
@@ -300,7 +304,7 @@ def main():
                          "kernel_ms": main_r["kernel_ms"], "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src},
             "cpu_baseline": {"value": cpu_rps, "unit": "rows/s", "cores": ncores, "kind": "port",
                              "sample": f"{nsample} of the same SSTs = {cpu_rows} rows, oracle (C restatement of the reference path), {ncores} threads"},
-            "e2e": {"value": rows_all / main_r["e2e_s"], "unit": "rows/s", "h2d_bytes_per_step": main_r["file_bytes"] * world,
+            "e2e": {"value": rows_all / main_r["e2e_s"], "unit": "rows/s", "h2d_bytes_per_step": int(main_r["h2d"]) * world,
                     "d2h_bytes_per_step": int(main_r["d2h"]) * world, "ms_per_step": main_r["e2e_s"] * 1e3},
             "gpu_launches": main_r["launches"],
             "clocks": main_r["clocks"],
