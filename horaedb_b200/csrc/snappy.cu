@@ -23,9 +23,10 @@ namespace k {
 namespace {
 
 constexpr int kWin = 256;          // compressed-stream window (bytes)
-constexpr int kHist = 1024;        // bytes of most recent output kept in shared memory
+constexpr int kRing = 4096;        // ring buffer of the most recent output (power of two)
 constexpr int kOut = 2048;         // max output of one batch: 32 elements x 64 bytes
-constexpr int kLevels = 5;         // J1, J2, J4, J8, J16
+constexpr int kHist = kRing - kOut;  // bytes before the current batch that are guaranteed to still be in the ring
+constexpr int kLevels = 6;         // J1, J2, J4, J8, J16, J32
 constexpr uint16_t kExit = 0xffff;
 constexpr uint16_t kDone = 0xffff;
 constexpr int kWarpsPerCta = 4;
@@ -33,8 +34,8 @@ constexpr int kWarpsPerCta = 4;
 struct alignas(16) WarpSmem {
   uint8_t win[kWin + 16];
   uint16_t J[kLevels][kWin];
-  uint8_t buf[kHist + kOut];       // [0, kHist) = tail of the output produced so far, [kHist, ..) = current batch
-  uint16_t ptr[kOut];              // per batch byte: index into buf of its source, or kDone
+  uint8_t ring[kRing];             // output byte at absolute position x lives at ring[x & (kRing-1)]
+  uint16_t ptr[kOut];              // per batch byte: batch-relative index of its source byte, or kDone
 };
 
 __host__ __device__ __forceinline__ uint64_t page_scratch2(uint32_t uncomp) { return (uint64_t(uncomp) + 15u) / 16u * 16u + 32u; }
@@ -72,22 +73,9 @@ __device__ __forceinline__ void warp_copy_in(uint8_t* dst, const uint8_t* src, u
   for (uint32_t i = done + lane; i < len; i += 32) dst[i] = __ldg(src + i);
 }
 
-// keep the last kHist bytes of [hist | batch of T bytes] as the new history
-__device__ __forceinline__ void shift_history(WarpSmem& sm, uint32_t T, int lane) {
-  if (T == 0) return;
-  __syncwarp();
-  if (T >= uint32_t(kHist)) {
-    for (uint32_t i = lane; i < uint32_t(kHist); i += 32) sm.buf[i] = sm.buf[T + i];   // src index > dst index, ascending i per lane
-  } else {
-    // overlapping forward move by T: do it in two synchronised phases through registers
-    uint8_t tmp[kHist / 32];
-#pragma unroll
-    for (int j = 0; j < kHist / 32; j++) tmp[j] = sm.buf[T + j * 32 + lane];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < kHist / 32; j++) sm.buf[j * 32 + lane] = tmp[j];
-  }
-  __syncwarp();
+// byte at absolute output position x (< o, i.e. produced by an earlier batch): ring if recent enough, else global
+__device__ __forceinline__ uint8_t old_byte(const WarpSmem& sm, const uint8_t* dst, uint32_t o, uint32_t x) {
+  return (o - x <= uint32_t(kHist)) ? sm.ring[x & (kRing - 1)] : ldcg_u8(dst + x);
 }
 
 __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, WarpSmem& sm,
@@ -100,7 +88,6 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
   }
   if (ulen != ulen_expected) { if (lane == 0) atomicExch(err, 101); return; }
   uint32_t o = 0;                 // bytes produced so far
-  uint32_t hist_valid = 0;        // how many bytes of history in sm.buf[kHist - hist_valid, kHist) are valid
   while (pos < n) {
     const uint32_t avail = n - pos;
     const uint32_t tag0 = __ldg(src + pos);
@@ -112,16 +99,10 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       if (1 + nb + len > avail || o + len > ulen) { if (lane == 0) atomicExch(err, 102); return; }
       const uint8_t* lsrc = src + pos + 1 + nb;
       warp_copy_in(dst + o, lsrc, len, lane);
-      // refresh history with the tail of the literal
       __syncwarp();
-      if (len >= uint32_t(kHist)) {
-        for (uint32_t i = lane; i < uint32_t(kHist); i += 32) sm.buf[i] = __ldg(lsrc + (len - kHist) + i);
-        hist_valid = kHist;
-      } else {
-        for (uint32_t i = lane; i < len; i += 32) sm.buf[kHist + i] = __ldg(lsrc + i);
-        shift_history(sm, len, lane);
-        hist_valid = hist_valid + len < uint32_t(kHist) ? hist_valid + len : uint32_t(kHist);
-      }
+      // the ring keeps the tail of the literal
+      const uint32_t keep = len < uint32_t(kRing) ? len : uint32_t(kRing);
+      for (uint32_t i = lane; i < keep; i += 32) sm.ring[(o + len - keep + i) & (kRing - 1)] = __ldg(lsrc + (len - keep) + i);
       __syncwarp();
       pos += 1 + nb + len;
       o += len;
@@ -154,119 +135,150 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       }
       __syncwarp();
     }
-    uint32_t q = 0;                                  // window-relative start of element `lane`
+    uint32_t q = 0;                                  // window-relative start of element `lane` of the current batch
 #pragma unroll
-    for (int lv = 0; lv < kLevels; lv++)
+    for (int lv = 0; lv < 5; lv++)
       if ((lane >> lv) & 1) q = q == kExit ? uint32_t(kExit) : sm.J[lv][q];
-    bool valid = q != kExit;
-    uint32_t len = 0, off = 0, hdr = 0, csz = 0;
-    bool is_lit = false;
-    if (valid) {
-      const uint32_t t = sm.win[q];
-      const uint32_t kind = t & 3;
-      if (kind == 0) {
-        if ((t >> 2) >= 60) valid = false;           // long literal: ends the batch, handled by the straight-copy path
-        else { is_lit = true; len = (t >> 2) + 1; hdr = 1; }
-      } else if (kind == 1) { len = ((t >> 2) & 7) + 4; off = ((t >> 5) << 8) | sm.win[q + 1]; hdr = 2; }
-      else if (kind == 2) { len = (t >> 2) + 1; off = uint32_t(sm.win[q + 1]) | (uint32_t(sm.win[q + 2]) << 8); hdr = 3; }
-      else { len = (t >> 2) + 1; off = uint32_t(sm.win[q + 1]) | (uint32_t(sm.win[q + 2]) << 8) | (uint32_t(sm.win[q + 3]) << 16) | (uint32_t(sm.win[q + 4]) << 24); hdr = 5; }
-      csz = hdr + (is_lit ? len : 0);
-      if (valid && q + csz > avail) valid = false;   // truncated stream: reported below through the size check
-    }
-    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-    const int m = (vm == 0xffffffffu) ? 32 : (__ffs(~vm) - 1);   // valid lanes form a prefix
-    if (m == 0) { if (lane == 0) atomicExch(err, 105); return; }
-    if (lane >= m) { len = 0; csz = 0; }
-    // exclusive prefix sum of the output lengths
-    uint32_t inc = len;
+    uint32_t next_pos = pos;
+    // up to three batches of 32 elements from one parsed window
+    for (int b = 0; b < 3; b++) {
+      if (b > 0) q = q == kExit ? uint32_t(kExit) : sm.J[5][q];
+      bool valid = q != kExit;
+      uint32_t len = 0, off = 0, hdr = 0, csz = 0;
+      bool is_lit = false;
+      if (valid) {
+        const uint32_t t = sm.win[q];
+        const uint32_t kind = t & 3;
+        if (kind == 0) {
+          if ((t >> 2) >= 60) valid = false;         // long literal: ends the batch, handled by the straight-copy path
+          else { is_lit = true; len = (t >> 2) + 1; hdr = 1; }
+        } else if (kind == 1) { len = ((t >> 2) & 7) + 4; off = ((t >> 5) << 8) | sm.win[q + 1]; hdr = 2; }
+        else if (kind == 2) { len = (t >> 2) + 1; off = uint32_t(sm.win[q + 1]) | (uint32_t(sm.win[q + 2]) << 8); hdr = 3; }
+        else { len = (t >> 2) + 1; off = uint32_t(sm.win[q + 1]) | (uint32_t(sm.win[q + 2]) << 8) | (uint32_t(sm.win[q + 3]) << 16) | (uint32_t(sm.win[q + 4]) << 24); hdr = 5; }
+        csz = hdr + (is_lit ? len : 0);
+        if (valid && q + csz > avail) valid = false; // truncated stream: caught by the final size check / m == 0
+      }
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
+      const int m = (vm == 0xffffffffu) ? 32 : (__ffs(~vm) - 1);   // valid lanes form a prefix
+      if (m == 0) {
+        if (b == 0) { if (lane == 0) atomicExch(err, 105); return; }
+        break;
+      }
+      if (lane >= m) { len = 0; csz = 0; }
+      uint32_t inc = len;                                          // exclusive prefix sum of the output lengths
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    const uint32_t doff = inc - len;
-    const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
-    const uint32_t next_pos = pos + __shfl_sync(0xffffffffu, q + csz, m - 1);
-    // sanity: copies must not reach before the start of the output
-    bool bad = lane < m && !is_lit && (off == 0 || off > o + doff);
-    if (__any_sync(0xffffffffu, bad) || o + T > ulen) { if (lane == 0) atomicExch(err, 103); return; }
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+      const uint32_t doff = inc - len;
+      const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
+      next_pos = pos + __shfl_sync(0xffffffffu, q + csz, m - 1);
+      bool bad = lane < m && !is_lit && (off == 0 || off > o + doff);
+      if (__any_sync(0xffffffffu, bad) || o + T > ulen) { if (lane == 0) atomicExch(err, 103); return; }
 
-    if (T <= uint32_t(m) * 16) {
-      // ---------------- tiny elements: byte-level source pointers + pointer jumping
-      if (lane < m) {
-        if (is_lit) {
-          const uint8_t* ls = src + pos + q + 1;
-          for (uint32_t i = 0; i < len; i++) {
-            const uint32_t wp = q + 1 + i;                               // literal bytes usually sit in the staged window
-            sm.buf[kHist + doff + i] = wp < uint32_t(kWin) ? sm.win[wp] : __ldg(ls + i);
-            sm.ptr[doff + i] = kDone;
-          }
-        } else {
-          for (uint32_t i = 0; i < len; i++) {
-            const uint32_t r = doff + i;
-            const int32_t sr = int32_t(kHist + r) - int32_t(off);       // index into buf of the source byte
-            if (sr >= int32_t(kHist)) sm.ptr[r] = uint16_t(sr - kHist);   // produced by this batch: resolve below
-            else {
-              uint8_t v;
-              if (sr >= int32_t(kHist - hist_valid) && sr >= 0) v = sm.buf[sr];
-              else v = ldcg_u8(dst + (o + r - off));                     // older than the history window
-              sm.buf[kHist + r] = v;
-              sm.ptr[r] = kDone;
+      if (T <= uint32_t(m) * 16) {
+        // ---------------- tiny elements: byte-level source pointers + pointer jumping
+        if (lane < m) {
+          if (is_lit) {
+            const uint8_t* ls = src + pos + q + 1;
+            for (uint32_t i = 0; i < len; i++) {
+              const uint32_t wp = q + 1 + i;                           // literal bytes usually sit in the staged window
+              sm.ring[(o + doff + i) & (kRing - 1)] = wp < uint32_t(kWin) ? sm.win[wp] : __ldg(ls + i);
+              sm.ptr[doff + i] = kDone;
+            }
+          } else {
+            for (uint32_t i = 0; i < len; i++) {
+              const uint32_t r = doff + i;
+              if (off <= r) sm.ptr[r] = uint16_t(r - off);             // produced by this batch: resolved below
+              else { sm.ring[(o + r) & (kRing - 1)] = old_byte(sm, dst, o, o + r - off); sm.ptr[r] = kDone; }
             }
           }
         }
-      }
-      __syncwarp();
-      const uint32_t trips = (T + 31) / 32;
-      for (;;) {
-        bool pending = false;
-        for (uint32_t j = 0; j < trips; j++) {
-          const uint32_t r = j * 32 + lane;
-          uint16_t pr = kDone, pq = kDone;
-          uint8_t vq = 0;
-          if (r < T) {
-            pr = sm.ptr[r];
-            if (pr != kDone) { pq = sm.ptr[pr]; vq = sm.buf[kHist + pr]; }
-          }
-          __syncwarp();
-          if (r < T && pr != kDone) {
-            if (pq == kDone) { sm.buf[kHist + r] = vq; sm.ptr[r] = kDone; }
-            else { sm.ptr[r] = pq; pending = true; }
-          }
-          __syncwarp();
-        }
-        if (!__any_sync(0xffffffffu, pending)) break;
-      }
-      for (uint32_t r = lane; r < T; r += 32) dst[o + r] = sm.buf[kHist + r];
-      shift_history(sm, T, lane);
-    } else {
-      // ---------------- long elements: one element per step, history served from shared memory
-      uint32_t produced = 0;                          // bytes of this batch already placed in buf[kHist..)
-      for (int e = 0; e < m; e++) {
-        const uint32_t elen = __shfl_sync(0xffffffffu, len, e);
-        const uint32_t eoff = __shfl_sync(0xffffffffu, off, e);
-        const uint32_t eq = __shfl_sync(0xffffffffu, q, e);
-        const bool elit = __shfl_sync(0xffffffffu, int(is_lit), e) != 0;
         __syncwarp();
-        if (elit) {
-          const uint8_t* ls = src + pos + eq + 1;
-          for (uint32_t i = lane; i < elen; i += 32) sm.buf[kHist + produced + i] = __ldg(ls + i);
+        if (T <= 256) {
+          // register-staged rounds: one barrier between the read and the write phase
+          for (;;) {
+            uint16_t pr[8], pq[8];
+            uint8_t vq[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const uint32_t r = j * 32 + lane;
+              pr[j] = kDone; pq[j] = kDone; vq[j] = 0;
+              if (r < T) {
+                pr[j] = sm.ptr[r];
+                if (pr[j] != kDone) { pq[j] = sm.ptr[pr[j]]; vq[j] = sm.ring[(o + pr[j]) & (kRing - 1)]; }
+              }
+            }
+            __syncwarp();
+            bool pending = false;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const uint32_t r = j * 32 + lane;
+              if (r < T && pr[j] != kDone) {
+                if (pq[j] == kDone) { sm.ring[(o + r) & (kRing - 1)] = vq[j]; sm.ptr[r] = kDone; }
+                else { sm.ptr[r] = pq[j]; pending = true; }
+              }
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, pending)) break;
+          }
         } else {
-          // source bytes all precede this element: out[x] = out[x - off] with x - off taken modulo the pattern length
-          for (uint32_t i = lane; i < elen; i += 32) {
-            const uint32_t back = eoff - (i % eoff);                   // distance from the element start to the source byte
-            const int32_t sr = int32_t(kHist + produced) - int32_t(back);
-            uint8_t v;
-            if (sr >= int32_t(kHist - hist_valid) && sr >= 0) v = sm.buf[sr];
-            else v = ldcg_u8(dst + (o + produced - back));
-            sm.buf[kHist + produced + i] = v;
+          const uint32_t trips = (T + 31) / 32;
+          for (;;) {
+            bool pending = false;
+            for (uint32_t j = 0; j < trips; j++) {
+              const uint32_t r = j * 32 + lane;
+              uint16_t pr = kDone, pq = kDone;
+              uint8_t vq = 0;
+              if (r < T) {
+                pr = sm.ptr[r];
+                if (pr != kDone) { pq = sm.ptr[pr]; vq = sm.ring[(o + pr) & (kRing - 1)]; }
+              }
+              __syncwarp();
+              if (r < T && pr != kDone) {
+                if (pq == kDone) { sm.ring[(o + r) & (kRing - 1)] = vq; sm.ptr[r] = kDone; }
+                else { sm.ptr[r] = pq; pending = true; }
+              }
+              __syncwarp();
+            }
+            if (!__any_sync(0xffffffffu, pending)) break;
           }
         }
-        __syncwarp();
-        for (uint32_t i = lane; i < elen; i += 32) dst[o + produced + i] = sm.buf[kHist + produced + i];
-        produced += elen;
+        for (uint32_t r = lane; r < T; r += 32) dst[o + r] = sm.ring[(o + r) & (kRing - 1)];
+      } else {
+        // ---------------- long elements.  Adjacent copies with the same offset continue one periodic pattern
+        // (out[x] = out[x - off] over the union), so they are merged into a single run and spread over the warp.
+        const uint32_t poff = __shfl_up_sync(0xffffffffu, off, 1);
+        const bool plit = __shfl_up_sync(0xffffffffu, int(is_lit), 1) != 0;
+        const bool head = lane < m && (lane == 0 || is_lit || plit || poff != off);
+        unsigned heads = __ballot_sync(0xffffffffu, head);
+        while (heads) {
+          const int e = __ffs(heads) - 1;
+          heads &= heads - 1;
+          const int enext = heads ? (__ffs(heads) - 1) : m;            // first lane of the next run
+          const uint32_t s0 = __shfl_sync(0xffffffffu, doff, e);
+          const uint32_t s1 = enext < 32 ? __shfl_sync(0xffffffffu, doff, enext & 31) : T;
+          const uint32_t rlen = (enext == m ? T : s1) - s0;
+          const uint32_t eoff = __shfl_sync(0xffffffffu, off, e);
+          const uint32_t eq = __shfl_sync(0xffffffffu, q, e);
+          const bool elit = __shfl_sync(0xffffffffu, int(is_lit), e) != 0;
+          __syncwarp();
+          if (elit) {
+            const uint8_t* ls = src + pos + eq + 1;
+            for (uint32_t i = lane; i < rlen; i += 32) sm.ring[(o + s0 + i) & (kRing - 1)] = __ldg(ls + i);
+          } else {
+            // every source byte precedes the run: x - off taken modulo the pattern length
+            const uint32_t start = o + s0;
+            for (uint32_t i = lane; i < rlen; i += 32) {
+              const uint32_t x = start - eoff + (i % eoff);
+              sm.ring[(start + i) & (kRing - 1)] = (start - x <= uint32_t(kHist) + s0) ? sm.ring[x & (kRing - 1)] : ldcg_u8(dst + x);
+            }
+          }
+          __syncwarp();
+          for (uint32_t i = lane; i < rlen; i += 32) dst[o + s0 + i] = sm.ring[(o + s0 + i) & (kRing - 1)];
+        }
       }
-      shift_history(sm, T, lane);
+      o += T;
+      if (m < 32) break;
     }
-    hist_valid = hist_valid + T < uint32_t(kHist) ? hist_valid + T : uint32_t(kHist);
-    o += T;
     pos = next_pos;
   }
   if (o != ulen) { if (lane == 0) atomicExch(err, 104); }
