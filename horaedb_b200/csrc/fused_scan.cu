@@ -823,7 +823,8 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   // split row groups into enough work items for ~8 items per resident warp (dynamic ticket => good balance);
   // boundaries are then aligned to key-run starts by item_bounds_kernel
   uint32_t split = 1;
-  while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * 8) split *= 2;
+  static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 8;
+  while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * uint64_t(items_per_warp)) split *= 2;
   const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
   DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj;
   CU_TRY(d_work.alloc(64, s));

@@ -78,6 +78,36 @@ __device__ __forceinline__ uint8_t old_byte(const WarpSmem& sm, const uint8_t* d
   return (o - x <= uint32_t(kHist)) ? sm.ring[x & (kRing - 1)] : ldcg_u8(dst + x);
 }
 
+// pointer jumping over at most kTrips*32 batch bytes, all state of a round staged in registers
+template <int kTrips>
+__device__ __forceinline__ void resolve_small(WarpSmem& sm, uint32_t o, uint32_t T, int lane) {
+  for (;;) {
+    uint16_t pr[kTrips], pq[kTrips];
+    uint8_t vq[kTrips];
+#pragma unroll
+    for (int j = 0; j < kTrips; j++) {
+      const uint32_t r = j * 32 + lane;
+      pr[j] = kDone; pq[j] = kDone; vq[j] = 0;
+      if (r < T) {
+        pr[j] = sm.ptr[r];
+        if (pr[j] != kDone) { pq[j] = sm.ptr[pr[j]]; vq[j] = sm.ring[(o + pr[j]) & (kRing - 1)]; }
+      }
+    }
+    __syncwarp();
+    bool pending = false;
+#pragma unroll
+    for (int j = 0; j < kTrips; j++) {
+      const uint32_t r = j * 32 + lane;
+      if (r < T && pr[j] != kDone) {
+        if (pq[j] == kDone) { sm.ring[(o + r) & (kRing - 1)] = vq[j]; sm.ptr[r] = kDone; }
+        else { sm.ptr[r] = pq[j]; pending = true; }
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, pending)) break;
+  }
+}
+
 __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, WarpSmem& sm,
                             int lane, int* err) {
   uint32_t pos = 0, ulen = 0;
@@ -195,31 +225,9 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
         __syncwarp();
         if (T <= 256) {
           // register-staged rounds: one barrier between the read and the write phase
-          for (;;) {
-            uint16_t pr[8], pq[8];
-            uint8_t vq[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const uint32_t r = j * 32 + lane;
-              pr[j] = kDone; pq[j] = kDone; vq[j] = 0;
-              if (r < T) {
-                pr[j] = sm.ptr[r];
-                if (pr[j] != kDone) { pq[j] = sm.ptr[pr[j]]; vq[j] = sm.ring[(o + pr[j]) & (kRing - 1)]; }
-              }
-            }
-            __syncwarp();
-            bool pending = false;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const uint32_t r = j * 32 + lane;
-              if (r < T && pr[j] != kDone) {
-                if (pq[j] == kDone) { sm.ring[(o + r) & (kRing - 1)] = vq[j]; sm.ptr[r] = kDone; }
-                else { sm.ptr[r] = pq[j]; pending = true; }
-              }
-            }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, pending)) break;
-          }
+          if (T <= 64) resolve_small<2>(sm, o, T, lane);
+          else if (T <= 128) resolve_small<4>(sm, o, T, lane);
+          else resolve_small<8>(sm, o, T, lane);
         } else {
           const uint32_t trips = (T + 31) / 32;
           for (;;) {
