@@ -734,6 +734,50 @@ static int check_device_error(hg_engine* e, PipelineState* st) {
   return HG_OK;
 }
 
+// ----------------------------------------------------------------------------------------------- pinned host pool
+// Result batches live in pinned host memory owned by the Arrow stream; cudaMallocHost is slow and synchronising, so
+// released buffers go back to a process-wide free list (bounded) instead of being freed.
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<size_t, void*>> free_list;
+  size_t pooled = 0;
+  static constexpr size_t kMaxPooled = size_t(16) << 30;
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 4095) & ~size_t(4095);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      size_t best = free_list.size();
+      for (size_t i = 0; i < free_list.size(); i++)
+        if (free_list[i].first >= bytes && free_list[i].first <= bytes * 2 + (1 << 20) && (best == free_list.size() || free_list[i].first < free_list[best].first)) best = i;
+      if (best != free_list.size()) {
+        void* p = free_list[best].second;
+        pooled -= free_list[best].first;
+        sizes[p] = free_list[best].first;
+        free_list.erase(free_list.begin() + best);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> g(mu);
+    sizes[p] = bytes;
+    return p;
+  }
+  void release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = sizes.find(p);
+    size_t b = it == sizes.end() ? 0 : it->second;
+    if (it != sizes.end()) sizes.erase(it);
+    if (b && pooled + b <= kMaxPooled) { free_list.emplace_back(b, p); pooled += b; }
+    else cudaFreeHost(p);
+  }
+  std::unordered_map<void*, size_t> sizes;
+};
+PinnedPool& pinned_pool() { static PinnedPool* p = new PinnedPool(); return *p; }
+}  // namespace
+
 // --------------------------------------------------------------------------------------------- Arrow C stream export
 struct HostColumn {
   std::string name;
@@ -749,8 +793,8 @@ struct StreamData {
   std::string last_error;
   ~StreamData() {
     for (auto& c : cols) {
-      if (c.vals) cudaFreeHost(c.vals);
-      if (c.bitmap) cudaFreeHost(c.bitmap);
+      pinned_pool().release(c.vals);
+      pinned_pool().release(c.bitmap);
     }
   }
 };
@@ -1041,12 +1085,14 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
     bool nulls = dc.valid.p != nullptr;
     if (nulls) { CU_TRY(gb[i].alloc(size_t(R) + 16, s)); CU_TRY(gm[i].alloc((size_t(R) + 7) / 8 + 16, s)); }
     k::gather_column(L, dc.view(), st.out_rows.as<uint32_t>(), st.d_r, R, gv[i].p, gb[i].as<uint8_t>());
-    CU_TRY(cudaMallocHost(&hcx.vals, size_t(R) * dc.width + 16));
+    hcx.vals = pinned_pool().alloc(size_t(R) * dc.width + 16);
+    if (!hcx.vals) return set_error(HG_ERR_OOM, "pinned host memory");
     CU_TRY(cudaMemcpyAsync(hcx.vals, gv[i].p, size_t(R) * dc.width, cudaMemcpyDeviceToHost, s));
     d2h += size_t(R) * dc.width;
     if (nulls) {
       k::pack_validity(L, gb[i].as<uint8_t>(), R, gm[i].as<uint8_t>(), d_null.as<unsigned long long>() + i);
-      CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&hcx.bitmap), (size_t(R) + 7) / 8 + 16));
+      hcx.bitmap = static_cast<uint8_t*>(pinned_pool().alloc((size_t(R) + 7) / 8 + 16));
+      if (!hcx.bitmap) return set_error(HG_ERR_OOM, "pinned host memory");
       CU_TRY(cudaMemcpyAsync(hcx.bitmap, gm[i].p, (size_t(R) + 7) / 8, cudaMemcpyDeviceToHost, s));
       d2h += (size_t(R) + 7) / 8;
     }
@@ -1217,7 +1263,8 @@ int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
     hc.type = sc.type;
     hc.width = sc.width;
     if (G) {
-      CU_TRY(cudaMallocHost(&hc.vals, size_t(G) * sc.width + 16));
+      hc.vals = pinned_pool().alloc(size_t(G) * sc.width + 16);
+      if (!hc.vals) return set_error(HG_ERR_OOM, "pinned host memory");
       CU_TRY(cudaMemcpyAsync(hc.vals, sc.dev, size_t(G) * sc.width, cudaMemcpyDeviceToHost, s));
       d2h += size_t(G) * sc.width;
     }
