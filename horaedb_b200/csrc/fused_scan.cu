@@ -180,8 +180,10 @@ struct Acc {
   double sum, mn, mx;
 };
 
-__device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item, uint32_t local) {
-  unsigned int slot = atomicAdd(&P.work[1], 1u);
+// Record slots are reserved 32 at a time per warp (slots = {next, end} in shared memory): one global atomic per 32 groups.
+__device__ __noinline__ void emit(const FParams& P, const Acc& a, uint32_t item, uint32_t local, uint32_t* slots) {
+  if (slots[0] == slots[1]) { slots[0] = atomicAdd(&P.work[1], 32u); slots[1] = slots[0] + 32u; }
+  unsigned int slot = slots[0]++;
   if (slot < P.rec_cap) {
     FRec r;
     r.item = item; r.local = local; r.gkey = a.g; r.bucket = a.bstart; r.count = a.cnt; r.sum = a.sum; r.mn = a.mn; r.mx = a.mx; r._pad = 0;
@@ -372,7 +374,7 @@ __device__ __forceinline__ double seq_sum_slice(double sum, unsigned keep_mask, 
 
 template <bool HAS_TS>
 __device__ __noinline__ void walk_slice(const FParams& P, Acc& acc, uint32_t& local, uint32_t item, unsigned keep_mask, bool keep, uint64_t g,
-                                        int64_t ts, double v, double* s_vals, int lane) {
+                                        int64_t ts, double v, double* s_vals, uint32_t* slots, int lane) {
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   const bool has_val = P.value_slot >= 0;
   bool ext = keep && acc.open && (!P.has_group || g == acc.g) && (!HAS_TS || (ts >= acc.blo && ts <= acc.bhi));
@@ -399,7 +401,7 @@ __device__ __noinline__ void walk_slice(const FParams& P, Acc& acc, uint32_t& lo
     uint64_t kg = P.has_group ? shfl64(g, l) : 0;
     int64_t kt = HAS_TS ? int64_t(shfl64(uint64_t(ts), l)) : 0;
     if (!acc.open || kg != acc.g || (HAS_TS && (kt < acc.blo || kt > acc.bhi))) {
-      if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
+      if (acc.open) { if (lane == 0) emit(P, acc, item, local, slots); local++; }
       acc.open = true; acc.g = kg; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
       if (HAS_TS) { Bucket b = bucket_range(kt, P.window_ms); acc.bstart = b.start; acc.blo = b.lo; acc.bhi = b.hi; }
       else { acc.bstart = 0; acc.blo = 0; acc.bhi = 0; }
@@ -451,7 +453,7 @@ struct Hot {
 template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool PARTIAL, int kPF>
 __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH>& H, const uint8_t* vq, uint32_t vs, Acc& acc, uint32_t& local,
                                                   uint32_t& n_alive, uint32_t& n_keep, uint32_t item, uint32_t csi, uint32_t row,
-                                                  uint32_t lim, uint32_t nrows, double* s_vals, int lane) {
+                                                  uint32_t lim, uint32_t nrows, double* s_vals, uint32_t* slots, int lane) {
   uint64_t hv[kU][NH];
   uint64_t vv[kU];
   uint64_t halo[2] = {0, 0};
@@ -545,7 +547,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
         uint64_t raw = DENSE ? vv[u] : (v8 ? ld8(vq, vs, i) : uint64_t(ld4(vq, vs, i)));
         v = to_double_kind(raw, P.kind[P.value_slot], P.cls[P.value_slot]);
       }
-      walk_slice<HAS_TS>(P, acc, local, item, keep_mask, keep, hv[u][0], int64_t(hv[u][1]), v, s_vals, lane);
+      walk_slice<HAS_TS>(P, acc, local, item, keep_mask, keep, hv[u][0], int64_t(hv[u][1]), v, s_vals, slots, lane);
     }
   }
   return kept_in_block;
@@ -556,8 +558,12 @@ template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS, int kPF>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P,
                                                                                     const uint64_t* __restrict__ adj) {
   __shared__ double s_vals_all[kWarpsPerCta][32];
+  __shared__ uint32_t s_slots[kWarpsPerCta][2];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* s_vals = s_vals_all[wid];
+  uint32_t* slots = s_slots[wid];
+  if (lane == 0) { slots[0] = 0; slots[1] = 0; }
+  __syncwarp();
   const uint32_t nsel = *P.d_nsel;
   const uint32_t nitems = nsel * P.split;
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
@@ -590,7 +596,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
     uint32_t item = 0;
     if (lane == 0) item = atomicAdd(&P.work[0], 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= nitems) return;
+    if (item >= nitems) {
+      // hand back the unused part of this warp's last reservation as invalid records
+      if (lane == 0) for (uint32_t sl = slots[0]; sl < slots[1]; sl++) if (sl < P.rec_cap) P.rec[sl].item = 0xffffffffu;
+      return;
+    }
     const uint64_t beg = adj[item], end = adj[item + 1];
     uint32_t csi = uint32_t(beg >> 32), row = uint32_t(beg);
     const uint32_t esi = uint32_t(end >> 32), erow = uint32_t(end);
@@ -613,15 +623,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
         if (row >= lim) break;
         uint32_t kept;
         if (row + 32u * kU < lim) {       // (< lim: the halo row is inside the row group as well)
-          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane)
-                       : process_block<kU, NH, X, HAS_TS, false, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
+          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, slots, lane)
+                       : process_block<kU, NH, X, HAS_TS, false, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, slots, lane);
         } else {
-          kept = process_block<kU, NH, X, HAS_TS, false, true, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, lane);
+          kept = process_block<kU, NH, X, HAS_TS, false, true, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, slots, lane);
         }
         dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
         row += 32 * kU;
       }
-      if (acc.open) { if (lane == 0) emit(P, acc, item, local); local++; }
+      if (acc.open) { if (lane == 0) emit(P, acc, item, local, slots); local++; }
     }
     if (lane == 0) {
       P.item_cnt[item] = local;
@@ -683,6 +693,7 @@ __global__ void scatter_records_kernel(const FRec* __restrict__ rec, const unsig
   uint32_t n = *nrec;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     FRec x = rec[r];
+    if (x.item == 0xffffffffu) continue;          // unused tail of a warp's slot reservation
     uint32_t pos = item_off[x.item] + x.local;
     switch (gwidth) {
       case 1: reinterpret_cast<uint8_t*>(out.gkey)[pos] = uint8_t(x.gkey); break;
@@ -833,7 +844,8 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   CU_TRY(cudaMemsetAsync(d_counters.p, 0, 64, s));
   CU_TRY(d_err.alloc(sizeof(int), s));
   CU_TRY(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
-  CU_TRY(d_rec.alloc(size_t(bound) * sizeof(FRec) + 64, s));
+  const uint64_t rec_cap = bound + 148ull * 8 * kWarpsPerCta * 32;   // + one partly used 32-slot reservation per warp
+  CU_TRY(d_rec.alloc(size_t(rec_cap) * sizeof(FRec) + 64, s));
   CU_TRY(d_item.alloc(size_t(nitems + 1) * sizeof(uint32_t) + 64, s));
   CU_TRY(d_adj.alloc(size_t(nitems + 2) * sizeof(uint64_t), s));
   CU_TRY(d_sel.alloc(size_t(total_rgs + 1) * sizeof(RgSel), s));
@@ -923,7 +935,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     }
     P.window_ms = has_ts ? agg->window_ms : 1;
     P.rec = d_rec.as<FRec>();
-    P.rec_cap = uint32_t(bound);
+    P.rec_cap = uint32_t(rec_cap);
     P.item_cnt = d_item.as<uint32_t>();
     P.work = d_work.as<unsigned int>();
     P.counters = d_counters.as<unsigned long long>();
@@ -972,7 +984,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     cudaEventElapsedTime(&kms, e->evk0, e->evk1);
     e->stats.kernel_ms = kms;
   }
-  out->G = global_mode ? (hc[1] > 0 ? 1u : 0u) : hw[0];   // like GROUP BY: no surviving rows, no group
+  out->G = global_mode ? (hc[1] > 0 ? 1u : 0u) : hw[1];   // hw[1] = groups counted by item_scan (hw[0] = reserved record slots)   // like GROUP BY: no surviving rows, no group
   e->stats.rows_in_files = rows_in_files;
   e->stats.rows_decoded = hc[2];
   e->stats.rows_filtered = hc[0];
