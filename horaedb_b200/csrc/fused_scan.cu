@@ -825,7 +825,9 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
         }
       }
     }
-    if (bound > rows_in_files / 4 + 1024) return NOT_APPLICABLE;     // groups ~ rows: not this kernel's regime
+    // more than ~1 group per warp-slice: the per-survivor walk dominates and the materialising pipeline (thread per
+    // group) is faster (measured: 16.7 M groups / 100 M rows: 16.8 ms fused vs ~6 ms general)
+    if (bound > rows_in_files / 32 + 1024) return NOT_APPLICABLE;
   }
   if (bound >= 0xfffffff0ull || rows_in_files >= 0xfffffff0ull) return NOT_APPLICABLE;
 
