@@ -160,6 +160,7 @@ def main():
     from horaedb_b200._ffi import DeviceArray, Engine, SchemaHandle, SstInput
 
     torch.cuda.set_device(local_rank)
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     schema = sstgen.metric_storage_schema()
@@ -174,18 +175,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def combine(dev):
-        """Cross-GPU combine of the per-GPU partial aggregates: ONE NCCL all-gather (horaedb_b200/parallel.py)."""
+    combiner = None
+    if world > 1:
+        from horaedb_b200.parallel import PartialCombiner
+        combiner = PartialCombiner()
+
+    def combine(dev, settle=False):
+        """Cross-GPU combine of the per-GPU partial aggregates: ONE NCCL all-gather per step (horaedb_b200/parallel.py).
+        The padded capacity is agreed during warm-up (`settle`); timed steps have no size exchange and no host sync."""
         g = int(dev.num_groups)
         if world == 1:
             return g
-        from horaedb_b200.parallel import combine_partials
 
         def view(ptr, ts):
             return torch.as_tensor(DeviceArray(ptr, g, ts), device="cuda") if g else torch.zeros(0, device="cuda", dtype=torch.int64 if ts == "<i8" else torch.float64)
-        res = combine_partials(view(dev.d_gkey, "<i8"), view(dev.d_bucket, "<i8"), view(dev.d_count, "<i8"), view(dev.d_sum, "<f8"),
-                               view(dev.d_min, "<f8"), view(dev.d_max, "<f8"))
-        return int(res[0].numel())
+        with torch.cuda.stream(stream):
+            out = combiner.gather(view(dev.d_gkey, "<i8"), view(dev.d_bucket, "<i8"), view(dev.d_count, "<i8"), view(dev.d_sum, "<f8"),
+                                  view(dev.d_min, "<f8"), view(dev.d_max, "<f8"), check_cap=settle)
+        return out
 
     def measure(codec, steps, warmup, e2e_steps):
         ssts = gen[codec]
@@ -228,9 +235,9 @@ def main():
         # ---- HBM-resident steps: make the SSTs resident once (untimed), then every step is one scan call
         for inp in inputs_host:
             eng.load_sst(handle, inp)
-        for _ in range(warmup):
+        for _ in range(max(warmup, 1)):
             dev = eng.scan_aggregate_device(handle, resident, P, group_col=0, ts_col=-1, window_ms=0, value_col=2)
-            combine(dev)
+            combine(dev, settle=True)
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -245,7 +252,7 @@ def main():
             kernel_ms.append(st["kernel_ms"])
             call_ms.append(st["gpu_ms"])
             launches += st["kernel_launches"]
-            total_groups = combine(dev)
+            last = combine(dev)
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -260,6 +267,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         st = eng.stats()
+        total_groups = last if world == 1 else int((last[:, 2, :] > 0).sum().item())
         return {"rows": rows, "file_bytes": file_bytes, "ms_total": ms, "ms_per_step": ms / steps, "kernel_ms": float(np.mean(kernel_ms)),
                 "call_ms": float(np.mean(call_ms)), "launches": launches, "e2e_s": e2e_dt, "d2h": d2h, "h2d": h2d, "stats": st,
                 "groups": total_groups, "groups_local": groups_local,
