@@ -126,6 +126,13 @@ def main():
     ap.add_argument("--no-variant", action="store_true", help="skip the secondary codec measurement")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE JSON line: route everything else (NCCL banners, library chatter) to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -147,7 +154,7 @@ def main():
                 "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": ncores, "kind": "port",
                                  "sample": f"{nsample} SSTs = {rows} rows per step (C restatement of the reference path; the Rust reference cannot be built here)"},
                 "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------------------------------------- our arm (GPU)
@@ -160,7 +167,6 @@ def main():
     from horaedb_b200._ffi import DeviceArray, Engine, SchemaHandle, SstInput
 
     torch.cuda.set_device(local_rank)
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     schema = sstgen.metric_storage_schema()
@@ -187,11 +193,8 @@ def main():
         if world == 1:
             return g
 
-        def view(ptr, ts):
-            return torch.as_tensor(DeviceArray(ptr, g, ts), device="cuda") if g else torch.zeros(0, device="cuda", dtype=torch.int64 if ts == "<i8" else torch.float64)
         with torch.cuda.stream(stream):
-            out = combiner.gather(view(dev.d_gkey, "<i8"), view(dev.d_bucket, "<i8"), view(dev.d_count, "<i8"), view(dev.d_sum, "<f8"),
-                                  view(dev.d_min, "<f8"), view(dev.d_max, "<f8"), check_cap=settle)
+            out = combiner.gather_packed(eng, g, torch.device("cuda", local_rank), check_cap=settle)
         return out
 
     def measure(codec, steps, warmup, e2e_steps):
@@ -321,7 +324,7 @@ def main():
                              "e2e_rows_per_s": r["rows"] * world / r["e2e_s"], "sst_bytes_per_gpu": r["file_bytes"],
                              "launches": r["launches"]} for c, r in res.items() if c != args.codec},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -71,7 +71,7 @@ class ArrowArrayStream(C.Structure):
 
 EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
-           "hg_scan_aggregate_device", "hg_last_stats"]
+           "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats"]
 
 _lib = None
 
@@ -244,6 +244,10 @@ class Engine:
         _check(self._L.hg_scan_aggregate_device(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p,
                                                 C.c_size_t(len(preds)), C.byref(spec), C.byref(out)))
         return out
+
+    def export_packed(self, d_dst: int, cap: int) -> None:
+        """Pack the last device aggregate into a caller-owned [6, cap] int64 device buffer (engine stream)."""
+        _check(self._L.hg_agg_export_packed(self._h, C.c_void_p(d_dst), C.c_uint64(cap)))
 
     def stats(self) -> dict:
         st = HgScanStats()

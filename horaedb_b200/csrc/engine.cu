@@ -986,6 +986,18 @@ int hg_sst_resident_bytes(hg_engine* e, uint64_t* out) {
   return HG_OK;
 }
 
+int hg_agg_export_packed(hg_engine* e, void* d_dst, uint64_t cap) {
+  if (!e || !d_dst) return set_error(HG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (cap < e->last_agg.num_groups) return set_error(HG_ERR_INVALID, "capacity smaller than the number of groups");
+  CU_TRY(cudaSetDevice(e->device));
+  AggOut in{const_cast<void*>(e->last_agg.d_gkey), const_cast<int64_t*>(e->last_agg.d_bucket), const_cast<uint64_t*>(e->last_agg.d_count),
+            const_cast<double*>(e->last_agg.d_sum), const_cast<double*>(e->last_agg.d_min), const_cast<double*>(e->last_agg.d_max)};
+  Launch L = e->L();
+  k::pack_agg(L, in, e->last_gwidth, e->last_agg.num_groups, cap, static_cast<long long*>(d_dst));
+  return HG_OK;
+}
+
 int hg_last_stats(hg_engine* e, hg_scan_stats* out) {
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
@@ -1010,6 +1022,7 @@ static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   CU_TRY(cudaSetDevice(e->device));
   std::memset(&e->stats, 0, sizeof(e->stats));
   e->launches = 0;
+  e->last_agg = hg_agg_device{};
   e->arena.reset();
   g_arena = &e->arena;
   CU_TRY(cudaEventRecord(e->ev0, e->stream));
@@ -1226,6 +1239,8 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
   out->d_sum = ab.sum.as<double>();
   out->d_min = ab.mn.as<double>();
   out->d_max = ab.mx.as<double>();
+  e->last_agg = *out;
+  e->last_gwidth = ab.gwidth;
   for (DevBuf* b : {&ab.gkey, &ab.bucket, &ab.count, &ab.sum, &ab.mn, &ab.mx}) b->release();   // arena memory: valid until the next call
   return HG_OK;
 }

@@ -217,6 +217,8 @@ struct hg_engine {
   void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
   size_t h_stage_bytes = 0;
   Arena arena;
+  hg_agg_device last_agg{};      // device pointers of the last aggregate (arena memory, valid until the next call)
+  uint32_t last_gwidth = 8;
   std::vector<uint64_t> transient_ids;   // SSTs loaded only for the running call
   Launch L() { return Launch{stream, &launches}; }
 };

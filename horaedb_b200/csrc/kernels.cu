@@ -735,6 +735,27 @@ __global__ void __launch_bounds__(kThreads) reduce_groups_kernel(AggSpecDev spec
   }
 }
 
+__global__ void pack_agg_kernel(AggOut in, uint32_t gwidth, uint64_t g, uint64_t cap, long long* __restrict__ dst) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < cap; i += uint64_t(gridDim.x) * blockDim.x) {
+    const bool v = i < g;
+    long long key = 0;
+    if (v) {
+      switch (gwidth) {
+        case 1: key = reinterpret_cast<const uint8_t*>(in.gkey)[i]; break;
+        case 2: key = reinterpret_cast<const uint16_t*>(in.gkey)[i]; break;
+        case 4: key = reinterpret_cast<const uint32_t*>(in.gkey)[i]; break;
+        default: key = (long long)reinterpret_cast<const uint64_t*>(in.gkey)[i];
+      }
+    }
+    dst[i] = key;
+    dst[cap + i] = v ? in.bucket[i] : 0;
+    dst[2 * cap + i] = v ? (long long)in.count[i] : 0;
+    dst[3 * cap + i] = v ? __double_as_longlong(in.sum[i]) : 0;
+    dst[4 * cap + i] = v ? __double_as_longlong(in.min[i]) : 0;
+    dst[5 * cap + i] = v ? __double_as_longlong(in.max[i]) : 0;
+  }
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
@@ -865,6 +886,11 @@ void reduce_groups(const Launch& L, const AggSpecDev& spec, const uint32_t* rows
                    const uint32_t* d_g, uint32_t cap, AggOut out) {
   if (!cap) return;
   reduce_groups_kernel<<<grid_for(cap), kThreads, 0, L.stream>>>(spec, rows, d_r, seg_start, d_g, out);
+  L.tick();
+}
+void pack_agg(const Launch& L, AggOut in, uint32_t gwidth, uint64_t g, uint64_t cap, long long* dst) {
+  if (!cap) return;
+  pack_agg_kernel<<<grid_for(cap), kThreads, 0, L.stream>>>(in, gwidth, g, cap, dst);
   L.tick();
 }
 void fill_u32(const Launch& L, uint32_t* p, uint32_t v, uint32_t n) {

@@ -71,6 +71,8 @@ void reduce_groups(const Launch& L, const AggSpecDev& spec, const uint32_t* rows
                    const uint32_t* seg_start, const uint32_t* d_g, uint32_t cap, AggOut out);
 
 void fill_u32(const Launch& L, uint32_t* p, uint32_t v, uint32_t n);
+// dst[6][cap] int64: key, bucket, count, sum/min/max bit patterns; zero beyond g
+void pack_agg(const Launch& L, AggOut in, uint32_t gwidth, uint64_t g, uint64_t cap, long long* dst);
 // chunk_end[c] = min((c+1)*batch, *d_m): SortPreservingMergeExec re-batches its output at batch_size rows
 void uniform_chunk_ends(const Launch& L, const uint32_t* d_m, uint32_t batch, uint32_t nchunks, uint32_t* chunk_end);
 // flags[i] = 0 for i in [*d_n, cap)

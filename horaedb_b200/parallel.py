@@ -51,6 +51,23 @@ class PartialCombiner:
         return self.out.view(dist.get_world_size(), 6, self.cap)
 
 
+    def gather_packed(self, engine, num_groups: int, device, check_cap: bool = False) -> torch.Tensor:
+        """Same collective, but the engine packs its last aggregate straight into the send block (one kernel, no
+        per-field tensor views): the steady-state step is one C call + one all-gather."""
+        if check_cap or self.block is None:
+            t = torch.tensor([num_groups], device=device, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            need = max(int(t.item()), 1)
+            if self.block is None or need > self.cap:
+                self.cap = need
+                self.block = torch.zeros(6, self.cap, device=device, dtype=torch.int64)
+                self.out = torch.zeros(dist.get_world_size() * 6, self.cap, device=device, dtype=torch.int64)
+        assert num_groups <= self.cap
+        engine.export_packed(self.block.data_ptr(), self.cap)
+        dist.all_gather_into_tensor(self.out, self.block)
+        return self.out.view(dist.get_world_size(), 6, self.cap)
+
+
 def combine_partials(gkey: torch.Tensor, bucket: torch.Tensor, count: torch.Tensor, sum_: torch.Tensor, mn: torch.Tensor,
                      mx: torch.Tensor, combiner: Optional[PartialCombiner] = None):
     """All ranks receive every rank's partial aggregate rows, ordered by (gkey, bucket).

@@ -162,6 +162,11 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
                              const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg,
                              hg_agg_device* out);
 
+/* Packs the last hg_scan_aggregate_device result into a caller-owned device buffer of 6 x cap int64 words
+ * (rows: group key, bucket, count, sum bits, min bits, max bits; columns >= num_groups are zero) on the engine's stream:
+ * the block one NCCL all-gather combines across GPUs.  HG_ERR_INVALID if cap < num_groups. */
+int hg_agg_export_packed(hg_engine* e, void* d_dst, uint64_t cap);
+
 int hg_last_stats(hg_engine* e, hg_scan_stats* out);
 
 #ifdef __cplusplus

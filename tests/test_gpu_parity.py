@@ -285,6 +285,15 @@ def test_aggregate_device_result(eng):
     dcnt = torch.as_tensor(DeviceArray(dev.d_count, 16, "<i8"), device="cuda")
     assert np.array_equal(dsum.cpu().numpy(), exp.sum)
     assert dcnt.cpu().numpy().astype(np.uint64).tolist() == exp.count.tolist()
+    # packed export (the block the NCCL all-gather sends): [6, cap] int64, zero padded
+    block = torch.zeros(6, 20, dtype=torch.int64, device="cuda")
+    eng.export_packed(block.data_ptr(), 20)
+    torch.cuda.synchronize()
+    hb = block.cpu().numpy()
+    assert hb[0, :16].astype(np.uint64).tolist() == exp.gkey.tolist() and hb[2, :16].tolist() == exp.count.astype(np.int64).tolist()
+    assert np.array_equal(hb[3, :16].view(np.float64), exp.sum) and not hb[:, 16:].any()
+    with pytest.raises(HgError):
+        eng.export_packed(block.data_ptr(), 3)
     st = eng.stats()
     assert st["rows_in_files"] == n and st["kernel_launches"] > 0 and st["gpu_ms"] > 0
 
