@@ -284,69 +284,112 @@ __global__ void __launch_bounds__(1024) select_rgs_kernel(const __grid_constant_
 // boundary" is monotone along the stream): 3 rounds cover a 8192-row group.
 struct KeyRef { uint64_t g; int64_t lo, hi; };
 
-template <bool HAS_TS>
-__device__ __forceinline__ bool key_differs(const FParams& P, const KeyRef& k, const uint8_t* b0, const uint8_t* b1, uint32_t row) {
-  if (P.has_group && load_kind(b0, P.kind[0], row) != k.g) return true;
-  if (HAS_TS) { int64_t ts = int64_t(load_kind(b1, P.kind[1], row)); if (ts < k.lo || ts > k.hi) return true; }
-  return false;
-}
-
 __device__ __forceinline__ uint64_t pack_pos(uint32_t si, uint32_t row) { return (uint64_t(si) << 32) | row; }
+
+// One boundary search, advanced one probing round at a time so that a warp can interleave several of them
+// (their dependent load chains overlap: the kernel is pure latency).
+template <bool HAS_TS>
+struct BoundSearch {
+  uint32_t j, si, row, L, H, ans;
+  KeyRef k;
+  const uint8_t *b0, *b1;
+  bool done, found;
+
+  __device__ __forceinline__ void finish(uint64_t* adj, uint64_t v, int lane) { if (lane == 0) adj[j] = v; done = true; }
+
+  __device__ __forceinline__ void open_rg(const FParams& P) {
+    b0 = P.has_group ? slot_base(P, si, 0) : nullptr;
+    b1 = HAS_TS ? slot_base(P, si, 1) : nullptr;
+    L = row;
+    H = P.sel[si].num_rows;
+    found = false;
+    ans = H;
+  }
+
+  __device__ __forceinline__ void init(const FParams& P, uint32_t jj, uint32_t nsel, uint32_t nitems, uint64_t* adj, int lane) {
+    j = jj;
+    done = false;
+    if (j > nitems) { done = true; return; }
+    if (j == nitems) { finish(adj, pack_pos(nsel, 0), lane); return; }
+    si = j / P.split;
+    const uint32_t w = j % P.split;
+    const uint32_t n = P.sel[si].num_rows;
+    const uint32_t sr = (((n + P.split - 1) / P.split) + 31u) & ~31u;
+    row = w * sr;
+    if (row >= n) { si++; row = 0; }                        // empty sub-range: same boundary as the next row group
+    if (si >= nsel) { finish(adj, pack_pos(nsel, 0), lane); return; }
+    if (P.global_mode || (si == 0 && row == 0)) { finish(adj, pack_pos(si, row), lane); return; }
+    uint32_t psi = si, prow = row;                          // key of the row just before the nominal boundary
+    if (prow == 0) { psi--; prow = P.sel[psi].num_rows - 1; } else prow--;
+    k.g = P.has_group ? fetch_val(P, psi, 0, prow) : 0;
+    k.lo = 0; k.hi = 0;
+    if (HAS_TS) { Bucket b = bucket_range(int64_t(fetch_val(P, psi, 1, prow)), P.window_ms); k.lo = b.lo; k.hi = b.hi; }
+    open_rg(P);
+  }
+
+  // probe position of this lane in the current window [L, H) (32 chunks; the lane looks at the last row of its chunk)
+  __device__ __forceinline__ uint32_t probe_pos(int lane, uint32_t* step) const {
+    const uint32_t span = H - L;
+    *step = (span + 31) / 32;
+    uint32_t p = L + (uint32_t(lane) + 1) * *step - 1;
+    return p >= H ? H - 1 : p;
+  }
+
+  __device__ __forceinline__ void advance(const FParams& P, unsigned m, uint32_t step, uint32_t nsel, uint64_t* adj, int lane) {
+    if (m == 0) L = H;                                      // the whole window continues the run
+    else {
+      const int f = __ffs(m) - 1;
+      uint32_t pf = L + (uint32_t(f) + 1) * step - 1;
+      if (pf >= H) pf = H - 1;
+      found = true;
+      ans = pf;
+      if (step == 1) L = H;                                 // exact
+      else { L = L + uint32_t(f) * step; H = pf; }          // rows [L, pf) still unknown; pf differs
+    }
+    if (L >= H) {
+      if (found) { finish(adj, pack_pos(si, ans), lane); return; }
+      si++;                                                 // the run covers the rest of this row group
+      row = 0;
+      if (si >= nsel) { finish(adj, pack_pos(nsel, 0), lane); return; }
+      open_rg(P);
+    }
+  }
+};
+
+constexpr int kBoundsPerWarp = 4;
 
 template <bool HAS_TS>
 __global__ void __launch_bounds__(256) item_bounds_kernel(const __grid_constant__ FParams P, uint64_t* __restrict__ adj) {
   const int lane = threadIdx.x & 31;
   const uint32_t nsel = *P.d_nsel;
   const uint32_t nitems = nsel * P.split;
-  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (j > nitems) return;
-  if (j == nitems) { if (lane == 0) adj[j] = pack_pos(nsel, 0); return; }
-  uint32_t si = j / P.split, w = j % P.split;
-  uint32_t n = P.sel[si].num_rows;
-  const uint32_t sr = (((n + P.split - 1) / P.split) + 31u) & ~31u;
-  uint32_t row = w * sr;
-  if (row >= n) { si++; row = 0; }                        // empty sub-range: same boundary as the next row group
-  if (si >= nsel) { if (lane == 0) adj[j] = pack_pos(nsel, 0); return; }
-  if (P.global_mode || (si == 0 && row == 0)) { if (lane == 0) adj[j] = pack_pos(si, row); return; }
-  // key of the row just before the nominal boundary
-  uint32_t psi = si, prow = row;
-  if (prow == 0) { psi--; prow = P.sel[psi].num_rows - 1; } else prow--;
-  KeyRef k;
-  k.g = P.has_group ? fetch_val(P, psi, 0, prow) : 0;
-  k.lo = 0; k.hi = 0;
-  if (HAS_TS) { Bucket b = bucket_range(int64_t(fetch_val(P, psi, 1, prow)), P.window_ms); k.lo = b.lo; k.hi = b.hi; }
-  // L = a position known to continue the run (start: the previous row); find the first later position that differs
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  BoundSearch<HAS_TS> bs[kBoundsPerWarp];
+#pragma unroll
+  for (int i = 0; i < kBoundsPerWarp; i++) bs[i].init(P, warp * kBoundsPerWarp + i, nsel, nitems, adj, lane);
   for (;;) {
-    n = P.sel[si].num_rows;
-    const uint8_t* b0 = P.has_group ? slot_base(P, si, 0) : nullptr;
-    const uint8_t* b1 = HAS_TS ? slot_base(P, si, 1) : nullptr;
-    uint32_t L = row, H = n;                              // candidates [L, H) in this row group
-    bool found = false;
-    uint32_t ans = H;
-    // invariant: every position < L (in this group) continues the run
-    while (L < H) {
-      uint32_t span = H - L;
-      uint32_t step = (span + 31) / 32;
-      uint32_t p = L + (uint32_t(lane) + 1) * step - 1;    // last position of lane's chunk
-      if (p >= H) p = H - 1;
-      bool ne = key_differs<HAS_TS>(P, k, b0, b1, p);
-      unsigned m = __ballot_sync(0xffffffffu, ne);
-      if (m == 0) { L = H; break; }                       // the whole window continues the run
-      int f = __ffs(m) - 1;
-      uint32_t pf = L + (uint32_t(f) + 1) * step - 1;
-      if (pf >= H) pf = H - 1;
-      uint32_t newL = L + uint32_t(f) * step;             // chunk f holds the first differing row
-      found = true;
-      ans = pf;
-      if (step == 1) break;
-      L = newL;
-      H = pf;                                             // rows [newL, pf) still unknown; pf differs
-      if (L >= H) break;
+    bool any = false;
+    uint32_t step[kBoundsPerWarp];
+    uint64_t v0[kBoundsPerWarp], v1[kBoundsPerWarp];
+#pragma unroll
+    for (int i = 0; i < kBoundsPerWarp; i++) {              // issue every search's probe loads first
+      v0[i] = 0; v1[i] = 0; step[i] = 1;
+      if (!bs[i].done) {
+        any = true;
+        const uint32_t p = bs[i].probe_pos(lane, &step[i]);
+        if (P.has_group) v0[i] = load_kind(bs[i].b0, P.kind[0], p);
+        if (HAS_TS) v1[i] = load_kind(bs[i].b1, P.kind[1], p);
+      }
     }
-    if (found) { if (lane == 0) adj[j] = pack_pos(si, ans); return; }
-    si++;                                                 // the run covers the rest of this row group
-    row = 0;
-    if (si >= nsel) { if (lane == 0) adj[j] = pack_pos(nsel, 0); return; }
+    if (!any) break;
+#pragma unroll
+    for (int i = 0; i < kBoundsPerWarp; i++) {
+      if (!bs[i].done) {
+        bool ne = (P.has_group && v0[i] != bs[i].k.g) || (HAS_TS && (int64_t(v1[i]) < bs[i].k.lo || int64_t(v1[i]) > bs[i].k.hi));
+        const unsigned m = __ballot_sync(0xffffffffu, ne);
+        bs[i].advance(P, m, step[i], nsel, adj, lane);
+      }
+    }
   }
 }
 
@@ -950,7 +993,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
                                          d_sel.as<RgSel>(), d_work.as<uint32_t>() + 3, d_counters.as<unsigned long long>());
     L.tick();
     {
-      const uint32_t nb = nitems + 1;
+      const uint32_t nb = (nitems + 1 + kBoundsPerWarp - 1) / kBoundsPerWarp;      // warps
       const int bctas = int((uint64_t(nb) * 32 + 255) / 256);
       if (has_ts) item_bounds_kernel<true><<<bctas, 256, 0, s>>>(P, d_adj.as<uint64_t>());
       else item_bounds_kernel<false><<<bctas, 256, 0, s>>>(P, d_adj.as<uint64_t>());
