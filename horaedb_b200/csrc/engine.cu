@@ -672,10 +672,12 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     CU_TRY(st->recA.alloc(size_t(N) * sizeof(SortRec) + 32, s));
     CU_TRY(st->recB.alloc(size_t(N) * sizeof(SortRec) + 32, s));
     k::build_records(L, pk, st->cols[seq_idx].view(), st->surv_ptr, st->d_m, N, st->recA.as<SortRec>());
+    DevBuf splits;
+    CU_TRY(splits.alloc(k::merge_split_elems(N) * sizeof(uint32_t), s));
     SortRec* src = st->recA.as<SortRec>();
     SortRec* dst = st->recB.as<SortRec>();
     for (int level = 0; (1 << level) < k; level++) {
-      k::merge_pass(L, src, dst, st->run_start.as<uint32_t>(), k, level, st->d_m, N);
+      k::merge_pass(L, src, dst, st->run_start.as<uint32_t>(), k, level, st->d_m, N, splits.as<uint32_t>());
       std::swap(src, dst);
     }
     CU_TRY(st->order.alloc(size_t(N) * 4 + 16, s));

@@ -521,39 +521,64 @@ __device__ __forceinline__ uint32_t merge_path(uint32_t diag, uint32_t na, uint3
 constexpr int kMergeVT = 4;
 constexpr int kMergeTile = kThreads * kMergeVT;  // 1024 records = 32 KB of shared memory
 
+struct PairView { uint32_t a0, a1, b1; };
+__device__ __forceinline__ PairView pair_of(const uint32_t* __restrict__ run_start, int k, int level, int nruns, uint32_t pos) {
+  auto rstart = [&](int r) -> uint32_t { long idx = long(r) << level; return run_start[idx > k ? k : idx]; };
+  int lo = 0, hi = nruns;        // upper_bound over rstart: pair containing pos = largest even r with rstart(r) <= pos
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (rstart(mid) <= pos) lo = mid + 1; else hi = mid; }
+  int r = (lo - 1) & ~1;
+  PairView p;
+  p.a0 = rstart(r);
+  p.a1 = rstart(r + 1 > nruns ? nruns : r + 1);
+  p.b1 = rstart(r + 2 > nruns ? nruns : r + 2);
+  return p;
+}
+
+// One thread per output tile: merge-path split (records taken from run A) at the tile's first output position.
+// Thousands of independent binary searches overlap their latency instead of stalling every merge CTA.
+__global__ void __launch_bounds__(kThreads) merge_partition_kernel(const SortRec* __restrict__ src, const uint32_t* __restrict__ run_start, int k,
+                                                                  int level, const uint32_t* d_m, uint32_t* __restrict__ splits) {
+  const uint32_t total = *d_m;
+  const int nruns = (k + (1 << level) - 1) >> level;
+  const uint32_t ntiles = (total + kMergeTile - 1) / kMergeTile;
+  for (uint32_t t = blockIdx.x * kThreads + threadIdx.x; t < ntiles; t += gridDim.x * kThreads) {
+    const uint32_t pos = t * kMergeTile;
+    PairView p = pair_of(run_start, k, level, nruns, pos);
+    const SortRec* A = src + p.a0;
+    const SortRec* B = src + p.a1;
+    splits[t] = merge_path(pos - p.a0, p.a1 - p.a0, p.b1 - p.a1, [&](uint32_t i) { return A[i]; }, [&](uint32_t i) { return B[i]; });
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const SortRec* __restrict__ src, SortRec* __restrict__ dst,
                                                              const uint32_t* __restrict__ run_start, int k, int level,
-                                                             const uint32_t* d_m) {
+                                                             const uint32_t* d_m, const uint32_t* __restrict__ splits) {
   __shared__ SortRec s_rec[kMergeTile];
-  __shared__ uint32_t s_split[2];
   const uint32_t total = *d_m;
   const int tid = threadIdx.x;
   const int nruns = (k + (1 << level) - 1) >> level;   // runs at this level
-  auto rstart = [&](int r) -> uint32_t { long idx = long(r) << level; return run_start[idx > k ? k : idx]; };
   const uint32_t ntiles = (total + kMergeTile - 1) / kMergeTile;
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     uint32_t pos = tile * kMergeTile;
-    uint32_t tile_hi = pos + kMergeTile < total ? pos + kMergeTile : total;
+    const uint32_t tile_hi = pos + kMergeTile < total ? pos + kMergeTile : total;
+    bool first = true;
     while (pos < tile_hi) {
-      // pair containing pos: largest even r with rstart(r) <= pos
-      int lo = 0, hi = nruns;        // upper_bound over rstart
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (rstart(mid) <= pos) lo = mid + 1; else hi = mid; }
-      int r = (lo - 1) & ~1;
-      uint32_t a0 = rstart(r), a1 = rstart(r + 1 > nruns ? nruns : r + 1), b1 = rstart(r + 2 > nruns ? nruns : r + 2);
-      uint32_t na = a1 - a0, nb = b1 - a1;
-      uint32_t seg_hi = tile_hi < b1 ? tile_hi : b1;
-      uint32_t d0 = pos - a0, d1 = seg_hi - a0;
-      const SortRec* A = src + a0;
-      const SortRec* B = src + a1;
-      if (tid == 0) s_split[0] = merge_path(d0, na, nb, [&](uint32_t i) { return A[i]; }, [&](uint32_t i) { return B[i]; });
-      if (tid == 32) s_split[1] = merge_path(d1, na, nb, [&](uint32_t i) { return A[i]; }, [&](uint32_t i) { return B[i]; });
-      __syncthreads();
-      uint32_t ia0 = s_split[0], ia1 = s_split[1];
-      uint32_t ib0 = d0 - ia0, ib1 = d1 - ia1;
-      uint32_t la = ia1 - ia0, lb = ib1 - ib0, n = la + lb;
+      const PairView p = pair_of(run_start, k, level, nruns, pos);
+      const uint32_t na = p.a1 - p.a0, nb = p.b1 - p.a1;
+      const uint32_t seg_hi = tile_hi < p.b1 ? tile_hi : p.b1;
+      const uint32_t d0 = pos - p.a0, d1 = seg_hi - p.a0;
+      const SortRec* A = src + p.a0;
+      const SortRec* B = src + p.a1;
+      // splits: the tile's own start comes from the partition kernel; later segments start at a pair start (0);
+      // a segment ends either at the pair end (na) or at the next tile's start (same pair)
+      const uint32_t ia0 = first ? splits[tile] : 0u;
+      const uint32_t ia1 = seg_hi == p.b1 ? na : splits[tile + 1];
+      first = false;
+      const uint32_t ib0 = d0 - ia0, ib1 = d1 - ia1;
+      const uint32_t la = ia1 - ia0, lb = ib1 - ib0, n = la + lb;
       for (uint32_t i = tid; i < n; i += kThreads) s_rec[i] = i < la ? A[ia0 + i] : B[ib0 + (i - la)];
       __syncthreads();
-      uint32_t t0 = uint32_t(tid) * kMergeVT;
+      const uint32_t t0 = uint32_t(tid) * kMergeVT;
       if (t0 < n) {
         const SortRec* sA = s_rec;
         const SortRec* sB = s_rec + la;
@@ -571,7 +596,7 @@ __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const SortRec* __r
           out[i] = takeA ? sA[ai++] : sB[bi++];
           cnt++;
         }
-        for (int i = 0; i < cnt; i++) dst[a0 + d0 + t0 + i] = out[i];
+        for (int i = 0; i < cnt; i++) dst[p.a0 + d0 + t0 + i] = out[i];
       }
       __syncthreads();
       pos = seg_hi;
@@ -821,10 +846,14 @@ void build_records(const Launch& L, const PkSet& pk, ColView seq, const uint32_t
   build_records_kernel<<<grid_for(cap), kThreads, 0, L.stream>>>(pk, seq, surv, d_m, rec);
   L.tick();
 }
+size_t merge_split_elems(uint32_t cap) { return size_t(cap) / kMergeTile + 2; }
 void merge_pass(const Launch& L, const SortRec* src, SortRec* dst, const uint32_t* run_start, int k, int level,
-                const uint32_t* d_m, uint32_t cap) {
+                const uint32_t* d_m, uint32_t cap, uint32_t* splits) {
   if (!cap) return;
-  merge_pass_kernel<<<grid_for(cap, kMergeTile, kSMs * 8), kThreads, 0, L.stream>>>(src, dst, run_start, k, level, d_m);
+  const uint32_t ntiles = (cap + kMergeTile - 1) / kMergeTile;
+  merge_partition_kernel<<<grid_for(ntiles), kThreads, 0, L.stream>>>(src, run_start, k, level, d_m, splits);
+  L.tick();
+  merge_pass_kernel<<<grid_for(cap, kMergeTile, kSMs * 8), kThreads, 0, L.stream>>>(src, dst, run_start, k, level, d_m, splits);
   L.tick();
 }
 void records_to_rows(const Launch& L, const SortRec* rec, const uint32_t* d_m, uint32_t cap, uint32_t* order) {

@@ -39,8 +39,11 @@ void survivor_run_starts(const Launch& L, const uint32_t* surv, const uint32_t* 
                          int k, uint32_t* run_start);
 void build_records(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* surv, const uint32_t* d_m,
                    uint32_t cap, SortRec* rec);
+// one pairwise pass = partition kernel (merge-path split per 1024-record tile) + merge kernel; splits holds
+// merge_split_elems(cap) uint32
 void merge_pass(const Launch& L, const SortRec* src, SortRec* dst, const uint32_t* run_start, int k, int level,
-                const uint32_t* d_m, uint32_t cap);
+                const uint32_t* d_m, uint32_t cap, uint32_t* splits);
+size_t merge_split_elems(uint32_t cap);
 void records_to_rows(const Launch& L, const SortRec* rec, const uint32_t* d_m, uint32_t cap, uint32_t* order);
 
 // S5/S6: PK-run boundaries, LastValue = keep the last row of each run ---------------------------------------------
