@@ -210,8 +210,43 @@ __device__ __forceinline__ int cmp3(uint64_t a, uint64_t b, uint32_t cls) {
   return a < b ? -1 : (a > b ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(1024) select_rgs_kernel(const __grid_constant__ FParams P, const FileDev* __restrict__ files, int nfiles,
-                                                          uint32_t total_rgs, int prune, RgSel* __restrict__ sel, uint32_t* d_nsel,
+// phase 1: one thread per row group, all blocks in parallel: keep flag (0/1) + rows
+__global__ void __launch_bounds__(256) prune_rgs_kernel(const __grid_constant__ FParams P, const FileDev* __restrict__ files, int nfiles,
+                                                        uint32_t total_rgs, int prune, uint32_t* __restrict__ keep_rows) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_rgs) return;
+  uint32_t f = 0;
+  while (f + 1 < uint32_t(nfiles) && idx >= files[f + 1].rg_base) f++;
+  const FileDev fd = files[f];
+  const uint32_t rg = idx - fd.rg_base;
+  const uint32_t rows = fd.rg_rows[rg];
+  uint32_t keep = rows > 0;
+  if (keep && prune) {
+    const RgCol* rc = fd.rgcol + size_t(rg) * fd.ncols;
+    for (int p = 0; p < P.npred && keep; p++) {
+      const RgCol c = rc[P.pcol[p]];
+      if (c.null_all) { keep = 0; break; }
+      if (!c.has_minmax) continue;
+      const uint64_t lit = P.plit[p];
+      const uint32_t cls = P.pcls[p];
+      bool ok = true;
+      switch (P.pop[p]) {
+        case OP_EQ: ok = cmp3(c.mn, lit, cls) <= 0 && cmp3(lit, c.mx, cls) <= 0; break;
+        case OP_NE: ok = cmp3(c.mn, lit, cls) != 0 || cmp3(lit, c.mx, cls) != 0; break;
+        case OP_LT: ok = cmp3(c.mn, lit, cls) < 0; break;
+        case OP_LE: ok = cmp3(c.mn, lit, cls) <= 0; break;
+        case OP_GT: ok = cmp3(c.mx, lit, cls) > 0; break;
+        default: ok = cmp3(c.mx, lit, cls) >= 0;
+      }
+      if (!ok) keep = 0;
+    }
+  }
+  keep_rows[idx] = keep ? rows : 0;             // rows > 0 doubles as the keep flag
+}
+
+// phase 2: one block compacts the kept row groups in stream order (coalesced reads of keep_rows)
+__global__ void __launch_bounds__(1024) select_rgs_kernel(const FileDev* __restrict__ files, int nfiles, uint32_t total_rgs,
+                                                          const uint32_t* __restrict__ keep_rows, RgSel* __restrict__ sel, uint32_t* d_nsel,
                                                           unsigned long long* counters) {
   __shared__ uint32_t s_w[33];
   __shared__ uint32_t s_carry;
@@ -221,34 +256,8 @@ __global__ void __launch_bounds__(1024) select_rgs_kernel(const __grid_constant_
   unsigned long long rows_sel = 0;
   for (uint32_t base = 0; base < total_rgs; base += 1024) {
     const uint32_t idx = base + threadIdx.x;
-    uint32_t keep = 0, f = 0, rg = 0, rows = 0;
-    if (idx < total_rgs) {
-      while (f + 1 < uint32_t(nfiles) && idx >= files[f + 1].rg_base) f++;
-      const FileDev fd = files[f];
-      rg = idx - fd.rg_base;
-      rows = fd.rg_rows[rg];
-      keep = rows > 0;
-      if (keep && prune) {
-        const RgCol* rc = fd.rgcol + size_t(rg) * fd.ncols;
-        for (int p = 0; p < P.npred && keep; p++) {
-          const RgCol c = rc[P.pcol[p]];
-          if (c.null_all) { keep = 0; break; }
-          if (!c.has_minmax) continue;
-          const uint64_t lit = P.plit[p];
-          const uint32_t cls = P.pcls[p];
-          bool ok = true;
-          switch (P.pop[p]) {
-            case OP_EQ: ok = cmp3(c.mn, lit, cls) <= 0 && cmp3(lit, c.mx, cls) <= 0; break;
-            case OP_NE: ok = cmp3(c.mn, lit, cls) != 0 || cmp3(lit, c.mx, cls) != 0; break;
-            case OP_LT: ok = cmp3(c.mn, lit, cls) < 0; break;
-            case OP_LE: ok = cmp3(c.mn, lit, cls) <= 0; break;
-            case OP_GT: ok = cmp3(c.mx, lit, cls) > 0; break;
-            default: ok = cmp3(c.mx, lit, cls) >= 0;
-          }
-          if (!ok) keep = 0;
-        }
-      }
-    }
+    const uint32_t rows = idx < total_rgs ? keep_rows[idx] : 0;
+    const uint32_t keep = rows > 0;
     uint32_t inc = keep;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
@@ -263,8 +272,10 @@ __global__ void __launch_bounds__(1024) select_rgs_kernel(const __grid_constant_
     }
     __syncthreads();
     if (keep) {
+      uint32_t f = 0;
+      while (f + 1 < uint32_t(nfiles) && idx >= files[f + 1].rg_base) f++;
       RgSel r;
-      r.sst = f; r.rg = rg; r.out_row = 0; r.num_rows = rows; r.scratch_off = 0;
+      r.sst = f; r.rg = idx - files[f].rg_base; r.out_row = 0; r.num_rows = rows; r.scratch_off = 0;
       sel[s_carry + s_w[w] + inc - 1] = r;
       rows_sel += rows;
     }
@@ -704,16 +715,15 @@ void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, co
 #undef HG_LAUNCH
 }
 
-// exclusive scan of per-item record counts (single block: each thread owns a contiguous chunk, one block-wide scan)
-__global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, const uint32_t* d_nsel, uint32_t split, uint32_t* total) {
-  const uint32_t n = *d_nsel * split;
+// exclusive scan of per-item record counts, two levels: every block scans 1024 items in place and publishes its sum;
+// the scatter kernel adds the (<= 1024-entry) prefix of the block sums on the fly.
+__global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, const uint32_t* d_nsel, uint32_t split, uint32_t* bsum) {
   __shared__ uint32_t s_w[33];
+  const uint32_t n = *d_nsel * split;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t per = (n + 1023) / 1024;
-  const uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
-  uint32_t sum = 0;
-  for (uint32_t i = lo; i < hi; i++) sum += cnt[i];
-  uint32_t inc = sum;
+  const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+  const uint32_t v = i < n ? cnt[i] : 0;
+  uint32_t inc = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
   if (lane == 31) s_w[w] = inc;
@@ -726,18 +736,28 @@ __global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, const ui
     if (lane == 31) s_w[32] = xi;
   }
   __syncthreads();
-  uint32_t run = s_w[w] + inc - sum;
-  for (uint32_t i = lo; i < hi; i++) { uint32_t c = cnt[i]; cnt[i] = run; run += c; }
-  if (threadIdx.x == 0) *total = s_w[32];
+  if (i < n) cnt[i] = s_w[w] + inc - v;
+  if (threadIdx.x == 0) bsum[blockIdx.x] = s_w[32];
 }
 
-__global__ void scatter_records_kernel(const FRec* __restrict__ rec, const unsigned int* nrec, const uint32_t* __restrict__ item_off,
-                                       uint32_t gwidth, AggOut out) {
+__global__ void __launch_bounds__(256) scatter_records_kernel(const FRec* __restrict__ rec, const unsigned int* nrec, const uint32_t* __restrict__ item_off,
+                                                              const uint32_t* __restrict__ bsum, uint32_t nblocks, uint32_t* d_total, uint32_t gwidth,
+                                                              AggOut out) {
+  __shared__ uint32_t s_boff[1024];
+  // exclusive prefix of the block sums (nblocks <= 1024), computed redundantly by every CTA
+  for (uint32_t b = threadIdx.x; b < 1024; b += blockDim.x) s_boff[b] = b < nblocks ? bsum[b] : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < nblocks; b++) { uint32_t c = s_boff[b]; s_boff[b] = run; run += c; }
+    if (blockIdx.x == 0) *d_total = run;
+  }
+  __syncthreads();
   uint32_t n = *nrec;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     FRec x = rec[r];
     if (x.item == 0xffffffffu) continue;          // unused tail of a warp's slot reservation
-    uint32_t pos = item_off[x.item] + x.local;
+    uint32_t pos = s_boff[x.item >> 10] + item_off[x.item] + x.local;
     switch (gwidth) {
       case 1: reinterpret_cast<uint8_t*>(out.gkey)[pos] = uint8_t(x.gkey); break;
       case 4: reinterpret_cast<uint32_t*>(out.gkey)[pos] = uint32_t(x.gkey); break;
@@ -882,7 +902,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 8;
   while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * uint64_t(items_per_warp)) split *= 2;
   const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
-  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj;
+  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj, d_keep, d_bsum;
   CU_TRY(d_work.alloc(64, s));
   CU_TRY(cudaMemsetAsync(d_work.p, 0, 64, s));
   CU_TRY(d_counters.alloc(64, s));
@@ -894,6 +914,9 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   CU_TRY(d_item.alloc(size_t(nitems + 1) * sizeof(uint32_t) + 64, s));
   CU_TRY(d_adj.alloc(size_t(nitems + 2) * sizeof(uint64_t), s));
   CU_TRY(d_sel.alloc(size_t(total_rgs + 1) * sizeof(RgSel), s));
+  CU_TRY(d_keep.alloc(size_t(total_rgs + 1) * sizeof(uint32_t), s));
+  CU_TRY(d_bsum.alloc(1024 * sizeof(uint32_t), s));
+  if ((uint64_t(nitems) + 1023) / 1024 > 1024) return NOT_APPLICABLE;   // two-level item scan covers 1 M work items
   out->gtype = has_group ? schema->types[0] : uint32_t(T_U64);
   out->gwidth = has_group ? type_width_host(out->gtype) : 8;
   CU_TRY(out->gkey.alloc(size_t(bound) * 8 + 16, s));
@@ -989,8 +1012,11 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
     static int variant = -1;
     if (variant < 0) { const char* v = getenv("HORAE_FUSED_VARIANT"); variant = v ? atoi(v) : 0; }
-    select_rgs_kernel<<<1, 1024, 0, s>>>(P, d_files.as<FileDev>(), int(files.size()), total_rgs, (e->flags & HG_FLAG_NO_PRUNING) ? 0 : 1,
-                                         d_sel.as<RgSel>(), d_work.as<uint32_t>() + 3, d_counters.as<unsigned long long>());
+    prune_rgs_kernel<<<(total_rgs + 255) / 256, 256, 0, s>>>(P, d_files.as<FileDev>(), int(files.size()), total_rgs,
+                                                             (e->flags & HG_FLAG_NO_PRUNING) ? 0 : 1, d_keep.as<uint32_t>());
+    L.tick();
+    select_rgs_kernel<<<1, 1024, 0, s>>>(d_files.as<FileDev>(), int(files.size()), total_rgs, d_keep.as<uint32_t>(), d_sel.as<RgSel>(),
+                                         d_work.as<uint32_t>() + 3, d_counters.as<unsigned long long>());
     L.tick();
     {
       const uint32_t nb = (nitems + 1 + kBoundsPerWarp - 1) / kBoundsPerWarp;      // warps
@@ -1012,9 +1038,11 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       global_count_kernel<<<1, 1, 0, s>>>(d_counters.as<unsigned long long>(), ao);
       L.tick();
     } else {
-      item_scan_kernel<<<1, 1024, 0, s>>>(d_item.as<uint32_t>(), d_work.as<uint32_t>() + 3, split, d_work.as<uint32_t>() + 2);
+      const uint32_t sblocks = (nitems + 1023) / 1024;
+      item_scan_kernel<<<sblocks, 1024, 0, s>>>(d_item.as<uint32_t>(), d_work.as<uint32_t>() + 3, split, d_bsum.as<uint32_t>());
       L.tick();
-      scatter_records_kernel<<<148 * 4, 256, 0, s>>>(d_rec.as<FRec>(), d_work.as<unsigned int>() + 1, d_item.as<uint32_t>(), out->gwidth, ao);
+      scatter_records_kernel<<<148 * 4, 256, 0, s>>>(d_rec.as<FRec>(), d_work.as<unsigned int>() + 1, d_item.as<uint32_t>(), d_bsum.as<uint32_t>(),
+                                                     sblocks, d_work.as<uint32_t>() + 2, out->gwidth, ao);
       L.tick();
     }
     auto t3 = now();
