@@ -45,7 +45,8 @@ def _gen_file(args):
 def gen_ssts(rank, codec, nfiles, workers):
     base = rank * FILES_PER_GPU * SERIES_PER_FILE
     jobs = [(base + f * SERIES_PER_FILE, 1_000_000 + rank * 1000 + f, codec) for f in range(nfiles)]
-    with ProcessPoolExecutor(max_workers=workers) as ex:
+    import multiprocessing
+    with ProcessPoolExecutor(max_workers=workers, mp_context=multiprocessing.get_context("spawn")) as ex:   # spawn: safe after CUDA init
         return list(ex.map(_gen_file, jobs))
 
 
