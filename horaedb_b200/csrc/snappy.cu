@@ -205,7 +205,47 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       if (__any_sync(0xffffffffu, bad) || o + T > ulen) { if (lane == 0) atomicExch(err, 103); return; }
 
       if (T <= uint32_t(m) * 16) {
-        // ---------------- tiny elements: byte-level source pointers + pointer jumping
+        // ---------------- tiny elements.
+        // Fast path: every copy either reads bytes older than the batch or reproduces exactly one earlier element of
+        // the batch (same start, same length) — the shape of fixed-width numeric columns.  Then the dependency graph is
+        // over ELEMENTS: parent links are collapsed with five register shuffles and each lane copies its own bytes.
+        bool elem_done = false;
+        {
+          uint8_t* tbl = reinterpret_cast<uint8_t*>(sm.ptr);            // start offset -> lane (no init: verified below)
+          if (lane < m) tbl[doff] = uint8_t(lane);
+          __syncwarp();
+          int parent = lane;
+          bool fail = false;
+          uint32_t dkind = 0, dpos = 0;                                  // 0: bytes at win[dpos..], 1: output bytes at abs dpos..
+          if (lane < m) {
+            if (is_lit) { dpos = q + 1; }
+            else {
+              const int32_t s0 = int32_t(doff) - int32_t(off);
+              if (s0 < 0) { if (s0 + int32_t(len) <= 0) { dkind = 1; dpos = o + doff - off; } else fail = true; }
+              else parent = tbl[s0] & 31;
+            }
+          }
+          const uint32_t pd = __shfl_sync(0xffffffffu, doff, parent), pl = __shfl_sync(0xffffffffu, len, parent);
+          if (lane < m && parent != lane && (parent >= lane || pd + off != doff || pl != len)) fail = true;
+          if (!__any_sync(0xffffffffu, fail)) {
+#pragma unroll
+            for (int it = 0; it < 5; it++) parent = __shfl_sync(0xffffffffu, parent, parent);
+            const uint32_t rk = __shfl_sync(0xffffffffu, dkind, parent), rp = __shfl_sync(0xffffffffu, dpos, parent);
+            if (lane < m) {
+              for (uint32_t i = 0; i < len; i++) {
+                uint8_t v;
+                if (rk == 0) { const uint32_t wp = rp + i; v = wp < uint32_t(kWin) ? sm.win[wp] : __ldg(src + pos + wp); }
+                else v = old_byte(sm, dst, o, rp + i);
+                sm.ring[(o + doff + i) & (kRing - 1)] = v;
+                dst[o + doff + i] = v;
+              }
+            }
+            elem_done = true;
+          }
+          __syncwarp();
+        }
+        if (!elem_done) {
+        // general case: byte-level source pointers + pointer jumping
         if (lane < m) {
           if (is_lit) {
             const uint8_t* ls = src + pos + q + 1;
@@ -251,6 +291,7 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
           }
         }
         for (uint32_t r = lane; r < T; r += 32) dst[o + r] = sm.ring[(o + r) & (kRing - 1)];
+        }
       } else {
         // ---------------- long elements.  Adjacent copies with the same offset continue one periodic pattern
         // (out[x] = out[x - off] over the union), so they are merged into a single run and spread over the warp.
