@@ -215,18 +215,18 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
           if (lane < m) tbl[doff] = uint8_t(lane);
           __syncwarp();
           int parent = lane;
-          bool fail = false;
+          bool fail = false, need_parent = false;
           uint32_t dkind = 0, dpos = 0;                                  // 0: bytes at win[dpos..], 1: output bytes at abs dpos..
           if (lane < m) {
             if (is_lit) { dpos = q + 1; }
             else {
               const int32_t s0 = int32_t(doff) - int32_t(off);
               if (s0 < 0) { if (s0 + int32_t(len) <= 0) { dkind = 1; dpos = o + doff - off; } else fail = true; }
-              else parent = tbl[s0] & 31;
+              else { parent = tbl[s0] & 31; need_parent = true; }
             }
           }
           const uint32_t pd = __shfl_sync(0xffffffffu, doff, parent), pl = __shfl_sync(0xffffffffu, len, parent);
-          if (lane < m && parent != lane && (parent >= lane || pd + off != doff || pl != len)) fail = true;
+          if (need_parent && (parent >= lane || pd + off != doff || pl != len)) fail = true;   // (a stale table entry may even name this lane)
           if (!__any_sync(0xffffffffu, fail)) {
 #pragma unroll
             for (int it = 0; it < 5; it++) parent = __shfl_sync(0xffffffffu, parent, parent);
