@@ -46,7 +46,9 @@ def gen_ssts(rank, codec, nfiles, workers):
     base = rank * FILES_PER_GPU * SERIES_PER_FILE
     jobs = [(base + f * SERIES_PER_FILE, 1_000_000 + rank * 1000 + f, codec) for f in range(nfiles)]
     import multiprocessing
-    with ProcessPoolExecutor(max_workers=workers, mp_context=multiprocessing.get_context("spawn")) as ex:   # spawn: safe after CUDA init
+    cuda_live = "torch" in sys.modules and sys.modules["torch"].cuda.is_initialized()
+    ctx = multiprocessing.get_context("spawn" if cuda_live else "fork")   # never fork a process that already owns a CUDA context
+    with ProcessPoolExecutor(max_workers=workers, mp_context=ctx) as ex:
         return list(ex.map(_gen_file, jobs))
 
 
