@@ -314,11 +314,17 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
             const uint8_t* ls = src + pos + eq + 1;
             for (uint32_t i = lane; i < rlen; i += 32) sm.ring[(o + s0 + i) & (kRing - 1)] = __ldg(ls + i);
           } else {
-            // every source byte precedes the run: x - off taken modulo the pattern length
+            // every source byte precedes the run: x - off taken modulo the pattern length (kept incrementally: no
+            // integer division per byte)
             const uint32_t start = o + s0;
+            const uint32_t stride = 32u % eoff;
+            uint32_t r = uint32_t(lane) % eoff;
+            const bool all_ring = eoff <= uint32_t(kHist);                 // the whole pattern is inside the ring window
             for (uint32_t i = lane; i < rlen; i += 32) {
-              const uint32_t x = start - eoff + (i % eoff);
-              sm.ring[(start + i) & (kRing - 1)] = (start - x <= uint32_t(kHist) + s0) ? sm.ring[x & (kRing - 1)] : ldcg_u8(dst + x);
+              const uint32_t x = start - eoff + r;
+              sm.ring[(start + i) & (kRing - 1)] = (all_ring || start - x <= uint32_t(kHist) + s0) ? sm.ring[x & (kRing - 1)] : ldcg_u8(dst + x);
+              r += stride;
+              if (r >= eoff) r -= eoff;
             }
           }
           __syncwarp();

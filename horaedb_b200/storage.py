@@ -107,10 +107,16 @@ class ObjectBasedStorage:
         self.schema_ = StorageSchema.try_new(arrow_schema, num_primary_keys, self.config.update_mode)
         self.manifest = Manifest()
         self.sst_path_gen = SstPathGenerator(path)
-        self.engine = engine or Engine()
+        self._engine = engine            # created on first use: the write path never touches the GPU
         self.handle = SchemaHandle(self.schema_.arrow_schema, num_primary_keys, self.config.update_mode)
         self.inused_memory = 0
         os.makedirs(os.path.join(path, "data"), exist_ok=True)
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine()
+        return self._engine
 
     def schema(self) -> pa.Schema:
         return self.schema_.arrow_schema
