@@ -25,6 +25,7 @@ namespace {
 constexpr int kWin = 256;          // compressed-stream window (bytes)
 constexpr int kRing = 4096;        // ring buffer of the most recent output (power of two)
 constexpr int kOut = 2048;         // max output of one batch: 32 elements x 64 bytes
+constexpr int kTiny = 512;         // max output of a tiny-element batch (byte-level resolve)
 constexpr int kHist = kRing - kOut;  // bytes before the current batch that are guaranteed to still be in the ring
 constexpr int kLevels = 6;         // J1, J2, J4, J8, J16, J32
 constexpr uint16_t kExit = 0xffff;
@@ -35,7 +36,7 @@ struct alignas(16) WarpSmem {
   uint8_t win[kWin + 16];
   uint16_t J[kLevels][kWin];
   uint8_t ring[kRing];             // output byte at absolute position x lives at ring[x & (kRing-1)]
-  uint16_t ptr[kOut];              // per batch byte: batch-relative index of its source byte, or kDone
+  uint16_t ptr[kTiny];             // tiny-element batches only (T <= 32*16): batch-relative source index, or kDone
 };
 
 __host__ __device__ __forceinline__ uint64_t page_scratch2(uint32_t uncomp) { return (uint64_t(uncomp) + 15u) / 16u * 16u + 32u; }
@@ -348,7 +349,7 @@ __device__ __forceinline__ uint64_t chunk_scratch_off2(const RgSel& rs, const Ch
   return off;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) snappy_chunks_v2_kernel(const SstDev* __restrict__ ssts, const RgSel* __restrict__ sel,
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_chunks_v2_kernel(const SstDev* __restrict__ ssts, const RgSel* __restrict__ sel,
                                                                              const ColSel* __restrict__ cols, int ncolsel, uint32_t nchunks,
                                                                              uint8_t* __restrict__ scratch, unsigned int* ticket, int* err) {
   __shared__ WarpSmem s_w[kWarpsPerCta];
@@ -390,7 +391,7 @@ void snappy_chunks_v2(const Launch& L, const SstDev* ssts, const RgSel* sel, uin
   if (!nsel || !ncolsel) return;
   const uint32_t nchunks = nsel * uint32_t(ncolsel);
   uint32_t ctas = (nchunks + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (ctas > 148u * 5) ctas = 148u * 5;
+  if (ctas > 148u * 6) ctas = 148u * 6;
   snappy_chunks_v2_kernel<<<ctas, kWarpsPerCta * 32, 0, L.stream>>>(ssts, sel, cols, ncolsel, nchunks, scratch, ticket, err);
   L.tick();
 }
