@@ -18,6 +18,7 @@ HG_TYPES = {pa.uint8(): 0, pa.int8(): 1, pa.uint16(): 2, pa.int16(): 3, pa.uint3
 HG_OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
 HG_FLAG_NO_PRUNING = 1
 HG_FLAG_NO_FUSED = 2
+HG_FLAG_NO_LATE_MATERIALIZATION = 4
 
 STATUS = {0: "OK", 1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "FORMAT", 5: "OOM", 6: "NOT_FOUND", 7: "INTERNAL"}
 
@@ -56,7 +57,8 @@ class HgAggSpec(C.Structure):
 class HgScanStats(C.Structure):
     _fields_ = [("rows_in_files", C.c_uint64), ("rows_decoded", C.c_uint64), ("rows_filtered", C.c_uint64),
                 ("rows_out", C.c_uint64), ("groups_out", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
-                ("kernel_launches", C.c_uint32), ("path", C.c_uint32), ("gpu_ms", C.c_float), ("kernel_ms", C.c_float), ("merge_ms", C.c_float), ("_pad2", C.c_float)]
+                ("kernel_launches", C.c_uint32), ("path", C.c_uint32), ("gpu_ms", C.c_float), ("kernel_ms", C.c_float), ("merge_ms", C.c_float), ("_pad2", C.c_float),
+                ("rows_materialized", C.c_uint64)]
 
 
 class HgAggDevice(C.Structure):
@@ -69,7 +71,7 @@ class ArrowArrayStream(C.Structure):
                 ("release", C.c_void_p), ("private_data", C.c_void_p)]
 
 
-EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_sst_load",
+EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_engine_set_flags", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
            "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats"]
 
@@ -87,6 +89,7 @@ def lib():
         L.hg_last_error.restype = C.c_char_p
         L.hg_engine_stream.restype = C.c_void_p
         L.hg_engine_stream.argtypes = [C.c_void_p]
+        L.hg_engine_set_flags.argtypes = [C.c_void_p, C.c_uint32]
         L.hg_engine_destroy.argtypes = [C.c_void_p]
         L.hg_engine_destroy.restype = None
         _lib = L
@@ -170,6 +173,9 @@ class Engine:
     @property
     def stream_ptr(self) -> int:
         return self._L.hg_engine_stream(self._h)
+
+    def set_flags(self, flags: int) -> None:
+        _check(self._L.hg_engine_set_flags(self._h, flags))
 
     # -- residency
     def _descs(self, ssts: Sequence[SstInput]):

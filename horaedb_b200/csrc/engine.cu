@@ -959,6 +959,12 @@ void hg_engine_destroy(hg_engine* e) {
 }
 
 void* hg_engine_stream(hg_engine* e) { return e ? reinterpret_cast<void*>(e->stream) : nullptr; }
+int hg_engine_set_flags(hg_engine* e, uint32_t flags) {
+  if (!e) return set_error(HG_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> g(e->mu);
+  e->flags = flags;
+  return HG_OK;
+}
 
 int hg_sst_load(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* sst) {
   if (!e || !schema || !sst) return set_error(HG_ERR_INVALID, "null argument");
@@ -1127,6 +1133,7 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->stats.rows_in_files = st.plan.rows_in_files;
   e->stats.rows_decoded = st.plan.rows_decoded;
+  e->stats.rows_materialized = st.plan.rows_decoded;
   e->stats.rows_filtered = M;
   e->stats.rows_out = R;
   e->stats.bytes_d2h = d2h;
@@ -1208,6 +1215,7 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
   if (G > 0) k::reduce_groups(L, spec, st.out_rows.as<uint32_t>(), st.d_r, seg.as<uint32_t>(), st.d_g, G, ao);
   e->stats.rows_in_files = st.plan.rows_in_files;
   e->stats.rows_decoded = st.plan.rows_decoded;
+  e->stats.rows_materialized = st.plan.rows_decoded;
   e->stats.rows_filtered = hc[0];
   e->stats.rows_out = hc[1];
   e->stats.groups_out = G;

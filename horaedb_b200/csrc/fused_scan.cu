@@ -41,6 +41,7 @@ struct FParams {
   const SstDev* ssts;
   const RgSel* sel;             // selected row groups in stream order, built on the device by select_rgs_kernel
   const uint32_t* d_nsel;       // their count
+  const uint8_t* const* bases;  // [selected row group][MAXC]: start of the PLAIN values of every slot (slot_bases_kernel)
   uint32_t split;               // sub-ranges (work items) per row group
   uint32_t pcol[MAX_PREDS], pcls[MAX_PREDS];   // schema column / comparison class of every predicate (statistics pruning)
   int nslots;
@@ -63,7 +64,8 @@ struct FParams {
   uint32_t rec_cap;
   uint32_t* item_cnt;
   unsigned int* work;           // [0] item ticket, [1] record slots
-  unsigned long long* counters; // [0] rows passing the predicate, [1] rows kept after dedup
+  unsigned long long* counters; // [0] rows passing the predicate, [1] rows kept after dedup, [2] rows of selected row groups,
+                                // [3] rows of blocks whose non-gate columns were loaded
   int* err;
 };
 
@@ -109,8 +111,9 @@ __device__ __forceinline__ bool pred_ok(uint64_t v, uint64_t lit, uint32_t cls, 
   }
 }
 
-// Start of the PLAIN values of column slot `s` in selected row group `si` (pointer chase through the resident tables).
-__device__ __forceinline__ const uint8_t* slot_base(const FParams& P, uint32_t si, int s) {
+// Start of the PLAIN values of column slot `s` in selected row group `si`: a pointer chase through the resident tables
+// (row group -> file -> chunk -> page -> def-level length), done once per (row group, slot) by slot_bases_kernel.
+__device__ __forceinline__ const uint8_t* slot_base_chase(const FParams& P, uint32_t si, int s) {
   RgSel rs = P.sel[si];
   SstDev sst = P.ssts[rs.sst];
   ChunkDev cd = sst.chunks[size_t(rs.rg) * sst.ncols + P.col[s]];
@@ -119,6 +122,7 @@ __device__ __forceinline__ const uint8_t* slot_base(const FParams& P, uint32_t s
   if (cd.optional) body += 4 + ld32u(body);      // [u32 len][RLE def levels] — all-valid pages only (planner)
   return body;
 }
+__device__ __forceinline__ const uint8_t* slot_base(const FParams& P, uint32_t si, int s) { return P.bases[size_t(si) * MAXC + s]; }
 // cold: one widened value addressed by (row group, slot, row)
 __device__ __noinline__ uint64_t fetch_val(const FParams& P, uint32_t si, int s, uint32_t row) {
   return load_kind(slot_base(P, si, s), P.kind[s], row);
@@ -208,6 +212,14 @@ __device__ __forceinline__ int cmp3(uint64_t a, uint64_t b, uint32_t cls) {
   }
   if (cls == C_SIGNED) { int64_t x = int64_t(a), y = int64_t(b); return x < y ? -1 : (x > y ? 1 : 0); }
   return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(256) slot_bases_kernel(const __grid_constant__ FParams P, const uint8_t** __restrict__ bases) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t si = idx / MAXC;
+  const int s = int(idx % MAXC);
+  if (si >= *P.d_nsel || s >= P.nslots) return;
+  bases[idx] = slot_base_chase(P, si, s);
 }
 
 // phase 1: one thread per row group, all blocks in parallel: keep flag (0/1) + rows
@@ -506,7 +518,7 @@ struct Hot {
 //   PARTIAL  the block may extend past `lim` (end of the item or of the row group): indices clamped, lanes masked
 template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool PARTIAL, int kPF>
 __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH>& H, const uint8_t* vq, uint32_t vs, Acc& acc, uint32_t& local,
-                                                  uint32_t& n_alive, uint32_t& n_keep, uint32_t item, uint32_t csi, uint32_t row,
+                                                  uint32_t& n_alive, uint32_t& n_keep, uint32_t& n_full, uint32_t item, uint32_t csi, uint32_t row,
                                                   uint32_t lim, uint32_t nrows, double* s_vals, uint32_t* slots, int lane) {
   uint64_t hv[kU][NH];
   uint64_t vv[kU];
@@ -524,6 +536,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
         asm volatile("prefetch.global.L2 [%0];" ::"l"(H.q[h] + size_t(r) * (w4 ? 4 : 8)));
     }
   }
+  n_full += PARTIAL ? (lim - row < 32u * kU ? lim - row : 32u * kU) : 32u * kU;
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     uint32_t i = row + u * 32 + lane;
@@ -607,8 +620,64 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
   return kept_in_block;
 }
 
+// Late materialisation: the LAST hot column (the planner puts the narrowest predicate column there) is the gate.  One
+// sweep tests the gate values of kGS consecutive slices (1-2 KB per warp in flight) and returns one bit per 32*kU-row
+// block that holds a passing row; only those blocks run the full block code (which reads the other columns).
+//   PARTIAL  the sweep may extend past `lim`: indices clamped to the row group, rows >= lim masked
+template <int kU, int NH, int X, int kGS, int kPF, bool PARTIAL>
+__device__ __forceinline__ uint32_t gate_sweep(const Hot<NH>& H, uint32_t row, uint32_t lim, uint32_t nrows, int lane) {
+  constexpr int G = NH - 1;
+  constexpr bool w4 = G >= 2 && ((X >> (G - 2)) & 1);
+  if (kPF > 0 && !PARTIAL) {                                // next-but-one sweep's gate bytes into L2, one line per lane
+    constexpr uint32_t per_line = w4 ? 32u : 16u;
+    const uint32_t r = row + 2u * 32u * kGS + uint32_t(lane) * per_line;
+    if (uint32_t(lane) < (32u * kGS) / per_line + 1 && r < nrows)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(H.q[G] + size_t(r) * (w4 ? 4 : 8)));
+  }
+  const uint32_t last = nrows - 1;
+  uint64_t gv[kGS];
+#pragma unroll
+  for (int u = 0; u < kGS; u++) {
+    uint32_t i = row + u * 32 + lane;
+    if (PARTIAL) i = i < last ? i : last;
+    gv[u] = w4 ? uint64_t(ld4(H.q[G], H.sh[G], i)) : ld8(H.q[G], H.sh[G], i);
+  }
+  uint32_t bm = 0;
+#pragma unroll
+  for (int u = 0; u < kGS; u++) {
+    bool pass = w4 ? ((uint32_t(gv[u]) ^ uint32_t(H.flip[G])) - uint32_t(H.lo[G]) <= uint32_t(H.span[G]))
+                   : ((gv[u] ^ H.flip[G]) - H.lo[G] <= H.span[G]);
+    if (PARTIAL) pass = pass && (row + u * 32 + lane < lim);
+    if (__ballot_sync(0xffffffffu, pass)) bm |= 1u << (u / kU);
+  }
+  return bm;
+}
+
+// After a sweep: start pulling the other columns (and the value column) of the blocks that will be materialised into L2,
+// all at once, so that the block code that follows finds them there instead of paying one DRAM round trip per block.
+template <int kU, int NH, int X, int kGS>
+__device__ __forceinline__ void prefetch_blocks(const Hot<NH>& H, const uint8_t* vq, bool has_val, bool v8, uint32_t bm, uint32_t row,
+                                                uint32_t nrows, int lane) {
+#pragma unroll
+  for (int h = 0; h < NH - 1; h++) {
+    const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
+    const uint32_t off = uint32_t(lane) * (w4 ? 32u : 16u);          // first row of this lane's 128-byte line
+    uint32_t blk = off / (32u * kU);
+    blk = blk < uint32_t(kGS / kU) ? blk : uint32_t(kGS / kU) - 1;   // (one extra line: the values are not line aligned)
+    if (off <= 32u * kGS && ((bm >> blk) & 1u) && row + off < nrows)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(H.q[h] + size_t(row + off) * (w4 ? 4 : 8)));
+  }
+  if (has_val) {
+    const uint32_t off = uint32_t(lane) * (v8 ? 16u : 32u);
+    uint32_t blk = off / (32u * kU);
+    blk = blk < uint32_t(kGS / kU) ? blk : uint32_t(kGS / kU) - 1;
+    if (off <= 32u * kGS && ((bm >> blk) & 1u) && row + off < nrows)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(vq + size_t(row + off) * (v8 ? 8 : 4)));
+  }
+}
+
 // kU = slices whose loads are issued together; NH = hot columns (pk0, pk1, + predicate columns) loaded for every row
-template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS, int kPF>
+template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS, int kPF, bool GATED>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P,
                                                                                     const uint64_t* __restrict__ adj) {
   __shared__ double s_vals_all[kWarpsPerCta][32];
@@ -620,6 +689,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
   __syncwarp();
   const uint32_t nsel = *P.d_nsel;
   const uint32_t nitems = nsel * P.split;
+  constexpr int kGS = ((NH - 1) >= 2 && ((X >> (NH - 3)) & 1)) ? 16 : 8;   // slices per gate sweep: 16 x 4-byte or 8 x 8-byte values per lane
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   Hot<NH> H;
 #pragma unroll
@@ -658,7 +728,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
     const uint64_t beg = adj[item], end = adj[item + 1];
     uint32_t csi = uint32_t(beg >> 32), row = uint32_t(beg);
     const uint32_t esi = uint32_t(end >> 32), erow = uint32_t(end);
-    uint32_t local = 0, n_alive = 0, n_keep = 0;
+    uint32_t local = 0, n_alive = 0, n_keep = 0, n_full = 0;
     if (beg < end) {
       Acc acc;
       acc.open = false; acc.g = 0; acc.bstart = 0; acc.blo = 0; acc.bhi = 0; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
@@ -676,11 +746,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
         const uint32_t lim = csi == esi ? erow : nrows;
         if (row >= lim) break;
         uint32_t kept;
-        if (row + 32u * kU < lim) {       // (< lim: the halo row is inside the row group as well)
-          kept = dense ? process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, slots, lane)
-                       : process_block<kU, NH, X, HAS_TS, false, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, slots, lane);
+        if constexpr (GATED) {
+          if (!dense) {
+            uint32_t bm = row + 32u * kGS < lim ? gate_sweep<kU, NH, X, kGS, kPF, false>(H, row, lim, nrows, lane)
+                                                : gate_sweep<kU, NH, X, kGS, kPF, true>(H, row, lim, nrows, lane);
+            kept = 0;
+            if (bm) prefetch_blocks<kU, NH, X, kGS>(H, vq, P.value_slot >= 0, P.value_slot >= 0 && P.kind[P.value_slot] == K_RAW64, bm, row, nrows, lane);
+            while (bm) {
+              const uint32_t r = row + (__ffs(bm) - 1) * 32u * kU;
+              bm &= bm - 1;
+              if (r + 32u * kU < lim)
+                kept += process_block<kU, NH, X, HAS_TS, false, false, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, r, lim, nrows, s_vals, slots, lane);
+              else
+                kept += process_block<kU, NH, X, HAS_TS, false, true, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, r, lim, nrows, s_vals, slots, lane);
+            }
+            const uint32_t swept = lim - row < 32u * kGS ? lim - row : 32u * kGS;
+            dense = P.value_slot >= 0 && kept >= swept / 4;
+            row += 32u * kGS;
+            continue;
+          }
+          // dense stretch (>= 1/4 of the rows survive): everything is needed anyway, load block by block
+          if (row + 32u * kU < lim)
+            kept = process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
+          else
+            kept = process_block<kU, NH, X, HAS_TS, false, true, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
         } else {
-          kept = process_block<kU, NH, X, HAS_TS, false, true, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, item, csi, row, lim, nrows, s_vals, slots, lane);
+          if (row + 32u * kU < lim) {       // (< lim: the halo row is inside the row group as well)
+            kept = dense ? process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane)
+                         : process_block<kU, NH, X, HAS_TS, false, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
+          } else {
+            kept = process_block<kU, NH, X, HAS_TS, false, true, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
+          }
         }
         dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
         row += 32 * kU;
@@ -691,16 +787,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
       P.item_cnt[item] = local;
       if (n_alive) atomicAdd(&P.counters[0], (unsigned long long)n_alive);
       if (n_keep) atomicAdd(&P.counters[1], (unsigned long long)n_keep);
+      if (n_full) atomicAdd(&P.counters[3], (unsigned long long)n_full);
     }
   }
 }
 
 template <int kU, int kMinBlocks, int kPF>
-void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, const FParams& P, const uint64_t* adj) {
+void launch_fused(int nhot, int xmask, bool has_ts, bool gated, int ctas, cudaStream_t s, const FParams& P, const uint64_t* adj) {
+#define HG_LAUNCH2(NH, XM, TS)                                                                                           \
+  do {                                                                                                                   \
+    if (gated) fused_scan_kernel<kU, kMinBlocks, NH, XM, TS, kPF, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);      \
+    else fused_scan_kernel<kU, kMinBlocks, NH, XM, TS, kPF, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);           \
+  } while (0)
 #define HG_LAUNCH(NH, XM)                                                                                                \
   do {                                                                                                                   \
-    if (has_ts) fused_scan_kernel<kU, kMinBlocks, NH, XM, true, kPF><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);              \
-    else fused_scan_kernel<kU, kMinBlocks, NH, XM, false, kPF><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);                    \
+    if (has_ts) HG_LAUNCH2(NH, XM, true);                                                                                \
+    else HG_LAUNCH2(NH, XM, false);                                                                                      \
   } while (0)
   if (nhot == 2) HG_LAUNCH(2, 0);
   else if (nhot == 3) { if (xmask & 1) HG_LAUNCH(3, 1); else HG_LAUNCH(3, 0); }
@@ -713,6 +815,7 @@ void launch_fused(int nhot, int xmask, bool has_ts, int ctas, cudaStream_t s, co
     }
   }
 #undef HG_LAUNCH
+#undef HG_LAUNCH2
 }
 
 // exclusive scan of per-item record counts, two levels: every block scans 1024 items in place and publishes its sum;
@@ -837,6 +940,12 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     }
   }
   for (int h = 0; h < kHot; h++) if (klo[h] > khi[h]) empty_interval = true;
+  // the LAST hot column is the gate of the late-materialising kernel: put the narrower of two extra columns there
+  if (nhot == 4 && type_width_host(schema->types[slots[hot_slot[2]]]) < type_width_host(schema->types[slots[hot_slot[3]]])) {
+    std::swap(hot_slot[2], hot_slot[3]);
+    std::swap(klo[2], klo[3]);
+    std::swap(khi[2], khi[3]);
+  }
 
   static const bool trace = getenv("HORAE_TRACE") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -902,7 +1011,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 8;
   while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * uint64_t(items_per_warp)) split *= 2;
   const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
-  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj, d_keep, d_bsum;
+  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj, d_keep, d_bsum, d_bases;
   CU_TRY(d_work.alloc(64, s));
   CU_TRY(cudaMemsetAsync(d_work.p, 0, 64, s));
   CU_TRY(d_counters.alloc(64, s));
@@ -916,6 +1025,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   CU_TRY(d_sel.alloc(size_t(total_rgs + 1) * sizeof(RgSel), s));
   CU_TRY(d_keep.alloc(size_t(total_rgs + 1) * sizeof(uint32_t), s));
   CU_TRY(d_bsum.alloc(1024 * sizeof(uint32_t), s));
+  CU_TRY(d_bases.alloc(size_t(total_rgs + 1) * MAXC * sizeof(uint8_t*), s));
   if ((uint64_t(nitems) + 1023) / 1024 > 1024) return NOT_APPLICABLE;   // two-level item scan covers 1 M work items
   out->gtype = has_group ? schema->types[0] : uint32_t(T_U64);
   out->gwidth = has_group ? type_width_host(out->gtype) : 8;
@@ -928,7 +1038,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   AggOut ao{out->gkey.p, out->bucket.as<int64_t>(), out->count.as<uint64_t>(), out->sum.as<double>(), out->mn.as<double>(), out->mx.as<double>()};
 
   auto t2 = now();
-  unsigned long long hc[3] = {0, 0, 0};
+  unsigned long long hc[4] = {0, 0, 0, 0};
   int herr = 0;
   uint32_t hw[2] = {0, 0};
   if (total_rgs > 0) {
@@ -953,6 +1063,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.ssts = d_ssts.as<SstDev>();
     P.sel = d_sel.as<RgSel>();
     P.d_nsel = d_work.as<uint32_t>() + 3;
+    P.bases = d_bases.as<const uint8_t*>();
     P.split = split;
     P.nslots = int(slots.size());
     for (size_t i = 0; i < slots.size(); i++) {
@@ -1009,14 +1120,17 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.counters = d_counters.as<unsigned long long>();
     P.err = d_err.as<int>();
 
-    int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("HORAE_FUSED_VARIANT"); variant = v ? atoi(v) : 0; }
+    int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 12));
+    // late materialisation needs a real interval test on the last hot column (the gate)
+    static const bool env_nogate = getenv("HORAE_NO_GATE") != nullptr;
+    const bool gated = !env_nogate && !(e->flags & HG_FLAG_NO_LATE_MATERIALIZATION) && P.hot_haspred[nhot - 1] != 0;
     prune_rgs_kernel<<<(total_rgs + 255) / 256, 256, 0, s>>>(P, d_files.as<FileDev>(), int(files.size()), total_rgs,
                                                              (e->flags & HG_FLAG_NO_PRUNING) ? 0 : 1, d_keep.as<uint32_t>());
     L.tick();
     select_rgs_kernel<<<1, 1024, 0, s>>>(d_files.as<FileDev>(), int(files.size()), total_rgs, d_keep.as<uint32_t>(), d_sel.as<RgSel>(),
                                          d_work.as<uint32_t>() + 3, d_counters.as<unsigned long long>());
+    L.tick();
+    slot_bases_kernel<<<(total_rgs * MAXC + 255) / 256, 256, 0, s>>>(P, d_bases.as<const uint8_t*>());
     L.tick();
     {
       const uint32_t nb = (nitems + 1 + kBoundsPerWarp - 1) / kBoundsPerWarp;      // warps
@@ -1026,12 +1140,12 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       L.tick();
     }
     CU_TRY(cudaEventRecord(e->evk0, s));
-    switch (variant) {            // developer override (HORAE_FUSED_VARIANT); default: 2 slices/block, 4 CTAs/SM, L2 prefetch 2 blocks ahead
-      case 1: launch_fused<2, 4, 0>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      case 2: launch_fused<2, 4, 4>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      case 3: launch_fused<2, 4, 3>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>()); break;
-      default: launch_fused<2, 4, 2>(nhot, xmask, has_ts, ctas, s, P, d_adj.as<uint64_t>());
-    }
+    // 2 slices per block, 4 CTAs/SM, L2 prefetch 2 blocks ahead (measured best of {0,2,3,4} blocks: profiles/README.md)
+    static const int mb = getenv("HORAE_FUSED_MINBLOCKS") ? atoi(getenv("HORAE_FUSED_MINBLOCKS")) : 4;
+    if (mb == 5) launch_fused<2, 5, 2>(nhot, xmask, has_ts, gated, int(std::min<uint64_t>(ctas, 148ull * 10)), s, P, d_adj.as<uint64_t>());
+    else if (mb == 6) launch_fused<2, 6, 2>(nhot, xmask, has_ts, gated, int(std::min<uint64_t>(ctas, 148ull * 12)), s, P, d_adj.as<uint64_t>());
+    else
+    launch_fused<2, 4, 2>(nhot, xmask, has_ts, gated, int(std::min<uint64_t>(ctas, 148ull * 8)), s, P, d_adj.as<uint64_t>());
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
     if (global_mode) {
@@ -1060,6 +1174,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   out->G = global_mode ? (hc[1] > 0 ? 1u : 0u) : hw[1];   // hw[1] = groups counted by item_scan (hw[0] = reserved record slots)   // like GROUP BY: no surviving rows, no group
   e->stats.rows_in_files = rows_in_files;
   e->stats.rows_decoded = hc[2];
+  e->stats.rows_materialized = hc[3];
   e->stats.rows_filtered = hc[0];
   e->stats.rows_out = hc[1];
   e->stats.groups_out = out->G;

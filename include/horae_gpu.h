@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 1u
+#define HG_ABI_VERSION 2u
 
 typedef struct hg_engine hg_engine;
 
@@ -80,6 +80,7 @@ typedef struct {
 
 #define HG_FLAG_NO_PRUNING 1u   /* disable row-group pruning by chunk statistics (for A/B measurements) */
 #define HG_FLAG_NO_FUSED 2u     /* force the general (materialising) pipeline even when the fused fast path applies */
+#define HG_FLAG_NO_LATE_MATERIALIZATION 4u   /* fused path: load every needed column of every row (no predicate gate) */
 
 /* SstFile + FileMeta (sst.rs:51-53, 155-160).  `data` may be NULL when the file is already resident (hg_sst_load). */
 typedef struct {
@@ -123,6 +124,8 @@ typedef struct {
   float kernel_ms;            /* device time of the call's dominant kernel alone (fused scan / page decode) */
   float merge_ms;             /* device time of S4-S6 (sort records, merge passes, dedup, compaction of survivors) */
   float _pad2;
+  uint64_t rows_materialized; /* fused path: rows whose non-gate columns were read (== rows_decoded without the gate);
+                                 general pipeline: rows_decoded */
 } hg_scan_stats;
 
 /* Device-resident aggregate (for the NCCL combine and HBM-resident timing); valid until the next call on the engine. */
@@ -142,6 +145,7 @@ const char* hg_last_error(void);
 int hg_engine_create(const hg_config* cfg, hg_engine** out);
 void hg_engine_destroy(hg_engine* e);
 void* hg_engine_stream(hg_engine* e); /* the cudaStream_t every kernel of this engine is launched on */
+int hg_engine_set_flags(hg_engine* e, uint32_t flags); /* replaces hg_config.flags for the following calls (A/B measurements) */
 
 int hg_sst_load(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* sst);
 int hg_sst_unload(hg_engine* e, uint64_t id);

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(L, sym), f"{sym} declared in horae_gpu.h but not exported"
     assert set(_ffi.EXPORTS) == declared
-    assert L.hg_abi_version() == 1
+    assert L.hg_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -23,7 +23,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.HgSstDesc) == 64
     assert C.sizeof(_ffi.HgSchemaDesc) == 32
     assert C.sizeof(_ffi.HgAggSpec) == 24
-    assert C.sizeof(_ffi.HgScanStats) == 80
+    assert C.sizeof(_ffi.HgScanStats) == 88
     assert C.sizeof(_ffi.ArrowArrayStream) == 40
 
 

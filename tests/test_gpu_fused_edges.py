@@ -127,3 +127,55 @@ def test_config2_full_size_properties():
     assert e2.stats()["path"] == 0 and ref.equals(got)
     e2.close()
     eng.close()
+
+
+def test_fused_late_materialization_gate():
+    """The fused kernel loads the narrowest predicate column first and the other columns only for blocks with a passing
+    row (fused_scan.cu process_block GATED).  Same answers as the oracle and as the ungated kernel, for every gate
+    position: a 4-byte extra column, the narrower of two extra columns, pk1 alone; selective and dense predicates."""
+    from horaedb_b200._ffi import HG_FLAG_NO_LATE_MATERIALIZATION
+    from horaedb_b200.types import StorageSchema
+    rng = np.random.default_rng(11)
+    user = pa.schema([pa.field("series_id", pa.uint64(), True), pa.field("ts", pa.int64(), True), pa.field("value", pa.float64(), True),
+                      pa.field("tag", pa.int32(), True), pa.field("big", pa.int64(), True)])
+    schema = StorageSchema.try_new(user, 2)
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    datas = []
+    for f, lo in enumerate((0, 700)):
+        lens = rng.integers(1, 400, 700)
+        sid = np.repeat(np.arange(lo, lo + 700), lens)
+        ts = sstgen.T0_MS + np.concatenate([np.arange(n) * 1000 for n in lens])
+        tag = np.repeat(rng.integers(-8, 8, 700), lens)                 # per-series tag: long all-fail stretches
+        big = rng.integers(-5, 5, len(sid)) * (1 << 40)                 # per-row 8-byte predicate column
+        batch = pa.RecordBatch.from_arrays([pa.array(sid.astype(np.uint64)), pa.array(ts.astype(np.int64)), pa.array(rng.random(len(sid))),
+                                            pa.array(tag.astype(np.int32)), pa.array(big.astype(np.int64))], schema=user)
+        datas.append(sstgen.write_sst(schema, batch, seq=970 + f,
+                                      cfg=WriteConfig(compression=ParquetCompression.Uncompressed, max_row_group_size=5000), presorted=True))
+    eng = Engine(device=0)
+    ref = Engine(device=0, flags=HG_FLAG_NO_LATE_MATERIALIZATION)
+    cases = [([("tag", "eq", -3)], True),
+             ([("big", "ge", 3 << 40), ("tag", "eq", 5)], True),                       # two extra columns: gate = the 4-byte one
+             ([("tag", "lt", 7), ("big", "gt", -(6 << 40))], False),                   # nearly everything passes (dense blocks)
+             ([("ts", "ge", sstgen.T0_MS + 390_000)], True),                           # gate on pk1
+             ([("big", "eq", 4 << 40)], False),                                       # 8-byte gate, ~10 % of rows scattered
+             ([("tag", "eq", 99)], True)]                                              # nothing passes (pruned by statistics)
+    for preds, selective in cases:
+        for kw in (dict(group_col=0, ts_col=-1, window_ms=0, value_col=2), dict(group_col=0, ts_col=1, window_ms=300_000, value_col=2),
+                   dict(group_col=-1, ts_col=-1, window_ms=0, value_col=-1)):
+            got = _agg(eng, handle, datas, preds, **kw)
+            st = eng.stats()
+            want = _agg(ref, handle, datas, preds, **kw)
+            sr = ref.stats()
+            assert st["path"] == 1 and sr["path"] == 1
+            assert sr["rows_materialized"] == sr["rows_decoded"] == st["rows_decoded"]
+            assert st["rows_materialized"] <= st["rows_decoded"]
+            if selective and st["rows_decoded"]:
+                assert st["rows_materialized"] < st["rows_decoded"] // 2
+            assert got.equals(want)
+            exp = oracle.scan_aggregate(datas, schema.arrow_schema, 2, preds, **kw)
+            if kw["group_col"] < 0:
+                assert got["count"].to_pylist() == exp.count.tolist()
+            else:
+                _check(got, exp, kw["ts_col"] >= 0)
+    eng.close()
+    ref.close()

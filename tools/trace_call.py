@@ -1,5 +1,4 @@
 import os, sys
 os.environ["HORAE_TRACE"] = "1"
-os.environ.setdefault("HORAE_FUSED_VARIANT", "2")
 sys.argv = [sys.argv[0], "none", "16", "5"]
 exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profile_fused.py")).read())
