@@ -260,44 +260,43 @@ __global__ void __launch_bounds__(256) prune_rgs_kernel(const __grid_constant__ 
 __global__ void __launch_bounds__(1024) select_rgs_kernel(const FileDev* __restrict__ files, int nfiles, uint32_t total_rgs,
                                                           const uint32_t* __restrict__ keep_rows, RgSel* __restrict__ sel, uint32_t* d_nsel,
                                                           unsigned long long* counters) {
+  // one block; every thread owns a contiguous chunk of row groups: count, ONE block-wide scan, write
   __shared__ uint32_t s_w[33];
-  __shared__ uint32_t s_carry;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
+  const uint32_t per = (total_rgs + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per;
+  const uint32_t hi = lo + per < total_rgs ? lo + per : total_rgs;
+  uint32_t cnt = 0;
   unsigned long long rows_sel = 0;
-  for (uint32_t base = 0; base < total_rgs; base += 1024) {
-    const uint32_t idx = base + threadIdx.x;
-    const uint32_t rows = idx < total_rgs ? keep_rows[idx] : 0;
-    const uint32_t keep = rows > 0;
-    uint32_t inc = keep;
+  for (uint32_t i = lo; i < hi; i++) { const uint32_t r = keep_rows[i]; cnt += r > 0; rows_sel += r; }
+  uint32_t inc = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) s_w[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t x = s_w[lane], xi = x;
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = s_w[lane], xi = x;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
-      s_w[lane] = xi - x;
-      if (lane == 31) s_w[32] = xi;
-    }
-    __syncthreads();
-    if (keep) {
-      uint32_t f = 0;
-      while (f + 1 < uint32_t(nfiles) && idx >= files[f + 1].rg_base) f++;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+    s_w[lane] = xi - x;
+    if (lane == 31) s_w[32] = xi;
+  }
+  __syncthreads();
+  if (cnt) {
+    uint32_t pos = s_w[w] + inc - cnt;
+    uint32_t f = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint32_t rows = keep_rows[i];
+      if (rows == 0) continue;
+      while (f + 1 < uint32_t(nfiles) && i >= files[f + 1].rg_base) f++;
       RgSel r;
-      r.sst = f; r.rg = idx - files[f].rg_base; r.out_row = 0; r.num_rows = rows; r.scratch_off = 0;
-      sel[s_carry + s_w[w] + inc - 1] = r;
-      rows_sel += rows;
+      r.sst = f; r.rg = i - files[f].rg_base; r.out_row = 0; r.num_rows = rows; r.scratch_off = 0;
+      sel[pos++] = r;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry += s_w[32];
-    __syncthreads();
   }
   for (int d = 16; d > 0; d >>= 1) rows_sel += __shfl_down_sync(0xffffffffu, rows_sel, d);
   if (lane == 0 && rows_sel) atomicAdd(&counters[2], rows_sel);
-  if (threadIdx.x == 0) *d_nsel = s_carry;
+  if (threadIdx.x == 0) *d_nsel = s_w[32];
 }
 
 // ------------------------------------------------------------------------------------------------ item boundaries
@@ -513,20 +512,24 @@ struct Hot {
 
 // One block = kU slices of 32 rows.  Phase 1 issues every load of the block as straight-line code: kU*NH*2 loads per
 // lane in flight.  Phase 2 walks the slices in stream order; everything beyond the interval tests runs only when a
-// slice has survivors.
-//   X        bit k set => extra hot column 2+k is a 4-byte column (pk0 / pk1 are always 8-byte here)
-//   PARTIAL  the block may extend past `lim` (end of the item or of the row group): indices clamped, lanes masked
-template <int kU, int NH, int X, bool HAS_TS, bool DENSE, bool PARTIAL, int kPF>
+// slice has survivors.  Only `dense` is a compile-time choice (two copies per kernel); clamping / masking and the
+// prefetch are runtime, warp-uniform choices: the kernel's instruction footprint matters — with four specialised copies
+// a fifth of the stall samples were instruction-cache misses.
+//   X      bit k set => extra hot column 2+k is a 4-byte column (pk0 / pk1 are always 8-byte here)
+//   dense  most rows survive: the value column and the halo row are loaded with the block, not per survivor
+//   pf     prefetch the block two iterations ahead into L2 (sequential walks only)
+// The block may extend past `lim` (end of the item or of the row group): indices are clamped, lanes masked.
+template <int kU, int NH, int X, bool HAS_TS, bool dense>
 __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH>& H, const uint8_t* vq, uint32_t vs, Acc& acc, uint32_t& local,
                                                   uint32_t& n_alive, uint32_t& n_keep, uint32_t& n_full, uint32_t item, uint32_t csi, uint32_t row,
-                                                  uint32_t lim, uint32_t nrows, double* s_vals, uint32_t* slots, int lane) {
+                                                  uint32_t lim, uint32_t nrows, bool pf, double* s_vals, uint32_t* slots, int lane) {
   uint64_t hv[kU][NH];
   uint64_t vv[kU];
   uint64_t halo[2] = {0, 0};
   const uint32_t last = nrows - 1;
-  if (kPF > 0 && !PARTIAL) {
-    // pull the hot columns of the block kPF blocks ahead into L2: one 128-byte line per lane
-    const uint32_t prow = row + kPF * 32 * kU;
+  if (pf) {
+    // pull the hot columns of the block two blocks ahead into L2: one 128-byte line per lane
+    const uint32_t prow = row + 2 * 32 * kU;
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
@@ -536,27 +539,27 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
         asm volatile("prefetch.global.L2 [%0];" ::"l"(H.q[h] + size_t(r) * (w4 ? 4 : 8)));
     }
   }
-  n_full += PARTIAL ? (lim - row < 32u * kU ? lim - row : 32u * kU) : 32u * kU;
+  n_full += lim - row < 32u * kU ? lim - row : 32u * kU;
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     uint32_t i = row + u * 32 + lane;
-    if (PARTIAL) i = i < last ? i : last;
+    i = i < last ? i : last;
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
       hv[u][h] = w4 ? uint64_t(ld4(H.q[h], H.sh[h], i)) : ld8(H.q[h], H.sh[h], i);
     }
   }
-  if (DENSE) {
+  const bool v8 = P.value_slot >= 0 && P.kind[P.value_slot] == K_RAW64;
+  if (dense) {
     uint32_t i = row + kU * 32;
     i = i < last ? i : last;
     halo[0] = ld8(H.q[0], H.sh[0], i);
     halo[1] = ld8(H.q[1], H.sh[1], i);
-    const bool v8 = P.kind[P.value_slot] == K_RAW64;
 #pragma unroll
     for (int u = 0; u < kU; u++) {
       uint32_t i2 = row + u * 32 + lane;
-      if (PARTIAL) i2 = i2 < last ? i2 : last;
+      i2 = i2 < last ? i2 : last;
       vv[u] = v8 ? ld8(vq, vs, i2) : uint64_t(ld4(vq, vs, i2));
     }
   }
@@ -564,11 +567,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
 #pragma unroll
   for (int u = 0; u < kU; u++) {
     const uint32_t i = row + u * 32 + lane;
-    bool alive = true;
-    if (PARTIAL) {
-      alive = i < lim;
-      if (__ballot_sync(0xffffffffu, alive) == 0) continue;
-    }
+    bool alive = i < lim;
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       const bool w4 = h >= 2 && ((X >> (h - 2)) & 1);
@@ -586,7 +585,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
       uint64_t f0 = shfl64(hv[u + 1 < kU ? u + 1 : u][0], 0), f1 = shfl64(hv[u + 1 < kU ? u + 1 : u][1], 0);
       if (lane == 31) { n0 = f0; n1 = f1; }
     } else {
-      if (!DENSE && (alive_mask >> 31)) {              // sparse blocks fetch the halo row only when lane 31 survives
+      if (!dense && (alive_mask >> 31)) {              // sparse blocks fetch the halo row only when lane 31 survives
         uint32_t ih = row + kU * 32;
         ih = ih < last ? ih : last;
         halo[0] = ld8(H.q[0], H.sh[0], ih);
@@ -609,9 +608,9 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
     kept_in_block += __popc(keep_mask);
     if (!P.global_mode && keep_mask) {
       double v = 0.0;
-      if (keep && P.value_slot >= 0) {
-        const bool v8 = P.kind[P.value_slot] == K_RAW64;
-        uint64_t raw = DENSE ? vv[u] : (v8 ? ld8(vq, vs, i) : uint64_t(ld4(vq, vs, i)));
+      if (P.value_slot >= 0) {
+        uint64_t raw = vv[u];
+        if (!dense) raw = keep ? (v8 ? ld8(vq, vs, i) : uint64_t(ld4(vq, vs, i))) : 0ull;
         v = to_double_kind(raw, P.kind[P.value_slot], P.cls[P.value_slot]);
       }
       walk_slice<HAS_TS>(P, acc, local, item, keep_mask, keep, hv[u][0], int64_t(hv[u][1]), v, s_vals, slots, lane);
@@ -623,12 +622,12 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
 // Late materialisation: the LAST hot column (the planner puts the narrowest predicate column there) is the gate.  One
 // sweep tests the gate values of kGS consecutive slices (1-2 KB per warp in flight) and returns one bit per 32*kU-row
 // block that holds a passing row; only those blocks run the full block code (which reads the other columns).
-//   PARTIAL  the sweep may extend past `lim`: indices clamped to the row group, rows >= lim masked
-template <int kU, int NH, int X, int kGS, int kPF, bool PARTIAL>
+// The sweep may extend past `lim`: indices are clamped to the row group, rows >= lim masked.
+template <int kU, int NH, int X, int kGS>
 __device__ __forceinline__ uint32_t gate_sweep(const Hot<NH>& H, uint32_t row, uint32_t lim, uint32_t nrows, int lane) {
   constexpr int G = NH - 1;
   constexpr bool w4 = G >= 2 && ((X >> (G - 2)) & 1);
-  if (kPF > 0 && !PARTIAL) {                                // next-but-one sweep's gate bytes into L2, one line per lane
+  {                                                         // next-but-one sweep's gate bytes into L2, one line per lane
     constexpr uint32_t per_line = w4 ? 32u : 16u;
     const uint32_t r = row + 2u * 32u * kGS + uint32_t(lane) * per_line;
     if (uint32_t(lane) < (32u * kGS) / per_line + 1 && r < nrows)
@@ -639,7 +638,7 @@ __device__ __forceinline__ uint32_t gate_sweep(const Hot<NH>& H, uint32_t row, u
 #pragma unroll
   for (int u = 0; u < kGS; u++) {
     uint32_t i = row + u * 32 + lane;
-    if (PARTIAL) i = i < last ? i : last;
+    i = i < last ? i : last;
     gv[u] = w4 ? uint64_t(ld4(H.q[G], H.sh[G], i)) : ld8(H.q[G], H.sh[G], i);
   }
   uint32_t bm = 0;
@@ -647,7 +646,7 @@ __device__ __forceinline__ uint32_t gate_sweep(const Hot<NH>& H, uint32_t row, u
   for (int u = 0; u < kGS; u++) {
     bool pass = w4 ? ((uint32_t(gv[u]) ^ uint32_t(H.flip[G])) - uint32_t(H.lo[G]) <= uint32_t(H.span[G]))
                    : ((gv[u] ^ H.flip[G]) - H.lo[G] <= H.span[G]);
-    if (PARTIAL) pass = pass && (row + u * 32 + lane < lim);
+    pass = pass && (row + u * 32 + lane < lim);
     if (__ballot_sync(0xffffffffu, pass)) bm |= 1u << (u / kU);
   }
   return bm;
@@ -733,6 +732,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
       Acc acc;
       acc.open = false; acc.g = 0; acc.bstart = 0; acc.blo = 0; acc.bhi = 0; acc.cnt = 0; acc.sum = 0.0; acc.mn = kInf; acc.mx = -kInf;
       bool dense = false;                 // most rows survive: load the value column with the block, not per survivor
+      uint32_t bm = 0, sweep_kept = 0;    // gated kernels: blocks of the current sweep still to be materialised
       uint32_t nrows = P.sel[csi].num_rows;
       set_cursor(csi);
       for (;;) {
@@ -745,41 +745,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
         }
         const uint32_t lim = csi == esi ? erow : nrows;
         if (row >= lim) break;
-        uint32_t kept;
-        if constexpr (GATED) {
-          if (!dense) {
-            uint32_t bm = row + 32u * kGS < lim ? gate_sweep<kU, NH, X, kGS, kPF, false>(H, row, lim, nrows, lane)
-                                                : gate_sweep<kU, NH, X, kGS, kPF, true>(H, row, lim, nrows, lane);
-            kept = 0;
-            if (bm) prefetch_blocks<kU, NH, X, kGS>(H, vq, P.value_slot >= 0, P.value_slot >= 0 && P.kind[P.value_slot] == K_RAW64, bm, row, nrows, lane);
-            while (bm) {
-              const uint32_t r = row + (__ffs(bm) - 1) * 32u * kU;
-              bm &= bm - 1;
-              if (r + 32u * kU < lim)
-                kept += process_block<kU, NH, X, HAS_TS, false, false, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, r, lim, nrows, s_vals, slots, lane);
-              else
-                kept += process_block<kU, NH, X, HAS_TS, false, true, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, r, lim, nrows, s_vals, slots, lane);
-            }
-            const uint32_t swept = lim - row < 32u * kGS ? lim - row : 32u * kGS;
-            dense = P.value_slot >= 0 && kept >= swept / 4;
-            row += 32u * kGS;
-            continue;
-          }
-          // dense stretch (>= 1/4 of the rows survive): everything is needed anyway, load block by block
-          if (row + 32u * kU < lim)
-            kept = process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
-          else
-            kept = process_block<kU, NH, X, HAS_TS, false, true, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
-        } else {
-          if (row + 32u * kU < lim) {       // (< lim: the halo row is inside the row group as well)
-            kept = dense ? process_block<kU, NH, X, HAS_TS, true, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane)
-                         : process_block<kU, NH, X, HAS_TS, false, false, kPF>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
-          } else {
-            kept = process_block<kU, NH, X, HAS_TS, false, true, 0>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows, s_vals, slots, lane);
-          }
+        if (dense) {
+          // dense stretch (>= 1/4 of the rows survive): everything is needed, value column loaded with the block
+          const uint32_t kept = process_block<kU, NH, X, HAS_TS, true>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows,
+                                                                      true, s_vals, slots, lane);
+          dense = kept >= 32u * kU / 4;
+          row += 32 * kU;
+          continue;
         }
-        dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
-        row += 32 * kU;
+        uint32_t brow = row;
+        if (GATED) {
+          if (bm == 0) {
+            // late materialisation, coarse step: test the gate column of kGS slices, then run the block code only on the
+            // 32*kU-row blocks that hold a passing row
+            bm = gate_sweep<kU, NH, X, kGS>(H, row, lim, nrows, lane);
+            sweep_kept = 0;
+            if (bm == 0) { row += 32u * kGS; continue; }
+            prefetch_blocks<kU, NH, X, kGS>(H, vq, P.value_slot >= 0, P.value_slot >= 0 && P.kind[P.value_slot] == K_RAW64, bm, row, nrows, lane);
+          }
+          brow = row + (__ffs(bm) - 1) * 32u * kU;
+          bm &= bm - 1;
+        }
+        const uint32_t kept = process_block<kU, NH, X, HAS_TS, false>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, brow, lim, nrows,
+                                                                     !GATED, s_vals, slots, lane);
+        if (GATED) {
+          sweep_kept += kept;
+          if (bm == 0) {                              // sweep finished
+            const uint32_t swept = lim - row < 32u * kGS ? lim - row : 32u * kGS;
+            dense = P.value_slot >= 0 && sweep_kept >= swept / 4;
+            row += 32u * kGS;
+          }
+        } else {
+          dense = P.value_slot >= 0 && kept >= 32u * kU / 4;
+          row += 32 * kU;
+        }
       }
       if (acc.open) { if (lane == 0) emit(P, acc, item, local, slots); local++; }
     }
@@ -1005,10 +1004,10 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
 
   cudaStream_t s = e->stream;
   Launch L = e->L();
-  // split row groups into enough work items for ~8 items per resident warp (dynamic ticket => good balance);
+  // split row groups into enough work items for ~4 items per resident warp (dynamic ticket => good balance);
   // boundaries are then aligned to key-run starts by item_bounds_kernel
   uint32_t split = 1;
-  static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 8;
+  static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 4;
   while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * uint64_t(items_per_warp)) split *= 2;
   const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
   DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj, d_keep, d_bsum, d_bases;
@@ -1120,7 +1119,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.counters = d_counters.as<unsigned long long>();
     P.err = d_err.as<int>();
 
-    int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 12));
+    int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
     // late materialisation needs a real interval test on the last hot column (the gate)
     static const bool env_nogate = getenv("HORAE_NO_GATE") != nullptr;
     const bool gated = !env_nogate && !(e->flags & HG_FLAG_NO_LATE_MATERIALIZATION) && P.hot_haspred[nhot - 1] != 0;
@@ -1141,11 +1140,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     }
     CU_TRY(cudaEventRecord(e->evk0, s));
     // 2 slices per block, 4 CTAs/SM, L2 prefetch 2 blocks ahead (measured best of {0,2,3,4} blocks: profiles/README.md)
-    static const int mb = getenv("HORAE_FUSED_MINBLOCKS") ? atoi(getenv("HORAE_FUSED_MINBLOCKS")) : 4;
-    if (mb == 5) launch_fused<2, 5, 2>(nhot, xmask, has_ts, gated, int(std::min<uint64_t>(ctas, 148ull * 10)), s, P, d_adj.as<uint64_t>());
-    else if (mb == 6) launch_fused<2, 6, 2>(nhot, xmask, has_ts, gated, int(std::min<uint64_t>(ctas, 148ull * 12)), s, P, d_adj.as<uint64_t>());
-    else
-    launch_fused<2, 4, 2>(nhot, xmask, has_ts, gated, int(std::min<uint64_t>(ctas, 148ull * 8)), s, P, d_adj.as<uint64_t>());
+    launch_fused<2, 4, 2>(nhot, xmask, has_ts, gated, ctas, s, P, d_adj.as<uint64_t>());
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
     if (global_mode) {
