@@ -209,8 +209,10 @@ static bool rg_may_match(const RgCol* rc, uint32_t num_rows, const hg_schema_des
   return true;
 }
 
+// Small host -> device uploads go through one pinned staging buffer.  The cursor is per CALL (reset in begin_call, when the
+// stream is idle): copies are asynchronous, so a region must not be reused before the stream has consumed it.
 int stage_upload(hg_engine* e, void* dst, const void* src, size_t bytes, size_t* stage_off) {
-  size_t off = (*stage_off + 255) & ~size_t(255);
+  size_t off = (e->stage_cursor + 255) & ~size_t(255);
   if (off + bytes > e->h_stage_bytes) {
     // grow (rare): everything staged so far in this call must reach the device first
     CU_TRY(cudaStreamSynchronize(e->stream));
@@ -224,7 +226,8 @@ int stage_upload(hg_engine* e, void* dst, const void* src, size_t bytes, size_t*
   }
   std::memcpy(static_cast<char*>(e->h_stage) + off, src, bytes);
   CU_TRY(cudaMemcpyAsync(dst, static_cast<char*>(e->h_stage) + off, bytes, cudaMemcpyHostToDevice, e->stream));
-  *stage_off = off + bytes;
+  e->stage_cursor = off + bytes;
+  if (stage_off) *stage_off = e->stage_cursor;
   return HG_OK;
 }
 
@@ -260,6 +263,10 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
                           const hg_predicate* preds, size_t np, std::vector<uint32_t> need_cols, bool seq_if_overlap,
                           const std::vector<size_t>& resident_idx) {
   const size_t k = pending.size();
+  static const bool trace = getenv("HORAE_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  const auto tt0 = now();
   std::vector<std::unique_ptr<SstResident>> rs(k);
   std::vector<std::vector<PageDev>> pages(k);
   std::vector<std::vector<ChunkDev>> chunks(k);
@@ -299,6 +306,7 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
     for (auto& t : th) t.join();
   }
   for (size_t j = 0; j < k; j++) if (codes[j]) return set_error(codes[j], errs[j]);
+  const auto tt1 = now();
   // ---- __seq__ is only needed when the inputs are not provably PK-disjoint (a real merge will run)
   if (seq_if_overlap) {
     std::vector<const SstResident*> all;
@@ -321,60 +329,157 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
   const bool prune = !(e->flags & HG_FLAG_NO_PRUNING);
   uint64_t lits[MAX_PREDS];
   for (size_t i = 0; i < np; i++) lits[i] = pred_literal(preds[i], schema->types[preds[i].column]);
-  std::vector<CopyRange> ranges;
-  size_t stage_off = 0;
-  uint64_t copied = 0;
-  for (size_t j = 0; j < k; j++) {
-    SstResident& r = *rs[j];
-    const FileMetaData& m = r.meta;
-    r.d_bytes = static_cast<uint8_t*>(g_arena->alloc(r.size + 64));
-    r.d_pages = static_cast<PageDev*>(g_arena->alloc(std::max<size_t>(pages[j].size(), 1) * sizeof(PageDev)));
-    r.d_chunks = static_cast<ChunkDev*>(g_arena->alloc(std::max<size_t>(chunks[j].size(), 1) * sizeof(ChunkDev)));
-    r.d_rgcol = static_cast<RgCol*>(g_arena->alloc(std::max<size_t>(r.rgcol.size(), 1) * sizeof(RgCol)));
-    r.d_rg_rows = static_cast<uint32_t*>(g_arena->alloc(std::max<size_t>(r.rg_rows.size(), 1) * sizeof(uint32_t)));
-    if (!r.d_bytes || !r.d_pages || !r.d_chunks || !r.d_rgcol || !r.d_rg_rows) return set_error(HG_ERR_OOM, "out of device memory for transient SST");
-    int rc = 0;
-    if (!pages[j].empty()) rc = stage_upload(e, r.d_pages, pages[j].data(), pages[j].size() * sizeof(PageDev), &stage_off);
-    if (!rc && !chunks[j].empty()) rc = stage_upload(e, r.d_chunks, chunks[j].data(), chunks[j].size() * sizeof(ChunkDev), &stage_off);
-    if (!rc && !r.rgcol.empty()) rc = stage_upload(e, r.d_rgcol, r.rgcol.data(), r.rgcol.size() * sizeof(RgCol), &stage_off);
-    if (!rc && !r.rg_rows.empty()) rc = stage_upload(e, r.d_rg_rows, r.rg_rows.data(), r.rg_rows.size() * sizeof(uint32_t), &stage_off);
-    if (rc) return rc;
-    copied += pages[j].size() * sizeof(PageDev) + chunks[j].size() * sizeof(ChunkDev) + r.rgcol.size() * sizeof(RgCol);
-    const size_t ncols = size_t(m.ncols);
-    for (size_t g = 0; g < m.rgs.size(); g++) {
-      if (r.rg_rows[g] == 0) continue;
-      if (prune && np && !rg_may_match(&r.rgcol[g * ncols], r.rg_rows[g], schema, preds, lits, np)) continue;
-      for (uint32_t c : need_cols) {
-        const ChunkMeta& cm = m.rgs[g].cols[c];
-        uint64_t lo = uint64_t(cm.data_page_offset), hi = lo + uint64_t(cm.total_compressed);
-        if (hi > r.size) hi = r.size;
-        hi = std::min<uint64_t>(r.size, hi + 16);               // the unaligned 8-byte loads may touch one word past the values
-        if (!ranges.empty() && ranges.back().src + ranges.back().bytes >= datas[j] + lo && ranges.back().src <= datas[j] + lo &&
-            ranges.back().dst == r.d_bytes + (ranges.back().src - datas[j])) {
-          uint64_t end = std::max<uint64_t>(uint64_t(ranges.back().src - datas[j]) + ranges.back().bytes, hi);
-          ranges.back().bytes = end - uint64_t(ranges.back().src - datas[j]);
-        } else ranges.push_back(CopyRange{datas[j] + lo, r.d_bytes + lo, hi - lo});
-      }
-    }
-  }
-  for (auto& cr : ranges) copied += cr.bytes;
-  // ---- move the bytes
-  bool all_pinned = !ranges.empty();
+  bool all_pinned = k > 0;
   for (size_t j = 0; j < k && all_pinned; j++) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, datas[j]) != cudaSuccess || at.type != cudaMemoryTypeHost) { all_pinned = false; cudaGetLastError(); }
   }
-  if (all_pinned) {
-    CopyRange* d_ranges = static_cast<CopyRange*>(g_arena->alloc(ranges.size() * sizeof(CopyRange)));
-    if (!d_ranges) return set_error(HG_ERR_OOM, "out of device memory");
-    int rc = stage_upload(e, d_ranges, ranges.data(), ranges.size() * sizeof(CopyRange), &stage_off);
+  size_t stage_off = 0;
+  uint64_t copied = 0;
+  size_t n_ranges = 0;
+  // moves a batch of byte ranges host -> device on the engine's stream
+  auto move_ranges = [&](std::vector<CopyRange>& ranges) -> int {
+    n_ranges += ranges.size();
+    for (auto& cr : ranges) copied += cr.bytes;
+    if (ranges.empty()) return HG_OK;
+    if (all_pinned) {
+      CopyRange* d_ranges = static_cast<CopyRange*>(g_arena->alloc(ranges.size() * sizeof(CopyRange)));
+      if (!d_ranges) return set_error(HG_ERR_OOM, "out of device memory");
+      int rc = stage_upload(e, d_ranges, ranges.data(), ranges.size() * sizeof(CopyRange), &stage_off);
+      if (rc) return rc;
+      gather_ranges_kernel<<<int(std::min<size_t>(ranges.size(), 148 * 8)), 256, 0, e->stream>>>(d_ranges, uint32_t(ranges.size()));
+      e->launches++;
+    } else {
+      for (auto& cr : ranges) CU_TRY(cudaMemcpyAsync(cr.dst, cr.src, cr.bytes, cudaMemcpyHostToDevice, e->stream));
+    }
+    return HG_OK;
+  };
+  auto add_range = [&](std::vector<CopyRange>& ranges, size_t j, uint32_t g, uint32_t c) {
+    SstResident& r = *rs[j];
+    const ChunkMeta& cm = r.meta.rgs[g].cols[c];
+    uint64_t lo = uint64_t(cm.data_page_offset), hi = lo + uint64_t(cm.total_compressed);
+    if (hi > r.size) hi = r.size;
+    hi = std::min<uint64_t>(r.size, hi + 16);               // the unaligned 8-byte loads may touch one word past the values
+    if (!ranges.empty() && ranges.back().src + ranges.back().bytes >= datas[j] + lo && ranges.back().src <= datas[j] + lo &&
+        ranges.back().dst == r.d_bytes + (ranges.back().src - datas[j])) {
+      uint64_t end = std::max<uint64_t>(uint64_t(ranges.back().src - datas[j]) + ranges.back().bytes, hi);
+      ranges.back().bytes = end - uint64_t(ranges.back().src - datas[j]);
+    } else ranges.push_back(CopyRange{datas[j] + lo, r.d_bytes + lo, hi - lo});
+  };
+  // row groups that survive statistics pruning, in file order
+  struct KeptRg { uint32_t j, g; };
+  std::vector<KeptRg> kept;
+  for (size_t j = 0; j < k; j++) {
+    SstResident& r = *rs[j];
+    r.d_bytes = static_cast<uint8_t*>(g_arena->alloc(r.size + 64));
+    if (!r.d_bytes) return set_error(HG_ERR_OOM, "out of device memory for transient SST");
+    const size_t ncols = size_t(r.meta.ncols);
+    for (size_t g = 0; g < r.meta.rgs.size(); g++) {
+      if (r.rg_rows[g] == 0) continue;
+      if (prune && np && !rg_may_match(&r.rgcol[g * ncols], r.rg_rows[g], schema, preds, lits, np)) continue;
+      kept.push_back(KeptRg{uint32_t(j), uint32_t(g)});
+    }
+  }
+  // ---- late materialisation across PCIe: when one predicate column is plain and null-free in every file, move ITS chunks
+  //      first, let the device find the row groups that hold a passing row, and move the other columns only for those.
+  int gate_col = -1;
+  if (prune && np && !(e->flags & HG_FLAG_NO_LATE_MATERIALIZATION) && need_cols.size() > 1 && !kept.empty()) {
+    uint32_t best_w = 16;
+    for (size_t i = 0; i < np; i++) {
+      const uint32_t c = preds[i].column;
+      bool ok = c < uint32_t(MAX_COLS);
+      for (size_t j = 0; j < k && ok; j++) ok = rs[j]->rows_total == 0 || (rs[j]->col_all_simple[c] && rs[j]->col_null_none[c]);
+      const uint32_t w = type_width_host(schema->types[c]) <= 4 ? 4u : 8u;
+      if (ok && w < best_w) { best_w = w; gate_col = int(c); }
+    }
+    uint32_t need_w = 0;
+    for (uint32_t c : need_cols) need_w += type_width_host(schema->types[c]) <= 4 ? 4u : 8u;
+    if (gate_col >= 0 && best_w * 3 > need_w) gate_col = -1;          // the gate would be most of the bytes anyway
+  }
+  if (gate_col >= 0) {
+    std::vector<CopyRange> ranges;
+    std::vector<fused::GateRg> descs(kept.size());
+    for (size_t i = 0; i < kept.size(); i++) {
+      const size_t j = kept[i].j;
+      const uint32_t g = kept[i].g;
+      SstResident& r = *rs[j];
+      add_range(ranges, j, g, uint32_t(gate_col));
+      const ChunkDev& cd = chunks[j][size_t(g) * size_t(r.meta.ncols) + size_t(gate_col)];
+      uint64_t off = pages[j][cd.first_page].payload_off;
+      if (cd.optional) {                                    // [u32 len][RLE def levels] in front of the values (all valid here)
+        uint32_t len = 0;
+        if (off + 4 > r.size) return set_error(HG_ERR_FORMAT, "page payload out of bounds");
+        std::memcpy(&len, datas[j] + off, 4);
+        off += 4 + uint64_t(len);
+      }
+      if (off + uint64_t(r.rg_rows[g]) * (type_width_host(schema->types[gate_col]) <= 4 ? 4u : 8u) > r.size)
+        return set_error(HG_ERR_FORMAT, "column chunk out of bounds");
+      descs[i] = fused::GateRg{r.d_bytes + off, r.rg_rows[g], 0};
+    }
+    int rc = move_ranges(ranges);
     if (rc) return rc;
-    gather_ranges_kernel<<<int(std::min<size_t>(ranges.size(), 148 * 8)), 256, 0, e->stream>>>(d_ranges, uint32_t(ranges.size()));
-    e->launches++;
-  } else {
-    for (auto& cr : ranges) CU_TRY(cudaMemcpyAsync(cr.dst, cr.src, cr.bytes, cudaMemcpyHostToDevice, e->stream));
+    fused::GateRg* d_descs = static_cast<fused::GateRg*>(g_arena->alloc(descs.size() * sizeof(fused::GateRg)));
+    uint8_t* d_flags = static_cast<uint8_t*>(g_arena->alloc(kept.size() + 16));
+    if (!d_descs || !d_flags) return set_error(HG_ERR_OOM, "out of device memory");
+    rc = stage_upload(e, d_descs, descs.data(), descs.size() * sizeof(fused::GateRg), &stage_off);
+    if (rc) return rc;
+    hg_predicate gp[MAX_PREDS];
+    size_t ngp = 0;
+    for (size_t i = 0; i < np; i++) if (int(preds[i].column) == gate_col) gp[ngp++] = preds[i];
+    rc = fused::gate_row_groups(e, d_descs, uint32_t(kept.size()), schema->types[gate_col], gp, ngp, d_flags);
+    if (rc) return rc;
+    std::vector<uint8_t> flags(kept.size());
+    CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, kept.size(), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->stats.bytes_d2h += kept.size();
+    e->stage_cursor = 0;                                    // the stream is idle: the staging buffer can be reused
+    for (size_t j = 0; j < k; j++) rs[j]->rg_dead.assign(rs[j]->rg_rows.size(), 0);
+    std::vector<KeptRg> alive;
+    for (size_t i = 0; i < kept.size(); i++) {
+      if (flags[i]) alive.push_back(kept[i]);
+      else rs[kept[i].j]->rg_dead[kept[i].g] = 1;
+    }
+    kept.swap(alive);
+  }
+  // ---- the remaining columns of the row groups still in play
+  {
+    std::vector<CopyRange> ranges;
+    for (const KeptRg& kr : kept)
+      for (uint32_t c : need_cols)
+        if (int(c) != gate_col) add_range(ranges, kr.j, kr.g, c);
+    int rc = move_ranges(ranges);
+    if (rc) return rc;
+  }
+  // ---- planning tables (device copies: dead row groups have zero rows => pruned by every device-side planner)
+  for (size_t j = 0; j < k; j++) {
+    SstResident& r = *rs[j];
+    r.d_pages = static_cast<PageDev*>(g_arena->alloc(std::max<size_t>(pages[j].size(), 1) * sizeof(PageDev)));
+    r.d_chunks = static_cast<ChunkDev*>(g_arena->alloc(std::max<size_t>(chunks[j].size(), 1) * sizeof(ChunkDev)));
+    r.d_rgcol = static_cast<RgCol*>(g_arena->alloc(std::max<size_t>(r.rgcol.size(), 1) * sizeof(RgCol)));
+    r.d_rg_rows = static_cast<uint32_t*>(g_arena->alloc(std::max<size_t>(r.rg_rows.size(), 1) * sizeof(uint32_t)));
+    if (!r.d_pages || !r.d_chunks || !r.d_rgcol || !r.d_rg_rows) return set_error(HG_ERR_OOM, "out of device memory for transient SST");
+    int rc = 0;
+    if (!pages[j].empty()) rc = stage_upload(e, r.d_pages, pages[j].data(), pages[j].size() * sizeof(PageDev), &stage_off);
+    if (!rc && !chunks[j].empty()) rc = stage_upload(e, r.d_chunks, chunks[j].data(), chunks[j].size() * sizeof(ChunkDev), &stage_off);
+    if (!rc && !r.rgcol.empty()) rc = stage_upload(e, r.d_rgcol, r.rgcol.data(), r.rgcol.size() * sizeof(RgCol), &stage_off);
+    if (!rc && !r.rg_rows.empty()) {
+      if (r.rg_dead.empty()) rc = stage_upload(e, r.d_rg_rows, r.rg_rows.data(), r.rg_rows.size() * sizeof(uint32_t), &stage_off);
+      else {
+        std::vector<uint32_t> live(r.rg_rows);
+        for (size_t g = 0; g < live.size(); g++) if (r.rg_dead[g]) live[g] = 0;
+        rc = stage_upload(e, r.d_rg_rows, live.data(), live.size() * sizeof(uint32_t), &stage_off);
+      }
+    }
+    if (rc) return rc;
+    copied += pages[j].size() * sizeof(PageDev) + chunks[j].size() * sizeof(ChunkDev) + r.rgcol.size() * sizeof(RgCol);
   }
   e->stats.bytes_h2d += copied;
+  if (trace) {
+    const auto tt2 = now();
+    cudaStreamSynchronize(e->stream);
+    fprintf(stderr, "[transient] %zu files: parse %.0f us, ranges+tables %.0f us (%zu ranges, %.1f MB, gate column %d), copy wait %.0f us\n", k,
+            us(tt0, tt1), us(tt1, tt2), n_ranges, copied / 1e6, gate_col, us(tt2, now()));
+  }
   for (size_t j = 0; j < k; j++) {
     e->transient_ids.push_back(rs[j]->id);
     e->ssts[rs[j]->id] = std::move(rs[j]);
@@ -407,6 +512,7 @@ int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ss
       const uint32_t rows = f.rg_rows[g];
       plan->rows_in_files += rows;
       if (rows == 0) continue;
+      if (!f.rg_dead.empty() && f.rg_dead[g]) continue;          // transient load: no row of this row group passes the predicate
       const RgCol* rc = &f.rgcol[g * ncols];
       if (prune && np && !rg_may_match(rc, rows, schema, preds, lits, np)) continue;
       fs[i].rgs.push_back(uint32_t(g));
@@ -1030,6 +1136,7 @@ static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   CU_TRY(cudaSetDevice(e->device));
   std::memset(&e->stats, 0, sizeof(e->stats));
   e->launches = 0;
+  e->stage_cursor = 0;
   e->last_agg = hg_agg_device{};
   e->arena.reset();
   g_arena = &e->arena;

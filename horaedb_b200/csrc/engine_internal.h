@@ -109,6 +109,7 @@ struct SstResident {
   FileMetaData meta;
   std::vector<RgCol> rgcol;      // [rg * ncols + col]
   std::vector<uint32_t> rg_rows;
+  std::vector<uint8_t> rg_dead;        // transient loads: row groups proven (on the device) to hold no row passing the predicate
   RgCol* d_rgcol = nullptr;      // the same two tables in HBM (device-side pruning of the fused path)
   uint32_t* d_rg_rows = nullptr;
   // per-file planning facts (over ALL row groups of the file)
@@ -213,6 +214,7 @@ struct hg_engine {
   uint64_t resident_bytes = 0;
   hg_scan_stats stats{};
   uint32_t launches = 0;
+  size_t stage_cursor = 0;             // next free byte of h_stage in the current call
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evm0 = nullptr, evm1 = nullptr;  // call / dominant-kernel / merge brackets
   void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
   size_t h_stage_bytes = 0;

@@ -883,7 +883,40 @@ __global__ void global_count_kernel(const unsigned long long* counters, AggOut o
 
 bool is_int_type(uint32_t t) { return t != T_F32 && t != T_F64; }
 
+struct GatePreds { int n; uint32_t kind, cls, _pad; uint32_t op[MAX_PREDS]; uint64_t lit[MAX_PREDS]; };
+__global__ void __launch_bounds__(256) gate_rgs_kernel(const GateRg* __restrict__ rgs, uint32_t n, const __grid_constant__ GatePreds gp,
+                                                       uint8_t* __restrict__ flags) {
+  for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
+    const GateRg g = rgs[r];
+    bool any = false;
+    for (uint32_t i = threadIdx.x; i < g.nrows; i += 256) {
+      const uint64_t v = load_kind(g.vals, gp.kind, i);
+      bool ok = true;
+      for (int p = 0; p < gp.n; p++) ok = ok && pred_ok(v, gp.lit[p], gp.cls, gp.op[p]);
+      any = any || ok;
+    }
+    const int a = __syncthreads_or(any);
+    if (threadIdx.x == 0) flags[r] = a ? 1 : 0;
+  }
+}
+
 }  // namespace
+
+int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type, const hg_predicate* preds, size_t np, uint8_t* d_flags) {
+  if (n == 0) return HG_OK;
+  if (np == 0 || np > size_t(MAX_PREDS)) return set_error(HG_ERR_INTERNAL, "gate_row_groups: bad predicate count");
+  GatePreds gp;
+  std::memset(&gp, 0, sizeof(gp));
+  gp.n = int(np);
+  gp.kind = (type == T_U64 || type == T_I64 || type == T_F64) ? K_RAW64
+                                                               : (type == T_F32 ? K_F32 : ((type == T_I8 || type == T_I16 || type == T_I32) ? K_I32 : K_U32));
+  gp.cls = type_is_float(type) ? C_FLOAT : (type_is_signed(type) ? C_SIGNED : C_UNSIGNED);
+  for (size_t i = 0; i < np; i++) { gp.op[i] = preds[i].op; gp.lit[i] = pred_literal(preds[i], type); }
+  gate_rgs_kernel<<<int(std::min<uint32_t>(n, 148u * 16u)), 256, 0, e->stream>>>(d_rgs, n, gp, d_flags);
+  e->launches++;
+  CU_TRY(cudaGetLastError());
+  return HG_OK;
+}
 
 int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
                        size_t np, const hg_agg_spec* agg, AggBuffers* out) {

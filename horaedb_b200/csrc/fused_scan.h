@@ -9,5 +9,12 @@ constexpr int NOT_APPLICABLE = -1000;
 // runs), otherwise an hg_status.
 int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
                        size_t np, const hg_agg_spec* agg, AggBuffers* out);
+
+// Data-driven row-group pruning for transient (host-resident) SSTs: evaluates the conjunction of the predicates on ONE
+// column over the PLAIN values of n row groups (already on the device) and writes flags[i] = 1 iff some row passes.
+// The filter runs before merge/dedup (read.rs:459-480), so a row group without a passing row contributes nothing and
+// its other columns never have to cross PCIe.  Launched on the engine's stream.
+struct GateRg { const uint8_t* vals; uint32_t nrows, _pad; };
+int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type, const hg_predicate* preds, size_t np, uint8_t* d_flags);
 }  // namespace fused
 }  // namespace horae

@@ -167,10 +167,11 @@ def test_fused_late_materialization_gate():
             want = _agg(ref, handle, datas, preds, **kw)
             sr = ref.stats()
             assert st["path"] == 1 and sr["path"] == 1
-            assert sr["rows_materialized"] == sr["rows_decoded"] == st["rows_decoded"]
+            # (the inputs are host bytes: the transient load already drops row groups without a passing gate row)
+            assert sr["rows_materialized"] == sr["rows_decoded"] >= st["rows_decoded"]
             assert st["rows_materialized"] <= st["rows_decoded"]
-            if selective and st["rows_decoded"]:
-                assert st["rows_materialized"] < st["rows_decoded"] // 2
+            if selective and sr["rows_decoded"]:
+                assert st["rows_materialized"] < sr["rows_decoded"] // 2
             assert got.equals(want)
             exp = oracle.scan_aggregate(datas, schema.arrow_schema, 2, preds, **kw)
             if kw["group_col"] < 0:

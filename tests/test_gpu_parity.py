@@ -332,6 +332,44 @@ def test_transient_selective_load_matches_resident(eng):
                 eng.scan(handle, [SstInput(id=ids[0])], [])
 
 
+def test_transient_gate_column_prunes_row_groups(eng):
+    """Transient loads move the narrowest plain predicate column first, let the device find the row groups that hold a
+    passing row, and move the other columns only for those (engine.cu load_transient).  Row groups whose statistics admit
+    tag = 3 (tags wrap 15 -> 0 inside them) but which hold no such row must not cost PCIe bytes, and nothing may change
+    in the results (the filter runs before merge/dedup, read.rs:459-480)."""
+    import torch
+    from horaedb_b200._ffi import HG_FLAG_NO_LATE_MATERIALIZATION
+    schema = sstgen.metric_storage_schema()
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    files = [sstgen.synth_sst(lo, lo + 40, 2000, 1000, seq=80 + i, compression=ParquetCompression.Uncompressed) for i, lo in enumerate((6, 46))]
+    ids = [next(_ids) for _ in files]
+    pinned = []
+    for d, n in files:
+        t = torch.empty(len(d), dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = np.frombuffer(d, dtype=np.uint8)
+        pinned.append(t)
+    ins = [SstInput(id=sid, ptr=t.data_ptr(), size=t.numel()) for sid, t in zip(ids, pinned)]
+    datas = [d for d, _ in files]
+    try:
+        for preds in ([("tag", "eq", 3)], [("tag", "eq", 3), ("ts", "lt", sstgen.T0_MS + 500_000)], [("ts", "eq", sstgen.T0_MS + 1_500)]):     # off the 1000 ms grid: statistics keep every row group, no row matches
+            res = {}
+            for flags in (0, HG_FLAG_NO_LATE_MATERIALIZATION):
+                eng.set_flags(flags)
+                agg = eng.scan_aggregate(handle, ins, preds, group_col=0, ts_col=-1, window_ms=0, value_col=2)
+                st = eng.stats()
+                rows = eng.scan(handle, ins, preds).read_all()
+                res[flags] = (agg, st, rows, eng.stats())
+            (a0, s0, r0, t0), (a1, s1, r1, t1) = res[0], res[HG_FLAG_NO_LATE_MATERIALIZATION]
+            assert a0.equals(a1) and r0.equals(r1)
+            assert s0["bytes_h2d"] < s1["bytes_h2d"] and t0["bytes_h2d"] < t1["bytes_h2d"], preds
+            assert s0["rows_decoded"] <= s1["rows_decoded"] and s0["rows_filtered"] == s1["rows_filtered"] and s0["rows_out"] == s1["rows_out"]
+            exp = oracle.scan_aggregate(datas, schema.arrow_schema, 2, preds, group_col=0, ts_col=-1, window_ms=0, value_col=2)
+            assert a0["series_id"].to_numpy().tolist() == exp.gkey.tolist() and a0["count"].to_numpy().tolist() == exp.count.tolist()
+            assert np.array_equal(a0["sum"].to_numpy(), exp.sum)
+    finally:
+        eng.set_flags(0)
+
+
 # ------------------------------------------------------------------------------------------------------- edge / errors
 def test_empty_inputs(eng):
     schema = sstgen.metric_storage_schema()
