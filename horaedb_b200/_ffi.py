@@ -158,6 +158,7 @@ class Engine:
         cfg = HgConfig(device, batch_size, hbm_budget_bytes, flags, 0)
         _check(self._L.hg_engine_create(C.byref(cfg), C.byref(self._h)))
         self._keep = []
+        self._stats_buf = HgScanStats()
 
     def close(self):
         if self._h:
@@ -251,6 +252,16 @@ class Engine:
                                                 C.c_size_t(len(preds)), C.byref(spec), C.byref(out)))
         return out
 
+    def prepare_aggregate(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (), group_col: int = 0,
+                          ts_col: int = -1, window_ms: int = 0, value_col: int = -1) -> "PreparedAggregate":
+        """Marshal the arguments of `scan_aggregate_device` once; `run()` is then a single C call (what a compiled host pays)."""
+        return PreparedAggregate(self, schema, ssts, preds, group_col, ts_col, window_ms, value_col)
+
+    def stats_struct(self) -> "HgScanStats":
+        """hg_last_stats into a reused ctypes struct (no dict): for tight measurement loops."""
+        _check(self._L.hg_last_stats(self._h, C.byref(self._stats_buf)))
+        return self._stats_buf
+
     def export_packed(self, d_dst: int, cap: int) -> None:
         """Pack the last device aggregate into a caller-owned [6, cap] int64 device buffer (engine stream)."""
         _check(self._L.hg_agg_export_packed(self._h, C.c_void_p(d_dst), C.c_uint64(cap)))
@@ -259,3 +270,24 @@ class Engine:
         st = HgScanStats()
         _check(self._L.hg_last_stats(self._h, C.byref(st)))
         return {f[0]: getattr(st, f[0]) for f in HgScanStats._fields_ if not f[0].startswith("_")}
+
+
+class PreparedAggregate:
+    """The ctypes argument block of one `hg_scan_aggregate_device` call, built once and reused."""
+
+    def __init__(self, eng: Engine, schema: SchemaHandle, ssts, preds, group_col, ts_col, window_ms, value_col):
+        self._eng = eng
+        self._schema = schema
+        self._arr, self._keep = eng._descs(ssts)
+        self._p = _make_preds(schema.arrow_schema, preds)
+        self._spec = HgAggSpec(group_col, ts_col, window_ms, value_col, 0)
+        self.out = HgAggDevice()
+        self._fn = eng._L.hg_scan_aggregate_device
+        self._args = (eng._h, C.byref(schema.desc), self._arr, C.c_size_t(len(ssts)), self._p, C.c_size_t(len(preds)),
+                      C.byref(self._spec), C.byref(self.out))
+
+    def run(self) -> HgAggDevice:
+        rc = self._fn(*self._args)
+        if rc:
+            _check(rc)
+        return self.out

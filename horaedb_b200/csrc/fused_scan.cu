@@ -258,11 +258,18 @@ __global__ void __launch_bounds__(256) prune_rgs_kernel(const __grid_constant__ 
 
 // phase 2: one block compacts the kept row groups in stream order (coalesced reads of keep_rows)
 __global__ void __launch_bounds__(1024) select_rgs_kernel(const FileDev* __restrict__ files, int nfiles, uint32_t total_rgs,
-                                                          const uint32_t* __restrict__ keep_rows, RgSel* __restrict__ sel, uint32_t* d_nsel,
-                                                          unsigned long long* counters) {
-  // one block; every thread owns a contiguous chunk of row groups: count, ONE block-wide scan, write
+                                                          const uint32_t* keep_rows, RgSel* __restrict__ sel, uint32_t* d_nsel,
+                                                          unsigned long long* counters, uint32_t smem_words) {
+  // one block; every thread owns a contiguous chunk of row groups: count, ONE block-wide scan, write.  The keep flags are
+  // staged in shared memory with coalesced loads first (smem_words == 0: too many row groups, read them in place).
+  extern __shared__ uint32_t s_keep[];
   __shared__ uint32_t s_w[33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (smem_words) {
+    for (uint32_t i = threadIdx.x; i < total_rgs; i += 1024) s_keep[i] = keep_rows[i];
+    __syncthreads();
+    keep_rows = s_keep;
+  }
   const uint32_t per = (total_rgs + 1023u) / 1024u;
   const uint32_t lo = threadIdx.x * per;
   const uint32_t hi = lo + per < total_rgs ? lo + per : total_rgs;
@@ -1043,13 +1050,13 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 4;
   while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * uint64_t(items_per_warp)) split *= 2;
   const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
-  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_counters, d_err, d_adj, d_keep, d_bsum, d_bases;
-  CU_TRY(d_work.alloc(64, s));
-  CU_TRY(cudaMemsetAsync(d_work.p, 0, 64, s));
-  CU_TRY(d_counters.alloc(64, s));
-  CU_TRY(cudaMemsetAsync(d_counters.p, 0, 64, s));
-  CU_TRY(d_err.alloc(sizeof(int), s));
-  CU_TRY(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_adj, d_keep, d_bsum, d_bases;
+  // ticket / slot counters, row counters and the error word share one zeroed block (one memset node per call)
+  CU_TRY(d_work.alloc(256, s));
+  CU_TRY(cudaMemsetAsync(d_work.p, 0, 256, s));
+  uint8_t* const zblock = static_cast<uint8_t*>(d_work.p);
+  unsigned long long* const counters_p = reinterpret_cast<unsigned long long*>(zblock + 64);
+  int* const err_p = reinterpret_cast<int*>(zblock + 128);
   const uint64_t rec_cap = bound + 148ull * 8 * kWarpsPerCta * 32;   // + one partly used 32-slot reservation per warp
   CU_TRY(d_rec.alloc(size_t(rec_cap) * sizeof(FRec) + 64, s));
   CU_TRY(d_item.alloc(size_t(nitems + 1) * sizeof(uint32_t) + 64, s));
@@ -1149,8 +1156,8 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     P.rec_cap = uint32_t(rec_cap);
     P.item_cnt = d_item.as<uint32_t>();
     P.work = d_work.as<unsigned int>();
-    P.counters = d_counters.as<unsigned long long>();
-    P.err = d_err.as<int>();
+    P.counters = counters_p;
+    P.err = err_p;
 
     int ctas = int(std::min<uint64_t>((uint64_t(nitems) + kWarpsPerCta - 1) / kWarpsPerCta, 148ull * 8));
     // late materialisation needs a real interval test on the last hot column (the gate)
@@ -1159,8 +1166,12 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     prune_rgs_kernel<<<(total_rgs + 255) / 256, 256, 0, s>>>(P, d_files.as<FileDev>(), int(files.size()), total_rgs,
                                                              (e->flags & HG_FLAG_NO_PRUNING) ? 0 : 1, d_keep.as<uint32_t>());
     L.tick();
-    select_rgs_kernel<<<1, 1024, 0, s>>>(d_files.as<FileDev>(), int(files.size()), total_rgs, d_keep.as<uint32_t>(), d_sel.as<RgSel>(),
-                                         d_work.as<uint32_t>() + 3, d_counters.as<unsigned long long>());
+    {
+      CU_TRY(cudaFuncSetAttribute(select_rgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
+      const uint32_t smem_words = size_t(total_rgs) * 4 <= 200 * 1024 ? total_rgs : 0;
+      select_rgs_kernel<<<1, 1024, size_t(smem_words) * 4, s>>>(d_files.as<FileDev>(), int(files.size()), total_rgs, d_keep.as<uint32_t>(),
+                                                                d_sel.as<RgSel>(), d_work.as<uint32_t>() + 3, counters_p, smem_words);
+    }
     L.tick();
     slot_bases_kernel<<<(total_rgs * MAXC + 255) / 256, 256, 0, s>>>(P, d_bases.as<const uint8_t*>());
     L.tick();
@@ -1177,7 +1188,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
     if (global_mode) {
-      global_count_kernel<<<1, 1, 0, s>>>(d_counters.as<unsigned long long>(), ao);
+      global_count_kernel<<<1, 1, 0, s>>>(counters_p, ao);
       L.tick();
     } else {
       const uint32_t sblocks = (nitems + 1023) / 1024;
@@ -1188,10 +1199,15 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       L.tick();
     }
     auto t3 = now();
-    CU_TRY(cudaMemcpyAsync(hw, d_work.as<uint32_t>() + 1, sizeof(hw), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(hc, d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(&herr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
+    {
+      // one D2H copy of the zeroed block: [4..12) record slots / groups, [64..96) row counters, [128] error word
+      alignas(8) uint8_t hb[192];
+      CU_TRY(cudaMemcpyAsync(hb, zblock, sizeof(hb), cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      std::memcpy(hw, hb + 4, sizeof(hw));
+      std::memcpy(hc, hb + 64, sizeof(hc));
+      std::memcpy(&herr, hb + 128, sizeof(int));
+    }
     auto t4 = now();
     if (trace) fprintf(stderr, "[fused] plan %.0f us, bound+alloc %.0f us, upload+launch %.0f us, wait %.0f us (row groups %u, max items %u)\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), total_rgs, nitems);
     if (herr) return set_error(HG_ERR_INTERNAL, "fused scan: device error " + std::to_string(herr));

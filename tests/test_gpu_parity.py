@@ -296,6 +296,15 @@ def test_aggregate_device_result(eng):
         eng.export_packed(block.data_ptr(), 3)
     st = eng.stats()
     assert st["rows_in_files"] == n and st["kernel_launches"] > 0 and st["gpu_ms"] > 0
+    # the same call with its arguments marshalled once (what bench.py's timed loop uses)
+    prep = eng.prepare_aggregate(handle, _inputs([data]), [("tag", "le", 7)], group_col=0, ts_col=-1, window_ms=0, value_col=2)
+    exp2 = oracle.scan_aggregate([data], schema.arrow_schema, 2, [("tag", "le", 7)], group_col=0, value_col=2)
+    for _ in range(3):
+        d2 = prep.run()
+        assert d2.num_groups == len(exp2.count)
+        s2 = torch.as_tensor(DeviceArray(d2.d_sum, int(d2.num_groups), "<f8"), device="cuda")
+        assert np.array_equal(s2.cpu().numpy(), exp2.sum)
+        assert eng.stats_struct().rows_out == int(exp2.count.sum())
 
 
 def test_transient_selective_load_matches_resident(eng):
