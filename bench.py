@@ -148,12 +148,12 @@ def main():
         if rank != 0:
             return
         nsample = args.files
-        ssts = gen_ssts(0, "snappy", nsample, min(ncores, nsample))   # WriteConfig::default = Snappy (config.rs:120-133)
+        ssts = gen_ssts(0, args.codec, nsample, min(ncores, nsample))  # the SAME files as our arm's main line (same codec)
         rps, rows, dt, _ = cpu_reference(ssts, ncores, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": "scanned rows/s", "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "codec": "snappy"},
+                "config": {"workload": workload, "codec": args.codec},
                 "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": ncores, "kind": "port",
                                  "sample": f"{nsample} SSTs = {rows} rows per step (C restatement of the reference path; the Rust reference cannot be built here)"},
                 "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -329,7 +329,10 @@ def main():
             "metric": "scanned rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "codec": args.codec, "rows_per_gpu": main_r["rows"], "sst_bytes_per_gpu": main_r["file_bytes"],
+            "config": {"workload": workload, "codec": args.codec,
+                       "codec_note": "main line = the SURVEY 8(d) UNCOMPRESSED writer variant (HBM-roofline case); the reference-default "
+                                     "Snappy run of the same workload is under `variants`; --codec snappy swaps them",
+                       "rows_per_gpu": main_r["rows"], "sst_bytes_per_gpu": main_r["file_bytes"],
                        "l2_policy": "inputs (>=1.4 GB per step) far exceed the 126 MB L2; no flush needed",
                        "path": "fused" if st["path"] == 1 else "general", "rows_decoded_per_gpu": st["rows_decoded"],
                        "rows_filtered_per_gpu": st["rows_filtered"], "groups": main_r["groups"],
