@@ -330,8 +330,9 @@ def main():
             "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "codec": args.codec,
-                       "codec_note": "main line = the SURVEY 8(d) UNCOMPRESSED writer variant (HBM-roofline case); the reference-default "
-                                     "Snappy run of the same workload is under `variants`; --codec snappy swaps them",
+                       "codec_note": ("main line = the SURVEY 8(d) UNCOMPRESSED writer variant (HBM-roofline case); the reference-default "
+                                      "Snappy run of the same workload is under `variants`; --codec snappy swaps them") if args.codec == "none"
+                       else "main line = WriteConfig::default (Snappy); the UNCOMPRESSED variant is under `variants`",
                        "rows_per_gpu": main_r["rows"], "sst_bytes_per_gpu": main_r["file_bytes"],
                        "l2_policy": "inputs (>=1.4 GB per step) far exceed the 126 MB L2; no flush needed",
                        "path": "fused" if st["path"] == 1 else "general", "rows_decoded_per_gpu": st["rows_decoded"],
