@@ -1053,6 +1053,7 @@ void hg_engine_destroy(hg_engine* e) {
   g_arena = nullptr;
   e->arena.destroy();
   if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->h_small) cudaFreeHost(e->h_small);
   e->ssts.clear();
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);

@@ -218,6 +218,7 @@ struct hg_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evm0 = nullptr, evm1 = nullptr;  // call / dominant-kernel / merge brackets
   void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
   size_t h_stage_bytes = 0;
+  void* h_small = nullptr;       // 256 pinned bytes: the per-call counter block comes back here (one small D2H)
   Arena arena;
   hg_agg_device last_agg{};      // device pointers of the last aggregate (arena memory, valid until the next call)
   uint32_t last_gwidth = 8;

@@ -4,12 +4,17 @@
 // (group by pk0 [, time bucket of pk1]: count / sequential f64 sum / min / max) with no intermediate column ever
 // written to HBM: algorithmic traffic = the bytes of the columns the query touches (24-28 B/row).
 //
-// Work decomposition: every selected row group is split into `split` (1..8) sub-ranges; one warp owns one sub-range (taken
-// from an atomic ticket, so 148 SMs x resident warps stay busy until the stream is exhausted).  A group (key-run) is
-// owned by the sub-range in which it STARTS: the owner reads past the end of its sub-range until the key changes
-// ("overrun"), the next owner skips the rows of a run it does not own.  This keeps every group's f64 additions in
-// strict stream order (bit-exact with the oracle) without any cross-warp communication.  Group records are appended
-// unordered, tagged (item, local index), and a tiny scatter pass puts them in stream order.
+// Work decomposition: every selected row group is split into `split` (1..8) sub-ranges whose boundaries
+// item_bounds_kernel moves to the next key-run start, so the work items are disjoint, cover the stream, and no group
+// spans two of them.  One warp owns one item (taken from an atomic ticket, so 148 SMs x resident warps stay busy until the
+// stream is exhausted) and sums its groups in strict stream order (bit-exact with the oracle) without any cross-warp
+// communication.  Group records are appended unordered, tagged (item, local index), and a tiny scatter pass puts them
+// in stream order.
+//
+// Late materialisation (GATED kernels): the narrowest predicate column is swept first, 512 rows per warp step; the other
+// columns are read only for the 64-row blocks that hold a passing row, the value column only for survivors.  The
+// reference filters before it merges and dedups (read.rs:459-480), so rows that fail the predicate take part in
+// nothing downstream.
 #include "fused_scan.h"
 
 #include <algorithm>
@@ -683,7 +688,7 @@ __device__ __forceinline__ void prefetch_blocks(const Hot<NH>& H, const uint8_t*
 }
 
 // kU = slices whose loads are issued together; NH = hot columns (pk0, pk1, + predicate columns) loaded for every row
-template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS, int kPF, bool GATED>
+template <int kU, int kMinBlocks, int NH, int X, bool HAS_TS, bool GATED>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kernel(const __grid_constant__ FParams P,
                                                                                     const uint64_t* __restrict__ adj) {
   __shared__ double s_vals_all[kWarpsPerCta][32];
@@ -798,12 +803,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
   }
 }
 
-template <int kU, int kMinBlocks, int kPF>
+template <int kU, int kMinBlocks>
 void launch_fused(int nhot, int xmask, bool has_ts, bool gated, int ctas, cudaStream_t s, const FParams& P, const uint64_t* adj) {
 #define HG_LAUNCH2(NH, XM, TS)                                                                                           \
   do {                                                                                                                   \
-    if (gated) fused_scan_kernel<kU, kMinBlocks, NH, XM, TS, kPF, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);      \
-    else fused_scan_kernel<kU, kMinBlocks, NH, XM, TS, kPF, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);           \
+    if (gated) fused_scan_kernel<kU, kMinBlocks, NH, XM, TS, true><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);      \
+    else fused_scan_kernel<kU, kMinBlocks, NH, XM, TS, false><<<ctas, kWarpsPerCta * 32, 0, s>>>(P, adj);           \
   } while (0)
 #define HG_LAUNCH(NH, XM)                                                                                                \
   do {                                                                                                                   \
@@ -1183,8 +1188,8 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       L.tick();
     }
     CU_TRY(cudaEventRecord(e->evk0, s));
-    // 2 slices per block, 4 CTAs/SM, L2 prefetch 2 blocks ahead (measured best of {0,2,3,4} blocks: profiles/README.md)
-    launch_fused<2, 4, 2>(nhot, xmask, has_ts, gated, ctas, s, P, d_adj.as<uint64_t>());
+    // 2 slices per block, 4 CTAs/SM (measured best of {3,4,5,6}: profiles/README.md), L2 prefetch 2 blocks / sweeps ahead
+    launch_fused<2, 4>(nhot, xmask, has_ts, gated, ctas, s, P, d_adj.as<uint64_t>());
     L.tick();
     CU_TRY(cudaEventRecord(e->evk1, s));
     if (global_mode) {
@@ -1201,8 +1206,9 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     auto t3 = now();
     {
       // one D2H copy of the zeroed block: [4..12) record slots / groups, [64..96) row counters, [128] error word
-      alignas(8) uint8_t hb[192];
-      CU_TRY(cudaMemcpyAsync(hb, zblock, sizeof(hb), cudaMemcpyDeviceToHost, s));
+      if (!e->h_small) CU_TRY(cudaMallocHost(&e->h_small, 256));
+      uint8_t* const hb = static_cast<uint8_t*>(e->h_small);
+      CU_TRY(cudaMemcpyAsync(hb, zblock, 192, cudaMemcpyDeviceToHost, s));
       CU_TRY(cudaStreamSynchronize(s));
       std::memcpy(hw, hb + 4, sizeof(hw));
       std::memcpy(hc, hb + 64, sizeof(hc));
