@@ -71,9 +71,22 @@ class ArrowArrayStream(C.Structure):
                 ("release", C.c_void_p), ("private_data", C.c_void_p)]
 
 
+class HgParquetSummary(C.Structure):
+    _fields_ = [("num_rows", C.c_uint64), ("num_row_groups", C.c_uint32), ("num_columns", C.c_uint32), ("num_data_pages", C.c_uint64),
+                ("sum_page_values", C.c_uint64), ("sum_uncompressed_bytes", C.c_uint64), ("sum_compressed_bytes", C.c_uint64),
+                ("codec_mask", C.c_uint32), ("max_pages_per_chunk", C.c_uint32)]
+
+
+class HgParquetChunk(C.Structure):
+    _fields_ = [("num_rows", C.c_uint64), ("num_values", C.c_uint64), ("data_page_offset", C.c_int64), ("total_compressed_size", C.c_int64),
+                ("null_count", C.c_int64), ("min", C.c_uint8 * 8), ("max", C.c_uint8 * 8), ("has_min_max", C.c_uint32),
+                ("physical_type", C.c_uint32), ("codec", C.c_uint32), ("num_pages", C.c_uint32), ("first_page_payload_offset", C.c_uint64),
+                ("first_page_num_values", C.c_uint32), ("first_page_type", C.c_uint32)]
+
+
 EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_engine_set_flags", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
-           "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats"]
+           "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info"]
 
 _lib = None
 
@@ -291,3 +304,22 @@ class PreparedAggregate:
         if rc:
             _check(rc)
         return self.out
+
+
+def parquet_inspect(data: bytes) -> dict:
+    """Host-only (no GPU): the library's reading of an SST's footer and page headers."""
+    L = lib()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = HgParquetSummary()
+    _check(L.hg_parquet_inspect(C.c_void_p(buf.ctypes.data), C.c_uint64(buf.nbytes), C.byref(out)))
+    return {f[0]: getattr(out, f[0]) for f in HgParquetSummary._fields_}
+
+
+def parquet_chunk_info(data: bytes, row_group: int, column: int) -> dict:
+    L = lib()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = HgParquetChunk()
+    _check(L.hg_parquet_chunk_info(C.c_void_p(buf.ctypes.data), C.c_uint64(buf.nbytes), C.c_uint32(row_group), C.c_uint32(column), C.byref(out)))
+    d = {f[0]: getattr(out, f[0]) for f in HgParquetChunk._fields_}
+    d["min"], d["max"] = bytes(out.min), bytes(out.max)
+    return d

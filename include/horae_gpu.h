@@ -173,6 +173,34 @@ int hg_agg_export_packed(hg_engine* e, void* d_dst, uint64_t cap);
 
 int hg_last_stats(hg_engine* e, hg_scan_stats* out);
 
+/* ---- host-only inspection of an SST (no engine, no GPU): what the planner reads from the footer and the page headers.
+ * In the reference this is parquet-rs's metadata reader behind ParquetExec (read.rs:66-93, 442-465); the CPU test-suite
+ * checks it against pyarrow's reading of the same bytes. */
+typedef struct {
+  uint64_t num_rows;
+  uint32_t num_row_groups, num_columns;
+  uint64_t num_data_pages;
+  uint64_t sum_page_values;          /* sum of num_values over all data pages */
+  uint64_t sum_uncompressed_bytes;   /* sum of uncompressed page payload sizes (page headers excluded) */
+  uint64_t sum_compressed_bytes;     /* the same, as stored */
+  uint32_t codec_mask;               /* bit c set: some column chunk uses Parquet codec id c (0 uncompressed, 1 Snappy) */
+  uint32_t max_pages_per_chunk;
+} hg_parquet_summary;
+
+typedef struct {
+  uint64_t num_rows;                 /* rows of the row group */
+  uint64_t num_values;               /* values of the column chunk (nulls included) */
+  int64_t data_page_offset, total_compressed_size;
+  int64_t null_count;                /* -1: not recorded */
+  uint8_t min[8], max[8];            /* PLAIN-encoded statistics (little endian), valid if has_min_max */
+  uint32_t has_min_max, physical_type, codec, num_pages;
+  uint64_t first_page_payload_offset;
+  uint32_t first_page_num_values, first_page_type;   /* 0 = DataPage V1, 3 = DataPage V2 */
+} hg_parquet_chunk;
+
+int hg_parquet_inspect(const uint8_t* data, uint64_t size, hg_parquet_summary* out);
+int hg_parquet_chunk_info(const uint8_t* data, uint64_t size, uint32_t row_group, uint32_t column, hg_parquet_chunk* out);
+
 #ifdef __cplusplus
 }
 #endif
