@@ -86,7 +86,7 @@ class HgParquetChunk(C.Structure):
 
 EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_engine_set_flags", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
-           "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info"]
+           "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info", "hg_plan_row_groups"]
 
 _lib = None
 
@@ -323,3 +323,16 @@ def parquet_chunk_info(data: bytes, row_group: int, column: int) -> dict:
     d = {f[0]: getattr(out, f[0]) for f in HgParquetChunk._fields_}
     d["min"], d["max"] = bytes(out.min), bytes(out.max)
     return d
+
+
+def plan_row_groups(schema: "SchemaHandle", data: bytes, preds: Sequence[tuple] = ()) -> list:
+    """Host-only (no GPU): the planner's statistics pruning for one SST -> one 0/1 flag per row group."""
+    L = lib()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    p = _make_preds(schema.arrow_schema, preds)
+    cap = 1 << 16
+    keep = (C.c_uint8 * cap)()
+    n = C.c_uint32()
+    _check(L.hg_plan_row_groups(C.byref(schema.desc), C.c_void_p(buf.ctypes.data), C.c_uint64(buf.nbytes), p, C.c_size_t(len(preds)),
+                                keep, C.c_uint32(cap), C.byref(n)))
+    return [int(keep[i]) for i in range(n.value)]

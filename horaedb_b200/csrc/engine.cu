@@ -1113,6 +1113,29 @@ int hg_agg_export_packed(hg_engine* e, void* d_dst, uint64_t cap) {
   return HG_OK;
 }
 
+int hg_plan_row_groups(const hg_schema_desc* schema, const uint8_t* data, uint64_t size, const hg_predicate* preds, size_t n_preds,
+                       uint8_t* keep, uint32_t cap, uint32_t* num_row_groups) {
+  if (!data || !keep || !num_row_groups || (n_preds && !preds)) return set_error(HG_ERR_INVALID, "null argument");
+  int rc = validate_schema(schema);
+  if (rc) return rc;
+  rc = validate_preds(schema, preds, n_preds);
+  if (rc) return rc;
+  SstResident r;
+  std::vector<PageDev> pages;
+  std::vector<ChunkDev> chunks;
+  std::string err;
+  rc = prepare_sst(schema, 0, data, size, &r, &pages, &chunks, &err);
+  if (rc) return set_error(rc, err);
+  const size_t nrg = r.rg_rows.size(), ncols = size_t(r.meta.ncols);
+  *num_row_groups = uint32_t(nrg);
+  if (nrg > cap) return set_error(HG_ERR_INVALID, "keep[] is smaller than the number of row groups");
+  uint64_t lits[MAX_PREDS];
+  for (size_t i = 0; i < n_preds; i++) lits[i] = pred_literal(preds[i], schema->types[preds[i].column]);
+  for (size_t g = 0; g < nrg; g++)
+    keep[g] = r.rg_rows[g] > 0 && (n_preds == 0 || rg_may_match(&r.rgcol[g * ncols], r.rg_rows[g], schema, preds, lits, n_preds)) ? 1 : 0;
+  return HG_OK;
+}
+
 int hg_last_stats(hg_engine* e, hg_scan_stats* out) {
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);

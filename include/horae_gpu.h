@@ -198,6 +198,13 @@ typedef struct {
   uint32_t first_page_num_values, first_page_type;   /* 0 = DataPage V1, 3 = DataPage V2 */
 } hg_parquet_chunk;
 
+/* The planner's statistics pruning for ONE SST, host only: keep[g] = 1 iff row group g can hold a row matching the
+ * conjunction (DataFusion's PruningPredicate as pinned by the plan text at read.rs:613: CASE WHEN null_count = row_count
+ * THEN false ELSE <min/max rewrite> END).  Also runs the schema / predicate / file validation every scan call runs.
+ * HG_ERR_INVALID if cap < number of row groups. */
+int hg_plan_row_groups(const hg_schema_desc* schema, const uint8_t* data, uint64_t size, const hg_predicate* preds, size_t n_preds,
+                       uint8_t* keep, uint32_t cap, uint32_t* num_row_groups);
+
 int hg_parquet_inspect(const uint8_t* data, uint64_t size, hg_parquet_summary* out);
 int hg_parquet_chunk_info(const uint8_t* data, uint64_t size, uint32_t row_group, uint32_t column, hg_parquet_chunk* out);
 
