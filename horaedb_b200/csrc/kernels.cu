@@ -47,14 +47,6 @@ __device__ __forceinline__ uint32_t ld32_any(const uint8_t* p) {
   return (lo >> sh) | (hi << (32 - sh));
 }
 
-__device__ __forceinline__ uint32_t type_width(uint32_t t) {
-  switch (t) {
-    case T_U8: case T_I8: return 1;
-    case T_U16: case T_I16: return 2;
-    case T_U32: case T_I32: case T_F32: return 4;
-    default: return 8;
-  }
-}
 __device__ __forceinline__ bool type_signed(uint32_t t) { return t == T_I8 || t == T_I16 || t == T_I32 || t == T_I64; }
 __device__ __forceinline__ bool type_float(uint32_t t) { return t == T_F32 || t == T_F64; }
 
@@ -564,7 +556,7 @@ __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const SortRec* __r
     bool first = true;
     while (pos < tile_hi) {
       const PairView p = pair_of(run_start, k, level, nruns, pos);
-      const uint32_t na = p.a1 - p.a0, nb = p.b1 - p.a1;
+      const uint32_t na = p.a1 - p.a0;
       const uint32_t seg_hi = tile_hi < p.b1 ? tile_hi : p.b1;
       const uint32_t d0 = pos - p.a0, d1 = seg_hi - p.a0;
       const SortRec* A = src + p.a0;
