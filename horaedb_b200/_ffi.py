@@ -155,10 +155,20 @@ def _make_preds(arrow_schema: pa.Schema, preds: Sequence[tuple]):
         arr[k].op = HG_OPS[op]
         if pa.types.is_floating(t):
             arr[k].f64 = float(lit)
-        elif pa.types.is_signed_integer(t):
-            arr[k].i64 = int(lit)
         else:
-            arr[k].u64 = int(lit)
+            # no silent truncation / wrap-around: a literal the column type cannot hold must be rewritten by the caller
+            # (DataFusion would coerce the comparison to a wider type; this ABI compares in the column's own domain)
+            if isinstance(lit, float) and not lit.is_integer():
+                raise HgError(1, f"predicate literal {lit!r} is not integral for column {arrow_schema.field(idx).name}")
+            iv = int(lit)
+            bits = t.bit_width
+            lo, hi = (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if pa.types.is_signed_integer(t) else (0, (1 << bits) - 1)
+            if not lo <= iv <= hi:
+                raise HgError(1, f"predicate literal {iv} does not fit column {arrow_schema.field(idx).name} ({t})")
+            if pa.types.is_signed_integer(t):
+                arr[k].i64 = iv
+            else:
+                arr[k].u64 = iv
     return arr
 
 

@@ -6,7 +6,21 @@
 namespace horae {
 
 enum : uint32_t { T_U8 = 0, T_I8, T_U16, T_I16, T_U32, T_I32, T_U64, T_I64, T_F32, T_F64 };
-enum : uint32_t { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE };
+enum : uint32_t { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN };
+
+#if defined(__CUDACC__)
+#define HORAE_HD __host__ __device__ __forceinline__
+#else
+#define HORAE_HD inline
+#endif
+// Floats compare in IEEE-754 totalOrder, like arrow-rs 53's comparison kernels behind DataFusion's FilterExec and
+// PruningPredicate (read.rs:459-470): -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN.  The key maps f64 bits to an
+// unsigned integer with the same order.
+HORAE_HD uint64_t f64_total_order_key(uint64_t bits) { return bits ^ ((bits >> 63) ? ~0ull : (1ull << 63)); }
+HORAE_HD int cmp_f64_total(uint64_t a, uint64_t b) {
+  const uint64_t x = f64_total_order_key(a), y = f64_total_order_key(b);
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
 
 // One data page (resident next to its SST's bytes).  32 bytes.
 struct PageDev {

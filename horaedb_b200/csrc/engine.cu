@@ -72,6 +72,37 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
         return fail(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED and SNAPPY are implemented)");
       if (cm.has_dict_page) return fail(HG_ERR_UNSUPPORTED, "dictionary-encoded column chunk");
       if (cm.scratch_bytes > 0xffffffffull) return fail(HG_ERR_UNSUPPORTED, "column chunk larger than 4 GiB");
+      // every kernel indexes a chunk by the ROW GROUP's row count: the chunk must hold exactly that many values, and an
+      // uncompressed page must really contain the bytes the decoders will read (compressed pages are bounded by their
+      // scratch size on the device)
+      if (cm.num_values != m.rgs[g].num_rows)
+        return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": column chunk value count differs from the row group's row count");
+      {
+        const uint32_t pw = (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4u : 8u;
+        const bool optional = m.repetition[c] == 1;
+        const bool no_nulls = !optional || (cm.stats.has_null_count && cm.stats.null_count == 0);
+        for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++) {
+          const PageMeta& pm = m.pages[pi];
+          if (pm.page_type == PAGE_DATA_V2) {
+            if (uint64_t(pm.v2_def_len) + pm.v2_rep_len > pm.comp_size || uint64_t(pm.v2_def_len) + pm.v2_rep_len > pm.uncomp_size)
+              return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": V2 level bytes exceed the page");
+            if (no_nulls && uint64_t(pm.v2_def_len) + pm.v2_rep_len + uint64_t(pm.num_values) * pw > pm.uncomp_size)
+              return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": page smaller than its values");
+          } else if (cm.codec == CODEC_UNCOMPRESSED) {
+            if (pm.comp_size != pm.uncomp_size) return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": uncompressed page with differing sizes");
+            uint64_t prefix = 0;
+            if (optional) {
+              if (pm.uncomp_size < 4) return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": page smaller than its level header");
+              uint32_t dl;
+              std::memcpy(&dl, data + pm.payload_off, 4);
+              prefix = 4 + uint64_t(dl);
+              if (prefix > pm.uncomp_size) return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": definition levels exceed the page");
+            }
+            if (no_nulls && prefix + uint64_t(pm.num_values) * pw > pm.uncomp_size)
+              return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": page smaller than its values");
+          }
+        }
+      }
       ChunkDev& cd = chunks[g * m.ncols + c];
       cd.first_page = cm.first_page;
       cd.num_pages = cm.num_pages;
@@ -133,9 +164,9 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
 static int read_whole_file(const char* path, std::vector<uint8_t>* buf) {
   FILE* f = std::fopen(path, "rb");
   if (!f) return set_error(HG_ERR_NOT_FOUND, std::string("cannot open ") + path);
-  std::fseek(f, 0, SEEK_END);
-  long n = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
+  long n = -1;
+  if (std::fseek(f, 0, SEEK_END) == 0) n = std::ftell(f);
+  if (n < 0 || std::fseek(f, 0, SEEK_SET) != 0) { std::fclose(f); return set_error(HG_ERR_NOT_FOUND, std::string("cannot size ") + path); }
   buf->resize(size_t(n));
   size_t got = std::fread(buf->data(), 1, size_t(n), f);
   std::fclose(f);
@@ -1182,6 +1213,10 @@ static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
 static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds,
                      size_t np, const uint32_t* projection, size_t nproj, int keep_builtin, struct ArrowArrayStream* out) {
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
+  {
+    int vrc = validate_schema(schema);     // before anything reads schema->num_columns
+    if (vrc) return vrc;
+  }
   std::lock_guard<std::mutex> g(e->mu);
   std::vector<uint32_t> touch;
   if (projection) for (size_t i = 0; i < nproj; i++) { if (projection[i] < schema->num_columns) touch.push_back(projection[i]); }
@@ -1418,13 +1453,14 @@ int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
     hc.name = sc.name;
     hc.type = sc.type;
     hc.width = sc.width;
+    data->cols.push_back(hc);                 // owned by the stream from here on: an early return releases the pinned buffer
     if (G) {
-      hc.vals = pinned_pool().alloc(size_t(G) * sc.width + 16);
-      if (!hc.vals) return set_error(HG_ERR_OOM, "pinned host memory");
-      CU_TRY(cudaMemcpyAsync(hc.vals, sc.dev, size_t(G) * sc.width, cudaMemcpyDeviceToHost, s));
+      HostColumn& col = data->cols.back();
+      col.vals = pinned_pool().alloc(size_t(G) * sc.width + 16);
+      if (!col.vals) return set_error(HG_ERR_OOM, "pinned host memory");
+      CU_TRY(cudaMemcpyAsync(col.vals, sc.dev, size_t(G) * sc.width, cudaMemcpyDeviceToHost, s));
       d2h += size_t(G) * sc.width;
     }
-    data->cols.push_back(hc);
   }
   CU_TRY(cudaEventRecord(e->ev1, s));
   CU_TRY(cudaStreamSynchronize(s));

@@ -74,12 +74,7 @@ inline uint64_t widen_stat(const uint8_t raw[8], int phys, uint32_t t) {
   return v;
 }
 inline int cmp_host(uint64_t a, uint64_t b, uint32_t t) {
-  if (type_is_float(t)) {
-    double x, y;
-    std::memcpy(&x, &a, 8);
-    std::memcpy(&y, &b, 8);
-    return x < y ? -1 : (x > y ? 1 : 0);
-  }
+  if (type_is_float(t)) return cmp_f64_total(a, b);   // IEEE totalOrder, like arrow-rs (device_types.h)
   if (type_is_signed(t)) {
     int64_t x = int64_t(a), y = int64_t(b);
     return x < y ? -1 : (x > y ? 1 : 0);

@@ -99,10 +99,8 @@ __device__ __forceinline__ uint64_t load_kind(const uint8_t* base, uint32_t kind
 }
 __device__ __forceinline__ bool pred_ok(uint64_t v, uint64_t lit, uint32_t cls, uint32_t op) {
   int c;
-  if (cls == C_FLOAT) {
-    double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)lit);
-    c = x < y ? -1 : (x > y ? 1 : 0);
-  } else if (cls == C_SIGNED) {
+  if (cls == C_FLOAT) c = cmp_f64_total(v, lit);
+  else if (cls == C_SIGNED) {
     int64_t x = int64_t(v), y = int64_t(lit);
     c = x < y ? -1 : (x > y ? 1 : 0);
   } else c = v < lit ? -1 : (v > lit ? 1 : 0);
@@ -211,10 +209,7 @@ struct FileDev {
 };
 
 __device__ __forceinline__ int cmp3(uint64_t a, uint64_t b, uint32_t cls) {
-  if (cls == C_FLOAT) {
-    double x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b);
-    return x < y ? -1 : (x > y ? 1 : 0);
-  }
+  if (cls == C_FLOAT) return cmp_f64_total(a, b);
   if (cls == C_SIGNED) { int64_t x = int64_t(a), y = int64_t(b); return x < y ? -1 : (x > y ? 1 : 0); }
   return a < b ? -1 : (a > b ? 1 : 0);
 }

@@ -73,10 +73,7 @@ __device__ __forceinline__ uint64_t col_widened(const ColView& c, uint32_t row) 
 __device__ __forceinline__ bool col_valid(const ColView& c, uint32_t row) { return c.valid == nullptr || c.valid[row] != 0; }
 
 __device__ __forceinline__ int cmp_widened(uint64_t a, uint64_t b, uint32_t t) {
-  if (type_float(t)) {
-    double x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b);
-    return x < y ? -1 : (x > y ? 1 : 0);
-  }
+  if (type_float(t)) return cmp_f64_total(a, b);
   if (type_signed(t)) {
     int64_t x = int64_t(a), y = int64_t(b);
     return x < y ? -1 : (x > y ? 1 : 0);
@@ -282,6 +279,10 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
         val_ptr = body + 4 + lv_len;
       } else val_ptr = body;
     }
+    // values available in this page (malformed pages must not make the decoder read past the page: ABI = HG_ERR_FORMAT)
+    const uint8_t* page_end = (ch.codec == 1 && !(pg.page_type == 3 && !pg.v2_compressed)) ? sc + (pg.page_type == 3 ? pg.uncomp_size - pg.v2_def_len - pg.v2_rep_len : pg.uncomp_size)
+                                                                                       : payload + pg.comp_size;
+    const uint32_t max_vals = val_ptr <= page_end ? uint32_t(size_t(page_end - val_ptr) / pw) : 0u;
     if (ch.codec == 1) sc += page_scratch(pg.uncomp_size);
 
     bool all_valid = true;
@@ -325,7 +326,9 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
         __syncthreads();
       }
     }
-    if (all_valid) {
+    if (all_valid && nv > max_vals) {
+      if (tid == 0) s_bad = 3;
+    } else if (all_valid) {
       if (pw == 8) {
         for (uint32_t j = tid; j < nv; j += kThreads) store_val<8>(cs.out_vals, row + j, ld64_any<false>(val_ptr + size_t(j) * 8));
       } else {
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
         uint32_t kidx = running + block_excl_scan(v, &total, s_warp);
         if (j < nv) {
           uint64_t x = 0;
+          if (v && kidx >= max_vals) { s_bad = 3; v = 0; }
           if (v) x = pw == 8 ? ld64_any<false>(val_ptr + size_t(kidx) * 8) : uint64_t(ld32_any(val_ptr + size_t(kidx) * 4));
           store_val_dyn(cs.out_vals, cs.out_width, row + j, x);
         }

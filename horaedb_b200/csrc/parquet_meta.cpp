@@ -29,6 +29,9 @@ class Compact {
   // Iterates the fields of a struct: cb(field_id, wire_type) must consume the value (or call skip).
   template <class F>
   void each_field(F&& cb) {
+    // nesting cap: footers / page headers are untrusted bytes and skip() recurses through structs, lists and maps
+    if (++depth_ > kMaxDepth) { fail(); --depth_; return; }
+    struct Leave { int& d; ~Leave() { --d; } } leave{depth_};
     int fid = 0;
     while (ok_) {
       if (p_ >= end_) { fail(); return; }
@@ -42,6 +45,8 @@ class Compact {
   // Iterates list elements: cb(index, elem_wire_type)
   template <class F>
   void each_elem(F&& cb) {
+    if (++depth_ > kMaxDepth) { fail(); --depth_; return; }
+    struct Leave { int& d; ~Leave() { --d; } } leave{depth_};
     if (p_ >= end_) { fail(); return; }
     uint8_t h = *p_++;
     uint64_t n = h >> 4;
@@ -80,7 +85,9 @@ class Compact {
         if (n == 0) return;
         if (p_ >= end_) { fail(); return; }
         uint8_t kv = *p_++;
+        if (++depth_ > kMaxDepth) { fail(); --depth_; return; }
         for (uint64_t i = 0; i < n && ok_; i++) { skip(kv >> 4); skip(kv & 0x0f); }
+        --depth_;
         return;
       }
       case 12: each_field([&](int, int t) { skip(t); }); return;
@@ -91,9 +98,11 @@ class Compact {
  private:
   uint64_t fail() { ok_ = false; return 0; }
   void advance(uint64_t n) { if (uint64_t(end_ - p_) < n) fail(); else p_ += n; }
+  static constexpr int kMaxDepth = 32;
   const uint8_t* p_;
   const uint8_t* end_;
   bool ok_ = true;
+  int depth_ = 0;
 };
 
 void read_stats(Compact& c, ColumnStats* st) {
@@ -135,7 +144,13 @@ bool read_page_header(const uint8_t* p, const uint8_t* end, PageHeader* h) {
     if (fid == 1) h->type = int(c.svar());
     else if (fid == 2) h->uncomp = int32_t(c.svar());
     else if (fid == 3) h->comp = int32_t(c.svar());
-    else if ((fid == 5 || fid == 7) && wt == 12) {
+    else if (fid == 5 && wt == 12) {
+      c.each_field([&](int f2, int t2) {
+        if (f2 == 1) h->num_values = int32_t(c.svar());
+        else if (f2 == 2) h->encoding = int32_t(c.svar());
+        else c.skip(t2);
+      });
+    } else if (fid == 7 && wt == 12) {      // DictionaryPageHeader
       c.each_field([&](int f2, int t2) {
         if (f2 == 1) h->num_values = int32_t(c.svar());
         else if (f2 == 2) h->encoding = int32_t(c.svar());
@@ -153,6 +168,7 @@ bool read_page_header(const uint8_t* p, const uint8_t* end, PageHeader* h) {
     } else c.skip(wt);
   });
   h->header_len = size_t(c.pos() - p);
+  if (h->uncomp < 0 || h->comp < 0 || h->num_values < 0 || h->v2_def_len < 0 || h->v2_rep_len < 0) return false;   // sizes are i32 on the wire
   return c.ok();
 }
 
@@ -232,7 +248,14 @@ bool parse_parquet(const uint8_t* data, size_t len, FileMetaData* out, std::stri
         uint64_t payload = pos + h.header_len;
         if (h.comp < 0 || payload + uint64_t(h.comp) > len) return bad("page payload beyond end of file");
         pos = payload + uint64_t(h.comp);
-        if (h.type == PAGE_DICT) { cm.has_dict_page = true; continue; }
+        if (h.type == PAGE_DICT) {
+          cm.has_dict_page = true;
+          cm.dict_payload_off = payload;
+          cm.dict_comp_size = uint32_t(h.comp);
+          cm.dict_uncomp_size = uint32_t(h.uncomp);
+          cm.dict_num_values = uint32_t(h.num_values);
+          continue;
+        }
         if (h.type != PAGE_DATA && h.type != PAGE_DATA_V2) continue;
         PageMeta pm;
         pm.payload_off = payload;

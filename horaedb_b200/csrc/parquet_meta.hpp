@@ -38,6 +38,8 @@ struct ChunkMeta {
   uint32_t first_page = 0, num_pages = 0;   // into FileMetaData::pages (data pages only)
   uint64_t scratch_bytes = 0;               // bytes of decompression scratch this chunk needs
   bool has_dict_page = false;
+  uint64_t dict_payload_off = 0;            // dictionary page (RLE_DICTIONARY chunks): PLAIN values
+  uint32_t dict_comp_size = 0, dict_uncomp_size = 0, dict_num_values = 0;
 };
 
 struct RowGroupMeta {

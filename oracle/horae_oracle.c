@@ -418,7 +418,12 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
 
 /* ---------------------------------------------------------------------------------------- typed compares */
 static int cmp_typed(uint64_t a, uint64_t b, int t) {
-    if (type_is_float(t)) { double x, y; memcpy(&x, &a, 8); memcpy(&y, &b, 8); return x < y ? -1 : (x > y ? 1 : 0); }
+    /* arrow-rs 53 comparison kernels (behind FilterExec / PruningPredicate, read.rs:459-470) order floats by IEEE-754
+       totalOrder: NaN is above +inf (below -inf when its sign bit is set) and -0.0 < +0.0 */
+    if (type_is_float(t)) {
+        uint64_t x = a ^ ((a >> 63) ? ~(uint64_t)0 : ((uint64_t)1 << 63)), y = b ^ ((b >> 63) ? ~(uint64_t)0 : ((uint64_t)1 << 63));
+        return x < y ? -1 : (x > y ? 1 : 0);
+    }
     if (type_is_signed(t)) { int64_t x = (int64_t)a, y = (int64_t)b; return x < y ? -1 : (x > y ? 1 : 0); }
     return a < b ? -1 : (a > b ? 1 : 0);
 }
