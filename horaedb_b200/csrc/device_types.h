@@ -38,7 +38,7 @@ struct ChunkDev {
   uint8_t phys;            // parquet physical type
   uint8_t codec;           // 0 uncompressed, 1 snappy
   uint8_t optional;        // max definition level 1
-  uint8_t _pad;
+  uint8_t stored;          // Snappy, one V1 page, stream = 1-2 literals whose value bytes are row-aligned: readable in place
 };
 
 struct SstDev {

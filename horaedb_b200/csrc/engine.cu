@@ -29,6 +29,62 @@ int set_error(int code, const std::string& msg) {
   return code;
 }
 
+// A Snappy stream that holds only literals is the page's bytes behind a few header bytes: incompressible columns (random
+// f64 values) are written as one literal per 64 KiB block.  Returns true when the single V1 page of the chunk is such a
+// stream with at most two literals, the level prefix lies inside the first one and the value bytes of both are whole
+// values, i.e. row i can be addressed in place: the fused scan then never decompresses the column.
+static bool classify_stored(const uint8_t* data, uint64_t size, const PageMeta& pm, bool optional, uint32_t width, uint64_t rows) {
+  const uint8_t* p = data + pm.payload_off;
+  const uint8_t* end = p + pm.comp_size;
+  if (pm.payload_off + pm.comp_size > size) return false;
+  uint64_t ulen = 0;
+  int sh = 0;
+  for (;;) {
+    if (p >= end || sh > 28) return false;
+    const uint8_t b = *p++;
+    ulen |= uint64_t(b & 0x7f) << sh;
+    sh += 7;
+    if (!(b & 0x80)) break;
+  }
+  if (ulen != pm.uncomp_size) return false;
+  uint64_t lens[2] = {0, 0};
+  const uint8_t* lit[2] = {nullptr, nullptr};
+  int n = 0;
+  uint64_t total = 0;
+  while (p < end) {
+    if (n == 2) return false;
+    const uint8_t t = *p;
+    if (t & 3) return false;                       // a copy element: real compression
+    uint64_t len = t >> 2;
+    uint32_t hdr = 1;
+    if (len >= 60) {
+      const uint32_t nb = uint32_t(len) - 59;
+      if (p + 1 + nb > end) return false;
+      len = 0;
+      for (uint32_t i = 0; i < nb; i++) len |= uint64_t(p[1 + i]) << (8 * i);
+      hdr = 1 + nb;
+    }
+    len += 1;
+    if (p + hdr + len > end) return false;
+    lit[n] = p + hdr;
+    lens[n] = len;
+    n++;
+    total += len;
+    p += hdr + len;
+  }
+  if (n == 0 || total != ulen) return false;
+  uint64_t prefix = 0;
+  if (optional) {
+    if (lens[0] < 4) return false;
+    uint32_t dl;
+    std::memcpy(&dl, lit[0], 4);
+    prefix = 4 + uint64_t(dl);
+    if (prefix > lens[0]) return false;
+  }
+  if ((lens[0] - prefix) % width != 0 || lens[1] % width != 0) return false;
+  return lens[0] - prefix + lens[1] == rows * width;
+}
+
 // Host-only, thread-safe: footer + page walk, validation against the schema, device tables, planning facts.
 static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t* data, uint64_t size, SstResident* r,
                        std::vector<PageDev>* pages_out, std::vector<ChunkDev>* chunks_out, std::string* errmsg) {
@@ -110,7 +166,10 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       cd.phys = uint8_t(cm.phys_type);
       cd.codec = uint8_t(cm.codec);
       cd.optional = uint8_t(m.repetition[c] == 1);
-      cd._pad = 0;
+      cd.stored = 0;
+      if (cm.codec == CODEC_SNAPPY && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.rgs[g].num_rows > 0)
+        cd.stored = classify_stored(data, size, m.pages[cm.first_page], cd.optional != 0,
+                                    (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4u : 8u, uint64_t(m.rgs[g].num_rows)) ? 1 : 0;
     }
   r->rgcol.resize(m.rgs.size() * size_t(m.ncols));
   r->rg_rows.resize(m.rgs.size());
@@ -130,11 +189,16 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       rc.snappy = cm.codec == CODEC_SNAPPY;
       rc.scratch = uint32_t(cm.scratch_bytes);
       rc.simple_page = cm.codec == CODEC_UNCOMPRESSED && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA;
+      rc.single_page = cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA;
+      rc.stored = chunks[g * m.ncols + c].stored;
     }
   }
   {
     const uint32_t t0 = schema->types[0];
-    for (int c = 0; c < m.ncols && c < MAX_COLS; c++) { r->col_all_simple[c] = true; r->col_null_none[c] = true; r->col_has_minmax[c] = true; }
+    for (int c = 0; c < m.ncols && c < MAX_COLS; c++) {
+      r->col_all_simple[c] = true; r->col_null_none[c] = true; r->col_has_minmax[c] = true;
+      r->col_all_single[c] = true; r->col_any_snappy[c] = false; r->col_snappy_all_stored[c] = true;
+    }
     bool first = true;
     r->pk0_range_ok = true;
     for (size_t g = 0; g < m.rgs.size(); g++) {
@@ -144,6 +208,10 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       const RgCol* rc = &r->rgcol[g * m.ncols];
       for (int c = 0; c < m.ncols && c < MAX_COLS; c++) {
         if (!rc[c].simple_page) r->col_all_simple[c] = false;
+        if (!rc[c].single_page) r->col_all_single[c] = false;
+        if (rc[c].snappy) { r->col_any_snappy[c] = true; if (!rc[c].stored) r->col_snappy_all_stored[c] = false; }
+        r->col_max_scratch[c] = std::max(r->col_max_scratch[c], rc[c].scratch);
+        r->col_comp_bytes[c] += uint64_t(m.rgs[g].cols[c].total_compressed);
         if (!rc[c].null_none) r->col_null_none[c] = false;
         if (!rc[c].has_minmax) r->col_has_minmax[c] = false;
       }
@@ -1069,6 +1137,8 @@ int hg_engine_create(const hg_config* cfg, hg_engine** out) {
   CU_TRY(cudaEventCreate(&e->evk1));
   CU_TRY(cudaEventCreate(&e->evm0));
   CU_TRY(cudaEventCreate(&e->evm1));
+  CU_TRY(cudaEventCreate(&e->evd0));
+  CU_TRY(cudaEventCreate(&e->evd1));
   cudaMemPool_t pool;
   CU_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
   uint64_t thresh = UINT64_MAX;
@@ -1092,6 +1162,8 @@ void hg_engine_destroy(hg_engine* e) {
   cudaEventDestroy(e->evk1);
   cudaEventDestroy(e->evm0);
   cudaEventDestroy(e->evm1);
+  cudaEventDestroy(e->evd0);
+  cudaEventDestroy(e->evd1);
   cudaStreamDestroy(e->stream);
   delete e;
 }

@@ -97,6 +97,9 @@ struct RgCol {
   uint64_t mn = 0, mx = 0;
   uint32_t scratch = 0;      // decompression scratch of the chunk
   uint8_t has_minmax = 0, null_all = 0, null_none = 0, snappy = 0, simple_page = 0;   // simple = 1 uncompressed V1 page
+  uint8_t single_page = 0;   // exactly one V1 PLAIN data page, UNCOMPRESSED or SNAPPY (what the fused scan can address by row)
+  uint8_t stored = 0;        // Snappy page whose stream is one or two literals (incompressible data): readable in place
+  uint8_t _pad = 0;
 };
 
 struct SstResident {
@@ -110,6 +113,11 @@ struct SstResident {
   // per-file planning facts (over ALL row groups of the file)
   uint64_t rows_total = 0;
   bool col_all_simple[MAX_COLS] = {false}, col_null_none[MAX_COLS] = {false}, col_has_minmax[MAX_COLS] = {false};
+  bool col_all_single[MAX_COLS] = {false};       // every chunk: one V1 PLAIN page (any supported codec)
+  bool col_any_snappy[MAX_COLS] = {false};
+  bool col_snappy_all_stored[MAX_COLS] = {false};  // every Snappy chunk of the column is a stored (literal-only) page
+  uint32_t col_max_scratch[MAX_COLS] = {0};      // largest decompression scratch of one chunk of the column
+  uint64_t col_comp_bytes[MAX_COLS] = {0};       // compressed bytes of the column (work estimate for the decompressor)
   uint64_t pk0_min = 0, pk0_max = 0;
   bool pk0_range_ok = false;
   uint64_t group_bound = 0;      // sum over row groups of min(#distinct pk0 possible, rows) + 1
@@ -210,7 +218,7 @@ struct hg_engine {
   hg_scan_stats stats{};
   uint32_t launches = 0;
   size_t stage_cursor = 0;             // next free byte of h_stage in the current call
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evm0 = nullptr, evm1 = nullptr;  // call / dominant-kernel / merge brackets
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evm0 = nullptr, evm1 = nullptr, evd0 = nullptr, evd1 = nullptr;  // call / dominant-kernel / merge brackets
   void* h_stage = nullptr;       // pinned staging for per-scan descriptor uploads
   size_t h_stage_bytes = 0;
   void* h_small = nullptr;       // 256 pinned bytes: the per-call counter block comes back here (one small D2H)

@@ -38,6 +38,9 @@ struct alignas(16) FRec {
   uint64_t _pad;
 };
 
+// In-place addressing of a stored (literal-only) Snappy page: rows [0, n0) start at the slot base, rows [n0, ..) at base1.
+struct VSeg { const uint8_t* base1; uint32_t n0, _pad; };
+
 enum : uint32_t { K_RAW64 = 0, K_U32 = 1, K_I32 = 2, K_F32 = 3 };   // how a PLAIN slot widens to 64 bits
 enum : uint32_t { C_UNSIGNED = 0, C_SIGNED = 1, C_FLOAT = 2 };          // comparison class
 constexpr int kHot = 4;
@@ -65,6 +68,13 @@ struct FParams {
   uint32_t pop[MAX_PREDS];
   uint64_t plit[MAX_PREDS];
   int64_t window_ms;
+  // Snappy SSTs: pages are decompressed into fixed-size scratch regions first (snappy.cu); region r of selected row
+  // group si starts at scratch + sel[si].scratch_off + r * scratch_stride
+  const uint8_t* scratch;
+  uint64_t scratch_stride;
+  int region[MAXC];             // scratch region of slot s, -1 = the slot is never decompressed
+  int value_stored;             // the value slot's Snappy pages are literal-only: read in place, in two segments (vseg)
+  VSeg* vseg;                   // [selected row group]
   FRec* rec;
   uint32_t rec_cap;
   uint32_t* item_cnt;
@@ -116,13 +126,50 @@ __device__ __forceinline__ bool pred_ok(uint64_t v, uint64_t lit, uint32_t cls, 
 
 // Start of the PLAIN values of column slot `s` in selected row group `si`: a pointer chase through the resident tables
 // (row group -> file -> chunk -> page -> def-level length), done once per (row group, slot) by slot_bases_kernel.
+// literal element at p: header length and literal length (the caller knows it is a literal: stored pages only)
+__device__ __forceinline__ uint32_t literal_header(const uint8_t* p, uint32_t* len) {
+  const uint32_t t = __ldg(p);
+  uint32_t l = t >> 2, hdr = 1;
+  if (l >= 60) {
+    const uint32_t nb = l - 59;
+    l = 0;
+    for (uint32_t i = 0; i < nb; i++) l |= uint32_t(__ldg(p + 1 + i)) << (8 * i);
+    hdr = 1 + nb;
+  }
+  *len = l + 1;
+  return hdr;
+}
+
 __device__ __forceinline__ const uint8_t* slot_base_chase(const FParams& P, uint32_t si, int s) {
   RgSel rs = P.sel[si];
   SstDev sst = P.ssts[rs.sst];
   ChunkDev cd = sst.chunks[size_t(rs.rg) * sst.ncols + P.col[s]];
   PageDev pg = sst.pages[cd.first_page];
   const uint8_t* body = sst.bytes + pg.payload_off;
+  const bool is_value = P.value_stored && s == P.value_slot;
+  if (cd.codec == 1) {
+    if (is_value && cd.stored) {
+      // stored page, read in place: [varint ulen][literal 0: level prefix + values][literal 1: values] (classify_stored)
+      const uint8_t* p = body;
+      while (__ldg(p) & 0x80) p++;
+      p++;
+      uint32_t len0 = 0, len1 = 0;
+      const uint32_t h0 = literal_header(p, &len0);
+      const uint8_t* lit0 = p + h0;
+      const uint32_t prefix = cd.optional ? 4 + ld32u(lit0) : 0;
+      const uint32_t w = P.kind[s] == K_RAW64 ? 8u : 4u;
+      VSeg v;
+      v.n0 = (len0 - prefix) / w;
+      v._pad = 0;
+      v.base1 = lit0 + prefix;
+      if (lit0 + len0 < body + pg.comp_size) v.base1 = lit0 + len0 + literal_header(lit0 + len0, &len1);
+      P.vseg[si] = v;
+      return lit0 + prefix;
+    }
+    body = P.scratch + rs.scratch_off + uint64_t(P.region[s]) * P.scratch_stride;
+  }
   if (cd.optional) body += 4 + ld32u(body);      // [u32 len][RLE def levels] — all-valid pages only (planner)
+  if (is_value) { VSeg v; v.base1 = body; v.n0 = rs.num_rows; v._pad = 0; P.vseg[si] = v; }
   return body;
 }
 __device__ __forceinline__ const uint8_t* slot_base(const FParams& P, uint32_t si, int s) { return P.bases[size_t(si) * MAXC + s]; }
@@ -214,12 +261,62 @@ __device__ __forceinline__ int cmp3(uint64_t a, uint64_t b, uint32_t cls) {
   return a < b ? -1 : (a > b ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(256) slot_bases_kernel(const __grid_constant__ FParams P, const uint8_t** __restrict__ bases) {
+__global__ void __launch_bounds__(256) slot_bases_kernel(const __grid_constant__ FParams P, const uint8_t** __restrict__ bases, int only_slot) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t si = idx / MAXC;
   const int s = int(idx % MAXC);
-  if (si >= *P.d_nsel || s >= P.nslots) return;
+  if (si >= *P.d_nsel || s >= P.nslots || (only_slot >= 0 && s != only_slot)) return;
   bases[idx] = slot_base_chase(P, si, s);
+}
+
+// Gate-first decompression of Snappy SSTs, row-group level: after the gate column's pages are decompressed, find the
+// row groups that hold a row passing the gate column's predicates; the other columns are decompressed only for those.
+// The filter runs before merge and dedup (read.rs:459-480), so a row group without a passing row contributes nothing.
+template <bool W4>
+__global__ void __launch_bounds__(256) gate_sel_kernel(const __grid_constant__ FParams P, int gate_slot, uint64_t flip, uint64_t lo, uint64_t span,
+                                                       uint8_t* __restrict__ flags) {
+  const uint32_t nsel = *P.d_nsel;
+  for (uint32_t si = blockIdx.x; si < nsel; si += gridDim.x) {
+    const uint8_t* base = P.bases[size_t(si) * MAXC + gate_slot];
+    const uint32_t nrows = P.sel[si].num_rows;
+    bool any = false;
+    for (uint32_t i = threadIdx.x; i < nrows && !any; i += 256) {
+      if (W4) any = (ld32u(base + size_t(i) * 4) ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span);
+      else any = (ld_bytes8(base + size_t(i) * 8) ^ flip) - lo <= span;
+    }
+    const int a = __syncthreads_or(any);
+    if (threadIdx.x == 0) flags[si] = a ? 1 : 0;
+  }
+}
+
+// one block: stable compaction of the selected row groups by flag (RgSel carries its scratch offset along)
+__global__ void __launch_bounds__(1024) compact_sel_kernel(const RgSel* __restrict__ in, const uint8_t* __restrict__ flags, uint32_t* d_nsel,
+                                                           RgSel* __restrict__ out) {
+  __shared__ uint32_t s_w[33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n = *d_nsel;
+  const uint32_t per = (n + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per;
+  const uint32_t hi = lo + per < n ? lo + per : n;
+  uint32_t cnt = 0;
+  for (uint32_t i = lo; i < hi; i++) cnt += flags[i] != 0;
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = s_w[lane], xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+    s_w[lane] = xi - x;
+    if (lane == 31) s_w[32] = xi;
+  }
+  __syncthreads();
+  uint32_t pos = s_w[w] + inc - cnt;
+  for (uint32_t i = lo; i < hi; i++) if (flags[i]) out[pos++] = in[i];
+  __syncthreads();
+  if (threadIdx.x == 0) *d_nsel = s_w[32];
 }
 
 // phase 1: one thread per row group, all blocks in parallel: keep flag (0/1) + rows
@@ -259,7 +356,7 @@ __global__ void __launch_bounds__(256) prune_rgs_kernel(const __grid_constant__ 
 // phase 2: one block compacts the kept row groups in stream order (coalesced reads of keep_rows)
 __global__ void __launch_bounds__(1024) select_rgs_kernel(const FileDev* __restrict__ files, int nfiles, uint32_t total_rgs,
                                                           const uint32_t* keep_rows, RgSel* __restrict__ sel, uint32_t* d_nsel,
-                                                          unsigned long long* counters, uint32_t smem_words) {
+                                                          unsigned long long* counters, uint32_t smem_words, uint64_t scratch_per_rg) {
   // one block; every thread owns a contiguous chunk of row groups: count, ONE block-wide scan, write.  The keep flags are
   // staged in shared memory with coalesced loads first (smem_words == 0: too many row groups, read them in place).
   extern __shared__ uint32_t s_keep[];
@@ -297,7 +394,7 @@ __global__ void __launch_bounds__(1024) select_rgs_kernel(const FileDev* __restr
       if (rows == 0) continue;
       while (f + 1 < uint32_t(nfiles) && i >= files[f + 1].rg_base) f++;
       RgSel r;
-      r.sst = f; r.rg = i - files[f].rg_base; r.out_row = 0; r.num_rows = rows; r.scratch_off = 0;
+      r.sst = f; r.rg = i - files[f].rg_base; r.out_row = 0; r.num_rows = rows; r.scratch_off = uint64_t(pos) * scratch_per_rg;
       sel[pos++] = r;
     }
   }
@@ -508,6 +605,21 @@ __device__ __forceinline__ uint32_t ld4(const uint8_t* q, uint32_t sh, uint32_t 
   return __funnelshift_r(lo, hi, sh);
 }
 
+// Cursor of the value column inside the current row group.  Normally one contiguous array (split = all rows); a stored
+// Snappy page is read in place as two arrays: rows [0, split) behind q0, rows [split, ..) behind q1.
+struct VCur {
+  const uint8_t *q0, *q1;    // bases rounded down to the value width
+  uint32_t s0, s1;           // bit shifts of the values inside their aligned words
+  uint32_t split;
+};
+__device__ __forceinline__ uint64_t ldv(const VCur& V, bool v8, uint32_t i) {
+  const bool a = i < V.split;
+  const uint8_t* q = a ? V.q0 : V.q1;
+  const uint32_t sh = a ? V.s0 : V.s1;
+  const uint32_t j = a ? i : i - V.split;
+  return v8 ? ld8(q, sh, j) : uint64_t(ld4(q, sh, j));
+}
+
 // Per-column constants of the hot columns, held in registers across the whole item.
 template <int NH>
 struct Hot {
@@ -527,7 +639,7 @@ struct Hot {
 //   pf     prefetch the block two iterations ahead into L2 (sequential walks only)
 // The block may extend past `lim` (end of the item or of the row group): indices are clamped, lanes masked.
 template <int kU, int NH, int X, bool HAS_TS, bool dense>
-__device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH>& H, const uint8_t* vq, uint32_t vs, Acc& acc, uint32_t& local,
+__device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH>& H, const VCur& V, Acc& acc, uint32_t& local,
                                                   uint32_t& n_alive, uint32_t& n_keep, uint32_t& n_full, uint32_t item, uint32_t csi, uint32_t row,
                                                   uint32_t lim, uint32_t nrows, bool pf, double* s_vals, uint32_t* slots, int lane) {
   uint64_t hv[kU][NH];
@@ -567,7 +679,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
     for (int u = 0; u < kU; u++) {
       uint32_t i2 = row + u * 32 + lane;
       i2 = i2 < last ? i2 : last;
-      vv[u] = v8 ? ld8(vq, vs, i2) : uint64_t(ld4(vq, vs, i2));
+      vv[u] = ldv(V, v8, i2);
     }
   }
   uint32_t kept_in_block = 0;
@@ -617,7 +729,7 @@ __device__ __forceinline__ uint32_t process_block(const FParams& P, const Hot<NH
       double v = 0.0;
       if (P.value_slot >= 0) {
         uint64_t raw = vv[u];
-        if (!dense) raw = keep ? (v8 ? ld8(vq, vs, i) : uint64_t(ld4(vq, vs, i))) : 0ull;
+        if (!dense) raw = keep ? ldv(V, v8, i) : 0ull;
         v = to_double_kind(raw, P.kind[P.value_slot], P.cls[P.value_slot]);
       }
       walk_slice<HAS_TS>(P, acc, local, item, keep_mask, keep, hv[u][0], int64_t(hv[u][1]), v, s_vals, slots, lane);
@@ -703,8 +815,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
     H.flip[h] = P.hot_flip[h]; H.lo[h] = P.hot_lo[h]; H.span[h] = P.hot_span[h]; H.haspred[h] = P.hot_haspred[h] != 0;
     H.q[h] = nullptr; H.sh[h] = 0;
   }
-  const uint8_t* vq = nullptr;
-  uint32_t vs = 0;
+  VCur V;
+  V.q0 = nullptr; V.q1 = nullptr; V.s0 = 0; V.s1 = 0; V.split = 0xffffffffu;
   auto set_cursor = [&](uint32_t si) {
     // every lane derives the same pointers (loads broadcast); keeps them in registers until the next row group
 #pragma unroll
@@ -718,8 +830,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
     if (P.value_slot >= 0) {
       const uintptr_t a = reinterpret_cast<uintptr_t>(slot_base(P, si, P.value_slot));
       const uintptr_t m = P.kind[P.value_slot] == K_RAW64 ? 7 : 3;
-      vq = reinterpret_cast<const uint8_t*>(a & ~m);
-      vs = uint32_t(a & m) * 8;
+      V.q0 = reinterpret_cast<const uint8_t*>(a & ~m);
+      V.s0 = uint32_t(a & m) * 8;
+      if (P.value_stored) {
+        const VSeg vg = P.vseg[si];
+        const uintptr_t b = reinterpret_cast<uintptr_t>(vg.base1);
+        V.q1 = reinterpret_cast<const uint8_t*>(b & ~m);
+        V.s1 = uint32_t(b & m) * 8;
+        V.split = vg.n0;
+      }
     }
   };
   for (;;) {
@@ -754,7 +873,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
         if (row >= lim) break;
         if (dense) {
           // dense stretch (>= 1/4 of the rows survive): everything is needed, value column loaded with the block
-          const uint32_t kept = process_block<kU, NH, X, HAS_TS, true>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows,
+          const uint32_t kept = process_block<kU, NH, X, HAS_TS, true>(P, H, V, acc, local, n_alive, n_keep, n_full, item, csi, row, lim, nrows,
                                                                       true, s_vals, slots, lane);
           dense = kept >= 32u * kU / 4;
           row += 32 * kU;
@@ -768,12 +887,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinBlocks) fused_scan_kern
             bm = gate_sweep<kU, NH, X, kGS>(H, row, lim, nrows, lane);
             sweep_kept = 0;
             if (bm == 0) { row += 32u * kGS; continue; }
-            prefetch_blocks<kU, NH, X, kGS>(H, vq, P.value_slot >= 0, P.value_slot >= 0 && P.kind[P.value_slot] == K_RAW64, bm, row, nrows, lane);
+            prefetch_blocks<kU, NH, X, kGS>(H, V.q0, P.value_slot >= 0, P.value_slot >= 0 && P.kind[P.value_slot] == K_RAW64, bm, row, nrows, lane);
           }
           brow = row + (__ffs(bm) - 1) * 32u * kU;
           bm &= bm - 1;
         }
-        const uint32_t kept = process_block<kU, NH, X, HAS_TS, false>(P, H, vq, vs, acc, local, n_alive, n_keep, n_full, item, csi, brow, lim, nrows,
+        const uint32_t kept = process_block<kU, NH, X, HAS_TS, false>(P, H, V, acc, local, n_alive, n_keep, n_full, item, csi, brow, lim, nrows,
                                                                      !GATED, s_vals, slots, lane);
         if (GATED) {
           sweep_kept += kept;
@@ -1002,7 +1121,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     rows_in_files += f->rows_total;
     if (f->rows_total == 0) continue;
     for (uint32_t c : slots)
-      if (!f->col_all_simple[c] || !f->col_null_none[c]) return NOT_APPLICABLE;
+      if (!f->col_all_single[c] || !f->col_null_none[c]) return NOT_APPLICABLE;
     if (!global_mode && (!f->col_has_minmax[0] || (has_ts && !f->col_has_minmax[1]))) return NOT_APPLICABLE;
     files.push_back(f);
   }
@@ -1014,6 +1133,29 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   }
   uint32_t total_rgs = 0;
   for (SstResident* f : files) total_rgs += uint32_t(f->rg_rows.size());
+  // ---- Snappy pages (WriteConfig::default, config.rs:120-133) are decompressed into per-(row group, slot) scratch
+  //      regions before the scan kernel runs; a value column whose pages are stored (literal-only) is read in place
+  bool slot_snappy[MAXC] = {false};
+  uint64_t slot_comp[MAXC] = {0};
+  uint64_t scratch_stride = 0;
+  bool value_stored = value_slot >= 0;
+  for (size_t i = 0; i < slots.size(); i++)
+    for (SstResident* f : files) {
+      const uint32_t c = slots[i];
+      if (f->col_any_snappy[c]) { slot_snappy[i] = true; scratch_stride = std::max<uint64_t>(scratch_stride, f->col_max_scratch[c]); }
+      slot_comp[i] += f->col_comp_bytes[c];
+      if (int(i) == value_slot && !f->col_snappy_all_stored[c]) value_stored = false;
+    }
+  if (value_slot >= 0) {
+    if (!slot_snappy[value_slot]) value_stored = false;
+    for (int h = 0; h < nhot; h++) if (hot_slot[h] == value_slot) value_stored = false;   // hot columns are addressed contiguously
+    for (int k2 = 0; k2 < int(schema->num_primary_keys); k2++) if (k2 == value_slot) value_stored = false;
+  }
+  scratch_stride = (scratch_stride + 255) & ~uint64_t(255);
+  int region[MAXC];
+  int nregions = 0;
+  for (size_t i = 0; i < slots.size(); i++) region[i] = (slot_snappy[i] && !(value_stored && int(i) == value_slot)) ? nregions++ : -1;
+  const bool need_snappy = nregions > 0;
   auto t1 = now();
 
   // ---- upper bound on the number of groups from chunk statistics (sizes the unordered record buffer)
@@ -1050,7 +1192,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 4;
   while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * uint64_t(items_per_warp)) split *= 2;
   const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
-  DevBuf d_ssts, d_files, d_sel, d_rec, d_item, d_work, d_adj, d_keep, d_bsum, d_bases;
+  DevBuf d_ssts, d_files, d_sel, d_sel2, d_rec, d_item, d_work, d_adj, d_keep, d_bsum, d_bases, d_vseg, d_gflags, d_scratch;
   // ticket / slot counters, row counters and the error word share one zeroed block (one memset node per call)
   CU_TRY(d_work.alloc(256, s));
   CU_TRY(cudaMemsetAsync(d_work.p, 0, 256, s));
@@ -1065,6 +1207,12 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   CU_TRY(d_keep.alloc(size_t(total_rgs + 1) * sizeof(uint32_t), s));
   CU_TRY(d_bsum.alloc(1024 * sizeof(uint32_t), s));
   CU_TRY(d_bases.alloc(size_t(total_rgs + 1) * MAXC * sizeof(uint8_t*), s));
+  if (value_stored) CU_TRY(d_vseg.alloc(size_t(total_rgs + 1) * sizeof(VSeg), s));
+  if (need_snappy) {
+    CU_TRY(d_sel2.alloc(size_t(total_rgs + 1) * sizeof(RgSel), s));
+    CU_TRY(d_gflags.alloc(size_t(total_rgs) + 16, s));
+    CU_TRY(d_scratch.alloc(size_t(total_rgs) * size_t(nregions) * scratch_stride + 256, s));
+  }
   if ((uint64_t(nitems) + 1023) / 1024 > 1024) return NOT_APPLICABLE;   // two-level item scan covers 1 M work items
   out->gtype = has_group ? schema->types[0] : uint32_t(T_U64);
   out->gwidth = has_group ? type_width_host(out->gtype) : 8;
@@ -1152,6 +1300,11 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       P.pcls[i] = type_is_float(schema->types[preds[i].column]) ? C_FLOAT : (type_is_signed(schema->types[preds[i].column]) ? C_SIGNED : C_UNSIGNED);
     }
     P.window_ms = has_ts ? agg->window_ms : 1;
+    P.scratch = d_scratch.as<uint8_t>();
+    P.scratch_stride = scratch_stride;
+    for (int i = 0; i < MAXC; i++) P.region[i] = i < int(slots.size()) ? region[i] : -1;
+    P.value_stored = value_stored ? 1 : 0;
+    P.vseg = d_vseg.as<VSeg>();
     P.rec = d_rec.as<FRec>();
     P.rec_cap = uint32_t(rec_cap);
     P.item_cnt = d_item.as<uint32_t>();
@@ -1170,10 +1323,54 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       CU_TRY(cudaFuncSetAttribute(select_rgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
       const uint32_t smem_words = size_t(total_rgs) * 4 <= 200 * 1024 ? total_rgs : 0;
       select_rgs_kernel<<<1, 1024, size_t(smem_words) * 4, s>>>(d_files.as<FileDev>(), int(files.size()), total_rgs, d_keep.as<uint32_t>(),
-                                                                d_sel.as<RgSel>(), d_work.as<uint32_t>() + 3, counters_p, smem_words);
+                                                                d_sel.as<RgSel>(), d_work.as<uint32_t>() + 3, counters_p, smem_words,
+                                                                uint64_t(nregions) * scratch_stride);
     }
     L.tick();
-    slot_bases_kernel<<<(total_rgs * MAXC + 255) / 256, 256, 0, s>>>(P, d_bases.as<const uint8_t*>());
+    CU_TRY(cudaEventRecord(e->evd0, s));
+    if (need_snappy) {
+      // decompression jobs: slots in descending order of compressed bytes (long pages first, short ones fill the tail)
+      auto make_job = [&](const std::vector<int>& job_slots, unsigned int* ticket) {
+        k::SnappyJob J;
+        std::memset(&J, 0, sizeof(J));
+        J.ssts = P.ssts; J.sel = P.sel; J.d_nsel = P.d_nsel; J.nsel = 0; J.ncols = int(job_slots.size());
+        std::vector<int> ord(job_slots.size());
+        for (size_t i = 0; i < ord.size(); i++) ord[i] = int(i);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return slot_comp[job_slots[a]] > slot_comp[job_slots[b]]; });
+        for (size_t i = 0; i < job_slots.size(); i++) {
+          J.col[i] = slots[job_slots[i]];
+          J.region[i] = uint32_t(region[job_slots[i]]);
+          J.order[i] = uint8_t(ord[i]);
+          J.skip_stored[i] = 0;
+        }
+        J.fixed_stride = scratch_stride; J.scratch = d_scratch.as<uint8_t>(); J.ticket = ticket; J.err = err_p;
+        return J;
+      };
+      unsigned int* tickets = reinterpret_cast<unsigned int*>(zblock + 136);
+      const int gate_slot = hot_slot[nhot - 1];
+      std::vector<int> first, rest;
+      for (int i = 0; i < int(slots.size()); i++) {
+        if (region[i] < 0) continue;
+        if (gated && i == gate_slot) first.push_back(i); else rest.push_back(i);
+      }
+      if (!first.empty()) {
+        // gate first: decompress the gate column, drop the row groups without a passing row, decompress the rest for the others
+        k::snappy_pages(L, make_job(first, tickets), total_rgs);
+        slot_bases_kernel<<<(total_rgs * MAXC + 255) / 256, 256, 0, s>>>(P, d_bases.as<const uint8_t*>(), gate_slot);
+        L.tick();
+        const uint32_t gt = schema->types[slots[gate_slot]];
+        const bool w4 = !(gt == T_U64 || gt == T_I64 || gt == T_F64);
+        if (w4) gate_sel_kernel<true><<<148 * 8, 256, 0, s>>>(P, gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
+        else gate_sel_kernel<false><<<148 * 8, 256, 0, s>>>(P, gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
+        L.tick();
+        compact_sel_kernel<<<1, 1024, 0, s>>>(d_sel.as<RgSel>(), d_gflags.as<uint8_t>(), d_work.as<uint32_t>() + 3, d_sel2.as<RgSel>());
+        L.tick();
+        P.sel = d_sel2.as<RgSel>();
+      }
+      if (!rest.empty()) k::snappy_pages(L, make_job(rest, tickets + 1), total_rgs * uint32_t(rest.size()));
+    }
+    CU_TRY(cudaEventRecord(e->evd1, s));
+    slot_bases_kernel<<<(total_rgs * MAXC + 255) / 256, 256, 0, s>>>(P, d_bases.as<const uint8_t*>(), -1);
     L.tick();
     {
       const uint32_t nb = (nitems + 1 + kBoundsPerWarp - 1) / kBoundsPerWarp;      // warps
@@ -1215,6 +1412,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     float kms = 0;
     cudaEventElapsedTime(&kms, e->evk0, e->evk1);
     e->stats.kernel_ms = kms;
+    if (need_snappy) { cudaEventElapsedTime(&kms, e->evd0, e->evd1); e->stats.decomp_ms = kms; }
   }
   out->G = global_mode ? (hc[1] > 0 ? 1u : 0u) : hw[1];   // hw[1] = groups counted by item_scan (hw[0] = reserved record slots)   // like GROUP BY: no surviving rows, no group
   e->stats.rows_in_files = rows_in_files;

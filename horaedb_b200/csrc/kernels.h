@@ -22,6 +22,27 @@ void snappy_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32
 // v2: parallel tag parse + pointer-jumping resolve (snappy.cu); `ticket` is a zeroed device counter
 void snappy_chunks_v2(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols, int ncolsel,
                       uint8_t* scratch, unsigned int* ticket, int* err);
+// The same decompressor driven by a job descriptor (fused Snappy path: row-group list and its length live on the device,
+// every (row group, column) gets a fixed-size scratch region addressed by RgSel::scratch_off + region * fixed_stride).
+constexpr int kSnappyMaxCols = 32;
+struct SnappyJob {
+  const SstDev* ssts;
+  const RgSel* sel;
+  const uint32_t* d_nsel;     // device-side count of row groups, or nullptr: use nsel
+  uint32_t nsel;
+  int ncols;                  // columns to decompress per row group
+  uint32_t col[kSnappyMaxCols];        // schema column of entry i
+  uint32_t region[kSnappyMaxCols];     // fixed_stride != 0: scratch region index of entry i inside the row group's block
+  uint8_t order[kSnappyMaxCols];       // processing order of the entries (heaviest column first)
+  uint8_t skip_stored[kSnappyMaxCols]; // entry i: leave stored (literal-only) pages alone, the consumer reads them in place
+  const ColSel* cols;         // general pipeline: column ids + variable scratch offsets come from the ColSel table
+  int col_from_cols;
+  uint64_t fixed_stride;      // bytes per scratch region, 0 = general pipeline layout
+  uint8_t* scratch;
+  unsigned int* ticket;       // zeroed device counter
+  int* err;
+};
+void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks);
 void decode_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols,
                    int ncolsel, const uint8_t* scratch, int* err);
 

@@ -17,6 +17,8 @@
 //   literals longer than 60 bytes (incompressible columns are one literal per 64 KiB block) are plain warp copies.
 #include "kernels.h"
 
+#include <cstring>
+
 namespace horae {
 namespace k {
 
@@ -349,25 +351,30 @@ __device__ __forceinline__ uint64_t chunk_scratch_off2(const RgSel& rs, const Ch
   return off;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_chunks_v2_kernel(const SstDev* __restrict__ ssts, const RgSel* __restrict__ sel,
-                                                                             const ColSel* __restrict__ cols, int ncolsel, uint32_t nchunks,
-                                                                             uint8_t* __restrict__ scratch, unsigned int* ticket, int* err) {
+// One warp per column chunk, chunks handed out by an atomic ticket in the order (column order[0] of every row group,
+// then order[1], ...): the host lists the columns with the most compressed bytes first, so the long pages start early
+// and the short ones fill the tail.
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_pages_kernel(const __grid_constant__ SnappyJob J) {
   __shared__ WarpSmem s_w[kWarpsPerCta];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpSmem& sm = s_w[wid];
+  const uint32_t nsel = J.d_nsel ? *J.d_nsel : J.nsel;
+  const uint32_t nchunks = nsel * uint32_t(J.ncols);
   for (;;) {
     uint32_t c = 0;
-    if (lane == 0) c = atomicAdd(ticket, 1u);
+    if (lane == 0) c = atomicAdd(J.ticket, 1u);
     c = __shfl_sync(0xffffffffu, c, 0);
     if (c >= nchunks) return;
-    const uint32_t si = c / ncolsel;
-    const int ci = int(c % ncolsel);
-    RgSel rs = sel[si];
-    SstDev sst = ssts[rs.sst];
+    const uint32_t si = c % nsel;
+    const int ci = J.order[c / nsel];
+    RgSel rs = J.sel[si];
+    SstDev sst = J.ssts[rs.sst];
     const ChunkDev* chunks = sst.chunks + size_t(rs.rg) * sst.ncols;
-    ChunkDev ch = chunks[cols[ci].col];
+    ChunkDev ch = chunks[J.col_from_cols ? J.cols[ci].col : J.col[ci]];
     if (ch.codec != 1) continue;
-    uint8_t* dst = scratch + chunk_scratch_off2(rs, chunks, cols, ci);
+    if (ch.stored && J.skip_stored[ci]) continue;                 // read in place by the consumer
+    uint8_t* dst = J.scratch + (J.fixed_stride ? rs.scratch_off + uint64_t(J.region[ci]) * J.fixed_stride
+                                               : chunk_scratch_off2(rs, chunks, J.cols, ci));
     for (uint32_t p = 0; p < ch.num_pages; p++) {
       PageDev pg = sst.pages[ch.first_page + p];
       const uint8_t* src = sst.bytes + pg.payload_off;
@@ -378,7 +385,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_chunks_v2_kernel(
         src += skip; n -= skip; ulen -= skip;
         compressed = pg.v2_compressed != 0;
       }
-      if (compressed) snappy_page(src, n, dst, ulen, sm, lane, err);
+      if (compressed) snappy_page(src, n, dst, ulen, sm, lane, J.err);
       dst += page_scratch2(pg.uncomp_size);
     }
   }
@@ -386,14 +393,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_chunks_v2_kernel(
 
 }  // namespace
 
+void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks) {
+  if (!max_chunks) return;
+  uint32_t ctas = (max_chunks + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (ctas > 148u * 6) ctas = 148u * 6;
+  snappy_pages_kernel<<<ctas, kWarpsPerCta * 32, 0, L.stream>>>(job);
+  L.tick();
+}
+
 void snappy_chunks_v2(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols, int ncolsel,
                       uint8_t* scratch, unsigned int* ticket, int* err) {
   if (!nsel || !ncolsel) return;
-  const uint32_t nchunks = nsel * uint32_t(ncolsel);
-  uint32_t ctas = (nchunks + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (ctas > 148u * 6) ctas = 148u * 6;
-  snappy_chunks_v2_kernel<<<ctas, kWarpsPerCta * 32, 0, L.stream>>>(ssts, sel, cols, ncolsel, nchunks, scratch, ticket, err);
-  L.tick();
+  SnappyJob J;
+  std::memset(&J, 0, sizeof(J));
+  J.ssts = ssts; J.sel = sel; J.d_nsel = nullptr; J.nsel = nsel; J.cols = cols; J.ncols = ncolsel;
+  J.scratch = scratch; J.ticket = ticket; J.err = err; J.fixed_stride = 0;
+  for (int i = 0; i < ncolsel && i < kSnappyMaxCols; i++) { J.order[i] = i; J.col[i] = 0; }
+  // general pipeline: the column ids live in the device-side ColSel array; copy them lazily inside the kernel
+  J.col_from_cols = 1;
+  snappy_pages(L, J, nsel * uint32_t(ncolsel));
 }
 
 }  // namespace k

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 2u
+#define HG_ABI_VERSION 3u
 
 typedef struct hg_engine hg_engine;
 
@@ -123,7 +123,7 @@ typedef struct {
   float gpu_ms;               /* device time of the last call, first kernel to last (CUDA events on the engine stream) */
   float kernel_ms;            /* device time of the call's dominant kernel alone (fused scan / page decode) */
   float merge_ms;             /* device time of S4-S6 (sort records, merge passes, dedup, compaction of survivors) */
-  float _pad2;
+  float decomp_ms;            /* device time of the page-decompression stage (Snappy), when one ran */
   uint64_t rows_materialized; /* fused path: rows whose non-gate columns were read (== rows_decoded without the gate);
                                  general pipeline: rows_decoded */
 } hg_scan_stats;

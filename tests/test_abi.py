@@ -14,7 +14,8 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(L, sym), f"{sym} declared in horae_gpu.h but not exported"
     assert set(_ffi.EXPORTS) == declared
-    assert L.hg_abi_version() == 2
+    want = int(re.search(r"#define HG_ABI_VERSION (\d+)u", hdr).group(1))
+    assert L.hg_abi_version() == want
 
 
 def test_struct_layouts_match_header():
