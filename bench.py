@@ -101,20 +101,50 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(ssts, threads, steps=1, warmup=0):
-    """The oracle port timed on the host cores.  Returns (rows/s, rows, seconds per step)."""
+def cpu_reference(ssts, threads, steps=1, warmup=0, queries=1):
+    """The oracle port timed on the host cores.  `queries` independent copies of the query run concurrently (each one
+    thread per SST, like the reference's one partition per file): the CPU analogue of `queries` GPUs scanning their own
+    shards.  Returns (rows/s over all queries, rows per query, seconds per step, result of one query)."""
     from horaedb_b200 import sstgen
     from oracle import oracle
     schema = sstgen.metric_storage_schema()
     datas = [d for _, d, _ in ssts]
     rows = sum(n for _, _, n in ssts)
+    out = [None] * queries
+
+    def one(i):
+        out[i] = oracle.scan_aggregate(datas, schema.arrow_schema, 2, preds(), group_col=0, value_col=2, threads=threads)
+
+    def step():
+        if queries == 1:
+            one(0)
+            return
+        ths = [threading.Thread(target=one, args=(i,)) for i in range(queries)]     # ctypes releases the GIL inside the oracle
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
     for _ in range(warmup):
-        oracle.scan_aggregate(datas, schema.arrow_schema, 2, preds(), group_col=0, value_col=2, threads=threads)
+        step()
     t = time.perf_counter()
     for _ in range(max(steps, 1)):
-        res = oracle.scan_aggregate(datas, schema.arrow_schema, 2, preds(), group_col=0, value_col=2, threads=threads)
+        step()
     dt = (time.perf_counter() - t) / max(steps, 1)
-    return rows / dt, rows, dt, res
+    return rows * queries / dt, rows, dt, out[0]
+
+
+def check_parity(tbl, exp):
+    """Bit-exact comparison of a GPU aggregate (pyarrow table: series_id, count, sum, min, max) with the oracle's result."""
+    def bits(a):
+        return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+    ok = (tbl.num_rows == len(exp.count)
+          and np.array_equal(tbl["series_id"].to_numpy(), exp.gkey)
+          and np.array_equal(tbl["count"].to_numpy(), exp.count)
+          and np.array_equal(bits(tbl["sum"].to_numpy()), bits(exp.sum))
+          and np.array_equal(bits(tbl["min"].to_numpy()), bits(exp.min))
+          and np.array_equal(bits(tbl["max"].to_numpy()), bits(exp.max)))
+    return bool(ok)
 
 
 def main():
@@ -123,7 +153,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--codec", default="none", choices=["none", "snappy"], help="SST page codec of the main line")
+    ap.add_argument("--codec", default="snappy", choices=["none", "snappy"],
+                    help="SST page codec of the main line (snappy = the reference's WriteConfig::default, config.rs:120-133)")
     ap.add_argument("--files", type=int, default=FILES_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-variant", action="store_true", help="skip the secondary codec measurement")
@@ -149,16 +180,18 @@ def main():
             return
         nsample = args.files
         ssts = gen_ssts(0, args.codec, nsample, min(ncores, nsample))  # the SAME files as our arm's main line (same codec)
-        rps, rows, dt, _ = cpu_reference(ssts, ncores, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
-        used = min(ncores, nsample)      # one decode/filter thread per SST (the reference's one partition per file, read.rs:442-450)
+        nq = max(1, args.gpus)           # our arm scans gpus x files: the CPU arm runs as many independent queries side by side
+        rps, rows, dt, _ = cpu_reference(ssts, ncores, steps=max(args.steps, 1), warmup=min(args.warmup, 1), queries=nq)
+        used = min(ncores, nsample * nq)  # one decode/filter thread per SST (the reference's one partition per file, read.rs:442-450)
         line = {"impl": "reference", "metric": "scanned rows/s", "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "codec": args.codec},
                 "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": used, "kind": "port",
-                                 "sample": f"{nsample} SSTs = {rows} rows per step (C restatement of the reference path; the Rust reference cannot be "
-                                           f"built here); {used} threads busy = one per SST like the reference's one partition per file, "
-                                           f"merge/dedup/aggregate single-threaded like MergeExec; host has {ncores} cores"},
+                                 "sample": f"{nq} concurrent quer{'y' if nq == 1 else 'ies'} x {nsample} SSTs = {rows * nq} rows per step (C restatement of the "
+                                           f"reference path; the Rust reference cannot be built here); {used} threads busy = one per SST like the "
+                                           f"reference's one partition per file, merge/dedup/aggregate single-threaded per query like MergeExec; "
+                                           f"host has {ncores} cores"},
                 "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return
@@ -203,6 +236,22 @@ def main():
             out = combiner.gather_packed(eng, g, torch.device("cuda", local_rank), check_cap=settle)
         return out
 
+    # ---- the CPU oracle's answer for THIS rank's files (same data under every codec): the timed GPU results are compared
+    #      with it bit for bit below; rank 0's run doubles as the cpu_baseline measurement
+    cpu_rps, cpu_rows, cpu_dt, expected = cpu_reference(gen[args.codec], ncores)
+
+    def packed_matches(block, exp):
+        """block: [6, cap] int64 host array (key, bucket, count, sum bits, min bits, max bits) vs the oracle result."""
+        g = len(exp.count)
+        if block.shape[1] < g or (block[2, g:] != 0).any():
+            return False
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+        return bool(np.array_equal(block[0, :g], exp.gkey.astype(np.int64)) and np.array_equal(block[2, :g], exp.count.astype(np.int64))
+                    and np.array_equal(block[3, :g], f(exp.sum)) and np.array_equal(block[4, :g], f(exp.min)) and np.array_equal(block[5, :g], f(exp.max)))
+
+    def block_checksum(block):
+        return int(block.astype(np.uint64).sum(dtype=np.uint64)) & 0x7FFFFFFFFFFFFFFF
+
     def measure(codec, steps, warmup, e2e_steps):
         ssts = gen[codec]
         rows = sum(n for _, _, n in ssts)
@@ -241,6 +290,7 @@ def main():
         else:
             e2e_dt = float(np.median(e2e_t))
         groups_local = tbl.num_rows
+        parity_e2e = check_parity(tbl, expected)
         # ---- HBM-resident steps: make the SSTs resident once (untimed), then every step is one scan call
         for inp in inputs_host:
             eng.load_sst(handle, inp)
@@ -253,7 +303,7 @@ def main():
             time.sleep(0.15)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kernel_ms, call_ms, launches = [], [], 0
+        kernel_ms, call_ms, decomp_ms, launches = [], [], [], 0
         prep = eng.prepare_aggregate(handle, resident, P, group_col=0, ts_col=-1, window_ms=0, value_col=2)   # arguments marshalled once
         prep.run()
         ev0.record(stream)
@@ -262,6 +312,7 @@ def main():
             sst_ = eng.stats_struct()
             kernel_ms.append(sst_.kernel_ms)
             call_ms.append(sst_.gpu_ms)
+            decomp_ms.append(sst_.decomp_ms)
             launches += sst_.kernel_launches
             last = combine(dev)
         ev1.record(stream)
@@ -278,6 +329,35 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         st = eng.stats()
+        # ---- parity of the TIMED configuration: the last timed step's device result against the oracle
+        g_local = int(dev.num_groups)
+        cap = max(g_local, 1)
+        blk = torch.zeros(6, cap, device="cuda", dtype=torch.int64)
+        with torch.cuda.stream(stream):
+            eng.export_packed(blk.data_ptr(), cap)
+        stream.synchronize()
+        own = blk.cpu().numpy()
+        parity_resident = packed_matches(own, expected)
+        parity_combined = None
+        if world > 1:
+            # every rank's slot of the gathered block must carry exactly that rank's partial (checked through checksums of
+            # the ranks' ORACLE results), and this rank's slot must equal its own oracle result bit for bit
+            gathered = last.cpu().numpy()                       # [world, 6, cap]
+            mine = gathered[rank]
+            ok = packed_matches(mine, expected)
+            exp_blk = np.zeros((6, len(expected.count)), dtype=np.int64)
+            f = lambda a: np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+            exp_blk[0], exp_blk[2] = expected.gkey.astype(np.int64), expected.count.astype(np.int64)
+            exp_blk[3], exp_blk[4], exp_blk[5] = f(expected.sum), f(expected.min), f(expected.max)
+            sums = torch.zeros(world, device="cuda", dtype=torch.int64)
+            sums[rank] = block_checksum(exp_blk)
+            dist.all_reduce(sums)
+            want = sums.cpu().numpy()
+            for r in range(world):
+                ok = ok and block_checksum(gathered[r]) == int(want[r])
+            flag = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int64)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity_combined = bool(flag.item())
         # A/B: the same resident scan with the late-materialisation gate off (every needed column of every row is read)
         ungated_ms = None
         if st["path"] == 1:
@@ -290,7 +370,9 @@ def main():
             ungated_ms = float(np.mean(ks[2:]))
             eng.set_flags(0)
         total_groups = last if world == 1 else int((last[:, 2, :] > 0).sum().item())
-        return {"ungated_kernel_ms": ungated_ms,"rows": rows, "file_bytes": file_bytes, "ms_total": ms, "ms_per_step": ms / steps, "kernel_ms": float(np.mean(kernel_ms)),
+        return {"parity": {"resident": parity_resident, "e2e": parity_e2e, "combined": parity_combined, "groups": g_local},
+                "decomp_ms": float(np.mean(decomp_ms)) if decomp_ms else 0.0,
+                "ungated_kernel_ms": ungated_ms,"rows": rows, "file_bytes": file_bytes, "ms_total": ms, "ms_per_step": ms / steps, "kernel_ms": float(np.mean(kernel_ms)),
                 "call_ms": float(np.mean(call_ms)), "launches": launches, "e2e_s": e2e_dt, "d2h": d2h, "h2d": h2d, "stats": st,
                 "groups": total_groups, "groups_local": groups_local,
                 "clocks": sampler.summary() if rank == 0 else None, "ssts": ssts}
@@ -310,75 +392,101 @@ def main():
         value = rows_all / (main_r["ms_per_step"] / 1e3)
         st = main_r["stats"]
         survey_bytes = st["rows_decoded"] * ALG_BYTES_PER_ROW      # every needed column of every decoded row
-        if st["path"] == 1:
-            # The fused kernel is late-materialising: the 4-byte gate column (tag) is read for every decoded row, series_id
-            # and ts only for blocks with a passing row (device counter rows_materialized), value only for survivors.
-            # `achieved` counts THOSE bytes (what this algorithm must read), so it stays comparable with the copy peak;
-            # the SURVEY figure is reported next to it.
-            alg_bytes = st["rows_decoded"] * 4 + st["rows_materialized"] * 16 + st["rows_filtered"] * 8
-        else:
-            alg_bytes = survey_bytes
-        achieved = alg_bytes / (main_r["kernel_ms"] / 1e3) / 1e9
-        traffic = None
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get("fused_scan_kernel" if st["path"] == 1 else "snappy_chunks_kernel")
+        gate_bytes = st["rows_decoded"] * 4 + st["rows_materialized"] * 16 + st["rows_filtered"] * 8
+        traffic_tbl = {}
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` captures
+            traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
-        # CPU oracle on a bounded sample of the same workload (same predicate, same files)
+
+        def scan_kernel_block(r):
+            """Roofline of the fused scan kernel: late-materialising, so `achieved` counts the bytes THAT algorithm must read."""
+            sr = r["stats"]
+            ab = (sr["rows_decoded"] * 4 + sr["rows_materialized"] * 16 + sr["rows_filtered"] * 8) if sr["path"] == 1 else sr["rows_decoded"] * ALG_BYTES_PER_ROW
+            ach = ab / (r["kernel_ms"] / 1e3) / 1e9
+            blk = {"kernel": "fused_scan_kernel" if sr["path"] == 1 else "decode_chunks", "kernel_ms": r["kernel_ms"], "alg_bytes_per_launch": ab,
+                   "achieved": ach, "frac": ach / peak, "traffic": traffic_tbl.get("fused_scan_kernel"),
+                   "bytes_model": "late materialisation: 4 B x rows_decoded + 16 B x rows_materialized + 8 B x rows_filtered",
+                   "rows_materialized": sr["rows_materialized"]}
+            if r["ungated_kernel_ms"]:
+                sb = sr["rows_decoded"] * ALG_BYTES_PER_ROW
+                blk["ungated"] = {"kernel_ms": r["ungated_kernel_ms"], "achieved": sb / (r["ungated_kernel_ms"] / 1e3) / 1e9,
+                                  "frac": sb / (r["ungated_kernel_ms"] / 1e3) / 1e9 / peak,
+                                  "note": "HG_FLAG_NO_LATE_MATERIALIZATION: all 28 B of every decoded row are read (SURVEY 8d byte model); "
+                                          "kernel_ms measured live after the timed region"}
+            return blk
+
+        if args.codec == "snappy" and main_r["decomp_ms"] > 0:
+            # dominant stage = Snappy page decompression (two launches of snappy_pages_kernel + the row-group gate between them).
+            # Algorithmic bytes = UNCOMPRESSED page bytes of the needed columns of every row group that survives statistics
+            # pruning (SURVEY 8d: 28 B x rows_decoded) — what a decompress-everything implementation must produce; this
+            # engine reaches the same result producing fewer (stored value pages are read in place, row groups without a
+            # passing row are only decompressed for the gate column).
+            alg_bytes = survey_bytes
+            kms = main_r["decomp_ms"]
+            achieved = alg_bytes / (kms / 1e3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic_tbl.get("snappy_pages_kernel"), "kernel": "snappy_pages_kernel (gate column, row-group gate, other columns)",
+                        "kernel_ms": kms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                        "bytes_model": "28 B x rows_decoded = uncompressed page bytes of series_id, ts, value, tag in the row groups that survive "
+                                       "statistics pruning, / device time of the decompression stage (CUDA events on the engine stream)",
+                        "scan_kernel": scan_kernel_block(main_r)}
+        else:
+            blk = scan_kernel_block(main_r)
+            roofline = {"bound": "hbm", "achieved": blk["achieved"], "peak": peak, "unit": "GB/s", "frac": blk["frac"], "traffic": blk["traffic"],
+                        "kernel": blk["kernel"], "kernel_ms": blk["kernel_ms"], "alg_bytes_per_launch": blk["alg_bytes_per_launch"],
+                        "peak_source": peak_src, "bytes_model": blk["bytes_model"], "rows_materialized": blk["rows_materialized"],
+                        "survey_bytes_per_launch": survey_bytes, "survey_GBps": survey_bytes / (main_r["kernel_ms"] / 1e3) / 1e9,
+                        "ungated": blk.get("ungated")}
         nsample = len(main_r["ssts"])
-        cpu_rps, cpu_rows, cpu_dt, cpu_res = cpu_reference(main_r["ssts"][:nsample], ncores)
+        parity_ok = all(r["parity"]["resident"] and r["parity"]["e2e"] and r["parity"]["combined"] is not False for r in res.values())
+        # all host cores: as many independent copies of the query as fit, side by side (one thread per SST each)
+        nq_all = max(1, ncores // max(1, min(ncores, nsample)))
+        all_rps, _, all_dt, _ = cpu_reference(main_r["ssts"], ncores, queries=nq_all) if nq_all > 1 else (cpu_rps, 0, cpu_dt, None)
         line = {
             "metric": "scanned rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "codec": args.codec,
-                       "codec_note": ("main line = the SURVEY 8(d) UNCOMPRESSED writer variant (HBM-roofline case); the reference-default "
-                                      "Snappy run of the same workload is under `variants`; --codec snappy swaps them") if args.codec == "none"
-                       else "main line = WriteConfig::default (Snappy); the UNCOMPRESSED variant is under `variants`",
+                       "codec_note": ("main line = WriteConfig::default (Snappy, config.rs:120-133); the UNCOMPRESSED writer variant of SURVEY 8(d) is "
+                                      "under `variants`") if args.codec == "snappy"
+                       else "main line = the SURVEY 8(d) UNCOMPRESSED writer variant; the reference-default Snappy run is under `variants`",
                        "rows_per_gpu": main_r["rows"], "sst_bytes_per_gpu": main_r["file_bytes"],
-                       "l2_policy": "inputs (>=1.4 GB per step) far exceed the 126 MB L2; no flush needed",
+                       "l2_policy": "inputs (>=1 GB per step) far exceed the 126 MB L2; no flush needed",
                        "path": "fused" if st["path"] == 1 else "general", "rows_decoded_per_gpu": st["rows_decoded"],
                        "rows_filtered_per_gpu": st["rows_filtered"], "groups": main_r["groups"],
                        "decoded_GBps": rows_all * ALG_BYTES_PER_ROW / (main_r["ms_per_step"] / 1e3) / 1e9,
-                       "decoded_GBps_note": "SURVEY 8(d) convention: ALL rows of the files x 28 B / step time.  Statistics pruning and late "
-                                            "materialisation skip bytes that cannot contribute, so this can exceed the HBM peak; the "
-                                            "physical figures are roofline.achieved / roofline.traffic"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "fused_scan_kernel" if st["path"] == 1 else "snappy_chunks+decode_chunks",
-                         "kernel_ms": main_r["kernel_ms"], "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "bytes_model": ("late materialisation: 4 B x rows_decoded + 16 B x rows_materialized + 8 B x rows_filtered"
-                                         if st["path"] == 1 else "28 B x rows_decoded"),
-                         "rows_materialized": st["rows_materialized"],
-                         "survey_bytes_per_launch": survey_bytes,
-                         "survey_GBps": survey_bytes / (main_r["kernel_ms"] / 1e3) / 1e9,
-                         "ungated": (None if not main_r["ungated_kernel_ms"] else
-                                     {"kernel_ms": main_r["ungated_kernel_ms"],
-                                      "achieved": survey_bytes / (main_r["ungated_kernel_ms"] / 1e3) / 1e9,
-                                      "frac": survey_bytes / (main_r["ungated_kernel_ms"] / 1e3) / 1e9 / peak,
-                                      "ms_per_step_est": main_r["ms_per_step"] - main_r["kernel_ms"] + main_r["ungated_kernel_ms"],
-                                      "rows_per_s_est": rows_all / ((main_r["ms_per_step"] - main_r["kernel_ms"] + main_r["ungated_kernel_ms"]) / 1e3),
-                                      "note": "HG_FLAG_NO_LATE_MATERIALIZATION: all 28 B of every decoded row are read; kernel_ms measured "
-                                              "live (CUDA events, 4 launches after the timed region); the step estimate swaps only the "
-                                              "fused kernel's time, every other kernel of the step is identical"})},
+                       "decoded_GBps_note": "SURVEY 8(d) convention: ALL rows of the files x 28 B / step time.  Statistics pruning, stored-page "
+                                            "bypass and late materialisation skip bytes that cannot contribute; the physical figures are "
+                                            "roofline.achieved / roofline.traffic",
+                       "late_materialisation_bytes": gate_bytes},
+            "roofline": roofline,
+            "parity": {"checked": True, "ok": parity_ok, "against": "CPU oracle on the same SSTs, bit-exact keys / counts / f64 sum, min, max",
+                       **{c: r["parity"] for c, r in res.items()}},
             "cpu_baseline": {"value": cpu_rps, "unit": "rows/s", "cores": min(ncores, nsample), "kind": "port",
                              "sample": f"{nsample} of the same SSTs = {cpu_rows} rows, oracle (C restatement of the reference path): "
                                        f"{min(ncores, nsample)} threads busy = one per SST like the reference's one partition per file "
-                                       f"(read.rs:442-450), merge/dedup/aggregate single-threaded like MergeExec; host has {ncores} cores"},
+                                       f"(read.rs:442-450), merge/dedup/aggregate single-threaded like MergeExec; host has {ncores} cores",
+                             "all_cores": {"value": all_rps, "unit": "rows/s", "cores": min(ncores, nsample * nq_all),
+                                           "sample": f"{nq_all} independent copies of the query side by side, {nsample} SSTs each"}},
             "e2e": {"value": rows_all / main_r["e2e_s"], "unit": "rows/s", "h2d_bytes_per_step": int(main_r["h2d"]) * world,
                     "d2h_bytes_per_step": int(main_r["d2h"]) * world, "ms_per_step": main_r["e2e_s"] * 1e3},
             "gpu_launches": main_r["launches"],
             "clocks": main_r["clocks"],
             "variants": {c: {"rows_per_s": r["rows"] * world / (r["ms_per_step"] / 1e3), "ms_per_step": r["ms_per_step"],
-                             "kernel_ms": r["kernel_ms"], "path": "fused" if r["stats"]["path"] == 1 else "general",
+                             "kernel_ms": r["kernel_ms"], "decomp_ms": r["decomp_ms"], "path": "fused" if r["stats"]["path"] == 1 else "general",
                              "e2e_rows_per_s": r["rows"] * world / r["e2e_s"], "sst_bytes_per_gpu": r["file_bytes"],
-                             "launches": r["launches"]} for c, r in res.items() if c != args.codec},
+                             "launches": r["launches"], "scan_kernel": scan_kernel_block(r)} for c, r in res.items() if c != args.codec},
         }
         emit(line)
+    ok_all = all(r["parity"]["resident"] and r["parity"]["e2e"] and r["parity"]["combined"] is not False for r in res.values())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
+    if not ok_all:
+        sys.stderr.write(f"[bench] rank {rank}: PARITY MISMATCH against the CPU oracle: { {c: r['parity'] for c, r in res.items()} }\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -5,15 +5,19 @@
 // read bytes produced by the element just before it.  One warp owns one page and breaks both dependencies:
 //
 //   parse    a 256-byte window of the compressed stream is staged in shared memory; every byte position computes
-//            "where would the next element start if one started here" (J1, a 256-entry LUT on the tag byte), four
-//            doubling steps give J2..J16, and lane k finds the start of the k-th element with 5 dependent lookups
-//            (binary lifting).  32 elements are decoded per step instead of one.
-//   execute  tiny elements (columns of 8-byte values compress to ~2.5-byte elements: literal(2) + copy(6, offset 8)):
-//            every output byte of the batch gets a source pointer (literal byte / earlier output byte); chains are
-//            collapsed by pointer jumping in shared memory (log2 of the chain length rounds), then the batch is
-//            written out.  Long elements (run-length-like columns: 64-byte copies at offset 8): one element per step,
-//            spread over the 32 lanes, reading the last kHist bytes of output from shared memory instead of waiting
-//            for the previous element's global stores.
+//            "where would the next element start if one started here" (J1, from the tag byte), five doubling steps give
+//            J2..J32, and lane k finds the start of the k-th element after ANY start position with 5 dependent lookups
+//            (binary lifting): 32 elements are decoded per step instead of one, and a batch may end after any element.
+//   execute  the longest prefix of the batch that one of two modes can take:
+//     word mode   elements of <= 8 bytes (fixed-width numeric columns compress to literal(1-2) + copy(6-7) pairs): every
+//                 lane builds its element's bytes in ONE 64-bit register — from the staged literal, from the ring / the
+//                 page's earlier output, or from an earlier element of the same batch (parent links collapsed with five
+//                 register shuffles) — and drops them into a shared-memory ring.  An element whose source straddles
+//                 two elements of the batch simply ends the prefix: it starts the next batch, where its source is old.
+//     run mode    a long element, or a run of copies with one offset (RLE-like columns: 64-byte copies at offset 4/8):
+//                 out[x] = out[x - off] over the union, i.e. one periodic pattern; for off in {1,2,4,8} that is a single
+//                 64-bit word stored to every aligned word of the run.
+//   flush    the ring is written to global memory in aligned 8-byte words, all lanes at once.
 //   literals longer than 60 bytes (incompressible columns are one literal per 64 KiB block) are plain warp copies.
 #include "kernels.h"
 
@@ -24,36 +28,62 @@ namespace k {
 
 namespace {
 
-constexpr int kWin = 256;          // compressed-stream window (bytes)
+constexpr int kWin = 256;          // compressed-stream window covered by the jump tables (bytes)
+constexpr int kWinPad = 16;        // staged beyond the window: the payload of a <= 8-byte literal that starts near its end
 constexpr int kRing = 4096;        // ring buffer of the most recent output (power of two)
-constexpr int kOut = 2048;         // max output of one batch: 32 elements x 64 bytes
-constexpr int kTiny = 512;         // max output of a tiny-element batch (byte-level resolve)
-constexpr int kHist = kRing - kOut;  // bytes before the current batch that are guaranteed to still be in the ring
+constexpr int kHist = 2048;        // bytes before the current batch that are guaranteed to still be in the ring
 constexpr int kLevels = 6;         // J1, J2, J4, J8, J16, J32
-constexpr uint16_t kExit = 0xffff;
-constexpr uint16_t kDone = 0xffff;
+constexpr uint32_t kExit = 0xffff;
 constexpr int kWarpsPerCta = 4;
+constexpr uint32_t kRestage = kWin - 96;   // start a new window when a batch would begin beyond this position
 
 struct alignas(16) WarpSmem {
-  uint8_t win[kWin + 16];
+  uint64_t ring64[kRing / 8];      // output byte at absolute position x lives at byte x & (kRing-1)
   uint16_t J[kLevels][kWin];
-  uint8_t ring[kRing];             // output byte at absolute position x lives at ring[x & (kRing-1)]
-  uint16_t ptr[kTiny];             // tiny-element batches only (T <= 32*16): batch-relative source index, or kDone
+  uint8_t win[kWin + kWinPad];
 };
 
 __host__ __device__ __forceinline__ uint64_t page_scratch2(uint32_t uncomp) { return (uint64_t(uncomp) + 15u) / 16u * 16u + 32u; }
 
+__device__ __forceinline__ uint64_t funnel64(uint64_t lo, uint64_t hi, uint32_t sh_bits) {   // sh_bits in {0, 8, .., 56}
+  return (lo >> sh_bits) | ((hi << 1) << (63 - sh_bits));
+}
+// 8 bytes of read-only input at any alignment
 __device__ __forceinline__ uint64_t ld8_any(const uint8_t* p) {
   uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  uint32_t sh = uint32_t(a & 7) * 8;
   const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
-  uint64_t lo = __ldg(q), hi = __ldg(q + 1);
-  return (lo >> sh) | ((hi << 1) << (63 - sh));
+  return funnel64(__ldg(q), __ldg(q + 1), uint32_t(a & 7) * 8);
+}
+// 8 bytes of this page's earlier OUTPUT at any alignment (written by this warp: coherent loads, never the read-only path)
+__device__ __forceinline__ uint64_t ld8_out(const uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+  uint64_t lo, hi;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(lo) : "l"(q));
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(hi) : "l"(q + 1));
+  return funnel64(lo, hi, uint32_t(a & 7) * 8);
 }
 __device__ __forceinline__ uint8_t ldcg_u8(const uint8_t* p) {
   uint32_t v;
   asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p));
   return uint8_t(v);
+}
+__device__ __forceinline__ uint8_t* ring_bytes(WarpSmem& sm) { return reinterpret_cast<uint8_t*>(sm.ring64); }
+// 8 ring bytes starting at absolute output position x (any alignment)
+__device__ __forceinline__ uint64_t ring_ld8(const WarpSmem& sm, uint32_t x) {
+  const uint32_t w = (x >> 3) & (kRing / 8 - 1);
+  return funnel64(sm.ring64[w], sm.ring64[(w + 1) & (kRing / 8 - 1)], (x & 7) * 8);
+}
+__device__ __forceinline__ uint64_t win_ld8(const WarpSmem& sm, uint32_t p) {          // p + 8 <= kWin + kWinPad
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(sm.win) + (p >> 2);
+  const uint32_t sh = (p & 3) * 8;
+  const uint32_t a = w[0], b = w[1], c = w[2];
+  return (uint64_t(__funnelshift_r(b, c, sh)) << 32) | __funnelshift_r(a, b, sh);
+}
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, uint32_t(v), src);
+  uint32_t hi = __shfl_sync(0xffffffffu, uint32_t(v >> 32), src);
+  return (uint64_t(hi) << 32) | lo;
 }
 
 // compressed size of the element whose tag byte is t; 0 = literal with a multi-byte length (handled separately)
@@ -71,44 +101,23 @@ __device__ __forceinline__ void warp_copy_in(uint8_t* dst, const uint8_t* src, u
   uint32_t nwords = (len - head) >> 3;
   uint64_t* d8 = reinterpret_cast<uint64_t*>(dst + head);
   const uint8_t* s = src + head;
+#pragma unroll 4
   for (uint32_t w = lane; w < nwords; w += 32) d8[w] = ld8_any(s + (size_t(w) << 3));
   uint32_t done = head + (nwords << 3);
   for (uint32_t i = done + lane; i < len; i += 32) dst[i] = __ldg(src + i);
 }
 
 // byte at absolute output position x (< o, i.e. produced by an earlier batch): ring if recent enough, else global
-__device__ __forceinline__ uint8_t old_byte(const WarpSmem& sm, const uint8_t* dst, uint32_t o, uint32_t x) {
-  return (o - x <= uint32_t(kHist)) ? sm.ring[x & (kRing - 1)] : ldcg_u8(dst + x);
+__device__ __forceinline__ uint8_t old_byte(WarpSmem& sm, const uint8_t* dst, uint32_t o, uint32_t x) {
+  return (o - x <= uint32_t(kHist)) ? ring_bytes(sm)[x & (kRing - 1)] : ldcg_u8(dst + x);
 }
 
-// pointer jumping over at most kTrips*32 batch bytes, all state of a round staged in registers
-template <int kTrips>
-__device__ __forceinline__ void resolve_small(WarpSmem& sm, uint32_t o, uint32_t T, int lane) {
-  for (;;) {
-    uint16_t pr[kTrips], pq[kTrips];
-    uint8_t vq[kTrips];
-#pragma unroll
-    for (int j = 0; j < kTrips; j++) {
-      const uint32_t r = j * 32 + lane;
-      pr[j] = kDone; pq[j] = kDone; vq[j] = 0;
-      if (r < T) {
-        pr[j] = sm.ptr[r];
-        if (pr[j] != kDone) { pq[j] = sm.ptr[pr[j]]; vq[j] = sm.ring[(o + pr[j]) & (kRing - 1)]; }
-      }
-    }
-    __syncwarp();
-    bool pending = false;
-#pragma unroll
-    for (int j = 0; j < kTrips; j++) {
-      const uint32_t r = j * 32 + lane;
-      if (r < T && pr[j] != kDone) {
-        if (pq[j] == kDone) { sm.ring[(o + r) & (kRing - 1)] = vq[j]; sm.ptr[r] = kDone; }
-        else { sm.ptr[r] = pq[j]; pending = true; }
-      }
-    }
-    __syncwarp();
-    if (!__any_sync(0xffffffffu, pending)) break;
-  }
+// ring -> global, aligned 8-byte words [fl, align_down(upto)); returns the new flush position
+__device__ __forceinline__ uint32_t flush_words(const WarpSmem& sm, uint8_t* dst, uint32_t fl, uint32_t upto, int lane) {
+  const uint32_t w0 = fl >> 3, w1 = upto >> 3;
+  uint64_t* d8 = reinterpret_cast<uint64_t*>(dst);
+  for (uint32_t w = w0 + lane; w < w1; w += 32) d8[w] = sm.ring64[w & (kRing / 8 - 1)];
+  return w1 << 3;
 }
 
 __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, WarpSmem& sm,
@@ -120,7 +129,9 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
     if (!(b & 0x80)) break;
   }
   if (ulen != ulen_expected) { if (lane == 0) atomicExch(err, 101); return; }
+  uint8_t* const ring = ring_bytes(sm);
   uint32_t o = 0;                 // bytes produced so far
+  uint32_t fl = 0;                // output bytes [0, fl) are in global memory (fl is a multiple of 8, fl <= o)
   while (pos < n) {
     const uint32_t avail = n - pos;
     const uint32_t tag0 = __ldg(src + pos);
@@ -129,53 +140,62 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       uint32_t nb = (tag0 >> 2) - 59, len = 0;
       for (uint32_t i = 0; i < nb; i++) len |= uint32_t(__ldg(src + pos + 1 + i)) << (8 * i);
       len += 1;
-      if (1 + nb + len > avail || o + len > ulen) { if (lane == 0) atomicExch(err, 102); return; }
+      if (1 + nb + len > avail || o + len > ulen || len < 1) { if (lane == 0) atomicExch(err, 102); return; }
       const uint8_t* lsrc = src + pos + 1 + nb;
-      warp_copy_in(dst + o, lsrc, len, lane);
       __syncwarp();
-      // the ring keeps the tail of the literal
-      const uint32_t keep = len < uint32_t(kRing) ? len : uint32_t(kRing);
-      for (uint32_t i = lane; i < keep; i += 32) sm.ring[(o + len - keep + i) & (kRing - 1)] = __ldg(lsrc + (len - keep) + i);
+      if (uint32_t(lane) < o - fl) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];     // pending partial word
+      warp_copy_in(dst + o, lsrc, len, lane);
+      // the ring keeps the tail of the literal (whole words where possible)
+      const uint32_t keep = len < uint32_t(kHist) ? len : uint32_t(kHist);
+      const uint32_t k0 = o + len - keep, k1 = o + len;
+      const uint32_t a0 = (k0 + 7) & ~7u, a1 = k1 & ~7u;
+      if (a0 < a1) {
+        for (uint32_t w = (a0 >> 3) + lane; w < (a1 >> 3); w += 32) sm.ring64[w & (kRing / 8 - 1)] = ld8_any(lsrc + ((w << 3) - o));
+        if (k0 + lane < a0) ring[(k0 + lane) & (kRing - 1)] = __ldg(lsrc + (k0 + lane - o));
+        if (a1 + lane < k1) ring[(a1 + lane) & (kRing - 1)] = __ldg(lsrc + (a1 + lane - o));
+      } else {
+        for (uint32_t i = k0 + lane; i < k1; i += 32) ring[i & (kRing - 1)] = __ldg(lsrc + (i - o));
+      }
       __syncwarp();
       pos += 1 + nb + len;
       o += len;
+      fl = o & ~7u;
       continue;
     }
-    // ---- stage the window and build the jump tables
+    // ---- stage the window and build the jump tables.  Lane l owns positions l, l+32, ..: conflict-free table rows.
     __syncwarp();
     {
       uint64_t w = (uint32_t(lane) * 8 < avail + 8) ? ld8_any(src + pos + lane * 8) : 0ull;
-      *reinterpret_cast<uint64_t*>(&sm.win[lane * 8]) = w;
-      if (lane < 2) *reinterpret_cast<uint64_t*>(&sm.win[kWin + lane * 8]) = 0ull;
+      reinterpret_cast<uint64_t*>(sm.win)[lane] = w;
+      if (lane < kWinPad / 8) reinterpret_cast<uint64_t*>(sm.win)[32 + lane] = (uint32_t(kWin + lane * 8) < avail + 8) ? ld8_any(src + pos + kWin + lane * 8) : 0ull;
     }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t p = lane * 8 + j;
+    for (int j = 0; j < kWin / 32; j++) {
+      const uint32_t p = j * 32 + lane;
       const uint32_t sz = elem_csize(sm.win[p]);
       const uint32_t nx = p + sz;
       // the NEXT element must start inside the stream and have its (<= 5 byte) header inside the window
-      sm.J[0][p] = (sz == 0 || p >= avail || nx + 5 > uint32_t(kWin) || nx >= avail) ? kExit : uint16_t(nx);
+      sm.J[0][p] = (sz == 0 || p >= avail || nx + 5 > uint32_t(kWin) || nx >= avail) ? uint16_t(kExit) : uint16_t(nx);
     }
     __syncwarp();
 #pragma unroll
     for (int lv = 1; lv < kLevels; lv++) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const uint32_t p = lane * 8 + j;
-        const uint16_t a = sm.J[lv - 1][p];
-        sm.J[lv][p] = a == kExit ? kExit : sm.J[lv - 1][a];
+      for (int j = 0; j < kWin / 32; j++) {
+        const uint32_t p = j * 32 + lane;
+        const uint32_t a = sm.J[lv - 1][p];
+        sm.J[lv][p] = a == kExit ? uint16_t(kExit) : sm.J[lv - 1][a];
       }
       __syncwarp();
     }
-    uint32_t q = 0;                                  // window-relative start of element `lane` of the current batch
+    uint32_t qs = 0;                                   // window-relative start of the next batch
+    bool first = true;
+    for (;;) {
+      uint32_t q = qs;
 #pragma unroll
-    for (int lv = 0; lv < 5; lv++)
-      if ((lane >> lv) & 1) q = q == kExit ? uint32_t(kExit) : sm.J[lv][q];
-    uint32_t next_pos = pos;
-    // up to three batches of 32 elements from one parsed window
-    for (int b = 0; b < 3; b++) {
-      if (b > 0) q = q == kExit ? uint32_t(kExit) : sm.J[5][q];
+      for (int lv = 0; lv < 5; lv++)
+        if ((lane >> lv) & 1) q = q == kExit ? kExit : sm.J[lv][q];
       bool valid = q != kExit;
       uint32_t len = 0, off = 0, hdr = 0, csz = 0;
       bool is_lit = false;
@@ -189,156 +209,153 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
         else if (kind == 2) { len = (t >> 2) + 1; off = uint32_t(sm.win[q + 1]) | (uint32_t(sm.win[q + 2]) << 8); hdr = 3; }
         else { len = (t >> 2) + 1; off = uint32_t(sm.win[q + 1]) | (uint32_t(sm.win[q + 2]) << 8) | (uint32_t(sm.win[q + 3]) << 16) | (uint32_t(sm.win[q + 4]) << 24); hdr = 5; }
         csz = hdr + (is_lit ? len : 0);
-        if (valid && q + csz > avail) valid = false; // truncated stream: caught by the final size check / m == 0
+        if (q + csz > avail) valid = false;          // truncated stream: caught by m == 0 / the final size check
       }
       const unsigned vm = __ballot_sync(0xffffffffu, valid);
       const int m = (vm == 0xffffffffu) ? 32 : (__ffs(~vm) - 1);   // valid lanes form a prefix
       if (m == 0) {
-        if (b == 0) { if (lane == 0) atomicExch(err, 105); return; }
+        if (first) { if (lane == 0) atomicExch(err, 105); return; }
+        pos += qs;                                                 // a long literal (or the window's end) starts here: restage
         break;
       }
-      if (lane >= m) { len = 0; csz = 0; }
-      uint32_t inc = len;                                          // exclusive prefix sum of the output lengths
+      first = false;
+      if (lane >= m) { len = 0; csz = 0; off = 1; is_lit = true; }
+      uint32_t inc = len;                                          // inclusive prefix sum of the output lengths
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
       const uint32_t doff = inc - len;
-      const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
-      next_pos = pos + __shfl_sync(0xffffffffu, q + csz, m - 1);
-      bool bad = lane < m && !is_lit && (off == 0 || off > o + doff);
-      if (__any_sync(0xffffffffu, bad) || o + T > ulen) { if (lane == 0) atomicExch(err, 103); return; }
-
-      if (T <= uint32_t(m) * 16) {
-        // ---------------- tiny elements.
-        // Fast path: every copy either reads bytes older than the batch or reproduces exactly one earlier element of
-        // the batch (same start, same length) — the shape of fixed-width numeric columns.  Then the dependency graph is
-        // over ELEMENTS: parent links are collapsed with five register shuffles and each lane copies its own bytes.
-        bool elem_done = false;
+      {
+        const bool bad = lane < m && !is_lit && (off == 0 || off > o + doff);
+        if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicExch(err, 103); return; }
+      }
+      const uint32_t len0 = __shfl_sync(0xffffffffu, len, 0);
+      int cnt;                                                     // elements executed by this step (a prefix of the batch)
+      uint32_t T;                                                  // their output bytes
+      if (len0 <= 8) {
+        // ---------------- word mode
+        // where does this element's data come from?  0 literal bytes in the window, 1 earlier output (ring / global),
+        // 2 one earlier element of this batch (parent, byte delta).  Anything else ends the prefix.
+        uint32_t skind = 0, spos = q + 1;
+        int parent = lane;
+        uint32_t delta = 0;
+        bool fail = len > 8;
+        if (!is_lit && !fail) {
+          const int32_t s0 = int32_t(doff) - int32_t(off);
+          if (off >= len) {
+            if (s0 + int32_t(len) <= 0) { skind = 1; spos = o + doff - off; }
+            else if (s0 < 0) fail = true;                          // straddles the batch start
+            else skind = 2;
+          } else {                                                 // self-overlapping (periodic) copy: fine if its pattern is old
+            if (doff == 0) { skind = 1; spos = o - off; } else fail = true;
+          }
+        }
+        // parent = the element that contains byte s0 (binary search over the element starts, register shuffles only)
         {
-          uint8_t* tbl = reinterpret_cast<uint8_t*>(sm.ptr);            // start offset -> lane (no init: verified below)
-          if (lane < m) tbl[doff] = uint8_t(lane);
-          __syncwarp();
-          int parent = lane;
-          bool fail = false, need_parent = false;
-          uint32_t dkind = 0, dpos = 0;                                  // 0: bytes at win[dpos..], 1: output bytes at abs dpos..
-          if (lane < m) {
-            if (is_lit) { dpos = q + 1; }
-            else {
-              const int32_t s0 = int32_t(doff) - int32_t(off);
-              if (s0 < 0) { if (s0 + int32_t(len) <= 0) { dkind = 1; dpos = o + doff - off; } else fail = true; }
-              else { parent = tbl[s0] & 31; need_parent = true; }
-            }
-          }
-          const uint32_t pd = __shfl_sync(0xffffffffu, doff, parent), pl = __shfl_sync(0xffffffffu, len, parent);
-          if (need_parent && (parent >= lane || pd + off != doff || pl != len)) fail = true;   // (a stale table entry may even name this lane)
-          if (!__any_sync(0xffffffffu, fail)) {
+          const uint32_t s0 = doff - off;
+          int lo = 0;
 #pragma unroll
-            for (int it = 0; it < 5; it++) parent = __shfl_sync(0xffffffffu, parent, parent);
-            const uint32_t rk = __shfl_sync(0xffffffffu, dkind, parent), rp = __shfl_sync(0xffffffffu, dpos, parent);
-            if (lane < m) {
-              for (uint32_t i = 0; i < len; i++) {
-                uint8_t v;
-                if (rk == 0) { const uint32_t wp = rp + i; v = wp < uint32_t(kWin) ? sm.win[wp] : __ldg(src + pos + wp); }
-                else v = old_byte(sm, dst, o, rp + i);
-                sm.ring[(o + doff + i) & (kRing - 1)] = v;
-                dst[o + doff + i] = v;
-              }
-            }
-            elem_done = true;
+          for (int step = 16; step > 0; step >>= 1) {
+            const int cand = lo + step;
+            const uint32_t d = __shfl_sync(0xffffffffu, doff, cand & 31);
+            if (skind == 2 && cand < lane && d <= s0) lo = cand;
           }
-          __syncwarp();
-        }
-        if (!elem_done) {
-        // general case: byte-level source pointers + pointer jumping
-        if (lane < m) {
-          if (is_lit) {
-            const uint8_t* ls = src + pos + q + 1;
-            for (uint32_t i = 0; i < len; i++) {
-              const uint32_t wp = q + 1 + i;                           // literal bytes usually sit in the staged window
-              sm.ring[(o + doff + i) & (kRing - 1)] = wp < uint32_t(kWin) ? sm.win[wp] : __ldg(ls + i);
-              sm.ptr[doff + i] = kDone;
-            }
-          } else {
-            for (uint32_t i = 0; i < len; i++) {
-              const uint32_t r = doff + i;
-              if (off <= r) sm.ptr[r] = uint16_t(r - off);             // produced by this batch: resolved below
-              else { sm.ring[(o + r) & (kRing - 1)] = old_byte(sm, dst, o, o + r - off); sm.ptr[r] = kDone; }
-            }
+          const uint32_t pd = __shfl_sync(0xffffffffu, doff, lo), pl = __shfl_sync(0xffffffffu, len, lo);
+          if (skind == 2) {
+            if (lo >= lane || s0 < pd || s0 + len > pd + pl) fail = true;     // not inside ONE earlier element
+            else { parent = lo; delta = s0 - pd; }
           }
         }
-        __syncwarp();
-        if (T <= 256) {
-          // register-staged rounds: one barrier between the read and the write phase
-          if (T <= 64) resolve_small<2>(sm, o, T, lane);
-          else if (T <= 128) resolve_small<4>(sm, o, T, lane);
-          else resolve_small<8>(sm, o, T, lane);
-        } else {
-          const uint32_t trips = (T + 31) / 32;
-          for (;;) {
-            bool pending = false;
-            for (uint32_t j = 0; j < trips; j++) {
-              const uint32_t r = j * 32 + lane;
-              uint16_t pr = kDone, pq = kDone;
-              uint8_t vq = 0;
-              if (r < T) {
-                pr = sm.ptr[r];
-                if (pr != kDone) { pq = sm.ptr[pr]; vq = sm.ring[(o + pr) & (kRing - 1)]; }
-              }
-              __syncwarp();
-              if (r < T && pr != kDone) {
-                if (pq == kDone) { sm.ring[(o + r) & (kRing - 1)] = vq; sm.ptr[r] = kDone; }
-                else { sm.ptr[r] = pq; pending = true; }
-              }
-              __syncwarp();
+        const unsigned fm = __ballot_sync(0xffffffffu, fail || lane >= m);
+        cnt = fm ? __ffs(fm) - 1 : 32;                             // >= 1: element 0 has len <= 8 and an old / literal source
+        if (lane >= cnt) { parent = lane; delta = 0; }
+        // collapse parent chains (parents are always earlier lanes inside the prefix)
+#pragma unroll
+        for (int it = 0; it < 5; it++) {
+          const uint32_t d2 = __shfl_sync(0xffffffffu, delta, parent);
+          const int p2 = __shfl_sync(0xffffffffu, parent, parent);
+          delta += d2;
+          parent = p2;
+        }
+        uint64_t w = 0;
+        if (lane < cnt && skind != 2) {
+          if (skind == 0) w = win_ld8(sm, spos);
+          else {
+            w = (o - spos <= uint32_t(kHist)) ? ring_ld8(sm, spos) : ld8_out(dst + spos);
+            if (off < len) {                                       // periodic: repeat the first `off` bytes
+              w &= (off >= 8) ? ~0ull : ((1ull << (8 * off)) - 1);
+              for (uint32_t f = off; f < 8; f <<= 1) w |= w << (8 * f);
             }
-            if (!__any_sync(0xffffffffu, pending)) break;
           }
         }
-        for (uint32_t r = lane; r < T; r += 32) dst[o + r] = sm.ring[(o + r) & (kRing - 1)];
+        {
+          const uint64_t wr = shfl64(w, parent);
+          if (skind == 2) w = wr >> (8 * delta);
+        }
+        T = __shfl_sync(0xffffffffu, inc, cnt - 1);
+        if (o + T > ulen) { if (lane == 0) atomicExch(err, 103); return; }
+        if (lane < cnt) {
+          const uint32_t base = o + doff;
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            if (uint32_t(i) < len) ring[(base + i) & (kRing - 1)] = uint8_t(w >> (8 * i));
         }
       } else {
-        // ---------------- long elements.  Adjacent copies with the same offset continue one periodic pattern
-        // (out[x] = out[x - off] over the union), so they are merged into a single run and spread over the warp.
-        const uint32_t poff = __shfl_up_sync(0xffffffffu, off, 1);
-        const bool plit = __shfl_up_sync(0xffffffffu, int(is_lit), 1) != 0;
-        const bool head = lane < m && (lane == 0 || is_lit || plit || poff != off);
-        unsigned heads = __ballot_sync(0xffffffffu, head);
-        while (heads) {
-          const int e = __ffs(heads) - 1;
-          heads &= heads - 1;
-          const int enext = heads ? (__ffs(heads) - 1) : m;            // first lane of the next run
-          const uint32_t s0 = __shfl_sync(0xffffffffu, doff, e);
-          const uint32_t s1 = enext < 32 ? __shfl_sync(0xffffffffu, doff, enext & 31) : T;
-          const uint32_t rlen = (enext == m ? T : s1) - s0;
-          const uint32_t eoff = __shfl_sync(0xffffffffu, off, e);
-          const uint32_t eq = __shfl_sync(0xffffffffu, q, e);
-          const bool elit = __shfl_sync(0xffffffffu, int(is_lit), e) != 0;
-          __syncwarp();
-          if (elit) {
-            const uint8_t* ls = src + pos + eq + 1;
-            for (uint32_t i = lane; i < rlen; i += 32) sm.ring[(o + s0 + i) & (kRing - 1)] = __ldg(ls + i);
+        // ---------------- run mode: element 0 is long.  A literal goes alone; a copy takes every following copy with the
+        // same offset along (one periodic pattern over the union).
+        const uint32_t off0 = __shfl_sync(0xffffffffu, off, 0);
+        const bool lit0 = __shfl_sync(0xffffffffu, int(is_lit), 0) != 0;
+        if (lit0) cnt = 1;
+        else {
+          const unsigned brk = __ballot_sync(0xffffffffu, lane >= m || is_lit || off != off0);
+          cnt = brk ? __ffs(brk) - 1 : 32;
+        }
+        T = __shfl_sync(0xffffffffu, inc, cnt - 1);
+        if (o + T > ulen) { if (lane == 0) atomicExch(err, 103); return; }
+        __syncwarp();
+        if (lit0) {
+          const uint32_t q0 = __shfl_sync(0xffffffffu, q, 0);
+          const uint8_t* ls = src + pos + q0 + 1;
+          for (uint32_t i = lane; i < T; i += 32) ring[(o + i) & (kRing - 1)] = __ldg(ls + i);
+        } else if (off0 == 8 || off0 == 4 || off0 == 2 || off0 == 1) {
+          // the pattern as one 64-bit word, phased for 8-aligned absolute positions (off0 divides 8)
+          uint64_t pw = ring_ld8(sm, o - off0);
+          pw &= (off0 >= 8) ? ~0ull : ((1ull << (8 * off0)) - 1);
+          for (uint32_t f = off0; f < 8; f <<= 1) pw |= pw << (8 * f);
+          const uint32_t c = (off0 - (o % off0)) % off0;         // (aligned address - o) mod off0
+          const uint64_t W = c ? ((pw >> (8 * c)) | (pw << (64 - 8 * c))) : pw;
+          const uint32_t a0 = (o + 7) & ~7u, a1 = (o + T) & ~7u;
+          if (a0 < a1) {
+            for (uint32_t wd = (a0 >> 3) + lane; wd < (a1 >> 3); wd += 32) sm.ring64[wd & (kRing / 8 - 1)] = W;
+            if (o + lane < a0) ring[(o + lane) & (kRing - 1)] = uint8_t(W >> (8 * ((o + lane) & 7)));
+            if (a1 + lane < o + T) ring[(a1 + lane) & (kRing - 1)] = uint8_t(W >> (8 * lane));
           } else {
-            // every source byte precedes the run: x - off taken modulo the pattern length (kept incrementally: no
-            // integer division per byte)
-            const uint32_t start = o + s0;
-            const uint32_t stride = 32u % eoff;
-            uint32_t r = uint32_t(lane) % eoff;
-            const bool all_ring = eoff <= uint32_t(kHist);                 // the whole pattern is inside the ring window
-            for (uint32_t i = lane; i < rlen; i += 32) {
-              const uint32_t x = start - eoff + r;
-              sm.ring[(start + i) & (kRing - 1)] = (all_ring || start - x <= uint32_t(kHist) + s0) ? sm.ring[x & (kRing - 1)] : ldcg_u8(dst + x);
-              r += stride;
-              if (r >= eoff) r -= eoff;
-            }
+            for (uint32_t i = o + lane; i < o + T; i += 32) ring[i & (kRing - 1)] = uint8_t(W >> (8 * (i & 7)));
           }
-          __syncwarp();
-          for (uint32_t i = lane; i < rlen; i += 32) dst[o + s0 + i] = sm.ring[(o + s0 + i) & (kRing - 1)];
+        } else {
+          // any other offset: byte i of the run = old byte (i mod off0) of the pattern (kept incrementally: no division per byte)
+          const uint32_t stride = 32u % off0;
+          uint32_t r = uint32_t(lane) % off0;
+          for (uint32_t i = lane; i < T; i += 32) {
+            const uint32_t x = o - off0 + r;
+            ring[(o + i) & (kRing - 1)] = old_byte(sm, dst, o, x);
+            r += stride;
+            if (r >= off0) r -= off0;
+          }
         }
       }
+      __syncwarp();
       o += T;
-      if (m < 32) break;
+      fl = flush_words(sm, dst, fl, o, lane);
+      // where the next batch starts: right after the last executed element
+      const uint32_t adv = __shfl_sync(0xffffffffu, q + csz, cnt - 1);
+      if (cnt == 32) qs = sm.J[5][qs];
+      else qs = __shfl_sync(0xffffffffu, q, cnt & 31);
+      if (qs == kExit || qs != adv || adv > kRestage) { pos += adv; break; }
+      __syncwarp();
     }
-    pos = next_pos;
   }
+  __syncwarp();
+  if (fl + lane < o) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];
   if (o != ulen) { if (lane == 0) atomicExch(err, 104); }
 }
 
@@ -408,9 +425,8 @@ void snappy_chunks_v2(const Launch& L, const SstDev* ssts, const RgSel* sel, uin
   std::memset(&J, 0, sizeof(J));
   J.ssts = ssts; J.sel = sel; J.d_nsel = nullptr; J.nsel = nsel; J.cols = cols; J.ncols = ncolsel;
   J.scratch = scratch; J.ticket = ticket; J.err = err; J.fixed_stride = 0;
-  for (int i = 0; i < ncolsel && i < kSnappyMaxCols; i++) { J.order[i] = i; J.col[i] = 0; }
-  // general pipeline: the column ids live in the device-side ColSel array; copy them lazily inside the kernel
-  J.col_from_cols = 1;
+  for (int i = 0; i < ncolsel && i < kSnappyMaxCols; i++) J.order[i] = uint8_t(i);
+  J.col_from_cols = 1;      // general pipeline: column ids and the variable scratch layout come from the ColSel table
   snappy_pages(L, J, nsel * uint32_t(ncolsel));
 }
 

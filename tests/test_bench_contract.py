@@ -17,7 +17,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "scanned rows/s" and d["unit"] == "rows/s" and d["higher_is_better"] is True
     for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
-    assert d["value"] > 0 and d["config"]["workload"].startswith("config2") and d["config"]["codec"] == "none"
+    assert d["value"] > 0 and d["config"]["workload"].startswith("config2") and d["config"]["codec"] == "snappy"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "sample" in cb       # one SST -> one busy thread
     assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
