@@ -19,6 +19,8 @@ HG_OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
 HG_FLAG_NO_PRUNING = 1
 HG_FLAG_NO_FUSED = 2
 HG_FLAG_NO_LATE_MATERIALIZATION = 4
+HG_FLAG_PAIRWISE_MERGE = 8
+HG_AGG_RUNS, HG_AGG_HASH = 0, 1
 
 STATUS = {0: "OK", 1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "FORMAT", 5: "OOM", 6: "NOT_FOUND", 7: "INTERNAL"}
 
@@ -51,7 +53,7 @@ class HgPredicate(C.Structure):
 
 class HgAggSpec(C.Structure):
     _fields_ = [("group_col", C.c_int32), ("ts_col", C.c_int32), ("window_ms", C.c_int64), ("value_col", C.c_int32),
-                ("_pad", C.c_uint32)]
+                ("mode", C.c_uint32)]
 
 
 class HgScanStats(C.Structure):
@@ -256,29 +258,29 @@ class Engine:
         return pa.RecordBatchReader._import_from_c(C.addressof(stream))
 
     def scan_aggregate(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (), group_col: int = 0,
-                       ts_col: int = -1, window_ms: int = 0, value_col: int = -1) -> pa.Table:
+                       ts_col: int = -1, window_ms: int = 0, value_col: int = -1, mode: int = 0) -> pa.Table:
         arr, keep = self._descs(ssts)
         p = _make_preds(schema.arrow_schema, preds)
-        spec = HgAggSpec(group_col, ts_col, window_ms, value_col, 0)
+        spec = HgAggSpec(group_col, ts_col, window_ms, value_col, mode)
         stream = ArrowArrayStream()
         _check(self._L.hg_scan_aggregate(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p, C.c_size_t(len(preds)),
                                          C.byref(spec), C.byref(stream)))
         return pa.RecordBatchReader._import_from_c(C.addressof(stream)).read_all()
 
     def scan_aggregate_device(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (),
-                              group_col: int = 0, ts_col: int = -1, window_ms: int = 0, value_col: int = -1) -> HgAggDevice:
+                              group_col: int = 0, ts_col: int = -1, window_ms: int = 0, value_col: int = -1, mode: int = 0) -> HgAggDevice:
         arr, keep = self._descs(ssts)
         p = _make_preds(schema.arrow_schema, preds)
-        spec = HgAggSpec(group_col, ts_col, window_ms, value_col, 0)
+        spec = HgAggSpec(group_col, ts_col, window_ms, value_col, mode)
         out = HgAggDevice()
         _check(self._L.hg_scan_aggregate_device(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p,
                                                 C.c_size_t(len(preds)), C.byref(spec), C.byref(out)))
         return out
 
     def prepare_aggregate(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (), group_col: int = 0,
-                          ts_col: int = -1, window_ms: int = 0, value_col: int = -1) -> "PreparedAggregate":
+                          ts_col: int = -1, window_ms: int = 0, value_col: int = -1, mode: int = 0) -> "PreparedAggregate":
         """Marshal the arguments of `scan_aggregate_device` once; `run()` is then a single C call (what a compiled host pays)."""
-        return PreparedAggregate(self, schema, ssts, preds, group_col, ts_col, window_ms, value_col)
+        return PreparedAggregate(self, schema, ssts, preds, group_col, ts_col, window_ms, value_col, mode)
 
     def stats_struct(self) -> "HgScanStats":
         """hg_last_stats into a reused ctypes struct (no dict): for tight measurement loops."""
@@ -298,12 +300,12 @@ class Engine:
 class PreparedAggregate:
     """The ctypes argument block of one `hg_scan_aggregate_device` call, built once and reused."""
 
-    def __init__(self, eng: Engine, schema: SchemaHandle, ssts, preds, group_col, ts_col, window_ms, value_col):
+    def __init__(self, eng: Engine, schema: SchemaHandle, ssts, preds, group_col, ts_col, window_ms, value_col, mode=0):
         self._eng = eng
         self._schema = schema
         self._arr, self._keep = eng._descs(ssts)
         self._p = _make_preds(schema.arrow_schema, preds)
-        self._spec = HgAggSpec(group_col, ts_col, window_ms, value_col, 0)
+        self._spec = HgAggSpec(group_col, ts_col, window_ms, value_col, mode)
         self.out = HgAggDevice()
         self._fn = eng._L.hg_scan_aggregate_device
         self._args = (eng._h, C.byref(schema.desc), self._arr, C.c_size_t(len(ssts)), self._p, C.c_size_t(len(preds)),

@@ -874,6 +874,60 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     CU_TRY(st->run_start.alloc((k + 2) * sizeof(uint32_t), s));
     CU_TRY(cudaMemcpyAsync(st->file_base.p, plan.file_base.data(), (k + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     k::survivor_run_starts(L, st->surv_ptr, st->d_m, st->file_base.as<uint32_t>(), k, st->run_start.as<uint32_t>());
+    // single pass over packed 64-bit keys when (pk..., __seq__, stream) fit in 52 bits after rebasing to the chunk statistics
+    k::KeyPack kp;
+    bool packed = k <= k::kMaxMergeRuns && !(e->flags & HG_FLAG_PAIRWISE_MERGE);
+    if (packed) {
+      std::memset(&kp, 0, sizeof(kp));
+      const int npk = int(schema->num_primary_keys);
+      uint64_t lo[MAX_PK + 1], hi[MAX_PK + 1];
+      bool seen = false, seq_nullable = false;
+      for (const RgSel& rs : plan.sel) {
+        const SstResident* f = plan.files[rs.sst];
+        const RgCol* rc = &f->rgcol[size_t(rs.rg) * size_t(f->meta.ncols)];
+        for (int c = 0; c <= npk && packed; c++) {
+          const uint32_t col = c < npk ? uint32_t(c) : seq_idx;
+          const RgCol& x = rc[col];
+          if (c == npk && x.null_all) { seq_nullable = true; continue; }
+          if (!x.has_minmax) { packed = false; break; }
+          const uint64_t flip = (c < npk && type_is_signed(schema->types[col])) ? (1ull << 63) : 0ull;
+          const uint64_t a = x.mn ^ flip, b = x.mx ^ flip;
+          if (c == npk && !x.null_none) seq_nullable = true;
+          if (!seen || a < lo[c]) lo[c] = a;
+          if (!seen || b > hi[c]) hi[c] = b;
+        }
+        seen = true;
+      }
+      if (packed && seen) {
+        auto bits = [](uint64_t span) { int b = 0; while (span) { b++; span >>= 1; } return b; };
+        int rb = 0;
+        while ((1 << rb) < k) rb++;
+        // seq lives in the (value + 1, NULL = 0) domain
+        if (hi[npk] == ~0ull) packed = false;
+        kp.seq_min = seq_nullable ? 0 : lo[npk] + 1;
+        kp.seq_span = hi[npk] + 1 - kp.seq_min;
+        kp.seq_shift = uint32_t(rb);
+        int used = rb + bits(kp.seq_span);
+        kp.pk_shift = uint32_t(used);
+        for (int c = npk - 1; c >= 0 && packed; c--) {
+          kp.mn[c] = lo[c];
+          kp.span[c] = hi[c] - lo[c];
+          kp.shift[c] = uint32_t(used);
+          used += bits(kp.span[c]);
+        }
+        if (used > 52) packed = false;
+      } else packed = false;
+    }
+    if (packed) {
+      uint32_t ranges = 1;
+      DevBuf ktmp;
+      CU_TRY(ktmp.alloc(k::kway_tmp_bytes(N, k, &ranges), s));
+      CU_TRY(st->order.alloc(size_t(N) * 4 + 16, s));
+      k::kway_merge(L, pk, st->cols[seq_idx].view(), st->surv_ptr, st->d_m, N, st->run_start.as<uint32_t>(), k, kp, ktmp.p,
+                    st->counters() + 5, st->order.as<uint32_t>(), st->keep.as<uint8_t>(), st->d_err.as<int>());
+      order = st->order.as<uint32_t>();
+      st->surv_ptr = nullptr;
+    } else {
     CU_TRY(st->recA.alloc(size_t(N) * sizeof(SortRec) + 32, s));
     CU_TRY(st->recB.alloc(size_t(N) * sizeof(SortRec) + 32, s));
     k::build_records(L, pk, st->cols[seq_idx].view(), st->surv_ptr, st->d_m, N, st->recA.as<SortRec>());
@@ -891,8 +945,9 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     order = st->order.as<uint32_t>();
     st->recA.reset();
     st->recB.reset();
-    st->surv.reset();
     st->surv_ptr = nullptr;  // (no longer valid)
+    }
+    st->surv.reset();
   } else if (N > 0) {
     k::dedup_flags_cols(L, pk, order, st->d_m, N, st->keep.as<uint8_t>());
   }
@@ -1406,8 +1461,12 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
   if (agg->group_col >= 0) { ab->gtype = schema->types[agg->group_col]; ab->gwidth = type_width_host(ab->gtype); }
   if (n == 0) { ab->G = 0; return HG_OK; }
 
-  // fused fast path: sorted PK-disjoint inputs, one uncompressed PLAIN page per chunk, group = pk0, time = pk1
-  if (!(e->flags & HG_FLAG_NO_FUSED)) {
+  if (agg->mode > HG_AGG_HASH) return set_error(HG_ERR_INVALID, "aggregation mode");
+  // HASH mode only differs from RUNS when the key is not a prefix of the sort order (pk0 [, bucket of pk1]) / not global
+  const bool prefix_key = (agg->group_col < 0 && !has_ts) || (agg->group_col == 0 && (!has_ts || agg->ts_col == 1));
+  const bool hash_sort = agg->mode == HG_AGG_HASH && !prefix_key;
+  // fused fast path: sorted PK-disjoint inputs, one PLAIN page per chunk, group = pk0, time = pk1
+  if (!(e->flags & HG_FLAG_NO_FUSED) && !hash_sort) {
     int frc = fused::try_scan_aggregate(e, schema, ssts, n, preds, np, agg, ab);
     if (frc != fused::NOT_APPLICABLE) return frc;
   }
@@ -1429,12 +1488,41 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
   if (spec.has_group) spec.group = st.cols[agg->group_col].view();
   if (spec.has_ts) spec.ts = st.cols[agg->ts_col].view();
   if (spec.has_value) spec.value = st.cols[agg->value_col].view();
-  DevBuf head, seg;
+  DevBuf head, seg, gk, gk2, vals, vals2, rcounts;
+  const uint32_t* agg_rows = st.out_rows.as<uint32_t>();
+  if (hash_sort && N > 0) {
+    // radix partition: stable sort of the surviving rows by (group value, bucket) — bucket first, then the group value
+    CU_TRY(gk.alloc(size_t(N) * 8 + 16, s));
+    CU_TRY(gk2.alloc(size_t(N) * 8 + 16, s));
+    CU_TRY(vals.alloc(size_t(N) * 4 + 16, s));
+    CU_TRY(vals2.alloc(size_t(N) * 4 + 16, s));
+    CU_TRY(rcounts.alloc(k::radix_tmp_elems(N) * sizeof(uint32_t), s));
+    const uint32_t* cur = st.out_rows.as<uint32_t>();
+    if (spec.has_ts) {
+      k::group_sort_keys(L, spec, cur, st.d_r, N, nullptr, gk.as<uint64_t>(), vals.as<uint32_t>());
+      int w = k::radix_sort_pairs(L, gk.as<uint64_t>(), vals.as<uint32_t>(), gk2.as<uint64_t>(), vals2.as<uint32_t>(), st.d_r, N, 64, rcounts.as<uint32_t>());
+      if (w) std::swap(vals, vals2);
+      cur = vals.as<uint32_t>();
+    }
+    if (spec.has_group) {
+      // (vals2 receives the row ids again: the keys are recomputed in the order the first sort produced)
+      k::group_sort_keys(L, spec, cur, st.d_r, N, gk.as<uint64_t>(), nullptr, vals2.as<uint32_t>());
+      int w = k::radix_sort_pairs(L, gk.as<uint64_t>(), vals2.as<uint32_t>(), gk2.as<uint64_t>(), vals.as<uint32_t>(), st.d_r, N,
+                                  // unsigned values occupy their native width; signed / float keys are 64-bit images
+                                  (type_is_signed(schema->types[agg->group_col]) || type_is_float(schema->types[agg->group_col]))
+                                      ? 64 : 8 * int(type_width_host(schema->types[agg->group_col])),
+                                  rcounts.as<uint32_t>());
+      if (!w) std::swap(vals, vals2);
+      cur = vals.as<uint32_t>();
+    }
+    agg_rows = cur;
+    gk.reset();
+  }
   CU_TRY(head.alloc(size_t(N) + 16, s));
   CU_TRY(seg.alloc(size_t(N) * 4 + 16, s));
   uint32_t hc[8] = {0};
   if (N > 0) {
-    k::group_flags(L, spec, st.out_rows.as<uint32_t>(), st.d_r, N, head.as<uint8_t>());
+    k::group_flags(L, spec, agg_rows, st.d_r, N, head.as<uint8_t>());
     k::clear_tail(L, head.as<uint8_t>(), st.d_r, N);
     k::compact_flags(L, head.as<uint8_t>(), N, st.tmp.as<uint32_t>(), seg.as<uint32_t>(), st.counters() + 2);
   }
@@ -1450,7 +1538,7 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
   CU_TRY(ab->mn.alloc(size_t(G) * 8 + 16, s));
   CU_TRY(ab->mx.alloc(size_t(G) * 8 + 16, s));
   AggOut ao{ab->gkey.p, ab->bucket.as<int64_t>(), ab->count.as<uint64_t>(), ab->sum.as<double>(), ab->mn.as<double>(), ab->mx.as<double>()};
-  if (G > 0) k::reduce_groups(L, spec, st.out_rows.as<uint32_t>(), st.d_r, seg.as<uint32_t>(), st.d_g, G, ao);
+  if (G > 0) k::reduce_groups(L, spec, agg_rows, st.d_r, seg.as<uint32_t>(), st.d_g, G, ao);
   e->stats.rows_in_files = st.plan.rows_in_files;
   e->stats.rows_decoded = st.plan.rows_decoded;
   e->stats.rows_materialized = st.plan.rows_decoded;

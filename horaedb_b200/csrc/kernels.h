@@ -65,6 +65,20 @@ void build_records(const Launch& L, const PkSet& pk, ColView seq, const uint32_t
 void merge_pass(const Launch& L, const SortRec* src, SortRec* dst, const uint32_t* run_start, int k, int level,
                 const uint32_t* d_m, uint32_t cap, uint32_t* splits);
 size_t merge_split_elems(uint32_t cap);
+// Single-pass k-way merge over packed 64-bit keys (kway_merge.cu).  KeyPack = how (pk..., __seq__, stream) packs into
+// 52 bits: every field rebased to its minimum over the selected row groups (chunk statistics), stream index lowest.
+constexpr int kMaxMergeRuns = 128;
+struct KeyPack {
+  uint64_t mn[MAX_PK], span[MAX_PK];
+  uint32_t shift[MAX_PK];
+  uint64_t seq_min, seq_span;      // in the (value + 1, NULL = 0) domain of the sort records
+  uint32_t seq_shift, pk_shift;    // pk_shift = bits below the primary-key part (seq + stream)
+};
+// tmp must hold kway_tmp_bytes(cap, k, &ranges) bytes; order[j] = row id of the j-th merged record, keep[j] = 1 iff it is
+// the last of its primary-key run (== records_to_rows + dedup_flags_recs after the pairwise passes).
+size_t kway_tmp_bytes(uint32_t cap, int k, uint32_t* ranges);
+void kway_merge(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* surv, const uint32_t* d_m, uint32_t cap, const uint32_t* run_start,
+                int k, const KeyPack& kp, void* tmp, unsigned int* ticket, uint32_t* order, uint8_t* keep, int* err);
 void records_to_rows(const Launch& L, const SortRec* rec, const uint32_t* d_m, uint32_t cap, uint32_t* order);
 
 // S5/S6: PK-run boundaries, LastValue = keep the last row of each run ---------------------------------------------
@@ -94,6 +108,14 @@ void group_flags(const Launch& L, const AggSpecDev& spec, const uint32_t* rows, 
 void reduce_groups(const Launch& L, const AggSpecDev& spec, const uint32_t* rows, const uint32_t* d_r,
                    const uint32_t* seg_start, const uint32_t* d_g, uint32_t cap, AggOut out);
 
+// radix_agg.cu: stable LSD radix sort of (key, row) pairs by key bits [0, bits); count on the device.  Returns 0 if the
+// result is in (keys, vals), 1 if in (keys_tmp, vals_tmp).  counts: radix_tmp_elems(cap) uint32.
+size_t radix_tmp_elems(uint32_t cap);
+int radix_sort_pairs(const Launch& L, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, const uint32_t* d_n, uint32_t cap,
+                     int bits, uint32_t* counts);
+// order-preserving sort keys of the rows `rows[0..*d_r)`: gk = group value, bk = bucket start (either may be null); vals = rows
+void group_sort_keys(const Launch& L, const AggSpecDev& spec, const uint32_t* rows, const uint32_t* d_r, uint32_t cap, uint64_t* gk, uint64_t* bk,
+                     uint32_t* vals);
 void fill_u32(const Launch& L, uint32_t* p, uint32_t v, uint32_t n);
 // dst[6][cap] int64: key, bucket, count, sum/min/max bit patterns; zero beyond g
 void pack_agg(const Launch& L, AggOut in, uint32_t gwidth, uint64_t g, uint64_t cap, long long* dst);

@@ -81,6 +81,7 @@ typedef struct {
 #define HG_FLAG_NO_PRUNING 1u   /* disable row-group pruning by chunk statistics (for A/B measurements) */
 #define HG_FLAG_NO_FUSED 2u     /* force the general (materialising) pipeline even when the fused fast path applies */
 #define HG_FLAG_NO_LATE_MATERIALIZATION 4u   /* fused path: load every needed column of every row (no predicate gate) */
+#define HG_FLAG_PAIRWISE_MERGE 8u   /* k-way merge by log2(k) pairwise passes over 32-byte records even when the packed-key single pass applies (A/B) */
 
 /* SstFile + FileMeta (sst.rs:51-53, 155-160).  `data` may be NULL when the file is already resident (hg_sst_load). */
 typedef struct {
@@ -102,13 +103,18 @@ typedef struct {
   double f64;                 /* literal for float columns */
 } hg_predicate;
 
-/* GROUP BY (group column, time bucket) over the post-dedup scan output; groups come out in stream (key) order. */
+/* GROUP BY (group column, time bucket) over the post-dedup scan output.
+ * mode HG_AGG_RUNS: groups are the maximal runs of equal (group value, bucket) in the stream — exact GROUP BY when the key
+ *   is a prefix of the sort order (series_id [, ts bucket]); groups come out in stream (key) order.
+ * mode HG_AGG_HASH: true GROUP BY for ANY key (e.g. per-(tag, bucket)): radix-partitioned, every group's rows are added in
+ *   stream order, groups come out sorted by (group value, bucket).  Identical to RUNS for sort-prefix keys. */
+typedef enum { HG_AGG_RUNS = 0, HG_AGG_HASH = 1 } hg_agg_mode;
 typedef struct {
   int32_t group_col;          /* -1: one global group */
   int32_t ts_col;             /* -1: no bucketing */
   int64_t window_ms;          /* bucket = ts / window_ms * window_ms (truncating, types.rs:82-85) */
   int32_t value_col;          /* -1: count(*) only */
-  uint32_t _pad;
+  uint32_t mode;              /* hg_agg_mode */
 } hg_agg_spec;
 
 typedef struct {

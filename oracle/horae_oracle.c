@@ -784,6 +784,99 @@ int orc_scan_aggregate(const uint8_t **datas, const uint64_t *lens, int k, int n
     *out = a; return 0;
 }
 
+/* GROUP BY for keys that are not a prefix of the sort order (mode "hash"): every surviving row updates the accumulator
+ * of its (group value, bucket) in STREAM order — what a single-partition hash aggregation over the reference's scan output
+ * computes (the stage is todo!() in the reference, metric_engine/src/metric/mod.rs:37-49) — and the groups are emitted
+ * sorted by (group value in its type's order, bucket). */
+typedef struct { uint64_t k; int64_t b; int64_t gid; } hslot;
+static uint64_t hmix(uint64_t k, int64_t b) {
+    uint64_t z = k * 0x9E3779B97F4A7C15ull ^ ((uint64_t)b + 0x632BE59BD9B4E019ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+static int g_sort_type;
+static const orc_agg_result *g_sort_res;
+static int cmp_group_ids(const void *x, const void *y) {
+    int64_t a = *(const int64_t *)x, b = *(const int64_t *)y;
+    int c = cmp_typed(g_sort_res->gkey[a], g_sort_res->gkey[b], g_sort_type);
+    if (c) return c;
+    return g_sort_res->bucket[a] < g_sort_res->bucket[b] ? -1 : (g_sort_res->bucket[a] > g_sort_res->bucket[b] ? 1 : 0);
+}
+int orc_scan_aggregate_hash(const uint8_t **datas, const uint64_t *lens, int k, int ncols, const int *types, int num_pk,
+                            const orc_pred *preds, int np, int prune, int threads,
+                            int group_col, int ts_col, int64_t window_ms, int value_col,
+                            orc_agg_result **out) {
+    sst_stream *st; rowref *surv; int64_t ns; int64_t *bend; int nb; int64_t stats[4];
+    if (scan_core(datas, lens, k, ncols, types, num_pk, preds, np, 8192, prune, threads, &st, &surv, &ns, &bend, &nb, stats)) return -1;
+    free(bend);
+    orc_agg_result *a = calloc(1, sizeof *a);
+    int64_t cap = 1024, ng = 0;
+    a->gkey = malloc(8 * cap); a->bucket = malloc(8 * cap); a->count = malloc(8 * cap);
+    a->sum = malloc(8 * cap); a->min = malloc(8 * cap); a->max = malloc(8 * cap);
+    uint8_t *seen = malloc(cap);
+    int64_t hcap = 4096;
+    hslot *ht = malloc(sizeof(hslot) * hcap);
+    for (int64_t i = 0; i < hcap; i++) ht[i].gid = -1;
+    int64_t cur_g = -1; uint64_t cur_k = 0; int64_t cur_b = 0;
+    for (int64_t r = 0; r < ns; r++) {
+        const orc_table *t = st[surv[r].src].t; int64_t row = surv[r].row;
+        uint64_t kv = group_col >= 0 ? t->vals[group_col][row] : 0;
+        int64_t b = 0;
+        if (ts_col >= 0 && window_ms > 0) { int64_t ts = (int64_t)t->vals[ts_col][row]; b = ts / window_ms * window_ms; }
+        if (cur_g < 0 || kv != cur_k || b != cur_b) {
+            if ((ng + 1) * 2 > hcap) {                       /* grow + rehash */
+                int64_t nc = hcap * 2; hslot *nt = malloc(sizeof(hslot) * nc);
+                for (int64_t i = 0; i < nc; i++) nt[i].gid = -1;
+                for (int64_t i = 0; i < hcap; i++) if (ht[i].gid >= 0) {
+                    uint64_t h = hmix(ht[i].k, ht[i].b) & (uint64_t)(nc - 1);
+                    while (nt[h].gid >= 0) h = (h + 1) & (uint64_t)(nc - 1);
+                    nt[h] = ht[i];
+                }
+                free(ht); ht = nt; hcap = nc;
+            }
+            uint64_t h = hmix(kv, b) & (uint64_t)(hcap - 1);
+            while (ht[h].gid >= 0 && !(ht[h].k == kv && ht[h].b == b)) h = (h + 1) & (uint64_t)(hcap - 1);
+            if (ht[h].gid < 0) {
+                if (ng == cap) {
+                    cap *= 2;
+                    a->gkey = realloc(a->gkey, 8 * cap); a->bucket = realloc(a->bucket, 8 * cap); a->count = realloc(a->count, 8 * cap);
+                    a->sum = realloc(a->sum, 8 * cap); a->min = realloc(a->min, 8 * cap); a->max = realloc(a->max, 8 * cap);
+                    seen = realloc(seen, cap);
+                }
+                ht[h].k = kv; ht[h].b = b; ht[h].gid = ng;
+                a->gkey[ng] = kv; a->bucket[ng] = b; a->count[ng] = 0; a->sum[ng] = 0.0; a->min[ng] = INFINITY; a->max[ng] = -INFINITY; seen[ng] = 0;
+                ng++;
+            }
+            cur_g = ht[h].gid; cur_k = kv; cur_b = b;
+        }
+        a->count[cur_g]++;
+        if (value_col >= 0 && t->valid[value_col][row]) {
+            double v = slot_to_double(t->vals[value_col][row], types[value_col]);
+            a->sum[cur_g] += v;
+            if (!seen[cur_g] || v < a->min[cur_g]) a->min[cur_g] = v;
+            if (!seen[cur_g] || v > a->max[cur_g]) a->max[cur_g] = v;
+            seen[cur_g] = 1;
+        }
+    }
+    /* emit sorted by (group value, bucket) */
+    int64_t *ord = malloc(8 * (ng ? ng : 1));
+    for (int64_t i = 0; i < ng; i++) ord[i] = i;
+    g_sort_type = group_col >= 0 ? types[group_col] : OT_U64; g_sort_res = a;
+    qsort(ord, (size_t)ng, sizeof(int64_t), cmp_group_ids);
+    orc_agg_result *o = calloc(1, sizeof *o);
+    int64_t oc = ng ? ng : 1;
+    o->gkey = malloc(8 * oc); o->bucket = malloc(8 * oc); o->count = malloc(8 * oc); o->sum = malloc(8 * oc); o->min = malloc(8 * oc); o->max = malloc(8 * oc);
+    for (int64_t i = 0; i < ng; i++) {
+        int64_t g = ord[i];
+        o->gkey[i] = a->gkey[g]; o->bucket[i] = a->bucket[g]; o->count[i] = a->count[g]; o->sum[i] = a->sum[g]; o->min[i] = a->min[g]; o->max[i] = a->max[g];
+    }
+    o->ngroups = ng;
+    o->rows_in_files = stats[0]; o->rows_decoded = stats[1]; o->rows_filtered = stats[2]; o->rows_merged = stats[3]; o->rows_out = ns;
+    free(ord); free(ht); free(seen); orc_agg_result_free(a);
+    for (int i = 0; i < k; i++) { orc_table_free(st[i].t); free(st[i].chunk_end); }
+    free(st); free(surv);
+    *out = o; return 0;
+}
+
 /* S8: Timestamp::truncate_by (types.rs:82-85) */
 int64_t orc_truncate_by(int64_t ts, int64_t duration_ms) { return ts / duration_ms * duration_ms; }
 

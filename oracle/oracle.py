@@ -182,13 +182,16 @@ class AggResult:
 
 def scan_aggregate(ssts: Sequence[bytes], schema: pa.Schema, num_pk: int, preds=(), group_col: int = 0,
                    ts_col: int = -1, window_ms: int = 0, value_col: int = -1, prune: bool = True,
-                   threads: int = 1) -> AggResult:
+                   threads: int = 1, mode: int = 0) -> AggResult:
+    """mode 0: groups are runs of equal (group value, bucket) in the sorted stream; mode 1 ("hash"): true GROUP BY for any
+    key, rows accumulated in stream order, groups emitted sorted by (group value, bucket)."""
     L = lib()
     types = (C.c_int * len(schema))(*schema_types(schema))
     p = make_preds(schema, preds)
     bufs, ptrs, lens = _sst_args(ssts)
     out = C.c_void_p()
-    rc = L.orc_scan_aggregate(ptrs, lens, len(ssts), len(schema), types, num_pk, p, len(preds), int(prune), threads,
+    fn = L.orc_scan_aggregate_hash if mode == 1 else L.orc_scan_aggregate
+    rc = fn(ptrs, lens, len(ssts), len(schema), types, num_pk, p, len(preds), int(prune), threads,
                               group_col, ts_col, C.c_int64(window_ms), value_col, C.byref(out))
     if rc:
         raise RuntimeError(L.orc_last_error().decode())
