@@ -220,21 +220,30 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    combiner = None
     if world > 1:
-        from horaedb_b200.parallel import PartialCombiner
-        combiner = PartialCombiner()
+        # the library's own NCCL communicator (csrc/comm.cu); torch.distributed only ships the 128-byte id, like a Rust host's RPC
+        uid = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)
+    comb_state = {"cap": 0, "last": None}
 
     def combine(dev, settle=False):
-        """Cross-GPU combine of the per-GPU partial aggregates: ONE NCCL all-gather per step (horaedb_b200/parallel.py).
-        The padded capacity is agreed during warm-up (`settle`); timed steps have no size exchange and no host sync."""
+        """Cross-GPU combine of the per-GPU partial aggregates: ONE ncclAllGather per step, issued by the library on its combine
+        stream behind a pack kernel (hg_agg_combine): the next step's scan overlaps it.  The block width is agreed during
+        warm-up (`settle`); timed steps have no size exchange and no host sync."""
         g = int(dev.num_groups)
         if world == 1:
             return g
+        from horaedb_b200._ffi import HG_COMBINE_GATHER
+        cmb = eng.combine(HG_COMBINE_GATHER, 0 if settle else comb_state["cap"])
+        comb_state["cap"] = int(cmb.capacity)
+        comb_state["last"] = cmb
+        return cmb
 
-        with torch.cuda.stream(stream):
-            out = combiner.gather_packed(eng, g, torch.device("cuda", local_rank), check_cap=settle)
-        return out
+    def gathered_block(cmb):
+        eng.comm_sync()
+        cap = int(cmb.capacity)
+        return torch.as_tensor(DeviceArray(cmb.d_blocks, world * 6 * cap, "<i8"), device=f"cuda:{local_rank}").view(world, 6, cap)
 
     # ---- the CPU oracle's answer for THIS rank's files (same data under every codec): the timed GPU results are compared
     #      with it bit for bit below; rank 0's run doubles as the cpu_baseline measurement
@@ -315,9 +324,13 @@ def main():
             decomp_ms.append(sst_.decomp_ms)
             launches += sst_.kernel_launches
             last = combine(dev)
+        if world > 1:
+            eng.comm_sync()               # the last step's all-gather is part of the timed region
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            last = gathered_block(last)
         if rank == 0:
             # the K timed steps last only ~K ms; keep the same load running ~0.4 s so the clock sampler sees it
             t_end = time.perf_counter() + 0.4
@@ -481,6 +494,7 @@ def main():
         emit(line)
     ok_all = all(r["parity"]["resident"] and r["parity"]["e2e"] and r["parity"]["combined"] is not False for r in res.values())
     if world > 1:
+        eng.comm_destroy()
         dist.barrier()
         dist.destroy_process_group()
     eng.close()

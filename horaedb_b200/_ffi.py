@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libhorae_gpu.so")
 
 HG_TYPES = {pa.uint8(): 0, pa.int8(): 1, pa.uint16(): 2, pa.int16(): 3, pa.uint32(): 4, pa.int32(): 5,
             pa.uint64(): 6, pa.int64(): 7, pa.float32(): 8, pa.float64(): 9}
-HG_OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
+HG_OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5, "in": 6}
 HG_FLAG_NO_PRUNING = 1
 HG_FLAG_NO_FUSED = 2
 HG_FLAG_NO_LATE_MATERIALIZATION = 4
@@ -48,7 +48,8 @@ class HgSstDesc(C.Structure):
 
 
 class HgPredicate(C.Structure):
-    _fields_ = [("column", C.c_uint32), ("op", C.c_uint32), ("i64", C.c_int64), ("u64", C.c_uint64), ("f64", C.c_double)]
+    _fields_ = [("column", C.c_uint32), ("op", C.c_uint32), ("i64", C.c_int64), ("u64", C.c_uint64), ("f64", C.c_double),
+                ("in_values", C.POINTER(C.c_uint64)), ("in_count", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class HgAggSpec(C.Structure):
@@ -66,6 +67,14 @@ class HgScanStats(C.Structure):
 class HgAggDevice(C.Structure):
     _fields_ = [("num_groups", C.c_uint64), ("d_gkey", C.c_void_p), ("d_bucket", C.c_void_p), ("d_count", C.c_void_p),
                 ("d_sum", C.c_void_p), ("d_min", C.c_void_p), ("d_max", C.c_void_p)]
+
+
+class HgAggCombined(C.Structure):
+    _fields_ = [("capacity", C.c_uint64), ("world", C.c_uint32), ("_pad", C.c_uint32), ("d_blocks", C.c_void_p), ("num_groups", C.c_uint64),
+                ("reduced_capacity", C.c_uint64), ("d_reduced", C.c_void_p)]
+
+
+HG_COMBINE_GATHER, HG_COMBINE_REDUCE = 0, 1
 
 
 class ArrowArrayStream(C.Structure):
@@ -88,7 +97,8 @@ class HgParquetChunk(C.Structure):
 
 EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_engine_set_flags", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
-           "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info", "hg_plan_row_groups"]
+           "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info", "hg_plan_row_groups",
+           "hg_comm_unique_id", "hg_comm_init", "hg_comm_destroy", "hg_agg_combine", "hg_comm_sync"]
 
 _lib = None
 
@@ -107,6 +117,10 @@ def lib():
         L.hg_engine_set_flags.argtypes = [C.c_void_p, C.c_uint32]
         L.hg_engine_destroy.argtypes = [C.c_void_p]
         L.hg_engine_destroy.restype = None
+        L.hg_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.hg_comm_destroy.argtypes = [C.c_void_p]
+        L.hg_comm_sync.argtypes = [C.c_void_p]
+        L.hg_agg_combine.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -150,12 +164,26 @@ class SchemaHandle:
 
 def _make_preds(arrow_schema: pa.Schema, preds: Sequence[tuple]):
     arr = (HgPredicate * max(len(preds), 1))()
+    keep = []
     for k, (col, op, lit) in enumerate(preds):
         idx = col if isinstance(col, int) else arrow_schema.get_field_index(col)
         t = arrow_schema.field(idx).type
         arr[k].column = idx
         arr[k].op = HG_OPS[op]
-        if pa.types.is_floating(t):
+        if op == "in":
+            bits = []
+            for v in lit:
+                if pa.types.is_floating(t):
+                    bits.append(int(np.array([float(v)], dtype=np.float64).view(np.uint64)[0]))
+                else:
+                    if isinstance(v, float) and not v.is_integer():
+                        raise HgError(1, f"IN literal {v!r} is not integral for column {arrow_schema.field(idx).name}")
+                    bits.append(int(v) & 0xFFFFFFFFFFFFFFFF)
+            vals = (C.c_uint64 * max(len(bits), 1))(*bits)
+            keep.append(vals)
+            arr[k].in_values = vals
+            arr[k].in_count = len(bits)
+        elif pa.types.is_floating(t):
             arr[k].f64 = float(lit)
         else:
             # no silent truncation / wrap-around: a literal the column type cannot hold must be rewritten by the caller
@@ -171,6 +199,7 @@ def _make_preds(arrow_schema: pa.Schema, preds: Sequence[tuple]):
                 arr[k].i64 = iv
             else:
                 arr[k].u64 = iv
+    arr._keep = keep              # IN lists must outlive the call
     return arr
 
 
@@ -290,6 +319,28 @@ class Engine:
     def export_packed(self, d_dst: int, cap: int) -> None:
         """Pack the last device aggregate into a caller-owned [6, cap] int64 device buffer (engine stream)."""
         _check(self._L.hg_agg_export_packed(self._h, C.c_void_p(d_dst), C.c_uint64(cap)))
+
+    # -- multi-GPU combine (comm.cu): the NCCL id travels over the host's own channel (here: torch.distributed)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(lib().hg_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128)(*uid)
+        _check(self._L.hg_comm_init(self._h, buf, rank, world))
+
+    def comm_destroy(self) -> None:
+        _check(self._L.hg_comm_destroy(self._h))
+
+    def combine(self, mode: int = 0, capacity_hint: int = 0) -> "HgAggCombined":
+        out = HgAggCombined()
+        _check(self._L.hg_agg_combine(self._h, C.c_uint32(mode), C.c_uint64(capacity_hint), C.byref(out)))
+        return out
+
+    def comm_sync(self) -> None:
+        _check(self._L.hg_comm_sync(self._h))
 
     def stats(self) -> dict:
         st = HgScanStats()

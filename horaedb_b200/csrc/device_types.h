@@ -72,8 +72,9 @@ struct ColView {
 
 struct PredDev {
   ColView col;
-  uint32_t op, _pad;
+  uint32_t op, n_in;       // n_in: OP_IN list length
   uint64_t lit;            // literal bit pattern in the column's widened domain (i64 / u64 / f64)
+  const uint64_t* in_list; // OP_IN: device array of n_in literals
 };
 
 constexpr int MAX_PREDS = 8;

@@ -302,6 +302,10 @@ static bool rg_may_match(const RgCol* rc, uint32_t num_rows, const hg_schema_des
       case HG_OP_LE: ok = cmp_host(mn, lit, t) <= 0; break;
       case HG_OP_GT: ok = cmp_host(mx, lit, t) > 0; break;
       case HG_OP_GE: ok = cmp_host(mx, lit, t) >= 0; break;
+      case HG_OP_IN:    // PruningPredicate expands a short IN list into `c = v1 OR c = v2 ..`
+        ok = false;
+        for (uint32_t j = 0; j < preds[i].in_count && !ok; j++) ok = cmp_host(mn, preds[i].in_values[j], t) <= 0 && cmp_host(preds[i].in_values[j], mx, t) <= 0;
+        break;
     }
     if (!ok) return false;
   }
@@ -487,6 +491,7 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
     for (size_t i = 0; i < np; i++) {
       const uint32_t c = preds[i].column;
       bool ok = c < uint32_t(MAX_COLS);
+      for (size_t i2 = 0; i2 < np; i2++) if (preds[i2].column == c && preds[i2].op == HG_OP_IN) ok = false;   // the gate kernel tests intervals
       for (size_t j = 0; j < k && ok; j++) ok = rs[j]->rows_total == 0 || (rs[j]->col_all_simple[c] && rs[j]->col_null_none[c]);
       const uint32_t w = type_width_host(schema->types[c]) <= 4 ? 4u : 8u;
       if (ok && w < best_w) { best_w = w; gate_col = int(c); }
@@ -734,7 +739,9 @@ static int validate_preds(const hg_schema_desc* s, const hg_predicate* preds, si
   if (np > size_t(MAX_PREDS)) return set_error(HG_ERR_UNSUPPORTED, "more than 8 predicates");
   for (size_t i = 0; i < np; i++) {
     if (preds[i].column >= s->num_columns) return set_error(HG_ERR_INVALID, "predicate column out of range");
-    if (preds[i].op > HG_OP_GE) return set_error(HG_ERR_UNSUPPORTED, "predicate operator");
+    if (preds[i].op > HG_OP_IN) return set_error(HG_ERR_UNSUPPORTED, "predicate operator");
+    if (preds[i].op == HG_OP_IN && (preds[i].in_count > HG_MAX_IN_LIST || (preds[i].in_count && !preds[i].in_values)))
+      return set_error(HG_ERR_INVALID, "IN list: null pointer or more than HG_MAX_IN_LIST values");
   }
   return HG_OK;
 }
@@ -845,8 +852,19 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     for (size_t i = 0; i < np; i++) {
       ps.p[i].col = st->cols[preds[i].column].view();
       ps.p[i].op = preds[i].op;
-      ps.p[i]._pad = 0;
+      ps.p[i].n_in = 0;
+      ps.p[i].in_list = nullptr;
       ps.p[i].lit = pred_literal(preds[i], schema->types[preds[i].column]);
+      if (preds[i].op == HG_OP_IN) {
+        uint64_t* d_list = static_cast<uint64_t*>(g_arena->alloc(std::max<size_t>(preds[i].in_count, 1) * 8));
+        if (!d_list) return set_error(HG_ERR_OOM, "out of device memory");
+        if (preds[i].in_count) {
+          int urc = stage_upload(e, d_list, preds[i].in_values, size_t(preds[i].in_count) * 8, nullptr);
+          if (urc) return urc;
+        }
+        ps.p[i].n_in = preds[i].in_count;
+        ps.p[i].in_list = d_list;
+      }
     }
     CU_TRY(st->alive.alloc(size_t(N) + 16, s));
     CU_TRY(st->surv.alloc(size_t(N) * 4 + 16, s));
@@ -881,7 +899,9 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
       std::memset(&kp, 0, sizeof(kp));
       const int npk = int(schema->num_primary_keys);
       uint64_t lo[MAX_PK + 1], hi[MAX_PK + 1];
+      bool seen_c[MAX_PK + 1] = {false};
       bool seen = false, seq_nullable = false;
+      for (int c = 0; c <= MAX_PK; c++) { lo[c] = 0; hi[c] = 0; }
       for (const RgSel& rs : plan.sel) {
         const SstResident* f = plan.files[rs.sst];
         const RgCol* rc = &f->rgcol[size_t(rs.rg) * size_t(f->meta.ncols)];
@@ -893,11 +913,13 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
           const uint64_t flip = (c < npk && type_is_signed(schema->types[col])) ? (1ull << 63) : 0ull;
           const uint64_t a = x.mn ^ flip, b = x.mx ^ flip;
           if (c == npk && !x.null_none) seq_nullable = true;
-          if (!seen || a < lo[c]) lo[c] = a;
-          if (!seen || b > hi[c]) hi[c] = b;
+          if (!seen_c[c] || a < lo[c]) lo[c] = a;
+          if (!seen_c[c] || b > hi[c]) hi[c] = b;
+          seen_c[c] = true;
         }
         seen = true;
       }
+      if (!seen_c[npk]) { seq_nullable = true; lo[npk] = 0; hi[npk] = 0; }      // every __seq__ chunk is all-null
       if (packed && seen) {
         auto bits = [](uint64_t span) { int b = 0; while (span) { b++; span >>= 1; } return b; };
         int rb = 0;
@@ -905,7 +927,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
         // seq lives in the (value + 1, NULL = 0) domain
         if (hi[npk] == ~0ull) packed = false;
         kp.seq_min = seq_nullable ? 0 : lo[npk] + 1;
-        kp.seq_span = hi[npk] + 1 - kp.seq_min;
+        kp.seq_span = seen_c[npk] ? hi[npk] + 1 - kp.seq_min : 0;
         kp.seq_shift = uint32_t(rb);
         int used = rb + bits(kp.seq_span);
         kp.pk_shift = uint32_t(used);
@@ -1206,6 +1228,8 @@ void hg_engine_destroy(hg_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  hg_comm_free(e->comm);
+  e->comm = nullptr;
   g_arena = nullptr;
   e->arena.destroy();
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1577,6 +1601,7 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
   out->d_max = ab.mx.as<double>();
   e->last_agg = *out;
   e->last_gwidth = ab.gwidth;
+  e->last_gtype = ab.gtype;
   for (DevBuf* b : {&ab.gkey, &ab.bucket, &ab.count, &ab.sum, &ab.mn, &ab.mx}) b->release();   // arena memory: valid until the next call
   return HG_OK;
 }

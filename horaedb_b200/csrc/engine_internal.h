@@ -206,6 +206,9 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct hg_comm;
+void hg_comm_free(hg_comm* c);   // comm.cu
+
 struct hg_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -224,7 +227,8 @@ struct hg_engine {
   void* h_small = nullptr;       // 256 pinned bytes: the per-call counter block comes back here (one small D2H)
   Arena arena;
   hg_agg_device last_agg{};      // device pointers of the last aggregate (arena memory, valid until the next call)
-  uint32_t last_gwidth = 8;
+  uint32_t last_gwidth = 8, last_gtype = T_U64;
+  struct hg_comm* comm = nullptr;  // NCCL communicator + combine stream (comm.cu)
   std::vector<uint64_t> transient_ids;   // SSTs loaded only for the running call
   Launch L() { return Launch{stream, &launches}; }
 };

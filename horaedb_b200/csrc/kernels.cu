@@ -364,6 +364,13 @@ __global__ void __launch_bounds__(kThreads) eval_predicates_kernel(PredSet preds
     for (int p = 0; p < preds.n && keep; p++) {
       const PredDev& pd = preds.p[p];
       if (!col_valid(pd.col, i)) { keep = false; break; }      // NULL => false
+      if (pd.op == OP_IN) {
+        const uint64_t v = col_widened(pd.col, i);
+        bool any = false;
+        for (uint32_t j = 0; j < pd.n_in && !any; j++) any = cmp_widened(v, pd.in_list[j], pd.col.type) == 0;
+        keep = any;
+        continue;
+      }
       int c = cmp_widened(col_widened(pd.col, i), pd.lit, pd.col.type);
       switch (pd.op) {
         case OP_EQ: keep = c == 0; break;

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 3u
+#define HG_ABI_VERSION 4u
 
 typedef struct hg_engine hg_engine;
 
@@ -58,7 +58,8 @@ typedef enum {
 
 typedef enum { HG_UPDATE_OVERWRITE = 0, HG_UPDATE_APPEND = 1 } hg_update_mode; /* config.rs:166-172 */
 
-typedef enum { HG_OP_EQ = 0, HG_OP_NE = 1, HG_OP_LT = 2, HG_OP_LE = 3, HG_OP_GT = 4, HG_OP_GE = 5 } hg_op;
+typedef enum { HG_OP_EQ = 0, HG_OP_NE = 1, HG_OP_LT = 2, HG_OP_LE = 3, HG_OP_GT = 4, HG_OP_GE = 5, HG_OP_IN = 6 } hg_op;
+#define HG_MAX_IN_LIST 64u
 
 /* StorageSchema (types.rs:143-157): columns = pk0..pkN-1, values..., __seq__ (u64), __reserved__ (u64) */
 typedef struct {
@@ -101,6 +102,8 @@ typedef struct {
   int64_t i64;                /* literal for signed integer columns */
   uint64_t u64;               /* literal for unsigned integer columns */
   double f64;                 /* literal for float columns */
+  const uint64_t* in_values;  /* HG_OP_IN (`col IN (..)`, DataFusion InListExpr): in_count values in the column's widened domain */
+  uint32_t in_count, _pad;    /*   (i64 / u64 two's complement, f64 bit patterns); at most HG_MAX_IN_LIST; NULL IN (..) is false */
 } hg_predicate;
 
 /* GROUP BY (group column, time bucket) over the post-dedup scan output.
@@ -178,6 +181,34 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
 int hg_agg_export_packed(hg_engine* e, void* d_dst, uint64_t cap);
 
 int hg_last_stats(hg_engine* e, hg_scan_stats* out);
+
+/* ---- multi-GPU combine of the per-GPU partial aggregates: one engine per GPU / process, NCCL over NVLink.
+ * The aggregation stage and its combine are absent in the reference (metric_engine/src/metric/mod.rs:37-49 is todo!());
+ * SSTs shard by file (one partition per SST, read.rs:442-450), so every rank scans its own files and ONE collective
+ * combines the partials.  The host ships the NCCL id between ranks over its own channel. */
+#define HG_COMM_ID_BYTES 128
+typedef enum {
+  HG_COMBINE_GATHER = 0,  /* partials are disjoint (keys contain the series id): all-gather of the packed blocks */
+  HG_COMBINE_REDUCE = 1   /* keys cross ranks (per-(tag, bucket)): all-gather + per-group combine on every rank: counts summed,
+                             min / max taken, f64 sums added in RANK order (deterministic) */
+} hg_combine_mode;
+typedef struct {
+  uint64_t capacity;          /* columns per rank block */
+  uint32_t world, _pad;
+  const int64_t* d_blocks;    /* device, [world][6][capacity] int64: rows key, bucket, count, sum / min / max bits; count == 0 pads */
+  uint64_t num_groups;        /* REDUCE: groups of the combined table */
+  uint64_t reduced_capacity;
+  const int64_t* d_reduced;   /* REDUCE: device, [6][reduced_capacity], sorted by (key, bucket); identical on every rank */
+} hg_agg_combined;
+int hg_comm_unique_id(uint8_t* id /* HG_COMM_ID_BYTES */);
+int hg_comm_init(hg_engine* e, const uint8_t* id, int rank, int world);
+int hg_comm_destroy(hg_engine* e);
+/* Collective over all ranks of the communicator: combines the results of their last hg_scan_aggregate_device calls.  The pack
+ * kernel runs on the engine stream behind the scan, the collective on the engine's combine stream (the next scan overlaps it);
+ * GATHER results are valid after hg_comm_sync.  capacity_hint = 0: the ranks first agree on the block width (one extra small
+ * collective + host sync); > 0: every rank passes the same value and promises num_groups <= capacity_hint. */
+int hg_agg_combine(hg_engine* e, uint32_t mode, uint64_t capacity_hint, hg_agg_combined* out);
+int hg_comm_sync(hg_engine* e);
 
 /* ---- host-only inspection of an SST (no engine, no GPU): what the planner reads from the footer and the page headers.
  * In the reference this is parquet-rs's metadata reader behind ParquetExec (read.rs:66-93, 442-465); the CPU test-suite

@@ -39,7 +39,7 @@
 
 /* ------------------------------------------------------------------------------------------------ types */
 enum { OT_U8 = 0, OT_I8, OT_U16, OT_I16, OT_U32, OT_I32, OT_U64, OT_I64, OT_F32, OT_F64 };
-enum { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE };
+enum { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN };
 
 typedef struct {
     int32_t col;   /* column index in the storage schema */
@@ -47,6 +47,8 @@ typedef struct {
     int64_t i;     /* literal for signed columns */
     uint64_t u;    /* literal for unsigned columns */
     double f;      /* literal for float columns */
+    const uint64_t *in_vals;  /* OP_IN: the list, every value in the column's widened domain (i64 / u64 / f64 bits) */
+    int32_t in_count, _pad;
 } orc_pred;
 
 typedef struct {
@@ -433,6 +435,10 @@ static uint64_t pred_literal(const orc_pred *p, int t) {
     return p->u;
 }
 static int pred_eval(const orc_pred *p, int t, uint64_t v) {
+    if (p->op == OP_IN) {                       /* `col IN (v1, ..)`: DataFusion's InListExpr, NULL handled by the caller (NULL => false) */
+        for (int i = 0; i < p->in_count; i++) if (cmp_typed(v, p->in_vals[i], t) == 0) return 1;
+        return 0;
+    }
     int c = cmp_typed(v, pred_literal(p, t), t);
     switch (p->op) {
     case OP_EQ: return c == 0; case OP_NE: return c != 0; case OP_LT: return c < 0;
@@ -457,6 +463,11 @@ static int rg_may_match(const rg_meta *rg, const orc_pred *preds, int np, const 
         case OP_LE: ok = cmp_typed(mn, lit, t) <= 0; break;
         case OP_GT: ok = cmp_typed(mx, lit, t) > 0; break;
         case OP_GE: ok = cmp_typed(mx, lit, t) >= 0; break;
+        case OP_IN:   /* PruningPredicate rewrites a short IN list into `c = v1 OR c = v2 ..`: some value inside [min, max] */
+            ok = 0;
+            for (int j = 0; j < preds[i].in_count && !ok; j++)
+                ok = cmp_typed(mn, preds[i].in_vals[j], t) <= 0 && cmp_typed(preds[i].in_vals[j], mx, t) <= 0;
+            break;
         }
         if (!ok) return 0;
     }

@@ -21,11 +21,19 @@ OT = {pa.uint8(): 0, pa.int8(): 1, pa.uint16(): 2, pa.int16(): 3, pa.uint32(): 4
       pa.uint64(): 6, pa.int64(): 7, pa.float32(): 8, pa.float64(): 9}
 _NP = {0: np.uint8, 1: np.int8, 2: np.uint16, 3: np.int16, 4: np.uint32, 5: np.int32, 6: np.uint64, 7: np.int64,
        8: np.float32, 9: np.float64}
-OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
+OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5, "in": 6}
+
+
+def widened_bits(t: pa.DataType, v) -> int:
+    """A literal in the column's widened 64-bit domain: i64 / u64 two's complement, f64 bit pattern."""
+    if pa.types.is_floating(t):
+        return int(np.array([float(v)], dtype=np.float64).view(np.uint64)[0])
+    return int(v) & 0xFFFFFFFFFFFFFFFF
 
 
 class OrcPred(C.Structure):
-    _fields_ = [("col", C.c_int32), ("op", C.c_int32), ("i", C.c_int64), ("u", C.c_uint64), ("f", C.c_double)]
+    _fields_ = [("col", C.c_int32), ("op", C.c_int32), ("i", C.c_int64), ("u", C.c_uint64), ("f", C.c_double),
+                ("in_vals", C.POINTER(C.c_uint64)), ("in_count", C.c_int32), ("_pad", C.c_int32)]
 
 
 def build() -> str:
@@ -68,17 +76,24 @@ def schema_types(schema: pa.Schema) -> List[int]:
 def make_preds(schema: pa.Schema, preds: Sequence[tuple]):
     """preds: [(column name or index, op, literal)] — a conjunction (read.rs:459)."""
     arr = (OrcPred * max(len(preds), 1))()
+    keep = []
     for k, (col, op, lit) in enumerate(preds):
         idx = col if isinstance(col, int) else schema.get_field_index(col)
         t = schema.field(idx).type
         arr[k].col = idx
         arr[k].op = OPS[op]
-        if pa.types.is_floating(t):
+        if op == "in":
+            vals = (C.c_uint64 * max(len(lit), 1))(*[widened_bits(t, v) for v in lit])
+            keep.append(vals)
+            arr[k].in_vals = vals
+            arr[k].in_count = len(lit)
+        elif pa.types.is_floating(t):
             arr[k].f = float(lit)
         elif pa.types.is_signed_integer(t):
             arr[k].i = int(lit)
         else:
             arr[k].u = int(lit)
+    arr._keep = keep          # the IN lists must outlive the call
     return arr
 
 

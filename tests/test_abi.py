@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes as C
-    assert C.sizeof(_ffi.HgPredicate) == 32
+    assert C.sizeof(_ffi.HgPredicate) == 48
     assert C.sizeof(_ffi.HgSstDesc) == 64
     assert C.sizeof(_ffi.HgSchemaDesc) == 32
     assert C.sizeof(_ffi.HgAggSpec) == 24
