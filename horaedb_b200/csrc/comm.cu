@@ -219,6 +219,7 @@ void hg_comm_free(hg_comm* c) {
 extern "C" {
 
 int hg_comm_unique_id(uint8_t* id) {
+  HG_GUARD_BEGIN
   if (!id) return set_error(HG_ERR_INVALID, "null argument");
   NcclApi* api = nccl_api();
   if (!api->err.empty()) return set_error(HG_ERR_UNSUPPORTED, api->err);
@@ -226,9 +227,11 @@ int hg_comm_unique_id(uint8_t* id) {
   NCCL_TRY(api, api->GetUniqueId(&u));
   std::memcpy(id, u.internal, HG_COMM_ID_BYTES);
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_comm_init(hg_engine* e, const uint8_t* id, int rank, int world) {
+  HG_GUARD_BEGIN
   if (!e || !id || world < 1 || rank < 0 || rank >= world) return set_error(HG_ERR_INVALID, "bad argument");
   NcclApi* api = nccl_api();
   if (!api->err.empty()) return set_error(HG_ERR_UNSUPPORTED, api->err);
@@ -249,25 +252,31 @@ int hg_comm_init(hg_engine* e, const uint8_t* id, int rank, int world) {
   CU_TRY(cudaMallocHost(&c->h_sizes, (size_t(world) + 1) * 8));
   e->comm = c.release();
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_comm_destroy(hg_engine* e) {
+  HG_GUARD_BEGIN
   if (!e) return set_error(HG_ERR_INVALID, "null engine");
   std::lock_guard<std::mutex> g(e->mu);
   cudaSetDevice(e->device);
   hg_comm_free(e->comm);
   e->comm = nullptr;
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_comm_sync(hg_engine* e) {
+  HG_GUARD_BEGIN
   if (!e || !e->comm) return set_error(HG_ERR_INVALID, "no communicator");
   CU_TRY(cudaSetDevice(e->device));
   CU_TRY(cudaStreamSynchronize(e->comm->stream));
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_agg_combine(hg_engine* e, uint32_t mode, uint64_t capacity_hint, hg_agg_combined* out) {
+  HG_GUARD_BEGIN
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   if (mode > HG_COMBINE_REDUCE) return set_error(HG_ERR_INVALID, "combine mode");
   std::lock_guard<std::mutex> g(e->mu);
@@ -330,6 +339,7 @@ int hg_agg_combine(hg_engine* e, uint32_t mode, uint64_t capacity_hint, hg_agg_c
   }
   CU_TRY(cudaEventRecord(c->ev_done, c->stream));
   return HG_OK;
+  HG_GUARD_END
 }
 
 }  // extern "C"

@@ -1195,6 +1195,7 @@ uint32_t hg_abi_version(void) { return HG_ABI_VERSION; }
 const char* hg_last_error(void) { return g_last_error.c_str(); }
 
 int hg_engine_create(const hg_config* cfg, hg_engine** out) {
+  HG_GUARD_BEGIN
   if (!cfg || !out) return set_error(HG_ERR_INVALID, "null argument");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -1222,6 +1223,7 @@ int hg_engine_create(const hg_config* cfg, hg_engine** out) {
   CU_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
   *out = e.release();
   return HG_OK;
+  HG_GUARD_END
 }
 
 void hg_engine_destroy(hg_engine* e) {
@@ -1249,22 +1251,27 @@ void hg_engine_destroy(hg_engine* e) {
 
 void* hg_engine_stream(hg_engine* e) { return e ? reinterpret_cast<void*>(e->stream) : nullptr; }
 int hg_engine_set_flags(hg_engine* e, uint32_t flags) {
+  HG_GUARD_BEGIN
   if (!e) return set_error(HG_ERR_INVALID, "null engine");
   std::lock_guard<std::mutex> g(e->mu);
   e->flags = flags;
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_sst_load(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* sst) {
+  HG_GUARD_BEGIN
   if (!e || !schema || !sst) return set_error(HG_ERR_INVALID, "null argument");
   int rc = validate_schema(schema);
   if (rc) return rc;
   std::lock_guard<std::mutex> g(e->mu);
   CU_TRY(cudaSetDevice(e->device));
   return load_sst_locked(e, schema, sst);
+  HG_GUARD_END
 }
 
 int hg_sst_unload(hg_engine* e, uint64_t id) {
+  HG_GUARD_BEGIN
   if (!e) return set_error(HG_ERR_INVALID, "null engine");
   std::lock_guard<std::mutex> g(e->mu);
   auto it = e->ssts.find(id);
@@ -1274,16 +1281,20 @@ int hg_sst_unload(hg_engine* e, uint64_t id) {
   e->resident_bytes -= it->second->device_bytes;
   e->ssts.erase(it);
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_sst_resident_bytes(hg_engine* e, uint64_t* out) {
+  HG_GUARD_BEGIN
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
   *out = e->resident_bytes;
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_agg_export_packed(hg_engine* e, void* d_dst, uint64_t cap) {
+  HG_GUARD_BEGIN
   if (!e || !d_dst) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
   if (cap < e->last_agg.num_groups) return set_error(HG_ERR_INVALID, "capacity smaller than the number of groups");
@@ -1293,10 +1304,12 @@ int hg_agg_export_packed(hg_engine* e, void* d_dst, uint64_t cap) {
   Launch L = e->L();
   k::pack_agg(L, in, e->last_gwidth, e->last_agg.num_groups, cap, static_cast<long long*>(d_dst));
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_plan_row_groups(const hg_schema_desc* schema, const uint8_t* data, uint64_t size, const hg_predicate* preds, size_t n_preds,
                        uint8_t* keep, uint32_t cap, uint32_t* num_row_groups) {
+  HG_GUARD_BEGIN
   if (!data || !keep || !num_row_groups || (n_preds && !preds)) return set_error(HG_ERR_INVALID, "null argument");
   int rc = validate_schema(schema);
   if (rc) return rc;
@@ -1316,13 +1329,16 @@ int hg_plan_row_groups(const hg_schema_desc* schema, const uint8_t* data, uint64
   for (size_t g = 0; g < nrg; g++)
     keep[g] = r.rg_rows[g] > 0 && (n_preds == 0 || rg_may_match(&r.rgcol[g * ncols], r.rg_rows[g], schema, preds, lits, n_preds)) ? 1 : 0;
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_last_stats(hg_engine* e, hg_scan_stats* out) {
+  HG_GUARD_BEGIN
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
   *out = e->stats;
   return HG_OK;
+  HG_GUARD_END
 }
 
 static void end_call(hg_engine* e) {
@@ -1464,12 +1480,16 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
 
 int hg_scan_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
                  size_t n_preds, const uint32_t* projection, size_t n_projection, int keep_builtin, struct ArrowArrayStream* out) {
+  HG_GUARD_BEGIN
   return scan_impl(e, schema, ssts, n_ssts, preds, n_preds, projection, n_projection, keep_builtin, out);
+  HG_GUARD_END
 }
 
 int hg_compact_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, struct ArrowArrayStream* out) {
+  HG_GUARD_BEGIN
   // Executor::do_compaction builds the same plan with no predicate and keep_builtin = true (executor.rs:164-169)
   return scan_impl(e, schema, ssts, n_ssts, nullptr, 0, nullptr, 0, 1, out);
+  HG_GUARD_END
 }
 
 
@@ -1576,6 +1596,7 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
 
 int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
                              const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg, hg_agg_device* out) {
+  HG_GUARD_BEGIN
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
   std::vector<uint32_t> touch;
@@ -1604,10 +1625,12 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
   e->last_gtype = ab.gtype;
   for (DevBuf* b : {&ab.gkey, &ab.bucket, &ab.count, &ab.sum, &ab.mn, &ab.mx}) b->release();   // arena memory: valid until the next call
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
                       size_t n_preds, const hg_agg_spec* agg, struct ArrowArrayStream* out) {
+  HG_GUARD_BEGIN
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
   std::vector<uint32_t> touch;
@@ -1658,6 +1681,7 @@ int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   if (G) data->batch_start.push_back(G);
   make_stream(out, data);
   return HG_OK;
+  HG_GUARD_END
 }
 
 }  // extern "C"

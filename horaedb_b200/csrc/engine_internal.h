@@ -49,6 +49,15 @@ inline const char* arrow_format(uint32_t t) {
   return f[t];
 }
 
+// Exception barrier of the C ABI: nothing may unwind across an extern "C" frame (the caller is Rust / C).  Host containers
+// (std::vector / std::string / make_unique) can throw bad_alloc; everything else is reported as an internal error.
+#define HG_GUARD_BEGIN try {
+#define HG_GUARD_END                                                                                              \
+  }                                                                                                               \
+  catch (const std::bad_alloc&) { return set_error(HG_ERR_OOM, "host allocation failed"); }                      \
+  catch (const std::exception& ex) { return set_error(HG_ERR_INTERNAL, std::string("exception: ") + ex.what()); } \
+  catch (...) { return set_error(HG_ERR_INTERNAL, "unknown exception"); }
+
 // widen a PLAIN-encoded statistics value to the comparison domain (i64 / u64 / f64 bits)
 inline uint64_t widen_stat(const uint8_t raw[8], int phys, uint32_t t) {
   if (phys == PT_INT32) {

@@ -5,6 +5,15 @@
 #include "../../include/horae_gpu.h"
 #include "parquet_meta.hpp"
 
+#include <new>
+int set_error(int code, const std::string& msg);   // engine.cu
+#define HG_GUARD_BEGIN try {
+#define HG_GUARD_END                                                                                              \
+  }                                                                                                               \
+  catch (const std::bad_alloc&) { return set_error(HG_ERR_OOM, "host allocation failed"); }                      \
+  catch (const std::exception& ex) { return set_error(HG_ERR_INTERNAL, std::string("exception: ") + ex.what()); } \
+  catch (...) { return set_error(HG_ERR_INTERNAL, "unknown exception"); }
+
 int set_error(int code, const std::string& msg);   // engine.cu (thread-local message behind hg_last_error)
 
 using namespace horae;
@@ -12,6 +21,7 @@ using namespace horae;
 extern "C" {
 
 int hg_parquet_inspect(const uint8_t* data, uint64_t size, hg_parquet_summary* out) {
+  HG_GUARD_BEGIN
   if (!data || !out) return set_error(HG_ERR_INVALID, "null argument");
   FileMetaData m;
   std::string err;
@@ -33,9 +43,11 @@ int hg_parquet_inspect(const uint8_t* data, uint64_t size, hg_parquet_summary* o
     }
   *out = s;
   return HG_OK;
+  HG_GUARD_END
 }
 
 int hg_parquet_chunk_info(const uint8_t* data, uint64_t size, uint32_t row_group, uint32_t column, hg_parquet_chunk* out) {
+  HG_GUARD_BEGIN
   if (!data || !out) return set_error(HG_ERR_INVALID, "null argument");
   FileMetaData m;
   std::string err;
@@ -62,6 +74,7 @@ int hg_parquet_chunk_info(const uint8_t* data, uint64_t size, uint32_t row_group
   }
   *out = o;
   return HG_OK;
+  HG_GUARD_END
 }
 
 }  // extern "C"
