@@ -69,6 +69,15 @@ class HgAggDevice(C.Structure):
                 ("d_sum", C.c_void_p), ("d_min", C.c_void_p), ("d_max", C.c_void_p)]
 
 
+class HgWriteProps(C.Structure):
+    _fields_ = [("max_row_group_size", C.c_uint32), ("compression", C.c_uint32), ("enable_sorting_columns", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class HgFileMeta(C.Structure):
+    _fields_ = [("size", C.c_uint64), ("num_rows", C.c_uint32), ("_pad", C.c_uint32), ("time_start", C.c_int64), ("time_end", C.c_int64),
+                ("max_sequence", C.c_uint64)]
+
+
 class HgAggCombined(C.Structure):
     _fields_ = [("capacity", C.c_uint64), ("world", C.c_uint32), ("_pad", C.c_uint32), ("d_blocks", C.c_void_p), ("num_groups", C.c_uint64),
                 ("reduced_capacity", C.c_uint64), ("d_reduced", C.c_void_p)]
@@ -98,7 +107,7 @@ class HgParquetChunk(C.Structure):
 EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_engine_set_flags", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
            "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info", "hg_plan_row_groups",
-           "hg_comm_unique_id", "hg_comm_init", "hg_comm_destroy", "hg_agg_combine", "hg_comm_sync"]
+           "hg_compact_to_sst", "hg_comm_unique_id", "hg_comm_init", "hg_comm_destroy", "hg_agg_combine", "hg_comm_sync"]
 
 _lib = None
 
@@ -285,6 +294,15 @@ class Engine:
         stream = ArrowArrayStream()
         _check(self._L.hg_compact_open(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), C.byref(stream)))
         return pa.RecordBatchReader._import_from_c(C.addressof(stream))
+
+    def compact_to_sst(self, schema: SchemaHandle, ssts: Sequence[SstInput], out_path: str, max_row_group_size: int = 8192,
+                       compression: str = "snappy", enable_sorting_columns: bool = True) -> "HgFileMeta":
+        """`Executor::do_compaction` on the GPU end to end: merge + dedup + Parquet encode, written to `out_path`."""
+        arr, keep = self._descs(ssts)
+        props = HgWriteProps(max_row_group_size, {"none": 0, "uncompressed": 0, "snappy": 1}[compression.lower()], int(enable_sorting_columns), 0)
+        meta = HgFileMeta()
+        _check(self._L.hg_compact_to_sst(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), C.byref(props), out_path.encode(), C.byref(meta)))
+        return meta
 
     def scan_aggregate(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (), group_col: int = 0,
                        ts_col: int = -1, window_ms: int = 0, value_col: int = -1, mode: int = 0) -> pa.Table:

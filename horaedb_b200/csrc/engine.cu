@@ -21,6 +21,7 @@
 
 #include "engine_internal.h"
 #include "fused_scan.h"
+#include "sst_writer.h"
 
 thread_local Arena* g_arena = nullptr;
 static thread_local std::string g_last_error;
@@ -1482,6 +1483,81 @@ int hg_scan_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* 
                  size_t n_preds, const uint32_t* projection, size_t n_projection, int keep_builtin, struct ArrowArrayStream* out) {
   HG_GUARD_BEGIN
   return scan_impl(e, schema, ssts, n_ssts, preds, n_preds, projection, n_projection, keep_builtin, out);
+  HG_GUARD_END
+}
+
+int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_write_props* props,
+                      const char* out_path, hg_file_meta* out) {
+  HG_GUARD_BEGIN
+  if (!e || !props || !out_path || !out) return set_error(HG_ERR_INVALID, "null argument");
+  {
+    int vrc = validate_schema(schema);
+    if (vrc) return vrc;
+  }
+  std::lock_guard<std::mutex> g(e->mu);
+  std::vector<uint32_t> touch;
+  for (uint32_t c = 0; c < schema->num_columns; c++) touch.push_back(c);
+  int rc = begin_call(e, schema, ssts, n, nullptr, 0, touch, true);
+  if (rc) return rc;
+  CallGuard guard{e};
+  cudaStream_t s = e->stream;
+  Launch L = e->L();
+  std::memset(out, 0, sizeof(*out));
+  for (size_t i = 0; i < n; i++) {
+    if (i == 0 || ssts[i].time_start < out->time_start) out->time_start = ssts[i].time_start;
+    if (i == 0 || ssts[i].time_end > out->time_end) out->time_end = ssts[i].time_end;
+    out->max_sequence = std::max(out->max_sequence, ssts[i].max_sequence);
+  }
+  PipelineState st;
+  uint32_t R = 0;
+  std::vector<DevBuf> gv(schema->num_columns), gb(schema->num_columns);
+  std::vector<writer::ColIn> cols(schema->num_columns);
+  if (n > 0) {
+    rc = run_pipeline(e, schema, ssts, n, nullptr, 0, touch, /*want_batches=*/false, &st);
+    if (rc) return rc;
+    uint32_t hc[8] = {0};
+    CU_TRY(cudaMemcpyAsync(hc, st.d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    rc = check_device_error(e, &st);
+    if (rc) return rc;
+    R = hc[1];
+    e->stats.rows_in_files = st.plan.rows_in_files;
+    e->stats.rows_decoded = st.plan.rows_decoded;
+    e->stats.rows_materialized = st.plan.rows_decoded;
+    e->stats.rows_filtered = hc[0];
+    e->stats.rows_out = R;
+  }
+  for (uint32_t c = 0; c < schema->num_columns; c++) {
+    const uint32_t width = type_width_host(schema->types[c]);
+    cols[c] = writer::ColIn{nullptr, nullptr, schema->types[c], width};
+    if (R == 0) continue;
+    DecodedCol& dc = st.cols[c];
+    CU_TRY(gv[c].alloc(size_t(R) * width + 16, s));
+    const bool nulls = dc.valid.p != nullptr;
+    if (nulls) CU_TRY(gb[c].alloc(size_t(R) + 16, s));
+    k::gather_column(L, dc.view(), st.out_rows.as<uint32_t>(), st.d_r, R, gv[c].p, gb[c].as<uint8_t>());
+    cols[c].vals = gv[c].p;
+    cols[c].valid = nulls ? gb[c].as<uint8_t>() : nullptr;
+  }
+  uint8_t* host = nullptr;
+  uint64_t size = 0;
+  rc = writer::write_sst(e, schema, cols.data(), schema->num_columns, R, props, &host, &size);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord(e->ev1, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  FILE* f = std::fopen(out_path, "wb");
+  bool ok = f != nullptr;
+  if (ok) ok = std::fwrite(host, 1, size_t(size), f) == size_t(size);
+  if (f) ok = std::fclose(f) == 0 && ok;
+  cudaFreeHost(host);
+  if (!ok) return set_error(HG_ERR_NOT_FOUND, std::string("cannot write ") + out_path);
+  out->size = size;
+  out->num_rows = R;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.gpu_ms = ms;
+  e->stats.kernel_launches = e->launches;
+  if (st.N > 0) { float kms = 0; cudaEventElapsedTime(&kms, e->evm0, e->evm1); e->stats.merge_ms = kms; }
+  return HG_OK;
   HG_GUARD_END
 }
 

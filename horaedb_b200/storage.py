@@ -181,15 +181,26 @@ class ObjectBasedStorage:
             time_range = TimeRange(task.inputs[0].meta().time_range.start, task.inputs[0].meta().time_range.end)
             for f in task.inputs[1:]:
                 time_range.merge(f.meta().time_range)
-            reader = self.engine.compact(self.handle, self._inputs(task.inputs))   # same plan, keep_builtin=true
-            tbl = reader.read_all()
             file_id = allocate_id()
-            batch = tbl.combine_chunks().to_batches()[0] if tbl.num_rows else pa.RecordBatch.from_arrays(
-                [pa.array([], f.type) for f in self.schema_.arrow_schema], schema=self.schema_.arrow_schema)
-            data = sstgen.write_sst_with_seq(self.schema_, batch, self.config.write)
-            with open(self.sst_path_gen.generate(file_id), "wb") as f:
-                f.write(data)
-            new = SstFile(file_id, FileMeta(max_sequence=file_id, num_rows=tbl.num_rows, size=len(data), time_range=time_range))
+            w = self.config.write
+            if w.encoding == "PLAIN" and not w.enable_dict and not w.column_options and str(w.compression).lower() in ("snappy", "uncompressed", "none"):
+                # the whole of do_compaction on the GPU: merge + dedup (keep_builtin = true) AND the Parquet encode (hg_compact_to_sst)
+                meta = self.engine.compact_to_sst(self.handle, self._inputs(task.inputs), self.sst_path_gen.generate(file_id),
+                                                  max_row_group_size=w.max_row_group_size, compression=str(w.compression),
+                                                  enable_sorting_columns=w.enable_sorting_columns)
+                num_rows, size = meta.num_rows, meta.size
+            else:
+                # writer options the GPU encoder does not implement (dictionary / delta encodings, zstd ..): the merged stream comes
+                # back as Arrow batches (hg_compact_open) and the host writes the file, like the reference's AsyncArrowWriter
+                reader = self.engine.compact(self.handle, self._inputs(task.inputs))   # same plan, keep_builtin=true
+                tbl = reader.read_all()
+                batch = tbl.combine_chunks().to_batches()[0] if tbl.num_rows else pa.RecordBatch.from_arrays(
+                    [pa.array([], f.type) for f in self.schema_.arrow_schema], schema=self.schema_.arrow_schema)
+                data = sstgen.write_sst_with_seq(self.schema_, batch, self.config.write)
+                with open(self.sst_path_gen.generate(file_id), "wb") as f:
+                    f.write(data)
+                num_rows, size = tbl.num_rows, len(data)
+            new = SstFile(file_id, FileMeta(max_sequence=file_id, num_rows=num_rows, size=size, time_range=time_range))
             to_deletes = [f.id() for f in task.expireds] + [f.id() for f in task.inputs]
             self.manifest.update([new], to_deletes)          # manifest first, then delete (executor.rs:205-220)
             for fid in to_deletes:

@@ -167,6 +167,29 @@ int hg_scan_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* 
 int hg_compact_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
                     struct ArrowArrayStream* out);
 
+/* build_write_props (storage.rs:258-298) / WriteConfig (config.rs:120-133) as far as the GPU writer implements them:
+ * PLAIN values, RLE definition levels, dictionary off, bloom filters off, chunk statistics on, one DataPage V1 per chunk. */
+typedef struct {
+  uint32_t max_row_group_size;      /* 0 = 8192 (WriteConfig::default) */
+  uint32_t compression;             /* Parquet codec id: 0 UNCOMPRESSED, 1 SNAPPY (the default) */
+  uint32_t enable_sorting_columns;  /* sorting_columns = primary keys, ascending, nulls first */
+  uint32_t _pad;
+} hg_write_props;
+
+/* FileMeta (sst.rs:155-160) of the file just written.  num_rows / size are u32 in the reference: larger outputs are refused. */
+typedef struct {
+  uint64_t size;
+  uint32_t num_rows, _pad;
+  int64_t time_start, time_end;     /* union of the inputs' ranges (executor.rs:157-163) */
+  uint64_t max_sequence;            /* max over the inputs */
+} hg_file_meta;
+
+/* Executor::do_compaction end to end on the GPU (compaction/executor.rs:155-222): merge + dedup of the input SSTs (builtin
+ * columns kept) AND the Parquet encode of the result, written to `out_path` ("{root}/data/{id}.sst", sst.rs:202-204).
+ * The Rust side keeps the manifest update (executor.rs:206-216). */
+int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_write_props* props,
+                      const char* out_path, hg_file_meta* out);
+
 int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
                       const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg,
                       struct ArrowArrayStream* out);
