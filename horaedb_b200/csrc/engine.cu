@@ -106,8 +106,8 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
   pages.assign(m.pages.size(), PageDev());
   for (size_t i = 0; i < pages.size(); i++) {
     const PageMeta& pm = m.pages[i];
-    if (pm.encoding != ENC_PLAIN)
-      return fail(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (only PLAIN is implemented)");
+    if (pm.encoding != ENC_PLAIN && pm.encoding != ENC_DELTA_BINARY_PACKED)
+      return fail(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (PLAIN and DELTA_BINARY_PACKED are implemented)");
     PageDev& pd = pages[i];
     pd.payload_off = pm.payload_off;
     pd.comp_size = pm.comp_size;
@@ -143,7 +143,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
           if (pm.page_type == PAGE_DATA_V2) {
             if (uint64_t(pm.v2_def_len) + pm.v2_rep_len > pm.comp_size || uint64_t(pm.v2_def_len) + pm.v2_rep_len > pm.uncomp_size)
               return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": V2 level bytes exceed the page");
-            if (no_nulls && uint64_t(pm.v2_def_len) + pm.v2_rep_len + uint64_t(pm.num_values) * pw > pm.uncomp_size)
+            if (pm.encoding == ENC_PLAIN && no_nulls && uint64_t(pm.v2_def_len) + pm.v2_rep_len + uint64_t(pm.num_values) * pw > pm.uncomp_size)
               return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": page smaller than its values");
           } else if (cm.codec == CODEC_UNCOMPRESSED) {
             if (pm.comp_size != pm.uncomp_size) return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": uncompressed page with differing sizes");
@@ -155,7 +155,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
               prefix = 4 + uint64_t(dl);
               if (prefix > pm.uncomp_size) return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": definition levels exceed the page");
             }
-            if (no_nulls && prefix + uint64_t(pm.num_values) * pw > pm.uncomp_size)
+            if (pm.encoding == ENC_PLAIN && no_nulls && prefix + uint64_t(pm.num_values) * pw > pm.uncomp_size)
               return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": page smaller than its values");
           }
         }
@@ -168,6 +168,9 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       cd.codec = uint8_t(cm.codec);
       cd.optional = uint8_t(m.repetition[c] == 1);
       cd.stored = 0;
+      for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++)
+        if (m.pages[pi].encoding == ENC_DELTA_BINARY_PACKED && cm.phys_type != PT_INT32 && cm.phys_type != PT_INT64)
+          return fail(HG_ERR_FORMAT, "DELTA_BINARY_PACKED on a non-integer column");
       if (cm.codec == CODEC_SNAPPY && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.rgs[g].num_rows > 0)
         cd.stored = classify_stored(data, size, m.pages[cm.first_page], cd.optional != 0,
                                     (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4u : 8u, uint64_t(m.rgs[g].num_rows)) ? 1 : 0;
@@ -189,8 +192,9 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       rc.null_none = cm.stats.has_null_count && cm.stats.null_count == 0;
       rc.snappy = cm.codec == CODEC_SNAPPY;
       rc.scratch = uint32_t(cm.scratch_bytes);
-      rc.simple_page = cm.codec == CODEC_UNCOMPRESSED && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA;
-      rc.single_page = cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA;
+      const bool one_plain_v1 = cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.pages[cm.first_page].encoding == ENC_PLAIN;
+      rc.simple_page = cm.codec == CODEC_UNCOMPRESSED && one_plain_v1;
+      rc.single_page = one_plain_v1;
       rc.stored = chunks[g * m.ncols + c].stored;
     }
   }
@@ -671,7 +675,7 @@ int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ss
       s.scratch_off = scratch;
       for (uint32_t c : need_cols) {
         const RgCol& cc = rc[c];
-        if (cc.snappy) scratch += cc.scratch;
+        scratch += cc.scratch;             // 0 for uncompressed PLAIN chunks
         if (!cc.null_none) has_nulls[c] = 1;
         if (!cc.simple_page) plan->all_single_plain_page = false;
       }

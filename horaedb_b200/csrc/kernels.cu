@@ -191,8 +191,7 @@ __device__ void snappy_warp(const uint8_t* src, uint32_t n, uint8_t* dst, uint32
 __device__ __forceinline__ uint64_t chunk_scratch_off(const RgSel& rs, const ChunkDev* chunks, const ColSel* cols, int ci) {
   uint64_t off = rs.scratch_off;
   for (int j = 0; j < ci; j++) {
-    ChunkDev cj = chunks[cols[j].col];
-    if (cj.codec == 1) off += cj.scratch_bytes;
+    off += chunks[cols[j].col].scratch_bytes;      // 0 for uncompressed PLAIN chunks
   }
   return off;
 }
@@ -221,6 +220,7 @@ __global__ void __launch_bounds__(32) snappy_chunks_kernel(const SstDev* __restr
     }
     if (compressed) snappy_warp(src, n, dst, ulen, lane, err);
     dst += page_scratch(pg.uncomp_size);
+    if (pg.encoding == 5) dst += page_scratch(pg.num_values * 8u);
   }
 }
 
@@ -241,9 +241,119 @@ __device__ __forceinline__ void store_val_dyn(void* out, uint32_t ow, uint32_t r
   }
 }
 
+// ------------------------------------------------------------------------------------ DELTA_BINARY_PACKED -> PLAIN
+// (Apache Parquet Encodings.md; a per-column option of the reference's writer, config.rs:54-75.)  One block per page:
+// thread 0 walks the block headers (min delta, one bit width per miniblock), all threads unpack one block's deltas in
+// parallel and a block-wide prefix sum turns them into values.  Sums wrap in the physical width, like the reference decoder.
+__device__ __forceinline__ uint64_t block_incl_scan64(uint64_t v, uint64_t* total, uint64_t* s_w64 /*[9]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t lo = __shfl_up_sync(0xffffffffu, uint32_t(inc), d), hi = __shfl_up_sync(0xffffffffu, uint32_t(inc >> 32), d);
+    if (lane >= d) inc += (uint64_t(hi) << 32) | lo;
+  }
+  if (lane == 31) s_w64[w] = inc;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint64_t run = 0; for (int x = 0; x < kThreads / 32; x++) { const uint64_t c = s_w64[x]; s_w64[x] = run; run += c; } s_w64[8] = run; }
+  __syncthreads();
+  const uint64_t r = s_w64[w] + inc;
+  *total = s_w64[8];
+  __syncthreads();
+  return r;
+}
+
+__device__ bool delta_decode_page(const uint8_t* p, const uint8_t* end, uint32_t pw, uint32_t max_out, uint8_t* out, uint32_t* count_out) {
+  __shared__ uint64_t s_w64[9];
+  __shared__ uint64_t s_min, s_cur;
+  __shared__ uint32_t s_block, s_nmini, s_total, s_pos, s_ok;
+  __shared__ uint32_t s_bw[64], s_moff[64];
+  const int tid = threadIdx.x;
+  auto varint = [&](uint32_t& pos, uint64_t* v) -> bool {
+    uint64_t r = 0;
+    for (int sh = 0; sh < 70; sh += 7) {
+      if (p + pos >= end) return false;
+      const uint8_t b = __ldg(p + pos++);
+      r |= uint64_t(b & 0x7f) << sh;
+      if (!(b & 0x80)) { *v = r; return true; }
+    }
+    return false;
+  };
+  if (tid == 0) {
+    uint32_t pos = 0;
+    uint64_t block = 0, nmini = 0, total = 0, zz = 0;
+    bool ok = varint(pos, &block) && varint(pos, &nmini) && varint(pos, &total) && varint(pos, &zz);
+    ok = ok && nmini > 0 && nmini <= 64 && block > 0 && block <= 65536 && block % nmini == 0 && (block / nmini) % 32 == 0 && total <= max_out;
+    s_ok = ok;
+    s_block = uint32_t(block); s_nmini = uint32_t(nmini); s_total = uint32_t(total); s_pos = pos;
+    s_cur = (zz >> 1) ^ (0 - (zz & 1));
+    if (ok && total > 0) {
+      if (pw == 4) *reinterpret_cast<uint32_t*>(out) = uint32_t(s_cur); else *reinterpret_cast<uint64_t*>(out) = s_cur;
+    }
+  }
+  __syncthreads();
+  if (!s_ok) return false;
+  const uint32_t total = s_total, block = s_block, nmini = s_nmini, per = block / nmini;
+  *count_out = total;
+  uint32_t done = total ? 1u : 0u;
+  while (done < total) {
+    const uint32_t nvals = (total - done) < block ? (total - done) : block;
+    if (tid == 0) {
+      uint32_t pos = s_pos;
+      uint64_t mz = 0;
+      bool ok = varint(pos, &mz) && p + pos + nmini <= end;
+      s_min = (mz >> 1) ^ (0 - (mz & 1));
+      if (ok) {
+        const uint32_t bwpos = pos;
+        pos += nmini;
+        for (uint32_t m = 0; m < nmini; m++) {
+          const uint32_t b = __ldg(p + bwpos + m);
+          s_bw[m] = b;
+          s_moff[m] = pos;
+          if (m * per < nvals) { if (b > 64) ok = false; pos += per * b / 8; }      // miniblocks past the last value are not stored
+        }
+        if (p + pos > end) ok = false;
+      }
+      s_pos = pos;
+      s_ok = ok;
+    }
+    __syncthreads();
+    if (!s_ok) return false;
+    for (uint32_t base = 0; base < nvals; base += kThreads) {
+      const uint32_t v = base + tid;
+      uint64_t delta = 0;
+      if (v < nvals) {
+        const uint32_t m = v / per, j = v % per, b = s_bw[m];
+        if (b) {
+          const uint64_t bit = uint64_t(j) * b;
+          const uint8_t* q = p + s_moff[m] + (bit >> 3);
+          const uint32_t sh = uint32_t(bit & 7);
+          const uint64_t lo = ld64_any<false>(q);
+          uint64_t x = lo >> sh;
+          if (sh && b + sh > 64) x |= uint64_t(__ldg(q + 8)) << (64 - sh);
+          delta = b == 64 ? x : (x & ((1ull << b) - 1));
+        }
+        delta += s_min;
+      }
+      uint64_t tile_total;
+      const uint64_t incl = block_incl_scan64(delta, &tile_total, s_w64);
+      const uint64_t cur = s_cur;
+      if (v < nvals) {
+        const uint64_t val = cur + incl;
+        if (pw == 4) reinterpret_cast<uint32_t*>(out)[done + v] = uint32_t(val); else reinterpret_cast<uint64_t*>(out)[done + v] = val;
+      }
+      __syncthreads();
+      if (tid == 0) s_cur = cur + tile_total;
+      __syncthreads();
+    }
+    done += nvals;
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* __restrict__ ssts, const RgSel* __restrict__ sel,
                                                                 const ColSel* __restrict__ cols, int ncolsel,
-                                                                const uint8_t* __restrict__ scratch, int* err) {
+                                                                uint8_t* __restrict__ scratch, int* err) {
   __shared__ uint32_t s_warp[9];
   __shared__ uint32_t s_kind, s_count, s_val, s_bad;
   __shared__ const uint8_t* s_ptr;
@@ -256,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
   ColSel cs = cols[ci];
   ChunkDev ch = chunks[cs.col];
   const uint32_t pw = (ch.phys == 1 || ch.phys == 4) ? 4u : 8u;   // INT32/FLOAT : INT64/DOUBLE
-  const uint8_t* sc = scratch + (ch.codec == 1 ? chunk_scratch_off(rs, chunks, cols, ci) : 0);
+  uint8_t* sc = scratch + (ch.scratch_bytes ? chunk_scratch_off(rs, chunks, cols, ci) : 0);
   uint32_t row = rs.out_row;
   if (tid == 0) s_bad = 0;
   __syncthreads();
@@ -282,8 +392,20 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
     // values available in this page (malformed pages must not make the decoder read past the page: ABI = HG_ERR_FORMAT)
     const uint8_t* page_end = (ch.codec == 1 && !(pg.page_type == 3 && !pg.v2_compressed)) ? sc + (pg.page_type == 3 ? pg.uncomp_size - pg.v2_def_len - pg.v2_rep_len : pg.uncomp_size)
                                                                                        : payload + pg.comp_size;
-    const uint32_t max_vals = val_ptr <= page_end ? uint32_t(size_t(page_end - val_ptr) / pw) : 0u;
+    uint32_t max_vals = val_ptr <= page_end ? uint32_t(size_t(page_end - val_ptr) / pw) : 0u;
     if (ch.codec == 1) sc += page_scratch(pg.uncomp_size);
+    if (pg.encoding == 5) {
+      // DELTA_BINARY_PACKED: expand the values into the page's PLAIN image in scratch, then decode that like any PLAIN page
+      uint8_t* img = sc;
+      sc += page_scratch(nv * 8u);
+      uint32_t cnt = 0;
+      const bool ok = val_ptr <= page_end && delta_decode_page(val_ptr, page_end, pw, nv, img, &cnt);
+      __syncthreads();
+      if (!ok) { if (tid == 0) s_bad = 4; cnt = 0; }
+      val_ptr = img;
+      max_vals = cnt;
+      __syncthreads();
+    }
 
     bool all_valid = true;
     if (ch.optional) {
@@ -820,7 +942,7 @@ void snappy_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32
   L.tick();
 }
 void decode_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols, int ncolsel,
-                   const uint8_t* scratch, int* err) {
+                   uint8_t* scratch, int* err) {
   if (!nsel || !ncolsel) return;
   decode_chunks_kernel<<<nsel * ncolsel, kThreads, 0, L.stream>>>(ssts, sel, cols, ncolsel, scratch, err);
   L.tick();

@@ -44,7 +44,7 @@ struct SnappyJob {
 };
 void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks);
 void decode_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols,
-                   int ncolsel, const uint8_t* scratch, int* err);
+                   int ncolsel, uint8_t* scratch, int* err);
 
 // S3: predicate -> alive bytes -----------------------------------------------------------------------------------
 void eval_predicates(const Launch& L, const PredSet& preds, uint32_t n, uint8_t* alive);

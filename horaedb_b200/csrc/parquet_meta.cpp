@@ -1,6 +1,8 @@
 // parquet_meta.cpp — see parquet_meta.hpp.
 #include "parquet_meta.hpp"
 
+#include <algorithm>
+
 
 namespace horae {
 namespace {
@@ -268,7 +270,9 @@ bool parse_parquet(const uint8_t* data, size_t len, FileMetaData* out, std::stri
         pm.v2_rep_len = uint32_t(h.v2_rep_len);
         pm.v2_compressed = h.v2_compressed ? 1 : 0;
         out->pages.push_back(pm);
-        cm.scratch_bytes += page_scratch_bytes(pm.uncomp_size);
+        // device scratch of the page: the decompressed payload (compressed chunks) + the PLAIN image of a DELTA_BINARY_PACKED page
+        if (cm.codec != CODEC_UNCOMPRESSED) cm.scratch_bytes += page_scratch_bytes(pm.uncomp_size);
+        if (pm.encoding == ENC_DELTA_BINARY_PACKED) cm.scratch_bytes += page_scratch_bytes(uint32_t(std::min<uint64_t>(uint64_t(pm.num_values) * 8, 0xfffffff0ull)));
         seen += h.num_values;
         if (h.num_values <= 0) return bad("page with no values");
       }

@@ -362,8 +362,7 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
 __device__ __forceinline__ uint64_t chunk_scratch_off2(const RgSel& rs, const ChunkDev* chunks, const ColSel* cols, int ci) {
   uint64_t off = rs.scratch_off;
   for (int j = 0; j < ci; j++) {
-    ChunkDev cj = chunks[cols[j].col];
-    if (cj.codec == 1) off += cj.scratch_bytes;
+    off += chunks[cols[j].col].scratch_bytes;      // 0 for uncompressed PLAIN chunks
   }
   return off;
 }
@@ -404,6 +403,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_pages_kernel(cons
       }
       if (compressed) snappy_page(src, n, dst, ulen, sm, lane, J.err);
       dst += page_scratch2(pg.uncomp_size);
+      if (pg.encoding == 5) dst += page_scratch2(pg.num_values * 8u);     // PLAIN image of a DELTA_BINARY_PACKED page (decode_chunks)
     }
   }
 }

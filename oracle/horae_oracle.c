@@ -357,6 +357,45 @@ static uint64_t widen(const uint8_t *p, int phys, int otype) {
     else { uint64_t v; memcpy(&v, p, 8); return v; }
 }
 
+/* DELTA_BINARY_PACKED (Apache Parquet format spec, Encodings.md; selectable per column through config.rs:54-75):
+ * header = block size, miniblocks per block, total count, first value (zigzag); every block = min delta (zigzag), one bit
+ * width per miniblock, then the miniblocks' (delta - min delta) bit-packed LSB first.  All sums wrap in the physical width.
+ * Decodes `count` values into out[] as PLAIN bytes of width w (4 or 8). */
+static int delta_binary_unpack(const uint8_t *p, int64_t len, int w, int64_t count, uint8_t *out) {
+    const uint8_t *end = p + len;
+#define DVAR(var) do { uint64_t _v = 0; int _s = 0; for (;;) { if (p >= end || _s > 63) FAIL("delta: truncated varint"); uint8_t _b = *p++; _v |= (uint64_t)(_b & 0x7f) << _s; _s += 7; if (!(_b & 0x80)) break; } var = _v; } while (0)
+    uint64_t block, nmini, total, zz;
+    DVAR(block); DVAR(nmini); DVAR(total); DVAR(zz);
+    if (nmini == 0 || block == 0 || block % nmini || (block / nmini) % 32) FAIL("delta: bad block geometry");
+    if ((int64_t)total != count) FAIL("delta: %llu values in the page header, %lld expected", (unsigned long long)total, (long long)count);
+    uint64_t per = block / nmini;
+    uint64_t cur = (zz >> 1) ^ (uint64_t)-(int64_t)(zz & 1);
+    int64_t done = 0;
+    if (count > 0) { if (w == 4) { uint32_t x = (uint32_t)cur; memcpy(out, &x, 4); } else memcpy(out, &cur, 8); done = 1; }
+    while (done < count) {
+        uint64_t mz; DVAR(mz);
+        uint64_t min_delta = (mz >> 1) ^ (uint64_t)-(int64_t)(mz & 1);
+        if (p + nmini > end) FAIL("delta: truncated bit widths");
+        const uint8_t *bw = p; p += nmini;
+        for (uint64_t m = 0; m < nmini && done < count; m++) {
+            int b = bw[m];
+            if (b > 64) FAIL("delta: bit width %d", b);
+            if (p + per * b / 8 > end) FAIL("delta: truncated miniblock");
+            for (uint64_t j = 0; j < per && done < count; j++) {
+                uint64_t bit = j * (uint64_t)b, v = 0;
+                for (int k = 0; k < b; k++) { uint64_t q = bit + k; v |= (uint64_t)((p[q >> 3] >> (q & 7)) & 1) << k; }
+                cur += min_delta + v;
+                if (w == 4) { uint32_t x = (uint32_t)cur; memcpy(out + done * 4, &x, 4); cur = (uint64_t)(int64_t)(int32_t)x; }
+                else memcpy(out + done * 8, &cur, 8);
+                done++;
+            }
+            p += per * b / 8;
+        }
+    }
+#undef DVAR
+    return 0;
+}
+
 /* decode one column chunk into vals/valid[0..num_rows) */
 static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, int optional, int otype,
                         int64_t num_rows, uint64_t *vals, uint8_t *valid) {
@@ -377,7 +416,9 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
         pos += h.hdr_len + h.comp;
         if (h.type == 2) { rc = -1; snprintf(g_err, sizeof g_err, "oracle: dictionary page"); break; }
         if (h.type != 0 && h.type != 3) continue;
-        if (h.encoding != 0) { rc = -1; snprintf(g_err, sizeof g_err, "oracle: encoding %d unsupported", h.encoding); break; }
+        if (h.encoding != 0 && !(h.encoding == 5 && (cm->phys_type == 1 || cm->phys_type == 2))) {
+            rc = -1; snprintf(g_err, sizeof g_err, "oracle: encoding %d unsupported", h.encoding); break;
+        }
         int nv = h.num_values;
         if (row + nv > num_rows) { rc = -1; snprintf(g_err, sizeof g_err, "page rows overflow chunk"); break; }
         const uint8_t *body; int64_t body_len;
@@ -404,6 +445,14 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
         }
         if (optional) { if (decode_levels_bw1(levels, levels_len, nv, lv)) { rc = -1; break; } }
         else memset(lv, 1, nv);
+        uint8_t *dbuf = NULL;
+        if (h.encoding == 5) {                    /* DELTA_BINARY_PACKED: expand to PLAIN bytes, then the common path */
+            int64_t nn = 0;
+            for (int i = 0; i < nv; i++) nn += lv[i] != 0;
+            dbuf = malloc((size_t)(nn ? nn : 1) * w);
+            if (delta_binary_unpack(body, body_len, w, nn, dbuf)) { free(dbuf); rc = -1; break; }
+            body = dbuf; body_len = nn * w;
+        }
         int64_t k = 0;
         for (int i = 0; i < nv; i++) {
             if (lv[i]) {
@@ -411,6 +460,7 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
                 vals[row + i] = widen(body + k * w, cm->phys_type, otype); valid[row + i] = 1; k++;
             } else { vals[row + i] = 0; valid[row + i] = 0; }
         }
+        free(dbuf);
         if (rc) break;
         row += nv;
     }

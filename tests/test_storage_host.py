@@ -24,6 +24,10 @@ class FakeEngine:
         self.calls.append(("compact", [i.id for i in inputs]))
         raise RuntimeError("boom")
 
+    def compact_to_sst(self, handle, inputs, out_path, **kw):
+        self.calls.append(("compact_to_sst", [i.id for i in inputs], out_path, kw))
+        raise RuntimeError("boom")
+
     def unload_sst(self, id):
         pass
 
