@@ -107,7 +107,7 @@ class HgParquetChunk(C.Structure):
 EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_engine_set_flags", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
            "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info", "hg_plan_row_groups",
-           "hg_compact_to_sst", "hg_comm_unique_id", "hg_comm_init", "hg_comm_destroy", "hg_agg_combine", "hg_comm_sync"]
+           "hg_compact_to_sst", "hg_plan_pk_splitters", "hg_comm_unique_id", "hg_comm_init", "hg_comm_destroy", "hg_agg_combine", "hg_comm_sync"]
 
 _lib = None
 
@@ -296,12 +296,15 @@ class Engine:
         return pa.RecordBatchReader._import_from_c(C.addressof(stream))
 
     def compact_to_sst(self, schema: SchemaHandle, ssts: Sequence[SstInput], out_path: str, max_row_group_size: int = 8192,
-                       compression: str = "snappy", enable_sorting_columns: bool = True) -> "HgFileMeta":
-        """`Executor::do_compaction` on the GPU end to end: merge + dedup + Parquet encode, written to `out_path`."""
+                       compression: str = "snappy", enable_sorting_columns: bool = True, shard_preds: Sequence[tuple] = ()) -> "HgFileMeta":
+        """`Executor::do_compaction` on the GPU end to end: merge + dedup + Parquet encode, written to `out_path`.
+        `shard_preds` = this GPU's pk0 range in a multi-GPU compaction (see `plan_pk_splitters`)."""
         arr, keep = self._descs(ssts)
+        p = _make_preds(schema.arrow_schema, shard_preds)
         props = HgWriteProps(max_row_group_size, {"none": 0, "uncompressed": 0, "snappy": 1}[compression.lower()], int(enable_sorting_columns), 0)
         meta = HgFileMeta()
-        _check(self._L.hg_compact_to_sst(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), C.byref(props), out_path.encode(), C.byref(meta)))
+        _check(self._L.hg_compact_to_sst(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p, C.c_size_t(len(shard_preds)), C.byref(props),
+                                         out_path.encode(), C.byref(meta)))
         return meta
 
     def scan_aggregate(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (), group_col: int = 0,
@@ -404,6 +407,37 @@ def parquet_chunk_info(data: bytes, row_group: int, column: int) -> dict:
     d = {f[0]: getattr(out, f[0]) for f in HgParquetChunk._fields_}
     d["min"], d["max"] = bytes(out.min), bytes(out.max)
     return d
+
+
+def plan_pk_splitters(schema: "SchemaHandle", datas: Sequence[bytes], parts: int) -> list:
+    """Host-only (no GPU): `parts - 1` pk0 splitters that balance the rows of the inputs (multi-GPU compaction)."""
+    L = lib()
+    arr = (HgSstDesc * max(len(datas), 1))()
+    keep = []
+    for i, d in enumerate(datas):
+        buf = np.frombuffer(d, dtype=np.uint8)
+        keep.append(buf)
+        arr[i].id = i
+        arr[i].data = buf.ctypes.data
+        arr[i].size = buf.nbytes
+    out = (C.c_uint64 * max(parts - 1, 1))()
+    _check(L.hg_plan_pk_splitters(C.byref(schema.desc), arr, C.c_size_t(len(datas)), C.c_uint32(parts), out))
+    t = schema.arrow_schema.field(0).type
+    vals = [int(out[i]) for i in range(parts - 1)]
+    if pa.types.is_signed_integer(t):
+        vals = [v - (1 << 64) if v >= (1 << 63) else v for v in vals]
+    return vals
+
+
+def shard_range_preds(schema: "SchemaHandle", splitters: Sequence[int], rank: int) -> list:
+    """The pk0 range of `rank` among len(splitters) + 1 shards, as predicates for `compact_to_sst(shard_preds=...)`."""
+    name = schema.arrow_schema.field(0).name
+    preds = []
+    if rank > 0:
+        preds.append((name, "ge", splitters[rank - 1]))
+    if rank < len(splitters):
+        preds.append((name, "lt", splitters[rank]))
+    return preds
 
 
 def plan_row_groups(schema: "SchemaHandle", data: bytes, preds: Sequence[tuple] = ()) -> list:

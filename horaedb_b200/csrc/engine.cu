@@ -1490,10 +1490,76 @@ int hg_scan_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* 
   HG_GUARD_END
 }
 
-int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_write_props* props,
-                      const char* out_path, hg_file_meta* out) {
+int hg_plan_pk_splitters(const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, uint32_t parts, uint64_t* splitters) {
   HG_GUARD_BEGIN
-  if (!e || !props || !out_path || !out) return set_error(HG_ERR_INVALID, "null argument");
+  if (!ssts || !splitters || parts == 0) return set_error(HG_ERR_INVALID, "null argument");
+  int rc = validate_schema(schema);
+  if (rc) return rc;
+  const uint32_t t0 = schema->types[0];
+  struct Iv { uint64_t mn, mx, rows; };
+  std::vector<Iv> ivs;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    std::vector<uint8_t> filebuf;
+    const uint8_t* data = ssts[i].data;
+    uint64_t size = ssts[i].size;
+    if (!data) {
+      if (!ssts[i].path) return set_error(HG_ERR_NOT_FOUND, "hg_plan_pk_splitters needs the SST bytes or a path");
+      rc = read_whole_file(ssts[i].path, &filebuf);
+      if (rc) return rc;
+      data = filebuf.data();
+      size = filebuf.size();
+    }
+    SstResident r;
+    std::vector<PageDev> pages;
+    std::vector<ChunkDev> chunks;
+    std::string err;
+    rc = prepare_sst(schema, ssts[i].id, data, size, &r, &pages, &chunks, &err);
+    if (rc) return set_error(rc, err);
+    const size_t ncols = size_t(r.meta.ncols);
+    for (size_t g = 0; g < r.rg_rows.size(); g++) {
+      if (!r.rg_rows[g]) continue;
+      const RgCol& c0 = r.rgcol[g * ncols];
+      if (!c0.has_minmax) return set_error(HG_ERR_UNSUPPORTED, "pk0 statistics missing: cannot range-partition");
+      ivs.push_back(Iv{c0.mn, c0.mx, r.rg_rows[g]});
+      total += r.rg_rows[g];
+    }
+  }
+  // rows of a row group are taken as evenly spread over its [min, max] of pk0 (SSTs are PK-sorted, so they nearly are);
+  // splitter q = the smallest pk0 value below which at least q / parts of all rows lie under that model (bisection in the
+  // order-preserving unsigned image of the column).  A balance heuristic: any splitters give a correct partition.
+  const uint64_t flip = type_is_signed(t0) ? (1ull << 63) : 0ull;
+  uint64_t lo_all = ~0ull, hi_all = 0;
+  for (Iv& iv : ivs) { iv.mn ^= flip; iv.mx ^= flip; lo_all = std::min(lo_all, iv.mn); hi_all = std::max(hi_all, iv.mx); }
+  auto below = [&](uint64_t x) {       // modelled number of rows with pk0 < x
+    long double acc = 0;
+    for (const Iv& iv : ivs) {
+      if (x <= iv.mn) continue;
+      if (x > iv.mx) { acc += iv.rows; continue; }
+      acc += (long double)iv.rows * ((long double)(x - iv.mn) / ((long double)(iv.mx - iv.mn) + 1.0L));
+    }
+    return acc;
+  };
+  for (uint32_t q = 1; q < parts; q++) {
+    uint64_t sp = hi_all;
+    if (!ivs.empty()) {
+      const long double want = (long double)total * q / parts;
+      uint64_t a = lo_all, b = hi_all;
+      while (a < b) { const uint64_t mid = a + (b - a) / 2; if (below(mid) >= want) b = mid; else a = mid + 1; }
+      sp = a;
+    } else sp = 0;
+    splitters[q - 1] = sp ^ flip;
+  }
+  return HG_OK;
+  HG_GUARD_END
+}
+
+int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* shard_preds,
+                      size_t n_shard_preds, const hg_write_props* props, const char* out_path, hg_file_meta* out) {
+  HG_GUARD_BEGIN
+  if (!e || !props || !out_path || !out || (n_shard_preds && !shard_preds)) return set_error(HG_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < n_shard_preds; i++)
+    if (shard_preds[i].column != 0) return set_error(HG_ERR_INVALID, "compaction shards are ranges of the first primary-key column");
   {
     int vrc = validate_schema(schema);
     if (vrc) return vrc;
@@ -1501,7 +1567,7 @@ int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   std::lock_guard<std::mutex> g(e->mu);
   std::vector<uint32_t> touch;
   for (uint32_t c = 0; c < schema->num_columns; c++) touch.push_back(c);
-  int rc = begin_call(e, schema, ssts, n, nullptr, 0, touch, true);
+  int rc = begin_call(e, schema, ssts, n, shard_preds, n_shard_preds, touch, true);
   if (rc) return rc;
   CallGuard guard{e};
   cudaStream_t s = e->stream;
@@ -1517,7 +1583,7 @@ int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   std::vector<DevBuf> gv(schema->num_columns), gb(schema->num_columns);
   std::vector<writer::ColIn> cols(schema->num_columns);
   if (n > 0) {
-    rc = run_pipeline(e, schema, ssts, n, nullptr, 0, touch, /*want_batches=*/false, &st);
+    rc = run_pipeline(e, schema, ssts, n, shard_preds, n_shard_preds, touch, /*want_batches=*/false, &st);
     if (rc) return rc;
     uint32_t hc[8] = {0};
     CU_TRY(cudaMemcpyAsync(hc, st.d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));

@@ -187,8 +187,16 @@ typedef struct {
 /* Executor::do_compaction end to end on the GPU (compaction/executor.rs:155-222): merge + dedup of the input SSTs (builtin
  * columns kept) AND the Parquet encode of the result, written to `out_path` ("{root}/data/{id}.sst", sst.rs:202-204).
  * The Rust side keeps the manifest update (executor.rs:206-216). */
-int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_write_props* props,
-                      const char* out_path, hg_file_meta* out);
+int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* shard_preds,
+                      size_t n_shard_preds, const hg_write_props* props, const char* out_path, hg_file_meta* out);
+/* `shard_preds` (normally none) restricts the compaction to a primary-key range: the multi-GPU split of SURVEY 8(e) — GPU g
+ * compacts `pk0 >= splitter[g-1] AND pk0 < splitter[g]` of ALL inputs (only the row groups overlapping its range are read:
+ * SSTs are PK-sorted), the outputs concatenated in rank order are the globally sorted, deduplicated run.  A range on pk0
+ * never cuts a primary-key run, so LastValue sees every version of a key on one GPU.
+ *
+ * hg_plan_pk_splitters: host only, deterministic — every rank computes the same `parts - 1` splitters (pk0 values in the
+ * column's widened domain: i64 / u64 two's complement) from the row-group statistics of the inputs, balancing rows. */
+int hg_plan_pk_splitters(const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, uint32_t parts, uint64_t* splitters);
 
 int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
                       const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg,

@@ -147,3 +147,35 @@ def test_storage_compaction_uses_the_gpu_writer(tmp_path, golden):
     after = [b for b in storage.scan(ScanRequest(TimeRange.new(Timestamp(0), Timestamp.MAX), [], None))]
     assert pa.Table.from_batches(after).equals(pa.Table.from_batches(before))
     eng.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_range_sharded_compaction_equals_single_compaction(tmp_path, world):
+    """Multi-GPU merge-compaction (BASELINE config 5): every GPU compacts one pk0 range of ALL inputs; the shards'
+    outputs in rank order are the sorted, deduplicated run of the whole task.  Emulated on one GPU: `world` calls with the
+    shard predicates of ranks 0..world-1; the bytes every call moves shrink with the shard (only overlapping row groups)."""
+    from horaedb_b200._ffi import plan_pk_splitters, shard_range_preds
+    schema = sstgen.metric_storage_schema()
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    ssts = sstgen.synth_overlapping_ssts(12, series=300, points=400, delta_ms=1000, keep_frac=0.3, compression="snappy")
+    datas = [s[0] for s in ssts]
+    exp = pa.Table.from_batches(oracle.scan(datas, schema.arrow_schema, 2, (), True, 8192).batches)
+    eng = Engine(device=0)
+    sp = plan_pk_splitters(handle, datas, world)
+    parts, moved = [], []
+    for r in range(world):
+        path = str(tmp_path / f"shard{r}.sst")
+        meta = eng.compact_to_sst(handle, _inputs(datas), path, shard_preds=shard_range_preds(handle, sp, r))
+        moved.append(eng.stats()["bytes_h2d"])
+        t = pq.read_table(path)
+        assert t.num_rows == meta.num_rows
+        parts.append(t)
+    got = pa.concat_tables(parts)
+    assert got.num_rows == exp.num_rows
+    for name in exp.schema.names:
+        assert got[name].combine_chunks().equals(exp[name].combine_chunks()), name
+    sizes = [p.num_rows for p in parts]
+    assert max(sizes) < 1.5 * exp.num_rows / world, sizes                 # balanced shards
+    whole = sum(len(d) for d in datas)
+    assert max(moved) < 0.8 * whole, (moved, whole)                        # a shard does not pull the whole inputs over PCIe
+    eng.close()

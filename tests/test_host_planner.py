@@ -108,3 +108,37 @@ def test_validation_errors_without_a_gpu():
     fkey = StorageSchema.try_new(pa.schema([pa.field("a", pa.float64(), True), pa.field("b", pa.int64(), True), pa.field("c", pa.int64(), True)]), 1)
     with pytest.raises(HgError):                                                     # primary_key_eq has no float arm (read.rs:269-286)
         plan_row_groups(SchemaHandle(fkey.arrow_schema, 1), data, [])
+
+
+def test_pk_splitters_balance_rows_and_are_deterministic():
+    """hg_plan_pk_splitters (multi-GPU compaction): splitters from row-group statistics only; every shard's share of
+    the input rows is close to 1 / parts on uniformly overlapping inputs; signed keys; skewed inputs stay a valid partition."""
+    import numpy as np
+    import pyarrow as pa
+    from horaedb_b200 import sstgen
+    from horaedb_b200._ffi import SchemaHandle, plan_pk_splitters, shard_range_preds
+    from horaedb_b200.types import StorageSchema
+    schema = sstgen.metric_storage_schema()
+    h = SchemaHandle(schema.arrow_schema, 2)
+    ssts = sstgen.synth_overlapping_ssts(8, series=400, points=200, delta_ms=1000, keep_frac=0.3, compression="none")
+    datas = [s[0] for s in ssts]
+    import io
+
+    import pyarrow.parquet as pq
+    sid = np.concatenate([pq.read_table(io.BytesIO(d), columns=["series_id"])["series_id"].to_numpy() for d in datas])
+    for parts in (2, 4, 8):
+        sp = plan_pk_splitters(h, datas, parts)
+        assert sp == plan_pk_splitters(h, datas, parts) and sp == sorted(sp) and len(sp) == parts - 1
+        edges = [-1] + sp + [1 << 62]
+        shares = [np.count_nonzero((sid >= max(edges[i], 0)) & (sid < edges[i + 1])) / len(sid) for i in range(parts)]
+        assert abs(sum(shares) - 1.0) < 1e-9 and max(shares) < 1.25 / parts, shares
+        preds = [shard_range_preds(h, sp, r) for r in range(parts)]
+        assert preds[0] == [("series_id", "lt", sp[0])] and preds[-1] == [("series_id", "ge", sp[-1])]
+    # signed first key, heavy skew: still ordered, inside the key range
+    user = pa.schema([pa.field("a", pa.int64()), pa.field("b", pa.int64()), pa.field("v", pa.float64())])
+    s2 = StorageSchema.try_new(user, 2)
+    a = np.sort(np.concatenate([np.full(5000, -7), np.arange(-3000, 3000)])).astype(np.int64)
+    b = pa.RecordBatch.from_arrays([pa.array(a), pa.array(np.arange(len(a), dtype=np.int64)), pa.array(np.zeros(len(a)))], schema=user)
+    d = sstgen.write_sst(s2, b, 4, presorted=True)
+    sp = plan_pk_splitters(SchemaHandle(s2.arrow_schema, 2), [d], 4)
+    assert sp == sorted(sp) and -3000 <= sp[0] and sp[-1] <= 2999
