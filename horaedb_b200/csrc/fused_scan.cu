@@ -272,20 +272,35 @@ __global__ void __launch_bounds__(256) slot_bases_kernel(const __grid_constant__
 // Gate-first decompression of Snappy SSTs, row-group level: after the gate column's pages are decompressed, find the
 // row groups that hold a row passing the gate column's predicates; the other columns are decompressed only for those.
 // The filter runs before merge and dedup (read.rs:459-480), so a row group without a passing row contributes nothing.
+// It also records, per row group, how many leading rows can matter at all: everything behind the LAST row that passes the
+// gate fails the filter, so the remaining columns only have to be decompressed up to there (RgSel::out_row = that row + 2:
+// the row itself and its successor for the LastValue comparison).
 template <bool W4>
-__global__ void __launch_bounds__(256) gate_sel_kernel(const __grid_constant__ FParams P, int gate_slot, uint64_t flip, uint64_t lo, uint64_t span,
-                                                       uint8_t* __restrict__ flags) {
+__global__ void __launch_bounds__(256) gate_sel_kernel(const __grid_constant__ FParams P, RgSel* __restrict__ sel, int gate_slot, uint64_t flip,
+                                                       uint64_t lo, uint64_t span, uint8_t* __restrict__ flags) {
+  __shared__ uint32_t s_last;
   const uint32_t nsel = *P.d_nsel;
   for (uint32_t si = blockIdx.x; si < nsel; si += gridDim.x) {
     const uint8_t* base = P.bases[size_t(si) * MAXC + gate_slot];
-    const uint32_t nrows = P.sel[si].num_rows;
-    bool any = false;
-    for (uint32_t i = threadIdx.x; i < nrows && !any; i += 256) {
-      if (W4) any = (ld32u(base + size_t(i) * 4) ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span);
-      else any = (ld_bytes8(base + size_t(i) * 8) ^ flip) - lo <= span;
+    const uint32_t nrows = sel[si].num_rows;
+    if (threadIdx.x == 0) s_last = 0;
+    __syncthreads();
+    uint32_t last = 0;                                     // 1 + index of the last passing row seen by this thread
+    for (uint32_t i = threadIdx.x; i < nrows; i += 256) {
+      bool pass;
+      if (W4) pass = (ld32u(base + size_t(i) * 4) ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span);
+      else pass = (ld_bytes8(base + size_t(i) * 8) ^ flip) - lo <= span;
+      if (pass) last = i + 1;
     }
-    const int a = __syncthreads_or(any);
-    if (threadIdx.x == 0) flags[si] = a ? 1 : 0;
+    for (int d = 16; d > 0; d >>= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, last, d); last = o > last ? o : last; }
+    if ((threadIdx.x & 31) == 0 && last) atomicMax(&s_last, last);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t l = s_last;
+      flags[si] = l ? 1 : 0;
+      sel[si].out_row = l ? (l + 1 < nrows ? l + 1 : nrows) : 0;
+    }
+    __syncthreads();
   }
 }
 
@@ -1360,14 +1375,21 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
         L.tick();
         const uint32_t gt = schema->types[slots[gate_slot]];
         const bool w4 = !(gt == T_U64 || gt == T_I64 || gt == T_F64);
-        if (w4) gate_sel_kernel<true><<<148 * 8, 256, 0, s>>>(P, gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
-        else gate_sel_kernel<false><<<148 * 8, 256, 0, s>>>(P, gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
+        if (w4) gate_sel_kernel<true><<<148 * 8, 256, 0, s>>>(P, d_sel.as<RgSel>(), gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
+        else gate_sel_kernel<false><<<148 * 8, 256, 0, s>>>(P, d_sel.as<RgSel>(), gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
         L.tick();
         compact_sel_kernel<<<1, 1024, 0, s>>>(d_sel.as<RgSel>(), d_gflags.as<uint8_t>(), d_work.as<uint32_t>() + 3, d_sel2.as<RgSel>());
         L.tick();
         P.sel = d_sel2.as<RgSel>();
       }
-      if (!rest.empty()) k::snappy_pages(L, make_job(rest, tickets + 1), total_rgs * uint32_t(rest.size()));
+      if (!rest.empty()) {
+        k::SnappyJob J2 = make_job(rest, tickets + 1);
+        // after the row-group gate only the rows up to the last gate-passing row (+1) of a row group are ever read from the
+        // non-gate columns — except pk0, which the work-item boundaries probe anywhere (and pk1 when groups are time buckets)
+        if (!first.empty() && !has_ts)
+          for (size_t i = 0; i < rest.size(); i++) J2.partial[i] = rest[i] != 0 ? 1 : 0;
+        k::snappy_pages(L, J2, total_rgs * uint32_t(rest.size()));
+      }
     }
     CU_TRY(cudaEventRecord(e->evd1, s));
     slot_bases_kernel<<<(total_rgs * MAXC + 255) / 256, 256, 0, s>>>(P, d_bases.as<const uint8_t*>(), -1);

@@ -35,6 +35,7 @@ struct SnappyJob {
   uint32_t region[kSnappyMaxCols];     // fixed_stride != 0: scratch region index of entry i inside the row group's block
   uint8_t order[kSnappyMaxCols];       // processing order of the entries (heaviest column first)
   uint8_t skip_stored[kSnappyMaxCols]; // entry i: leave stored (literal-only) pages alone, the consumer reads them in place
+  uint8_t partial[kSnappyMaxCols];     // entry i: only rows [0, RgSel::out_row) of the (single) page are needed: stop decompressing there
   const ColSel* cols;         // general pipeline: column ids + variable scratch offsets come from the ColSel table
   int col_from_cols;
   uint64_t fixed_stride;      // bytes per scratch region, 0 = general pipeline layout

@@ -32,14 +32,14 @@ constexpr int kWin = 256;          // compressed-stream window covered by the ju
 constexpr int kWinPad = 16;        // staged beyond the window: the payload of a <= 8-byte literal that starts near its end
 constexpr int kRing = 4096;        // ring buffer of the most recent output (power of two)
 constexpr int kHist = 2048;        // bytes before the current batch that are guaranteed to still be in the ring
-constexpr int kLevels = 6;         // J1, J2, J4, J8, J16, J32
-constexpr uint32_t kExit = 0xffff;
+constexpr int kLevels = 5;         // J1, J2, J4, J8, J16 (the next batch starts right after the last executed element)
+constexpr uint32_t kExit = 0xff;      // positions inside the window are <= kWin - 5: one byte per table entry
 constexpr int kWarpsPerCta = 4;
 constexpr uint32_t kRestage = kWin - 96;   // start a new window when a batch would begin beyond this position
 
 struct alignas(16) WarpSmem {
   uint64_t ring64[kRing / 8];      // output byte at absolute position x lives at byte x & (kRing-1)
-  uint16_t J[kLevels][kWin];
+  uint8_t J[kLevels][kWin];
   uint8_t win[kWin + kWinPad];
 };
 
@@ -112,16 +112,18 @@ __device__ __forceinline__ uint8_t old_byte(WarpSmem& sm, const uint8_t* dst, ui
   return (o - x <= uint32_t(kHist)) ? ring_bytes(sm)[x & (kRing - 1)] : ldcg_u8(dst + x);
 }
 
-// ring -> global, aligned 8-byte words [fl, align_down(upto)); returns the new flush position
+// ring -> global in whole 32-byte sectors [fl, align_down(upto, 32)), one 8-byte word per lane and trip; returns the new flush
+// position.  (Partial sectors would make L2 fetch the rest of the sector from DRAM before the write-back.)
 __device__ __forceinline__ uint32_t flush_words(const WarpSmem& sm, uint8_t* dst, uint32_t fl, uint32_t upto, int lane) {
-  const uint32_t w0 = fl >> 3, w1 = upto >> 3;
+  const uint32_t w0 = fl >> 3, w1 = (upto >> 5) << 2;
   uint64_t* d8 = reinterpret_cast<uint64_t*>(dst);
   for (uint32_t w = w0 + lane; w < w1; w += 32) d8[w] = sm.ring64[w & (kRing / 8 - 1)];
   return w1 << 3;
 }
 
-__device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, WarpSmem& sm,
-                            int lane, int* err) {
+// stop_at: the consumer only needs the first stop_at bytes of the page (>= ulen: all of it).  Decoding may overshoot by one batch.
+__device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, uint32_t stop_at,
+                            WarpSmem& sm, int lane, int* err) {
   uint32_t pos = 0, ulen = 0;
   for (int sh = 0; pos < n && sh < 35; sh += 7) {
     uint32_t b = __ldg(src + pos++);
@@ -131,8 +133,8 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
   if (ulen != ulen_expected) { if (lane == 0) atomicExch(err, 101); return; }
   uint8_t* const ring = ring_bytes(sm);
   uint32_t o = 0;                 // bytes produced so far
-  uint32_t fl = 0;                // output bytes [0, fl) are in global memory (fl is a multiple of 8, fl <= o)
-  while (pos < n) {
+  uint32_t fl = 0;                // output bytes [0, fl) are in global memory (fl is a multiple of 32, fl <= o)
+  while (pos < n && o < stop_at) {
     const uint32_t avail = n - pos;
     const uint32_t tag0 = __ldg(src + pos);
     // ---- literal with an explicit length field: straight copy
@@ -143,7 +145,7 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       if (1 + nb + len > avail || o + len > ulen || len < 1) { if (lane == 0) atomicExch(err, 102); return; }
       const uint8_t* lsrc = src + pos + 1 + nb;
       __syncwarp();
-      if (uint32_t(lane) < o - fl) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];     // pending partial word
+      if (uint32_t(lane) < o - fl) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];     // pending partial sector (< 32 bytes)
       warp_copy_in(dst + o, lsrc, len, lane);
       // the ring keeps the tail of the literal (whole words where possible)
       const uint32_t keep = len < uint32_t(kHist) ? len : uint32_t(kHist);
@@ -159,7 +161,7 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       __syncwarp();
       pos += 1 + nb + len;
       o += len;
-      fl = o & ~7u;
+      fl = o & ~31u;
       continue;
     }
     // ---- stage the window and build the jump tables.  Lane l owns positions l, l+32, ..: conflict-free table rows.
@@ -176,7 +178,7 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       const uint32_t sz = elem_csize(sm.win[p]);
       const uint32_t nx = p + sz;
       // the NEXT element must start inside the stream and have its (<= 5 byte) header inside the window
-      sm.J[0][p] = (sz == 0 || p >= avail || nx + 5 > uint32_t(kWin) || nx >= avail) ? uint16_t(kExit) : uint16_t(nx);
+      sm.J[0][p] = (sz == 0 || p >= avail || nx + 5 > uint32_t(kWin) || nx >= avail) ? uint8_t(kExit) : uint8_t(nx);
     }
     __syncwarp();
 #pragma unroll
@@ -185,7 +187,7 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       for (int j = 0; j < kWin / 32; j++) {
         const uint32_t p = j * 32 + lane;
         const uint32_t a = sm.J[lv - 1][p];
-        sm.J[lv][p] = a == kExit ? uint16_t(kExit) : sm.J[lv - 1][a];
+        sm.J[lv][p] = a == kExit ? uint8_t(kExit) : sm.J[lv - 1][a];
       }
       __syncwarp();
     }
@@ -294,10 +296,17 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
         T = __shfl_sync(0xffffffffu, inc, cnt - 1);
         if (o + T > ulen) { if (lane == 0) atomicExch(err, 103); return; }
         if (lane < cnt) {
-          const uint32_t base = o + doff;
+          const uint32_t rb = (o + doff) & (kRing - 1);
+          uint8_t* rp = ring + rb;
+          if (rb <= uint32_t(kRing) - 8) {             // no wrap inside the element: fixed offsets from one pointer
 #pragma unroll
-          for (int i = 0; i < 8; i++)
-            if (uint32_t(i) < len) ring[(base + i) & (kRing - 1)] = uint8_t(w >> (8 * i));
+            for (int i = 0; i < 8; i++)
+              if (uint32_t(i) < len) rp[i] = uint8_t(w >> (8 * i));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if (uint32_t(i) < len) ring[(rb + i) & (kRing - 1)] = uint8_t(w >> (8 * i));
+          }
         }
       } else {
         // ---------------- run mode: element 0 is long.  A literal goes alone; a copy takes every following copy with the
@@ -348,15 +357,14 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       fl = flush_words(sm, dst, fl, o, lane);
       // where the next batch starts: right after the last executed element
       const uint32_t adv = __shfl_sync(0xffffffffu, q + csz, cnt - 1);
-      if (cnt == 32) qs = sm.J[5][qs];
-      else qs = __shfl_sync(0xffffffffu, q, cnt & 31);
-      if (qs == kExit || qs != adv || adv > kRestage) { pos += adv; break; }
+      if (adv > kRestage || adv >= avail || o >= stop_at) { pos += adv; break; }      // (kRestage + 5 <= kWin: the next header is staged)
+      qs = adv;
       __syncwarp();
     }
   }
   __syncwarp();
   if (fl + lane < o) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];
-  if (o != ulen) { if (lane == 0) atomicExch(err, 104); }
+  if (o != ulen && stop_at >= ulen) { if (lane == 0) atomicExch(err, 104); }
 }
 
 __device__ __forceinline__ uint64_t chunk_scratch_off2(const RgSel& rs, const ChunkDev* chunks, const ColSel* cols, int ci) {
@@ -370,7 +378,7 @@ __device__ __forceinline__ uint64_t chunk_scratch_off2(const RgSel& rs, const Ch
 // One warp per column chunk, chunks handed out by an atomic ticket in the order (column order[0] of every row group,
 // then order[1], ...): the host lists the columns with the most compressed bytes first, so the long pages start early
 // and the short ones fill the tail.
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_pages_kernel(const __grid_constant__ SnappyJob J) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(const __grid_constant__ SnappyJob J) {
   __shared__ WarpSmem s_w[kWarpsPerCta];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpSmem& sm = s_w[wid];
@@ -401,7 +409,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_pages_kernel(cons
         src += skip; n -= skip; ulen -= skip;
         compressed = pg.v2_compressed != 0;
       }
-      if (compressed) snappy_page(src, n, dst, ulen, sm, lane, J.err);
+      uint32_t stop_at = 0xffffffffu;
+      if (J.partial[ci]) {
+        // the consumer reads rows [0, rs.out_row) only (gate-first: nothing behind the last row that passes the gate column can
+        // survive the filter): level prefix (<= 16 + rows / 8 bytes) + that many values
+        const uint32_t w = (ch.phys == 1 || ch.phys == 4) ? 4u : 8u;
+        stop_at = 16u + (rs.num_rows + 7u) / 8u + 8u + rs.out_row * w;
+      }
+      if (compressed) snappy_page(src, n, dst, ulen, stop_at, sm, lane, J.err);
       dst += page_scratch2(pg.uncomp_size);
       if (pg.encoding == 5) dst += page_scratch2(pg.num_values * 8u);     // PLAIN image of a DELTA_BINARY_PACKED page (decode_chunks)
     }
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) snappy_pages_kernel(cons
 void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks) {
   if (!max_chunks) return;
   uint32_t ctas = (max_chunks + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (ctas > 148u * 6) ctas = 148u * 6;
+  if (ctas > 148u * 8) ctas = 148u * 8;
   snappy_pages_kernel<<<ctas, kWarpsPerCta * 32, 0, L.stream>>>(job);
   L.tick();
 }

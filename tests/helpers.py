@@ -22,6 +22,28 @@ def record_batch(schema: pa.Schema, cols: dict) -> pa.RecordBatch:
     return pa.RecordBatch.from_arrays(arrays, schema=schema)
 
 
+def arrays_equal(a, b) -> bool:
+    """Array equality that treats floats by BIT PATTERN (NaN == NaN, -0.0 != +0.0): parity means identical bytes."""
+    import numpy as np
+    if isinstance(a, pa.ChunkedArray):
+        a = a.combine_chunks()
+    if isinstance(b, pa.ChunkedArray):
+        b = b.combine_chunks()
+    if a.type != b.type:
+        a = a.cast(b.type)
+    if not pa.types.is_floating(b.type):
+        return a.equals(b)
+    if len(a) != len(b) or a.null_count != b.null_count:
+        return False
+    va, vb = a.is_valid().to_numpy(zero_copy_only=False), b.is_valid().to_numpy(zero_copy_only=False)
+    if not np.array_equal(va, vb):
+        return False
+    it = np.uint64 if b.type == pa.float64() else np.uint32
+    xa = a.fill_null(0).to_numpy(zero_copy_only=False).view(it)
+    xb = b.fill_null(0).to_numpy(zero_copy_only=False).view(it)
+    return bool(np.array_equal(xa[va], xb[vb]))
+
+
 def check_stream(actual_batches, expected_batches):
     """`check_stream` (test_util.rs:150-165): batch-by-batch equality INCLUDING batch boundaries."""
     actual_batches = list(actual_batches)
@@ -32,5 +54,5 @@ def check_stream(actual_batches, expected_batches):
         assert a.schema.names == e.schema.names, f"batch {i} names {a.schema.names} != {e.schema.names}"
         assert a.num_rows == e.num_rows, f"batch {i} rows {a.num_rows} != {e.num_rows}"
         for c in range(a.num_columns):
-            assert a.column(c).cast(e.column(c).type).equals(e.column(c)), (
+            assert arrays_equal(a.column(c), e.column(c)), (
                 f"batch {i} column {a.schema.names[c]}: {a.column(c)} != {e.column(c)}")

@@ -13,7 +13,7 @@ from horaedb_b200._ffi import Engine, SchemaHandle, SstInput, parquet_inspect
 from horaedb_b200.config import ParquetCompression, WriteConfig
 from oracle import oracle
 
-from helpers import arrow_schema, check_stream, record_batch
+from helpers import arrays_equal, arrow_schema, check_stream, record_batch
 
 pytestmark = pytest.mark.gpu
 _ids = iter(range(90_000_000, 95_000_000))
@@ -114,9 +114,9 @@ def test_writer_all_types_nulls_and_empty(tmp_path):
         got = pq.read_table(path)
         for name in exp.schema.names:
             assert got[name].type == exp[name].type, name
-            assert got[name].combine_chunks().equals(exp[name].combine_chunks()), name
+            assert arrays_equal(got[name], exp[name]), name
         again = pa.Table.from_batches(oracle.scan([open(path, "rb").read()], schema.arrow_schema, 2, (), True, 8192).batches)
-        assert again.equals(exp)
+        assert all(arrays_equal(again[name], exp[name]) for name in exp.schema.names)
         md = pq.ParquetFile(path).metadata
         st = md.row_group(0).column(exp.schema.names.index("i32")).statistics
         part = exp["i32"].combine_chunks().slice(0, 500)
