@@ -488,74 +488,160 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
       kept.push_back(KeptRg{uint32_t(j), uint32_t(g)});
     }
   }
-  // ---- late materialisation across PCIe: when one predicate column is plain and null-free in every file, move ITS chunks
-  //      first, let the device find the row groups that hold a passing row, and move the other columns only for those.
+  // ---- late materialisation across PCIe: when one predicate column is a single PLAIN page without NULLs in every file (Snappy or
+  //      not), move ITS chunks first, let the device find — per row group — the first and the last row that pass its predicates,
+  //      and move the other columns only for row groups that have one; of the non-key columns that can be addressed by row
+  //      (uncompressed PLAIN pages, stored Snappy pages) only the rows between the first and the last passing row.
+  //      The filter precedes merge and dedup (read.rs:459-480): rows that fail the gate take part in nothing downstream.
   int gate_col = -1;
   if (prune && np && !(e->flags & HG_FLAG_NO_LATE_MATERIALIZATION) && need_cols.size() > 1 && !kept.empty()) {
-    uint32_t best_w = 16;
+    uint64_t best_bytes = ~0ull;
     for (size_t i = 0; i < np; i++) {
       const uint32_t c = preds[i].column;
       bool ok = c < uint32_t(MAX_COLS);
       for (size_t i2 = 0; i2 < np; i2++) if (preds[i2].column == c && preds[i2].op == HG_OP_IN) ok = false;   // the gate kernel tests intervals
-      for (size_t j = 0; j < k && ok; j++) ok = rs[j]->rows_total == 0 || (rs[j]->col_all_simple[c] && rs[j]->col_null_none[c]);
-      const uint32_t w = type_width_host(schema->types[c]) <= 4 ? 4u : 8u;
-      if (ok && w < best_w) { best_w = w; gate_col = int(c); }
+      uint64_t bytes = 0;
+      for (size_t j = 0; j < k && ok; j++) {
+        ok = rs[j]->rows_total == 0 || (rs[j]->col_all_single[c] && rs[j]->col_null_none[c]);
+        bytes += rs[j]->col_comp_bytes[c];
+      }
+      if (ok && bytes < best_bytes) { best_bytes = bytes; gate_col = int(c); }
     }
-    uint32_t need_w = 0;
-    for (uint32_t c : need_cols) need_w += type_width_host(schema->types[c]) <= 4 ? 4u : 8u;
-    if (gate_col >= 0 && best_w * 3 > need_w) gate_col = -1;          // the gate would be most of the bytes anyway
+    uint64_t need_bytes = 0;
+    for (uint32_t c : need_cols) for (size_t j = 0; j < k; j++) need_bytes += rs[j]->col_comp_bytes[c];
+    if (gate_col >= 0 && best_bytes * 3 > need_bytes) gate_col = -1;          // the gate would be most of the bytes anyway
   }
+  std::vector<fused::GateOut> gate_out;
   if (gate_col >= 0) {
     std::vector<CopyRange> ranges;
     std::vector<fused::GateRg> descs(kept.size());
+    std::vector<k::RawPage> raw;
+    const uint32_t gw = type_width_host(schema->types[gate_col]) <= 4 ? 4u : 8u;
     for (size_t i = 0; i < kept.size(); i++) {
       const size_t j = kept[i].j;
       const uint32_t g = kept[i].g;
       SstResident& r = *rs[j];
       add_range(ranges, j, g, uint32_t(gate_col));
       const ChunkDev& cd = chunks[j][size_t(g) * size_t(r.meta.ncols) + size_t(gate_col)];
-      uint64_t off = pages[j][cd.first_page].payload_off;
-      if (cd.optional) {                                    // [u32 len][RLE def levels] in front of the values (all valid here)
-        uint32_t len = 0;
-        if (off + 4 > r.size) return set_error(HG_ERR_FORMAT, "page payload out of bounds");
-        std::memcpy(&len, datas[j] + off, 4);
-        off += 4 + uint64_t(len);
+      const PageDev& pg = pages[j][cd.first_page];
+      uint64_t off = pg.payload_off;
+      if (cd.codec == CODEC_SNAPPY) {
+        // decompressed on the device into arena scratch; the level prefix is skipped there
+        uint8_t* dst = static_cast<uint8_t*>(g_arena->alloc(page_scratch_bytes(pg.uncomp_size) + 16));
+        if (!dst) return set_error(HG_ERR_OOM, "out of device memory");
+        raw.push_back(k::RawPage{r.d_bytes + off, dst, pg.comp_size, pg.uncomp_size});
+        if (uint64_t(pg.uncomp_size) < uint64_t(r.rg_rows[g]) * gw) return set_error(HG_ERR_FORMAT, "column chunk smaller than its values");
+        descs[i] = fused::GateRg{dst, r.rg_rows[g], cd.optional ? 1u : 0u};
+      } else {
+        if (cd.optional) {                                  // [u32 len][RLE def levels] in front of the values (all valid here)
+          uint32_t len = 0;
+          if (off + 4 > r.size) return set_error(HG_ERR_FORMAT, "page payload out of bounds");
+          std::memcpy(&len, datas[j] + off, 4);
+          off += 4 + uint64_t(len);
+        }
+        if (off + uint64_t(r.rg_rows[g]) * gw > r.size) return set_error(HG_ERR_FORMAT, "column chunk out of bounds");
+        descs[i] = fused::GateRg{r.d_bytes + off, r.rg_rows[g], 0};
       }
-      if (off + uint64_t(r.rg_rows[g]) * (type_width_host(schema->types[gate_col]) <= 4 ? 4u : 8u) > r.size)
-        return set_error(HG_ERR_FORMAT, "column chunk out of bounds");
-      descs[i] = fused::GateRg{r.d_bytes + off, r.rg_rows[g], 0};
     }
     int rc = move_ranges(ranges);
     if (rc) return rc;
     fused::GateRg* d_descs = static_cast<fused::GateRg*>(g_arena->alloc(descs.size() * sizeof(fused::GateRg)));
-    uint8_t* d_flags = static_cast<uint8_t*>(g_arena->alloc(kept.size() + 16));
-    if (!d_descs || !d_flags) return set_error(HG_ERR_OOM, "out of device memory");
+    fused::GateOut* d_out = static_cast<fused::GateOut*>(g_arena->alloc(kept.size() * sizeof(fused::GateOut) + 16));
+    uint32_t* d_tick = static_cast<uint32_t*>(g_arena->alloc(64));
+    if (!d_descs || !d_out || !d_tick) return set_error(HG_ERR_OOM, "out of device memory");
+    CU_TRY(cudaMemsetAsync(d_tick, 0, 64, e->stream));
+    if (!raw.empty()) {
+      k::RawPage* d_raw = static_cast<k::RawPage*>(g_arena->alloc(raw.size() * sizeof(k::RawPage)));
+      if (!d_raw) return set_error(HG_ERR_OOM, "out of device memory");
+      rc = stage_upload(e, d_raw, raw.data(), raw.size() * sizeof(k::RawPage), &stage_off);
+      if (rc) return rc;
+      k::snappy_raw_pages(e->L(), d_raw, uint32_t(raw.size()), d_tick, reinterpret_cast<int*>(d_tick + 1));
+    }
     rc = stage_upload(e, d_descs, descs.data(), descs.size() * sizeof(fused::GateRg), &stage_off);
     if (rc) return rc;
     hg_predicate gp[MAX_PREDS];
     size_t ngp = 0;
     for (size_t i = 0; i < np; i++) if (int(preds[i].column) == gate_col) gp[ngp++] = preds[i];
-    rc = fused::gate_row_groups(e, d_descs, uint32_t(kept.size()), schema->types[gate_col], gp, ngp, d_flags);
+    rc = fused::gate_row_groups(e, d_descs, uint32_t(kept.size()), schema->types[gate_col], gp, ngp, d_out);
     if (rc) return rc;
-    std::vector<uint8_t> flags(kept.size());
-    CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, kept.size(), cudaMemcpyDeviceToHost, e->stream));
+    gate_out.resize(kept.size());
+    int herr = 0;
+    CU_TRY(cudaMemcpyAsync(gate_out.data(), d_out, kept.size() * sizeof(fused::GateOut), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(&herr, d_tick + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
-    e->stats.bytes_d2h += kept.size();
+    if (herr) return set_error(HG_ERR_FORMAT, "device decode error code " + std::to_string(herr) + " (gate column)");
+    e->stats.bytes_d2h += kept.size() * sizeof(fused::GateOut);
     e->stage_cursor = 0;                                    // the stream is idle: the staging buffer can be reused
     for (size_t j = 0; j < k; j++) rs[j]->rg_dead.assign(rs[j]->rg_rows.size(), 0);
     std::vector<KeptRg> alive;
+    std::vector<fused::GateOut> alive_out;
     for (size_t i = 0; i < kept.size(); i++) {
-      if (flags[i]) alive.push_back(kept[i]);
+      if (gate_out[i].first <= gate_out[i].last) { alive.push_back(kept[i]); alive_out.push_back(gate_out[i]); }
       else rs[kept[i].j]->rg_dead[kept[i].g] = 1;
     }
     kept.swap(alive);
+    gate_out.swap(alive_out);
   }
   // ---- the remaining columns of the row groups still in play
   {
     std::vector<CopyRange> ranges;
-    for (const KeptRg& kr : kept)
-      for (uint32_t c : need_cols)
-        if (int(c) != gate_col) add_range(ranges, kr.j, kr.g, c);
+    auto add_bytes = [&](size_t j, uint64_t lo, uint64_t hi) {           // file byte range [lo, hi) (+ slack for the unaligned loads)
+      SstResident& r = *rs[j];
+      hi = std::min<uint64_t>(r.size, hi + 16);
+      if (lo >= hi) return;
+      if (!ranges.empty() && ranges.back().src + ranges.back().bytes >= datas[j] + lo && ranges.back().src <= datas[j] + lo &&
+          ranges.back().dst == r.d_bytes + (ranges.back().src - datas[j])) {
+        const uint64_t b0 = uint64_t(ranges.back().src - datas[j]);
+        ranges.back().bytes = std::max<uint64_t>(b0 + ranges.back().bytes, hi) - b0;
+      } else ranges.push_back(CopyRange{datas[j] + lo, r.d_bytes + lo, hi - lo});
+    };
+    for (size_t i = 0; i < kept.size(); i++) {
+      const KeptRg& kr = kept[i];
+      SstResident& r = *rs[kr.j];
+      for (uint32_t c : need_cols) {
+        if (int(c) == gate_col) continue;
+        const ChunkDev& cd = chunks[kr.j][size_t(kr.g) * size_t(r.meta.ncols) + c];
+        const RgCol& rc = r.rgcol[size_t(kr.g) * size_t(r.meta.ncols) + c];
+        const bool by_row = !gate_out.empty() && c >= schema->num_primary_keys && rc.single_page && rc.null_none &&
+                            (cd.codec == CODEC_UNCOMPRESSED || cd.stored);
+        if (!by_row) { add_range(ranges, kr.j, kr.g, c); continue; }
+        // rows [first, last] of a page whose values can be addressed by row
+        const PageDev& pg = pages[kr.j][cd.first_page];
+        const uint32_t w = (cd.phys == PT_INT32 || cd.phys == PT_FLOAT) ? 4u : 8u;
+        const uint64_t first = gate_out[i].first, last = gate_out[i].last;
+        const uint8_t* base = datas[kr.j];
+        uint64_t body = pg.payload_off;
+        if (cd.codec == CODEC_UNCOMPRESSED) {
+          uint64_t prefix = 0;
+          if (cd.optional) { uint32_t dl; std::memcpy(&dl, base + body, 4); prefix = 4 + uint64_t(dl); }
+          add_bytes(kr.j, body, body + prefix);
+          add_bytes(kr.j, body + prefix + first * w, body + prefix + (last + 1) * w);
+        } else {
+          // stored page (classify_stored): [varint][literal 0 = level prefix + n0 values][literal 1 = the remaining values]
+          uint64_t p = body;
+          while (base[p] & 0x80) p++;
+          p++;
+          auto lit = [&](uint64_t at, uint64_t* len) -> uint64_t {
+            uint64_t l = base[at] >> 2, hdr = 1;
+            if (l >= 60) { const uint64_t nb = l - 59; l = 0; for (uint64_t q = 0; q < nb; q++) l |= uint64_t(base[at + 1 + q]) << (8 * q); hdr = 1 + nb; }
+            *len = l + 1;
+            return hdr;
+          };
+          uint64_t len0 = 0, len1 = 0;
+          const uint64_t lit0 = p + lit(p, &len0);
+          uint64_t prefix = 0;
+          if (cd.optional) { uint32_t dl; std::memcpy(&dl, base + lit0, 4); prefix = 4 + uint64_t(dl); }
+          const uint64_t n0 = (len0 - prefix) / w;
+          add_bytes(kr.j, body, lit0 + prefix);
+          if (first < n0) add_bytes(kr.j, lit0 + prefix + first * w, lit0 + prefix + (std::min<uint64_t>(last, n0 - 1) + 1) * w);
+          if (lit0 + len0 < body + pg.comp_size) {
+            const uint64_t lit1 = lit0 + len0 + lit(lit0 + len0, &len1);
+            add_bytes(kr.j, lit0 + len0, lit1);
+            if (last >= n0) add_bytes(kr.j, lit1 + (std::max<uint64_t>(first, n0) - n0) * w, lit1 + (last - n0 + 1) * w);
+          }
+        }
+      }
+    }
     int rc = move_ranges(ranges);
     if (rc) return rc;
   }

@@ -1026,24 +1026,31 @@ bool is_int_type(uint32_t t) { return t != T_F32 && t != T_F64; }
 
 struct GatePreds { int n; uint32_t kind, cls, _pad; uint32_t op[MAX_PREDS]; uint64_t lit[MAX_PREDS]; };
 __global__ void __launch_bounds__(256) gate_rgs_kernel(const GateRg* __restrict__ rgs, uint32_t n, const __grid_constant__ GatePreds gp,
-                                                       uint8_t* __restrict__ flags) {
+                                                       GateOut* __restrict__ out) {
+  __shared__ uint32_t s_first, s_last;
   for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
     const GateRg g = rgs[r];
-    bool any = false;
+    const uint8_t* vals = g.vals;
+    if (g.prefixed) vals += 4 + ld32u(vals);
+    if (threadIdx.x == 0) { s_first = 0xffffffffu; s_last = 0; }
+    __syncthreads();
+    uint32_t first = 0xffffffffu, last = 0;             // last = 1 + index
     for (uint32_t i = threadIdx.x; i < g.nrows; i += 256) {
-      const uint64_t v = load_kind(g.vals, gp.kind, i);
+      const uint64_t v = load_kind(vals, gp.kind, i);
       bool ok = true;
       for (int p = 0; p < gp.n; p++) ok = ok && pred_ok(v, gp.lit[p], gp.cls, gp.op[p]);
-      any = any || ok;
+      if (ok) { first = first < i ? first : i; last = i + 1; }
     }
-    const int a = __syncthreads_or(any);
-    if (threadIdx.x == 0) flags[r] = a ? 1 : 0;
+    if (last) { atomicMin(&s_first, first); atomicMax(&s_last, last); }
+    __syncthreads();
+    if (threadIdx.x == 0) out[r] = s_last ? GateOut{s_first, s_last - 1} : GateOut{1u, 0u};
+    __syncthreads();
   }
 }
 
 }  // namespace
 
-int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type, const hg_predicate* preds, size_t np, uint8_t* d_flags) {
+int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type, const hg_predicate* preds, size_t np, GateOut* d_out) {
   if (n == 0) return HG_OK;
   if (np == 0 || np > size_t(MAX_PREDS)) return set_error(HG_ERR_INTERNAL, "gate_row_groups: bad predicate count");
   GatePreds gp;
@@ -1053,7 +1060,7 @@ int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type
                                                                : (type == T_F32 ? K_F32 : ((type == T_I8 || type == T_I16 || type == T_I32) ? K_I32 : K_U32));
   gp.cls = type_is_float(type) ? C_FLOAT : (type_is_signed(type) ? C_SIGNED : C_UNSIGNED);
   for (size_t i = 0; i < np; i++) { gp.op[i] = preds[i].op; gp.lit[i] = pred_literal(preds[i], type); }
-  gate_rgs_kernel<<<int(std::min<uint32_t>(n, 148u * 16u)), 256, 0, e->stream>>>(d_rgs, n, gp, d_flags);
+  gate_rgs_kernel<<<int(std::min<uint32_t>(n, 148u * 16u)), 256, 0, e->stream>>>(d_rgs, n, gp, d_out);
   e->launches++;
   CU_TRY(cudaGetLastError());
   return HG_OK;

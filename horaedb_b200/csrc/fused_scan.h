@@ -14,7 +14,12 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
 // column over the PLAIN values of n row groups (already on the device) and writes flags[i] = 1 iff some row passes.
 // The filter runs before merge/dedup (read.rs:459-480), so a row group without a passing row contributes nothing and
 // its other columns never have to cross PCIe.  Launched on the engine's stream.
-struct GateRg { const uint8_t* vals; uint32_t nrows, _pad; };
-int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type, const hg_predicate* preds, size_t np, uint8_t* d_flags);
+struct GateRg {
+  const uint8_t* vals;       // PLAIN values of the gate column — or, with `prefixed`, the page body [u32 len][levels][values]
+  uint32_t nrows, prefixed;  //   (a Snappy page decompressed on the device: the level length is only known there)
+};
+// first / last = the first and the last row (0-based) that pass; first > last: no row passes
+struct GateOut { uint32_t first, last; };
+int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type, const hg_predicate* preds, size_t np, GateOut* d_out);
 }  // namespace fused
 }  // namespace horae

@@ -44,6 +44,9 @@ struct SnappyJob {
   int* err;
 };
 void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks);
+// raw Snappy streams by pointer: dst must be 16-byte aligned with uncomp_size + 48 bytes of room; ticket = zeroed device counter
+struct RawPage { const uint8_t* src; uint8_t* dst; uint32_t comp_size, uncomp_size; };
+void snappy_raw_pages(const Launch& L, const RawPage* d_pages, uint32_t n, unsigned int* ticket, int* err);
 void decode_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols,
                    int ncolsel, uint8_t* scratch, int* err);
 

@@ -423,7 +423,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
   }
 }
 
+// pages given by pointer (transient loads decompress the gate column before the SST's tables exist on the device)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_raw_kernel(const RawPage* __restrict__ pages, uint32_t n, unsigned int* ticket, int* err) {
+  __shared__ WarpSmem s_w[kWarpsPerCta];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (;;) {
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(ticket, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= n) return;
+    const RawPage pg = pages[c];
+    snappy_page(pg.src, pg.comp_size, pg.dst, pg.uncomp_size, 0xffffffffu, s_w[wid], lane, err);
+  }
+}
+
 }  // namespace
+
+void snappy_raw_pages(const Launch& L, const RawPage* d_pages, uint32_t n, unsigned int* ticket, int* err) {
+  if (!n) return;
+  uint32_t ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (ctas > 148u * 8) ctas = 148u * 8;
+  snappy_raw_kernel<<<ctas, kWarpsPerCta * 32, 0, L.stream>>>(d_pages, n, ticket, err);
+  L.tick();
+}
 
 void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks) {
   if (!max_chunks) return;
