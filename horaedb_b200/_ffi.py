@@ -107,7 +107,7 @@ class HgParquetChunk(C.Structure):
 EXPORTS = ["hg_abi_version", "hg_last_error", "hg_engine_create", "hg_engine_destroy", "hg_engine_stream", "hg_engine_set_flags", "hg_sst_load",
            "hg_sst_unload", "hg_sst_resident_bytes", "hg_scan_open", "hg_compact_open", "hg_scan_aggregate",
            "hg_scan_aggregate_device", "hg_agg_export_packed", "hg_last_stats", "hg_parquet_inspect", "hg_parquet_chunk_info", "hg_plan_row_groups",
-           "hg_compact_to_sst", "hg_plan_pk_splitters", "hg_comm_unique_id", "hg_comm_init", "hg_comm_destroy", "hg_agg_combine", "hg_comm_sync"]
+           "hg_compact_to_sst", "hg_write_batch", "hg_plan_pk_splitters", "hg_comm_unique_id", "hg_comm_init", "hg_comm_destroy", "hg_agg_combine", "hg_comm_sync"]
 
 _lib = None
 
@@ -305,6 +305,30 @@ class Engine:
         meta = HgFileMeta()
         _check(self._L.hg_compact_to_sst(self._h, C.byref(schema.desc), arr, C.c_size_t(len(ssts)), p, C.c_size_t(len(shard_preds)), C.byref(props),
                                          out_path.encode(), C.byref(meta)))
+        return meta
+
+    def write_batch(self, schema: SchemaHandle, batch: pa.RecordBatch, sequence: int, out_path: str, max_row_group_size: int = 8192,
+                    compression: str = "snappy", enable_sorting_columns: bool = True) -> "HgFileMeta":
+        """`ObjectBasedStorage::write_batch` on the GPU (storage.rs:189-225): sort by the primary keys, append the builtin columns,
+        encode, write `out_path`.  `batch` holds the USER columns; it travels as an Arrow C struct array."""
+        user = len(schema.arrow_schema) - 2
+        if batch.num_columns != user:
+            raise HgError(1, f"batch has {batch.num_columns} columns, the schema has {user} user columns")
+        cols = [batch.column(i).cast(schema.arrow_schema.field(i).type) for i in range(user)]
+        st = pa.StructArray.from_arrays(cols, fields=[schema.arrow_schema.field(i) for i in range(user)])
+
+        class _CArray(C.Structure):
+            _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64), ("n_children", C.c_int64),
+                        ("buffers", C.c_void_p), ("children", C.c_void_p), ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+        carr = _CArray()
+        st._export_to_c(C.addressof(carr))
+        props = HgWriteProps(max_row_group_size, {"none": 0, "uncompressed": 0, "snappy": 1}[compression.lower()], int(enable_sorting_columns), 0)
+        meta = HgFileMeta()
+        try:
+            _check(self._L.hg_write_batch(self._h, C.byref(schema.desc), C.byref(carr), C.c_uint64(sequence), C.byref(props), out_path.encode(), C.byref(meta)))
+        finally:
+            pa.Array._import_from_c(C.addressof(carr), st.type)      # takes the exported array back: its release callback runs on GC
         return meta
 
     def scan_aggregate(self, schema: SchemaHandle, ssts: Sequence[SstInput], preds: Sequence[tuple] = (), group_col: int = 0,

@@ -1717,6 +1717,116 @@ int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   HG_GUARD_END
 }
 
+int hg_write_batch(hg_engine* e, const hg_schema_desc* schema, const struct ArrowArray* batch, uint64_t sequence, const hg_write_props* props,
+                   const char* out_path, hg_file_meta* out) {
+  HG_GUARD_BEGIN
+  if (!e || !batch || !props || !out_path || !out) return set_error(HG_ERR_INVALID, "null argument");
+  int rc = validate_schema(schema);
+  if (rc) return rc;
+  const uint32_t ncols = schema->num_columns, user = ncols - 2, npk = schema->num_primary_keys;
+  if (batch->n_children != int64_t(user)) return set_error(HG_ERR_INVALID, "batch must hold the user columns of the schema");
+  if (batch->length < 0 || batch->length >= 0xfffffff0ll) return set_error(HG_ERR_UNSUPPORTED, "batch larger than 2^32 rows");
+  if (batch->null_count > 0) return set_error(HG_ERR_UNSUPPORTED, "NULL rows (struct-level validity) are not supported");
+  const uint32_t n = uint32_t(batch->length);
+  std::lock_guard<std::mutex> g(e->mu);
+  CU_TRY(cudaSetDevice(e->device));
+  std::memset(&e->stats, 0, sizeof(e->stats));
+  e->launches = 0;
+  e->stage_cursor = 0;
+  e->arena.reset();
+  g_arena = &e->arena;
+  cudaStream_t s = e->stream;
+  Launch L = e->L();
+  CU_TRY(cudaEventRecord(e->ev0, s));
+  // ---- upload the user columns (values + validity expanded to one byte per row)
+  std::vector<DevBuf> vals(ncols), valid(ncols), sorted(ncols), svalid(ncols);
+  std::vector<ColView> views(ncols);
+  uint64_t h2d = 0;
+  for (uint32_t c = 0; c < user; c++) {
+    const struct ArrowArray* col = batch->children[c];
+    if (!col || col->n_buffers < 2 || col->length != batch->length) return set_error(HG_ERR_INVALID, "column " + std::to_string(c) + ": not a primitive array of the batch's length");
+    const uint32_t w = type_width_host(schema->types[c]);
+    CU_TRY(vals[c].alloc(size_t(n) * w + 16, s));
+    if (n) {
+      if (!col->buffers[1]) return set_error(HG_ERR_INVALID, "column without a data buffer");
+      CU_TRY(cudaMemcpyAsync(vals[c].p, static_cast<const uint8_t*>(col->buffers[1]) + size_t(col->offset) * w, size_t(n) * w, cudaMemcpyHostToDevice, s));
+      h2d += size_t(n) * w;
+    }
+    const bool has_nulls = col->null_count != 0 && col->buffers[0] != nullptr;
+    if (has_nulls) {
+      if (c < npk) return set_error(HG_ERR_UNSUPPORTED, "NULL primary keys are not supported on the GPU path");
+      const size_t nbytes = size_t((col->offset + col->length + 7) / 8);
+      DevBuf bm;
+      CU_TRY(bm.alloc(nbytes + 16, s));
+      CU_TRY(cudaMemcpyAsync(bm.p, col->buffers[0], nbytes, cudaMemcpyHostToDevice, s));
+      CU_TRY(valid[c].alloc(size_t(n) + 16, s));
+      k::unpack_bitmap(L, bm.as<uint8_t>(), uint64_t(col->offset), n, valid[c].as<uint8_t>());
+      bm.release();                          // arena memory: stays valid until the next call
+      h2d += nbytes;
+    }
+    views[c] = ColView{vals[c].p, has_nulls ? valid[c].as<uint8_t>() : nullptr, schema->types[c], w};
+  }
+  // ---- sort by (pk0, .., pkN-1): LSD over the key columns, last key first; every pass is a stable radix sort
+  DevBuf perm, perm2, keys, keys2, counts, d_n;
+  CU_TRY(perm.alloc(size_t(n) * 4 + 16, s));
+  CU_TRY(perm2.alloc(size_t(n) * 4 + 16, s));
+  CU_TRY(keys.alloc(size_t(n) * 8 + 16, s));
+  CU_TRY(keys2.alloc(size_t(n) * 8 + 16, s));
+  CU_TRY(counts.alloc(k::radix_tmp_elems(n) * 4, s));
+  CU_TRY(d_n.alloc(16, s));
+  k::fill_u32(L, d_n.as<uint32_t>(), n, 4);
+  k::iota_u32(L, perm.as<uint32_t>(), n);
+  uint32_t* pcur = perm.as<uint32_t>();
+  uint32_t* palt = perm2.as<uint32_t>();
+  for (int c = int(npk) - 1; c >= 0 && n > 1; c--) {
+    k::column_sort_keys(L, views[c], pcur, n, keys.as<uint64_t>());
+    const uint32_t t = schema->types[c];
+    const int bits = (type_is_signed(t) || type_is_float(t)) ? 64 : 8 * int(type_width_host(t));
+    if (k::radix_sort_pairs(L, keys.as<uint64_t>(), pcur, keys2.as<uint64_t>(), palt, d_n.as<uint32_t>(), n, bits, counts.as<uint32_t>())) std::swap(pcur, palt);
+  }
+  // ---- gather into sorted columns, append the builtin columns
+  std::vector<writer::ColIn> cols(ncols);
+  for (uint32_t c = 0; c < user; c++) {
+    const uint32_t w = views[c].width;
+    CU_TRY(sorted[c].alloc(size_t(n) * w + 16, s));
+    if (views[c].valid) CU_TRY(svalid[c].alloc(size_t(n) + 16, s));
+    k::gather_column(L, views[c], pcur, d_n.as<uint32_t>(), n, sorted[c].p, svalid[c].as<uint8_t>());
+    cols[c] = writer::ColIn{sorted[c].p, views[c].valid ? svalid[c].as<uint8_t>() : nullptr, schema->types[c], w};
+  }
+  CU_TRY(sorted[user].alloc(size_t(n) * 8 + 16, s));
+  k::fill_u64(L, sorted[user].as<uint64_t>(), sequence, n);
+  cols[user] = writer::ColIn{sorted[user].p, nullptr, T_U64, 8};
+  CU_TRY(sorted[user + 1].alloc(size_t(n) * 8 + 16, s));
+  CU_TRY(svalid[user + 1].alloc(size_t(n) + 16, s));
+  CU_TRY(cudaMemsetAsync(sorted[user + 1].p, 0, size_t(n) * 8 + 16, s));
+  CU_TRY(cudaMemsetAsync(svalid[user + 1].p, 0, size_t(n) + 16, s));
+  cols[user + 1] = writer::ColIn{sorted[user + 1].p, svalid[user + 1].as<uint8_t>(), T_U64, 8};
+  uint8_t* host = nullptr;
+  uint64_t size = 0;
+  rc = writer::write_sst(e, schema, cols.data(), ncols, n, props, &host, &size);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord(e->ev1, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  FILE* f = std::fopen(out_path, "wb");
+  bool ok = f != nullptr;
+  if (ok) ok = std::fwrite(host, 1, size_t(size), f) == size_t(size);
+  if (f) ok = std::fclose(f) == 0 && ok;
+  cudaFreeHost(host);
+  if (!ok) return set_error(HG_ERR_NOT_FOUND, std::string("cannot write ") + out_path);
+  std::memset(out, 0, sizeof(*out));
+  out->size = size;
+  out->num_rows = n;
+  out->max_sequence = sequence;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.gpu_ms = ms;
+  e->stats.bytes_h2d = h2d;
+  e->stats.rows_out = n;
+  e->stats.kernel_launches = e->launches;
+  return HG_OK;
+  HG_GUARD_END
+}
+
 int hg_compact_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, struct ArrowArrayStream* out) {
   HG_GUARD_BEGIN
   // Executor::do_compaction builds the same plan with no predicate and keep_builtin = true (executor.rs:164-169)

@@ -120,6 +120,11 @@ int radix_sort_pairs(const Launch& L, uint64_t* keys, uint32_t* vals, uint64_t* 
 // order-preserving sort keys of the rows `rows[0..*d_r)`: gk = group value, bk = bucket start (either may be null); vals = rows
 void group_sort_keys(const Launch& L, const AggSpecDev& spec, const uint32_t* rows, const uint32_t* d_r, uint32_t cap, uint64_t* gk, uint64_t* bk,
                      uint32_t* vals);
+// write path helpers (radix_agg.cu)
+void column_sort_keys(const Launch& L, ColView col, const uint32_t* perm, uint32_t n, uint64_t* keys);
+void iota_u32(const Launch& L, uint32_t* p, uint32_t n);
+void fill_u64(const Launch& L, uint64_t* p, uint64_t v, uint32_t n);
+void unpack_bitmap(const Launch& L, const uint8_t* bitmap, uint64_t offset, uint32_t n, uint8_t* out);
 void fill_u32(const Launch& L, uint32_t* p, uint32_t v, uint32_t n);
 // dst[6][cap] int64: key, bucket, count, sum/min/max bit patterns; zero beyond g
 void pack_agg(const Launch& L, AggOut in, uint32_t gwidth, uint64_t g, uint64_t cap, long long* dst);

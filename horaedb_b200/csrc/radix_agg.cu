@@ -6,6 +6,8 @@
 // single-threaded hash aggregation that sees the rows in stream order (the oracle's definition).
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace horae {
 namespace k {
 
@@ -145,7 +147,52 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* counts, uint
   }
 }
 
+// write path (sort_batch, storage.rs:244-256): order-preserving key of one primary-key column for the rows perm[0..n)
+__global__ void __launch_bounds__(kThreads) column_sort_keys_kernel(ColView col, const uint32_t* __restrict__ perm, uint32_t n, uint64_t* __restrict__ keys) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    uint64_t v = widened_at(col, perm[i]);
+    const uint32_t t = col.type;
+    if (t == T_F32 || t == T_F64) v = f64_total_order_key(v);
+    else if (t == T_I8 || t == T_I16 || t == T_I32 || t == T_I64) v ^= 1ull << 63;
+    keys[i] = v;
+  }
+}
+__global__ void __launch_bounds__(kThreads) iota_kernel(uint32_t* p, uint32_t n) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) p[i] = i;
+}
+__global__ void __launch_bounds__(kThreads) fill_u64_kernel(uint64_t* p, uint64_t v, uint32_t n) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) p[i] = v;
+}
+// Arrow validity bitmap (bit i of byte i/8, LSB first, starting at bit `offset`) -> one byte per row
+__global__ void __launch_bounds__(kThreads) unpack_bitmap_kernel(const uint8_t* __restrict__ bitmap, uint64_t offset, uint32_t n, uint8_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const uint64_t b = offset + i;
+    out[i] = (bitmap[b >> 3] >> (b & 7)) & 1u;
+  }
+}
+
 }  // namespace
+
+void column_sort_keys(const Launch& L, ColView col, const uint32_t* perm, uint32_t n, uint64_t* keys) {
+  if (!n) return;
+  column_sort_keys_kernel<<<int(std::min<uint64_t>((uint64_t(n) + kThreads - 1) / kThreads, 148 * 16)), kThreads, 0, L.stream>>>(col, perm, n, keys);
+  L.tick();
+}
+void iota_u32(const Launch& L, uint32_t* p, uint32_t n) {
+  if (!n) return;
+  iota_kernel<<<int(std::min<uint64_t>((uint64_t(n) + kThreads - 1) / kThreads, 148 * 16)), kThreads, 0, L.stream>>>(p, n);
+  L.tick();
+}
+void fill_u64(const Launch& L, uint64_t* p, uint64_t v, uint32_t n) {
+  if (!n) return;
+  fill_u64_kernel<<<int(std::min<uint64_t>((uint64_t(n) + kThreads - 1) / kThreads, 148 * 16)), kThreads, 0, L.stream>>>(p, v, n);
+  L.tick();
+}
+void unpack_bitmap(const Launch& L, const uint8_t* bitmap, uint64_t offset, uint32_t n, uint8_t* out) {
+  if (!n) return;
+  unpack_bitmap_kernel<<<int(std::min<uint64_t>((uint64_t(n) + kThreads - 1) / kThreads, 148 * 16)), kThreads, 0, L.stream>>>(bitmap, offset, n, out);
+  L.tick();
+}
 
 size_t radix_tmp_elems(uint32_t cap) { return size_t(256) * ((size_t(cap) + kTile - 1) / kTile) + 16; }
 

@@ -128,11 +128,23 @@ class ObjectBasedStorage:
             ensure(_trunc_div(req.time_range.start, seg) == _trunc_div(req.time_range.end - 1, seg),
                    f"time range can't cross segment, value:{req.time_range!r}")
         file_id = allocate_id()
-        data = sstgen.write_sst(self.schema_, req.batch, file_id, self.config.write)
         fpath = self.sst_path_gen.generate(file_id)
-        with open(fpath, "wb") as f:
-            f.write(data)
-        self.manifest.add_file(file_id, FileMeta(max_sequence=file_id, num_rows=req.batch.num_rows, size=len(data),
+        w = self.config.write
+        gpu_writer = (hasattr(self.engine, "write_batch") and w.encoding == "PLAIN" and not w.enable_dict and not w.column_options
+                      and str(w.compression).lower() in ("snappy", "uncompressed", "none")
+                      and all(req.batch.column(i).null_count == 0 for i in range(self.schema_.num_primary_keys)))
+        if gpu_writer:
+            # write_batch on the GPU (hg_write_batch): PK sort, builtin columns, Parquet encode
+            meta = self.engine.write_batch(self.handle, req.batch, file_id, fpath, max_row_group_size=w.max_row_group_size,
+                                           compression=str(w.compression), enable_sorting_columns=w.enable_sorting_columns)
+            size = meta.size
+        else:
+            # writer options the GPU encoder does not implement (dictionary / delta encodings, zstd, NULL keys): host Parquet writer
+            data = sstgen.write_sst(self.schema_, req.batch, file_id, self.config.write)
+            with open(fpath, "wb") as f:
+                f.write(data)
+            size = len(data)
+        self.manifest.add_file(file_id, FileMeta(max_sequence=file_id, num_rows=req.batch.num_rows, size=size,
                                                  time_range=req.time_range))
 
     def _inputs(self, ssts: Sequence[SstFile]) -> List[SstInput]:

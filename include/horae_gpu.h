@@ -198,6 +198,14 @@ int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
  * column's widened domain: i64 / u64 two's complement) from the row-group statistics of the inputs, balancing rows. */
 int hg_plan_pk_splitters(const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, uint32_t parts, uint64_t* splitters);
 
+/* ObjectBasedStorage::write_batch on the GPU (storage.rs:189-225): sort the batch by its primary keys (sort_batch, storage.rs:244-256:
+ * ascending; equal keys keep their input order), append __seq__ = `sequence` and an all-null __reserved__ (fill_builtin_columns,
+ * types.rs:219-239), encode with the writer above and write `out_path`.  `batch` is an Arrow C struct array holding the USER columns
+ * (schema->num_columns - 2 children, primitive types matching schema->types); it stays owned by the caller.
+ * NULL primary keys are refused (HG_ERR_UNSUPPORTED), like everywhere else on the GPU path. */
+int hg_write_batch(hg_engine* e, const hg_schema_desc* schema, const struct ArrowArray* batch, uint64_t sequence, const hg_write_props* props,
+                   const char* out_path, hg_file_meta* out);
+
 int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
                       const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg,
                       struct ArrowArrayStream* out);

@@ -179,3 +179,45 @@ def test_range_sharded_compaction_equals_single_compaction(tmp_path, world):
     whole = sum(len(d) for d in datas)
     assert max(moved) < 0.8 * whole, (moved, whole)                        # a shard does not pull the whole inputs over PCIe
     eng.close()
+
+
+def test_write_batch_on_gpu_matches_the_host_writer(tmp_path):
+    """hg_write_batch = write_batch (storage.rs:189-225): unsorted user batch in, SST sorted by the primary keys out, __seq__ = file
+    id, __reserved__ all NULL.  Contents must equal what the host writer (pyarrow, the same format) produces for the same batch."""
+    from horaedb_b200.types import StorageSchema
+    rng = np.random.default_rng(12)
+    user = arrow_schema([("a", "int32"), ("b", "uint64"), ("c", "int8"), ("v", "float64"), ("w", "uint16")])
+    schema = StorageSchema.try_new(user, 3)
+    n = 30_000
+    a = rng.integers(-50, 50, n)
+    b = rng.integers(0, 2**40, n)
+    c = rng.integers(-128, 128, n)
+    cols = {"a": a.tolist(), "b": b.tolist(), "c": c.tolist(), "v": [None if rng.random() < 0.1 else float(x) for x in rng.random(n)],
+            "w": [None if rng.random() < 0.5 else int(x) for x in rng.integers(0, 65536, n)]}
+    batch = record_batch(user, cols)
+    handle = SchemaHandle(schema.arrow_schema, 3)
+    eng = Engine(device=0)
+    for codec, rg in (("snappy", 8192), ("none", 1000)):
+        path = str(tmp_path / f"w_{codec}.sst")
+        meta = eng.write_batch(handle, batch, 4242, path, max_row_group_size=rg, compression=codec)
+        assert meta.num_rows == n and meta.max_sequence == 4242
+        got = pq.read_table(path)
+        want = pq.read_table(io.BytesIO(sstgen.write_sst(schema, batch, 4242, WriteConfig(max_row_group_size=rg))))
+        assert got.schema.names == want.schema.names
+        for name in want.schema.names:
+            assert got[name].type == want[name].type and arrays_equal(got[name], want[name]), name
+        assert got["__seq__"].to_pylist()[:3] == [4242] * 3 and got["__reserved__"].null_count == n
+        # and the engine scans what it wrote
+        rescan = pa.Table.from_batches(list(eng.scan(handle, [SstInput(id=next(_ids), path=path)], (), None, True)))
+        exp = pa.Table.from_batches(oracle.scan([open(path, "rb").read()], schema.arrow_schema, 3, (), True, 8192).batches)
+        assert all(arrays_equal(rescan[name], exp[name]) for name in exp.schema.names)
+    # equal primary keys keep their input order (stable sort): the later row wins the LastValue dedup on scan
+    dup = record_batch(user, {"a": [1, 1, 0], "b": [5, 5, 9], "c": [0, 0, 0], "v": [1.0, 2.0, 3.0], "w": [1, 2, 3]})
+    path = str(tmp_path / "dup.sst")
+    eng.write_batch(handle, dup, 7, path)
+    t = pq.read_table(path)
+    assert t["a"].to_pylist() == [0, 1, 1] and t["v"].to_pylist() == [3.0, 1.0, 2.0]
+    # an empty batch is an empty SST
+    eng.write_batch(handle, batch.slice(0, 0), 8, str(tmp_path / "e.sst"))
+    assert pq.read_table(str(tmp_path / "e.sst")).num_rows == 0
+    eng.close()
