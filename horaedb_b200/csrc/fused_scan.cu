@@ -286,11 +286,26 @@ __global__ void __launch_bounds__(256) gate_sel_kernel(const __grid_constant__ F
     if (threadIdx.x == 0) s_last = 0;
     __syncthreads();
     uint32_t last = 0;                                     // 1 + index of the last passing row seen by this thread
-    for (uint32_t i = threadIdx.x; i < nrows; i += 256) {
-      bool pass;
-      if (W4) pass = (ld32u(base + size_t(i) * 4) ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span);
-      else pass = (ld_bytes8(base + size_t(i) * 8) ^ flip) - lo <= span;
-      if (pass) last = i + 1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(base) & 7) == 0;
+    if (W4 && aligned) {
+      // decompressed pages start 8-byte aligned behind their level prefix: two values per load, four loads in flight
+      const uint2* b2 = reinterpret_cast<const uint2*>(base);
+      const uint32_t npair = nrows >> 1;
+#pragma unroll 4
+      for (uint32_t i = threadIdx.x; i < npair; i += 256) {
+        const uint2 v = __ldg(b2 + i);
+        if ((v.x ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span)) last = 2 * i + 1;
+        if ((v.y ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span)) last = 2 * i + 2;
+      }
+      if ((nrows & 1) && threadIdx.x == 0 && (ld32u(base + size_t(nrows - 1) * 4) ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span)) last = nrows;
+    } else {
+#pragma unroll 4
+      for (uint32_t i = threadIdx.x; i < nrows; i += 256) {
+        bool pass;
+        if (W4) pass = (ld32u(base + size_t(i) * 4) ^ uint32_t(flip)) - uint32_t(lo) <= uint32_t(span);
+        else pass = (ld_bytes8(base + size_t(i) * 8) ^ flip) - lo <= span;
+        if (pass) last = i + 1;
+      }
     }
     for (int d = 16; d > 0; d >>= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, last, d); last = o > last ? o : last; }
     if ((threadIdx.x & 31) == 0 && last) atomicMax(&s_last, last);
