@@ -31,7 +31,7 @@ struct PageDev {
   uint8_t encoding, v2_compressed, _pad;
 };
 
-// One column chunk, indexed [row_group * ncols + column].  16 bytes.
+// One column chunk, indexed [row_group * ncols + column].  32 bytes.
 struct ChunkDev {
   uint32_t first_page, num_pages;
   uint32_t scratch_bytes;  // decompression scratch needed by this chunk
@@ -39,6 +39,9 @@ struct ChunkDev {
   uint8_t codec;           // 0 uncompressed, 1 snappy
   uint8_t optional;        // max definition level 1
   uint8_t stored;          // Snappy, one V1 page, stream = 1-2 literals whose value bytes are row-aligned: readable in place
+  // dictionary page of the chunk (RLE_DICTIONARY data pages index into its PLAIN values); dict_uncomp == 0: none
+  uint64_t dict_payload_off;
+  uint32_t dict_comp, dict_uncomp;
 };
 
 struct SstDev {

@@ -106,8 +106,8 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
   pages.assign(m.pages.size(), PageDev());
   for (size_t i = 0; i < pages.size(); i++) {
     const PageMeta& pm = m.pages[i];
-    if (pm.encoding != ENC_PLAIN && pm.encoding != ENC_DELTA_BINARY_PACKED)
-      return fail(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (PLAIN and DELTA_BINARY_PACKED are implemented)");
+    if (pm.encoding != ENC_PLAIN && pm.encoding != ENC_DELTA_BINARY_PACKED && pm.encoding != ENC_RLE_DICT && pm.encoding != ENC_PLAIN_DICT)
+      return fail(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (PLAIN, DELTA_BINARY_PACKED and RLE_DICTIONARY are implemented)");
     PageDev& pd = pages[i];
     pd.payload_off = pm.payload_off;
     pd.comp_size = pm.comp_size;
@@ -127,7 +127,6 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       const ChunkMeta& cm = m.rgs[g].cols[c];
       if (cm.codec != CODEC_UNCOMPRESSED && cm.codec != CODEC_SNAPPY)
         return fail(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED and SNAPPY are implemented)");
-      if (cm.has_dict_page) return fail(HG_ERR_UNSUPPORTED, "dictionary-encoded column chunk");
       if (cm.scratch_bytes > 0xffffffffull) return fail(HG_ERR_UNSUPPORTED, "column chunk larger than 4 GiB");
       // every kernel indexes a chunk by the ROW GROUP's row count: the chunk must hold exactly that many values, and an
       // uncompressed page must really contain the bytes the decoders will read (compressed pages are bounded by their
@@ -168,9 +167,15 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       cd.codec = uint8_t(cm.codec);
       cd.optional = uint8_t(m.repetition[c] == 1);
       cd.stored = 0;
-      for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++)
+      cd.dict_payload_off = cm.has_dict_page ? cm.dict_payload_off : 0;
+      cd.dict_comp = cm.has_dict_page ? cm.dict_comp_size : 0;
+      cd.dict_uncomp = cm.has_dict_page ? cm.dict_uncomp_size : 0;
+      for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++) {
         if (m.pages[pi].encoding == ENC_DELTA_BINARY_PACKED && cm.phys_type != PT_INT32 && cm.phys_type != PT_INT64)
           return fail(HG_ERR_FORMAT, "DELTA_BINARY_PACKED on a non-integer column");
+        if ((m.pages[pi].encoding == ENC_RLE_DICT || m.pages[pi].encoding == ENC_PLAIN_DICT) && !cm.has_dict_page)
+          return fail(HG_ERR_FORMAT, "dictionary-encoded page without a dictionary page");
+      }
       if (cm.codec == CODEC_SNAPPY && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.rgs[g].num_rows > 0)
         cd.stored = classify_stored(data, size, m.pages[cm.first_page], cd.optional != 0,
                                     (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4u : 8u, uint64_t(m.rgs[g].num_rows)) ? 1 : 0;
@@ -192,7 +197,8 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       rc.null_none = cm.stats.has_null_count && cm.stats.null_count == 0;
       rc.snappy = cm.codec == CODEC_SNAPPY;
       rc.scratch = uint32_t(cm.scratch_bytes);
-      const bool one_plain_v1 = cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.pages[cm.first_page].encoding == ENC_PLAIN;
+      const bool one_plain_v1 = cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.pages[cm.first_page].encoding == ENC_PLAIN &&
+                                !cm.has_dict_page;
       rc.simple_page = cm.codec == CODEC_UNCOMPRESSED && one_plain_v1;
       rc.single_page = one_plain_v1;
       rc.stored = chunks[g * m.ncols + c].stored;
@@ -509,7 +515,7 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
     }
     uint64_t need_bytes = 0;
     for (uint32_t c : need_cols) for (size_t j = 0; j < k; j++) need_bytes += rs[j]->col_comp_bytes[c];
-    if (gate_col >= 0 && best_bytes * 3 > need_bytes) gate_col = -1;          // the gate would be most of the bytes anyway
+    if (gate_col >= 0 && best_bytes * 2 > need_bytes) gate_col = -1;          // the gate would be most of the bytes anyway
   }
   std::vector<fused::GateOut> gate_out;
   if (gate_col >= 0) {

@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(32) snappy_chunks_kernel(const SstDev* __restr
   ChunkDev ch = chunks[cols[ci].col];
   if (ch.codec != 1) return;
   uint8_t* dst = scratch + chunk_scratch_off(rs, chunks, cols, ci);
+  if (ch.dict_uncomp) {
+    snappy_warp(sst.bytes + ch.dict_payload_off, ch.dict_comp, dst, ch.dict_uncomp, lane, err);
+    dst += page_scratch(ch.dict_uncomp);
+  }
   for (uint32_t p = 0; p < ch.num_pages; p++) {
     PageDev pg = sst.pages[ch.first_page + p];
     const uint8_t* src = sst.bytes + pg.payload_off;
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(32) snappy_chunks_kernel(const SstDev* __restr
     }
     if (compressed) snappy_warp(src, n, dst, ulen, lane, err);
     dst += page_scratch(pg.uncomp_size);
-    if (pg.encoding == 5) dst += page_scratch(pg.num_values * 8u);
+    if (pg.encoding == 5 || pg.encoding == 8 || pg.encoding == 2) dst += page_scratch(pg.num_values * 8u);
   }
 }
 
@@ -351,6 +355,78 @@ __device__ bool delta_decode_page(const uint8_t* p, const uint8_t* end, uint32_t
   return true;
 }
 
+// ------------------------------------------------------------------------------------ RLE_DICTIONARY -> PLAIN
+// Data page = [bit width][RLE / bit-packed hybrid runs of dictionary indices] (Parquet Encodings.md; enable_dict, config.rs:98-103).
+// Thread 0 walks the run headers, all threads expand a run: out[i] = dict[index_i] as PLAIN values of width pw.
+__device__ bool dict_decode_page(const uint8_t* p, const uint8_t* end, uint32_t pw, uint32_t max_out, const uint8_t* dict, uint32_t dict_n,
+                                 uint8_t* out, uint32_t* count_out) {
+  __shared__ uint32_t s_kind, s_cnt, s_idx, s_pos, s_ok, s_bad_idx;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_pos = 1; s_ok = p < end && __ldg(p) <= 32; s_bad_idx = 0; }
+  __syncthreads();
+  if (!s_ok) return false;
+  const uint32_t bw = __ldg(p);
+  uint32_t done = 0;
+  while (done < max_out) {
+    if (tid == 0) {
+      uint32_t pos = s_pos;
+      bool ok = true;
+      if (p + pos >= end) { s_cnt = 0; }
+      else {
+        uint64_t h = 0;
+        int sh = 0;
+        for (;;) {
+          if (p + pos >= end || sh > 35) { ok = false; break; }
+          const uint8_t b = __ldg(p + pos++);
+          h |= uint64_t(b & 0x7f) << sh;
+          sh += 7;
+          if (!(b & 0x80)) break;
+        }
+        if (ok && (h & 1)) {                           // bit-packed run: (h >> 1) groups of 8 indices
+          const uint64_t groups = h >> 1, bytes = groups * bw;
+          if (groups == 0 || p + pos + bytes > end) ok = false;
+          s_kind = 1; s_cnt = uint32_t(groups * 8 > 0xffffffffull ? 0xffffffffu : groups * 8); s_idx = pos;
+          pos += uint32_t(bytes);
+        } else if (ok) {                               // RLE run: count, then the index in ceil(bw / 8) bytes
+          const uint32_t nb = (bw + 7) / 8;
+          if ((h >> 1) == 0 || p + pos + nb > end) ok = false;
+          uint32_t idx = 0;
+          if (ok) for (uint32_t b = 0; b < nb; b++) idx |= uint32_t(__ldg(p + pos + b)) << (8 * b);
+          s_kind = 0; s_cnt = uint32_t((h >> 1) > 0xffffffffull ? 0xffffffffu : (h >> 1)); s_idx = idx;
+          pos += nb;
+        }
+      }
+      s_pos = pos;
+      s_ok = ok;
+    }
+    __syncthreads();
+    if (!s_ok) return false;
+    uint32_t cnt = s_cnt;
+    if (cnt == 0) break;                               // index bytes exhausted
+    if (cnt > max_out - done) cnt = max_out - done;
+    const uint32_t kind = s_kind, ref = s_idx;
+    for (uint32_t j = tid; j < cnt; j += kThreads) {
+      uint32_t idx = ref;
+      if (kind) {
+        const uint64_t bit = uint64_t(j) * bw;
+        const uint8_t* q = p + ref + (bit >> 3);
+        const uint64_t x = ld64_any<false>(q) >> (bit & 7);
+        idx = bw == 32 ? uint32_t(x) : uint32_t(x & ((1ull << bw) - 1));
+      }
+      if (idx >= dict_n) { s_bad_idx = 1; idx = 0; }
+      if (dict_n) {
+        if (pw == 4) reinterpret_cast<uint32_t*>(out)[done + j] = ld32_any(dict + size_t(idx) * 4);
+        else reinterpret_cast<uint64_t*>(out)[done + j] = ld64_any<false>(dict + size_t(idx) * 8);
+      }
+    }
+    done += cnt;
+    __syncthreads();
+  }
+  __syncthreads();
+  *count_out = done;
+  return s_bad_idx == 0;
+}
+
 __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* __restrict__ ssts, const RgSel* __restrict__ sel,
                                                                 const ColSel* __restrict__ cols, int ncolsel,
                                                                 uint8_t* __restrict__ scratch, int* err) {
@@ -367,6 +443,9 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
   ChunkDev ch = chunks[cs.col];
   const uint32_t pw = (ch.phys == 1 || ch.phys == 4) ? 4u : 8u;   // INT32/FLOAT : INT64/DOUBLE
   uint8_t* sc = scratch + (ch.scratch_bytes ? chunk_scratch_off(rs, chunks, cols, ci) : 0);
+  const uint8_t* dict = sst.bytes + ch.dict_payload_off;             // dictionary values (PLAIN): in place, or decompressed first in the scratch
+  if (ch.dict_uncomp && ch.codec == 1) { dict = sc; sc += page_scratch(ch.dict_uncomp); }
+  const uint32_t dict_n = ch.dict_uncomp / pw;
   uint32_t row = rs.out_row;
   if (tid == 0) s_bad = 0;
   __syncthreads();
@@ -402,6 +481,16 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
       const bool ok = val_ptr <= page_end && delta_decode_page(val_ptr, page_end, pw, nv, img, &cnt);
       __syncthreads();
       if (!ok) { if (tid == 0) s_bad = 4; cnt = 0; }
+      val_ptr = img;
+      max_vals = cnt;
+      __syncthreads();
+    } else if (pg.encoding == 8 || pg.encoding == 2) {
+      uint8_t* img = sc;
+      sc += page_scratch(nv * 8u);
+      uint32_t cnt = 0;
+      const bool ok = val_ptr <= page_end && dict_decode_page(val_ptr, page_end, pw, nv, dict, dict_n, img, &cnt);
+      __syncthreads();
+      if (!ok) { if (tid == 0) s_bad = 5; cnt = 0; }
       val_ptr = img;
       max_vals = cnt;
       __syncthreads();

@@ -239,9 +239,7 @@ bool parse_parquet(const uint8_t* data, size_t len, FileMetaData* out, std::stri
     for (auto& cm : rg.cols) {
       cm.first_page = uint32_t(out->pages.size());
       uint64_t pos = uint64_t(cm.data_page_offset);
-      if (cm.dict_page_offset > 0 && cm.dict_page_offset < cm.data_page_offset) {
-        cm.has_dict_page = true;
-      }
+      if (cm.dict_page_offset > 0 && cm.dict_page_offset < cm.data_page_offset) pos = uint64_t(cm.dict_page_offset);   // dictionary page first
       int64_t seen = 0;
       while (seen < cm.num_values) {
         if (pos >= len) return bad("page offset beyond end of file");
@@ -256,6 +254,7 @@ bool parse_parquet(const uint8_t* data, size_t len, FileMetaData* out, std::stri
           cm.dict_comp_size = uint32_t(h.comp);
           cm.dict_uncomp_size = uint32_t(h.uncomp);
           cm.dict_num_values = uint32_t(h.num_values);
+          if (cm.codec != CODEC_UNCOMPRESSED) cm.scratch_bytes += page_scratch_bytes(uint32_t(h.uncomp));   // decompressed dictionary: first in the chunk's scratch
           continue;
         }
         if (h.type != PAGE_DATA && h.type != PAGE_DATA_V2) continue;
@@ -272,7 +271,7 @@ bool parse_parquet(const uint8_t* data, size_t len, FileMetaData* out, std::stri
         out->pages.push_back(pm);
         // device scratch of the page: the decompressed payload (compressed chunks) + the PLAIN image of a DELTA_BINARY_PACKED page
         if (cm.codec != CODEC_UNCOMPRESSED) cm.scratch_bytes += page_scratch_bytes(pm.uncomp_size);
-        if (pm.encoding == ENC_DELTA_BINARY_PACKED) cm.scratch_bytes += page_scratch_bytes(uint32_t(std::min<uint64_t>(uint64_t(pm.num_values) * 8, 0xfffffff0ull)));
+        if (pm.encoding == ENC_DELTA_BINARY_PACKED || pm.encoding == ENC_RLE_DICT || pm.encoding == ENC_PLAIN_DICT) cm.scratch_bytes += page_scratch_bytes(uint32_t(std::min<uint64_t>(uint64_t(pm.num_values) * 8, 0xfffffff0ull)));
         seen += h.num_values;
         if (h.num_values <= 0) return bad("page with no values");
       }

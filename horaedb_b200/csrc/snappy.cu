@@ -399,6 +399,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
     if (ch.stored && J.skip_stored[ci]) continue;                 // read in place by the consumer
     uint8_t* dst = J.scratch + (J.fixed_stride ? rs.scratch_off + uint64_t(J.region[ci]) * J.fixed_stride
                                                : chunk_scratch_off2(rs, chunks, J.cols, ci));
+    if (ch.dict_uncomp) {                                        // compressed dictionary page: first in the chunk's scratch
+      const uint8_t* dsrc = sst.bytes + ch.dict_payload_off;
+      snappy_page(dsrc, ch.dict_comp, dst, ch.dict_uncomp, 0xffffffffu, sm, lane, J.err);
+      dst += page_scratch2(ch.dict_uncomp);
+    }
     for (uint32_t p = 0; p < ch.num_pages; p++) {
       PageDev pg = sst.pages[ch.first_page + p];
       const uint8_t* src = sst.bytes + pg.payload_off;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
       }
       if (compressed) snappy_page(src, n, dst, ulen, stop_at, sm, lane, J.err);
       dst += page_scratch2(pg.uncomp_size);
-      if (pg.encoding == 5) dst += page_scratch2(pg.num_values * 8u);     // PLAIN image of a DELTA_BINARY_PACKED page (decode_chunks)
+      if (pg.encoding == 5 || pg.encoding == 8 || pg.encoding == 2) dst += page_scratch2(pg.num_values * 8u);   // PLAIN image of a DELTA / dictionary page (decode_chunks)
     }
   }
 }

@@ -396,16 +396,53 @@ static int delta_binary_unpack(const uint8_t *p, int64_t len, int w, int64_t cou
     return 0;
 }
 
+/* RLE_DICTIONARY / PLAIN_DICTIONARY data page (enable_dict, config.rs:98-103,127): [bit width : 1 byte] then RLE / bit-packed
+ * hybrid runs of dictionary indices (Parquet Encodings.md); out[i] = dict[index_i] as PLAIN bytes of width w. */
+static int dict_indices_unpack(const uint8_t *p, int64_t len, int w, int64_t count, const uint8_t *dict, int64_t dict_n, uint8_t *out) {
+    const uint8_t *end = p + len;
+    if (count == 0) return 0;
+    if (p >= end) FAIL("dict: empty data page");
+    int bw = *p++;
+    if (bw > 32) FAIL("dict: bit width %d", bw);
+    int64_t i = 0;
+    while (i < count) {
+        uint64_t h = 0; int sh = 0;
+        for (;;) { if (p >= end) FAIL("dict: truncated run header"); uint8_t b = *p++; h |= (uint64_t)(b & 0x7f) << sh; if (!(b & 0x80)) break; sh += 7; }
+        if (h & 1) {                               /* bit-packed: groups of 8 indices */
+            int64_t groups = (int64_t)(h >> 1);
+            if (p + groups * bw > end) FAIL("dict: truncated bit-packed run");
+            for (int64_t k = 0; k < groups * 8 && i < count; k++, i++) {
+                uint64_t bit = (uint64_t)k * bw, idx = 0;
+                for (int b = 0; b < bw; b++) { uint64_t q = bit + b; idx |= (uint64_t)((p[q >> 3] >> (q & 7)) & 1) << b; }
+                if ((int64_t)idx >= dict_n) FAIL("dict: index out of range");
+                memcpy(out + i * w, dict + idx * w, w);
+            }
+            p += groups * bw;
+        } else {
+            int64_t run = (int64_t)(h >> 1);
+            int nb = (bw + 7) / 8;
+            if (p + nb > end) FAIL("dict: truncated RLE run");
+            uint64_t idx = 0;
+            for (int b = 0; b < nb; b++) idx |= (uint64_t)p[b] << (8 * b);
+            p += nb;
+            if (run > 0 && (int64_t)idx >= dict_n) FAIL("dict: index out of range");
+            for (int64_t k = 0; k < run && i < count; k++, i++) memcpy(out + i * w, dict + idx * w, w);
+            if (run == 0) FAIL("dict: empty run");
+        }
+    }
+    return 0;
+}
+
 /* decode one column chunk into vals/valid[0..num_rows) */
 static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, int optional, int otype,
                         int64_t num_rows, uint64_t *vals, uint8_t *valid) {
     int w = phys_width(cm->phys_type);
     if (!w) FAIL("oracle: unsupported physical type %d", cm->phys_type);
-    if (cm->dict_page_offset >= 0 && cm->dict_page_offset < cm->data_page_offset && cm->dict_page_offset > 0)
-        FAIL("oracle: dictionary pages unsupported");
     if (cm->codec != 0 && cm->codec != 1) FAIL("oracle: unsupported codec %d", cm->codec);
     int64_t pos = cm->data_page_offset, row = 0;
+    if (cm->dict_page_offset > 0 && cm->dict_page_offset < cm->data_page_offset) pos = cm->dict_page_offset;   /* dictionary page first */
     uint8_t *buf = NULL; int64_t bufcap = 0;
+    uint8_t *dict = NULL; int64_t dict_n = 0;
     uint8_t *lv = malloc(num_rows ? num_rows : 1);
     int rc = 0;
     while (row < num_rows) {
@@ -414,9 +451,16 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
         if (parse_page_header(data + pos, data + len, &h)) { rc = -1; break; }
         const uint8_t *payload = data + pos + h.hdr_len;
         pos += h.hdr_len + h.comp;
-        if (h.type == 2) { rc = -1; snprintf(g_err, sizeof g_err, "oracle: dictionary page"); break; }
+        if (h.type == 2) {                        /* dictionary page: PLAIN values, compressed like a data page */
+            free(dict);
+            dict = malloc((size_t)(h.uncomp > 0 ? h.uncomp : 1));
+            if (cm->codec == 1) { if (snappy_decompress(payload, h.comp, dict, h.uncomp)) { rc = -1; break; } }
+            else memcpy(dict, payload, (size_t)h.comp);
+            dict_n = h.uncomp / w;
+            continue;
+        }
         if (h.type != 0 && h.type != 3) continue;
-        if (h.encoding != 0 && !(h.encoding == 5 && (cm->phys_type == 1 || cm->phys_type == 2))) {
+        if (h.encoding != 0 && !(h.encoding == 5 && (cm->phys_type == 1 || cm->phys_type == 2)) && !((h.encoding == 8 || h.encoding == 2) && dict)) {
             rc = -1; snprintf(g_err, sizeof g_err, "oracle: encoding %d unsupported", h.encoding); break;
         }
         int nv = h.num_values;
@@ -453,6 +497,13 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
             if (delta_binary_unpack(body, body_len, w, nn, dbuf)) { free(dbuf); rc = -1; break; }
             body = dbuf; body_len = nn * w;
         }
+        if (h.encoding == 8 || h.encoding == 2) { /* dictionary indices: expand to PLAIN bytes, then the common path */
+            int64_t nn = 0;
+            for (int i = 0; i < nv; i++) nn += lv[i] != 0;
+            dbuf = malloc((size_t)(nn ? nn : 1) * w);
+            if (dict_indices_unpack(body, body_len, w, nn, dict, dict_n, dbuf)) { free(dbuf); rc = -1; break; }
+            body = dbuf; body_len = nn * w;
+        }
         int64_t k = 0;
         for (int i = 0; i < nv; i++) {
             if (lv[i]) {
@@ -464,7 +515,7 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
         if (rc) break;
         row += nv;
     }
-    free(buf); free(lv);
+    free(buf); free(lv); free(dict);
     return rc;
 }
 

@@ -169,3 +169,37 @@ def test_delta_binary_packed_columns_match_pyarrow():
             assert parquet_inspect(data)["num_rows"] == n
             keep = plan_row_groups(SchemaHandle(schema.arrow_schema, 2), data, [("t", "lt", 0)])
             assert 0 < sum(keep) < len(keep)
+
+
+def test_dictionary_encoded_columns_match_pyarrow():
+    """RLE_DICTIONARY (`enable_dict`, config.rs:98-103,127): the oracle's dictionary-page + index-run decoder against pyarrow, and the
+    library's host-side reader accepting such files."""
+    import io
+
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from horaedb_b200 import sstgen
+    from horaedb_b200._ffi import parquet_inspect
+    from horaedb_b200.config import WriteConfig
+    from horaedb_b200.types import StorageSchema
+    from oracle import oracle
+    rng = np.random.default_rng(2)
+    n = 25_000
+    user = pa.schema([pa.field("k", pa.uint64()), pa.field("t", pa.int64()), pa.field("c", pa.int32()), pa.field("f", pa.float32()),
+                      pa.field("w", pa.int64())])
+    schema = StorageSchema.try_new(user, 2)
+    batch = pa.RecordBatch.from_arrays(
+        [pa.array(np.arange(n, dtype=np.uint64) // 3), pa.array(np.arange(n, dtype=np.int64)),
+         pa.array([None if rng.random() < 0.15 else int(x) for x in rng.integers(-5, 5, n)], pa.int32()),
+         pa.array(rng.choice([0.5, -2.0, 7.25], n).astype(np.float32)), pa.array(rng.integers(-2**60, 2**60, n))], schema=user)
+    for comp in ("snappy", "none"):
+        for rg in (8192, 1111):
+            data = sstgen.write_sst(schema, batch, 3, WriteConfig(compression=comp, max_row_group_size=rg, enable_dict=True), presorted=True)
+            md = pq.ParquetFile(io.BytesIO(data)).metadata
+            assert md.row_group(0).column(2).has_dictionary_page
+            got = oracle.decode_sst(data, schema.arrow_schema)
+            ref = pq.read_table(io.BytesIO(data))
+            for c in ref.schema.names:
+                assert got[c].combine_chunks().equals(ref[c].combine_chunks()), (comp, rg, c)
+            assert parquet_inspect(data)["num_rows"] == n
