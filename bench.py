@@ -52,6 +52,31 @@ def gen_ssts(rank, codec, nfiles, workers):
         return list(ex.map(_gen_file, jobs))
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this rank (and therefore the pinned SST buffers it allocates next: first touch) to the NUMA node its GPU hangs off, like
+    `numactl --cpunodebind --membind` in a real deployment.  Best effort: returns the node or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)], capture_output=True, text=True,
+                             timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def preds():
     from horaedb_b200 import sstgen
     t0 = sstgen.T0_MS
@@ -206,6 +231,7 @@ def main():
     from horaedb_b200._ffi import DeviceArray, Engine, SchemaHandle, SstInput
 
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa(local_rank) if world > 1 else None      # several ranks share the host: keep each next to its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     schema = sstgen.metric_storage_schema()
@@ -472,7 +498,7 @@ def main():
                        "decoded_GBps_note": "SURVEY 8(d) convention: ALL rows of the files x 28 B / step time.  Statistics pruning, stored-page "
                                             "bypass and late materialisation skip bytes that cannot contribute; the physical figures are "
                                             "roofline.achieved / roofline.traffic",
-                       "late_materialisation_bytes": gate_bytes},
+                       "late_materialisation_bytes": gate_bytes, "numa_node_rank0": numa_node},
             "roofline": roofline,
             "parity": {"checked": True, "ok": parity_ok, "against": "CPU oracle on the same SSTs, bit-exact keys / counts / f64 sum, min, max",
                        **{c: r["parity"] for c, r in res.items()}},

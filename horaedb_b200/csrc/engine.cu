@@ -471,7 +471,9 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
   auto add_range = [&](std::vector<CopyRange>& ranges, size_t j, uint32_t g, uint32_t c) {
     SstResident& r = *rs[j];
     const ChunkMeta& cm = r.meta.rgs[g].cols[c];
-    uint64_t lo = uint64_t(cm.data_page_offset), hi = lo + uint64_t(cm.total_compressed);
+    uint64_t lo = uint64_t(cm.data_page_offset);
+    if (cm.dict_page_offset > 0 && uint64_t(cm.dict_page_offset) < lo) lo = uint64_t(cm.dict_page_offset);   // the chunk starts at its dictionary page
+    uint64_t hi = lo + uint64_t(cm.total_compressed);
     if (hi > r.size) hi = r.size;
     hi = std::min<uint64_t>(r.size, hi + 16);               // the unaligned 8-byte loads may touch one word past the values
     if (!ranges.empty() && ranges.back().src + ranges.back().bytes >= datas[j] + lo && ranges.back().src <= datas[j] + lo &&
