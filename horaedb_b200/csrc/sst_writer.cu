@@ -161,8 +161,16 @@ __global__ void __launch_bounds__(kThreads) page_body_kernel(const PageJob* __re
     const uint32_t k2 = running + block_scan(v, &total, s_w);
     if (v) {
       const uint64_t x = load_phys(j, row0 + i);
-      if (j.pwidth == 8) { uint8_t* q = vout + size_t(k2) * 8; for (int b = 0; b < 8; b++) q[b] = uint8_t(x >> (8 * b)); }
-      else { uint8_t* q = vout + size_t(k2) * 4; for (int b = 0; b < 4; b++) q[b] = uint8_t(x >> (8 * b)); }
+      // (the page body starts 64-byte aligned; the level prefix is usually 8 bytes, so the values are naturally aligned)
+      if (j.pwidth == 8) {
+        uint8_t* q = vout + size_t(k2) * 8;
+        if ((prefix & 7) == 0) *reinterpret_cast<uint64_t*>(q) = x;
+        else for (int b = 0; b < 8; b++) q[b] = uint8_t(x >> (8 * b));
+      } else {
+        uint8_t* q = vout + size_t(k2) * 4;
+        if ((prefix & 3) == 0) *reinterpret_cast<uint32_t*>(q) = uint32_t(x);
+        else for (int b = 0; b < 4; b++) q[b] = uint8_t(x >> (8 * b));
+      }
       bool nan;
       const uint64_t key = stat_key(x, j.type, &nan);
       if (!nan) { mn = key < mn ? key : mn; mx = key > mx ? key : mx; seen = true; }
@@ -225,7 +233,9 @@ __global__ void __launch_bounds__(kThreads) snappy_encode_kernel(const uint8_t* 
   uint32_t* run_out = run_pos + max_vals + 1;
   const int tid = threadIdx.x;
   const uint8_t* v = in + prefix;
+  const bool val_aligned = (prefix & (w - 1)) == 0;
   auto val_at = [&](uint32_t i) -> uint64_t {
+    if (val_aligned) return w == 8 ? *reinterpret_cast<const uint64_t*>(v + size_t(i) * 8) : uint64_t(*reinterpret_cast<const uint32_t*>(v + size_t(i) * 4));
     uint64_t x = 0;
     for (uint32_t b = 0; b < w; b++) x |= uint64_t(v[size_t(i) * w + b]) << (8 * b);
     return x;
@@ -320,7 +330,21 @@ __global__ void __launch_bounds__(kThreads) gather_pages_kernel(const uint8_t* _
   const GatherDesc g = d[blockIdx.x];
   const uint8_t* s = src + g.src_off;
   uint8_t* t = file + g.dst_off;
-  for (uint32_t i = threadIdx.x; i < g.bytes; i += kThreads) t[i] = s[i];
+  // destination-aligned 8-byte stores; the source word comes from two aligned loads + a funnel shift (any relative alignment)
+  uint32_t head = uint32_t((8 - (reinterpret_cast<uintptr_t>(t) & 7)) & 7);
+  if (head > g.bytes) head = g.bytes;
+  if (threadIdx.x < head) t[threadIdx.x] = s[threadIdx.x];
+  const uint32_t nwords = (g.bytes - head) >> 3;
+  uint64_t* t8 = reinterpret_cast<uint64_t*>(t + head);
+  const uint8_t* s0 = s + head;
+  for (uint32_t wi = threadIdx.x; wi < nwords; wi += kThreads) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s0 + (size_t(wi) << 3));
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+    const uint32_t sh = uint32_t(a & 7) * 8;
+    const uint64_t lo = q[0];
+    t8[wi] = sh ? ((lo >> sh) | (q[1] << (64 - sh))) : lo;
+  }
+  for (uint32_t i = head + (nwords << 3) + threadIdx.x; i < g.bytes; i += kThreads) t[i] = s[i];
 }
 
 // ------------------------------------------------------------------------------------------------ Thrift compact writer
