@@ -5,7 +5,7 @@
 
 namespace horae {
 
-enum : uint32_t { T_U8 = 0, T_I8, T_U16, T_I16, T_U32, T_I32, T_U64, T_I64, T_F32, T_F64 };
+enum : uint32_t { T_U8 = 0, T_I8, T_U16, T_I16, T_U32, T_I32, T_U64, T_I64, T_F32, T_F64, T_BINARY };
 enum : uint32_t { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN };
 
 #if defined(__CUDACC__)
@@ -62,8 +62,9 @@ struct RgSel {
 // A column to decode.
 struct ColSel {
   uint32_t col, type, out_width, _pad;
-  void* out_vals;
+  void* out_vals;          // Binary columns: one `const uint8_t*` per row pointing at the value's bytes (page payload / scratch)
   uint8_t* out_valid;      // one byte per row (1 = non-null)
+  uint32_t* out_lens;      // Binary columns only: byte length per row
 };
 
 // A decoded column.
@@ -71,6 +72,7 @@ struct ColView {
   const void* vals;
   const uint8_t* valid;
   uint32_t type, width;
+  const uint32_t* lens;    // Binary columns only (vals = per-row byte pointers), else nullptr
 };
 
 struct PredDev {

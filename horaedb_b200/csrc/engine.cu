@@ -136,7 +136,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       {
         const uint32_t pw = (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4u : 8u;
         const bool optional = m.repetition[c] == 1;
-        const bool no_nulls = !optional || (cm.stats.has_null_count && cm.stats.null_count == 0);
+        const bool no_nulls = cm.phys_type != PT_BYTE_ARRAY && (!optional || (cm.stats.has_null_count && cm.stats.null_count == 0));   // (byte arrays: variable width)
         for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++) {
           const PageMeta& pm = m.pages[pi];
           if (pm.page_type == PAGE_DATA_V2) {
@@ -167,6 +167,9 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       cd.codec = uint8_t(cm.codec);
       cd.optional = uint8_t(m.repetition[c] == 1);
       cd.stored = 0;
+      if (cm.phys_type == PT_BYTE_ARRAY)
+        for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++)
+          if (m.pages[pi].encoding != ENC_PLAIN) return fail(HG_ERR_UNSUPPORTED, "byte-array column: only PLAIN pages are implemented");
       cd.dict_payload_off = cm.has_dict_page ? cm.dict_payload_off : 0;
       cd.dict_comp = cm.has_dict_page ? cm.dict_comp_size : 0;
       cd.dict_uncomp = cm.has_dict_page ? cm.dict_uncomp_size : 0;
@@ -176,7 +179,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
         if ((m.pages[pi].encoding == ENC_RLE_DICT || m.pages[pi].encoding == ENC_PLAIN_DICT) && !cm.has_dict_page)
           return fail(HG_ERR_FORMAT, "dictionary-encoded page without a dictionary page");
       }
-      if (cm.codec == CODEC_SNAPPY && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.rgs[g].num_rows > 0)
+      if (cm.phys_type != PT_BYTE_ARRAY && cm.codec == CODEC_SNAPPY && cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.rgs[g].num_rows > 0)
         cd.stored = classify_stored(data, size, m.pages[cm.first_page], cd.optional != 0,
                                     (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4u : 8u, uint64_t(m.rgs[g].num_rows)) ? 1 : 0;
     }
@@ -188,7 +191,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       const ChunkMeta& cm = m.rgs[g].cols[c];
       RgCol& rc = r->rgcol[g * m.ncols + c];
       const uint32_t t = schema->types[c];
-      if (cm.stats.has_min && cm.stats.has_max) {
+      if (cm.stats.has_min && cm.stats.has_max && cm.phys_type != PT_BYTE_ARRAY) {
         rc.has_minmax = 1;
         rc.mn = widen_stat(cm.stats.min, cm.phys_type, t);
         rc.mx = widen_stat(cm.stats.max, cm.phys_type, t);
@@ -198,7 +201,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       rc.snappy = cm.codec == CODEC_SNAPPY;
       rc.scratch = uint32_t(cm.scratch_bytes);
       const bool one_plain_v1 = cm.num_pages == 1 && m.pages[cm.first_page].page_type == PAGE_DATA && m.pages[cm.first_page].encoding == ENC_PLAIN &&
-                                !cm.has_dict_page;
+                                !cm.has_dict_page && cm.phys_type != PT_BYTE_ARRAY;
       rc.simple_page = cm.codec == CODEC_UNCOMPRESSED && one_plain_v1;
       rc.single_page = one_plain_v1;
       rc.stored = chunks[g * m.ncols + c].stored;
@@ -590,6 +593,7 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
     kept.swap(alive);
     gate_out.swap(alive_out);
   }
+  const auto tt1b = now();
   // ---- the remaining columns of the row groups still in play
   {
     std::vector<CopyRange> ranges;
@@ -653,6 +657,7 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
     int rc = move_ranges(ranges);
     if (rc) return rc;
   }
+  const auto tt1c = now();
   // ---- planning tables (device copies: dead row groups have zero rows => pruned by every device-side planner)
   for (size_t j = 0; j < k; j++) {
     SstResident& r = *rs[j];
@@ -680,8 +685,8 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
   if (trace) {
     const auto tt2 = now();
     cudaStreamSynchronize(e->stream);
-    fprintf(stderr, "[transient] %zu files: parse %.0f us, ranges+tables %.0f us (%zu ranges, %.1f MB, gate column %d), copy wait %.0f us\n", k,
-            us(tt0, tt1), us(tt1, tt2), n_ranges, copied / 1e6, gate_col, us(tt2, now()));
+    fprintf(stderr, "[transient] %zu files: parse %.0f us, gate phase %.0f us, main ranges %.0f us, tables %.0f us (%zu ranges, %.1f MB, gate column %d), copy wait %.0f us\n", k,
+            us(tt0, tt1), us(tt1, tt1b), us(tt1b, tt1c), us(tt1c, tt2), n_ranges, copied / 1e6, gate_col, us(tt2, now()));
   }
   for (size_t j = 0; j < k; j++) {
     e->transient_ids.push_back(rs[j]->id);
@@ -791,10 +796,10 @@ int build_plan(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ss
 
 // ------------------------------------------------------------------------------------------- the general pipeline
 struct DecodedCol {
-  DevBuf vals, valid;
+  DevBuf vals, valid, lens;            // lens: Binary columns only (vals = one byte pointer per row)
   uint32_t type = 0, width = 0;
   bool present = false;
-  ColView view() const { return ColView{vals.p, reinterpret_cast<const uint8_t*>(valid.p), type, width}; }
+  ColView view() const { return ColView{vals.p, reinterpret_cast<const uint8_t*>(valid.p), type, width, reinterpret_cast<const uint32_t*>(lens.p)}; }
 };
 
 struct PipelineState {
@@ -805,6 +810,8 @@ struct PipelineState {
   DevBuf alive, surv, keep, out_pos, out_rows, tmp, run_start, file_base, recA, recB, order, chunk_end, piece_end, bound;
   uint32_t nchunks = 0;
   const uint32_t* surv_ptr = nullptr;    // nullptr = identity
+  bool keep_order = false;               // Append mode: the export needs the merged order of ALL surviving rows
+  const uint32_t* order_ptr = nullptr;   //   row id of the t-th surviving row in merged order (nullptr = identity), valid when keep_order
   const uint32_t* d_m = nullptr;
   const uint32_t* d_r = nullptr;
   const uint32_t* d_g = nullptr;
@@ -817,10 +824,12 @@ static int validate_schema(const hg_schema_desc* s) {
   if (s->num_columns < s->num_primary_keys + 3 || s->num_columns > uint32_t(MAX_COLS))
     return set_error(HG_ERR_INVALID, "schema needs pk columns, at least one value column and the two builtin columns");
   if (s->num_primary_keys > uint32_t(MAX_PK)) return set_error(HG_ERR_UNSUPPORTED, "more than 4 primary key columns");
-  if (s->update_mode != HG_UPDATE_OVERWRITE)
-    return set_error(HG_ERR_UNSUPPORTED, "UpdateMode::Append (BytesMergeOperator) is not implemented on the GPU path");
+  if (s->update_mode > HG_UPDATE_APPEND) return set_error(HG_ERR_INVALID, "bad update mode");
   uint32_t pk_bytes = 0;
-  for (uint32_t c = 0; c < s->num_columns; c++) if (s->types[c] > T_F64) return set_error(HG_ERR_INVALID, "bad column type");
+  for (uint32_t c = 0; c < s->num_columns; c++) if (s->types[c] > T_BINARY) return set_error(HG_ERR_INVALID, "bad column type");
+  if (s->update_mode == HG_UPDATE_APPEND)       // read.rs:485-490 + operator.rs:66-73: BytesMergeOperator over ALL value columns
+    for (uint32_t c = s->num_primary_keys; c + 2 < s->num_columns; c++)
+      if (s->types[c] != T_BINARY) return set_error(HG_ERR_INVALID, "MergeOperator is only used for binary column (UpdateMode::Append)");
   for (uint32_t c = 0; c < s->num_primary_keys; c++) {
     uint32_t t = s->types[c];
     // primary_key_eq supports exactly these (read.rs:269-286); other types silently compare equal there — fenced off here
@@ -839,6 +848,7 @@ static int validate_preds(const hg_schema_desc* s, const hg_predicate* preds, si
   for (size_t i = 0; i < np; i++) {
     if (preds[i].column >= s->num_columns) return set_error(HG_ERR_INVALID, "predicate column out of range");
     if (preds[i].op > HG_OP_IN) return set_error(HG_ERR_UNSUPPORTED, "predicate operator");
+    if (s->types[preds[i].column] == T_BINARY) return set_error(HG_ERR_UNSUPPORTED, "predicates on Binary columns are not implemented on the GPU path");
     if (preds[i].op == HG_OP_IN && (preds[i].in_count > HG_MAX_IN_LIST || (preds[i].in_count && !preds[i].in_values)))
       return set_error(HG_ERR_INVALID, "IN list: null pointer or more than HG_MAX_IN_LIST values");
   }
@@ -899,7 +909,8 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     dc.width = type_width_host(dc.type);
     dc.present = true;
     CU_TRY(dc.vals.alloc(size_t(N) * dc.width + 16, s));
-    if (plan.col_has_nulls[c]) CU_TRY(dc.valid.alloc(size_t(N) + 16, s));
+    if (plan.col_has_nulls[c] || dc.type == T_BINARY) CU_TRY(dc.valid.alloc(size_t(N) + 16, s));
+    if (dc.type == T_BINARY) CU_TRY(dc.lens.alloc(size_t(N) * 4 + 16, s));
     ColSel cs;
     cs.col = c;
     cs.type = dc.type;
@@ -907,6 +918,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     cs._pad = 0;
     cs.out_vals = dc.vals.p;
     cs.out_valid = reinterpret_cast<uint8_t*>(dc.valid.p);
+    cs.out_lens = reinterpret_cast<uint32_t*>(dc.lens.p);
     colsel.push_back(cs);
   }
   if (N > 0) {
@@ -1104,6 +1116,7 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
   }
   CU_TRY(cudaEventRecord(e->evm1, s));
   st->keep.reset();
+  if (st->keep_order) { st->order_ptr = order; return HG_OK; }       // (order points into st->order or st->surv: both stay allocated)
   st->order.reset();
   st->surv.reset();
   return HG_OK;
@@ -1165,8 +1178,9 @@ PinnedPool& pinned_pool() { static PinnedPool* p = new PinnedPool(); return *p; 
 struct HostColumn {
   std::string name;
   uint32_t type = 0, width = 0;
-  void* vals = nullptr;          // pinned host
+  void* vals = nullptr;          // pinned host: the values — for Binary columns the concatenated bytes
   uint8_t* bitmap = nullptr;     // pinned host, nullptr = no nulls
+  int32_t* offsets = nullptr;    // pinned host, Binary columns only: Arrow offsets (rows + 1)
   int64_t null_count = 0;
 };
 struct StreamData {
@@ -1178,6 +1192,7 @@ struct StreamData {
     for (auto& c : cols) {
       pinned_pool().release(c.vals);
       pinned_pool().release(c.bitmap);
+      pinned_pool().release(c.offsets);
     }
   }
 };
@@ -1213,7 +1228,7 @@ static void fill_schema(struct ArrowSchema* out, const std::shared_ptr<StreamDat
   out->private_data = nullptr;
   out->release = schema_release;
 }
-struct ArrayPriv { std::shared_ptr<StreamData> keep; const void* bufs[2]; };
+struct ArrayPriv { std::shared_ptr<StreamData> keep; const void* bufs[3]; };
 static void child_release(struct ArrowArray* a) {
   if (!a || !a->release) return;
   delete reinterpret_cast<ArrayPriv*>(a->private_data);
@@ -1239,7 +1254,7 @@ static int stream_get_next(struct ArrowArrayStream* st, struct ArrowArray* out) 
   if (d->next + 1 >= d->batch_start.size()) { out->release = nullptr; return 0; }  // end of stream
   uint32_t lo = d->batch_start[d->next], hi = d->batch_start[d->next + 1];
   d->next++;
-  ArrayPriv* top = new ArrayPriv{d, {nullptr, nullptr}};
+  ArrayPriv* top = new ArrayPriv{d, {nullptr, nullptr, nullptr}};
   out->length = hi - lo;
   out->null_count = 0;
   out->offset = 0;
@@ -1250,11 +1265,13 @@ static int stream_get_next(struct ArrowArrayStream* st, struct ArrowArray* out) 
   for (size_t i = 0; i < d->cols.size(); i++) {
     ArrowArray* c = new ArrowArray();
     std::memset(c, 0, sizeof(*c));
-    ArrayPriv* p = new ArrayPriv{d, {d->cols[i].bitmap, d->cols[i].vals}};
+    const bool bin = d->cols[i].type == T_BINARY;          // Binary: validity, int32 offsets, data
+    ArrayPriv* p = bin ? new ArrayPriv{d, {d->cols[i].bitmap, d->cols[i].offsets, d->cols[i].vals}}
+                       : new ArrayPriv{d, {d->cols[i].bitmap, d->cols[i].vals, nullptr}};
     c->length = hi - lo;
     c->offset = lo;
     c->null_count = d->cols[i].bitmap ? -1 : 0;
-    c->n_buffers = 2;
+    c->n_buffers = bin ? 3 : 2;
     c->buffers = p->bufs;
     c->private_data = p;
     c->release = child_release;
@@ -1516,7 +1533,9 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
   data->batch_start.push_back(0);
   if (n == 0) { make_stream(out, data); return HG_OK; }   // EmptyRecordBatchStream (storage.rs:337-341)
 
+  const bool append = schema->update_mode == HG_UPDATE_APPEND;
   PipelineState st;
+  st.keep_order = append;
   rc = run_pipeline(e, schema, ssts, n, preds, np, out_cols, /*want_batches=*/true, &st);
   if (rc) return rc;
   const uint32_t N = st.N;
@@ -1531,13 +1550,68 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
   CU_TRY(cudaMemsetAsync(d_null.p, 0, sizeof(unsigned long long) * out_cols.size() + 16, s));
   std::vector<DevBuf> gv(out_cols.size()), gb(out_cols.size()), gm(out_cols.size());
   uint64_t d2h = 0;
+  // which row stands for an output row in the fixed-width columns: the run's LAST row (LastValueOperator, operator.rs:39-44) or,
+  // in Append mode, its FIRST row (BytesMergeOperator takes column.slice(0, 1), operator.rs:96-100)
+  DevBuf first_rows;
+  const uint32_t* rep_rows = st.out_rows.as<uint32_t>();
+  if (append && R > 0) {
+    CU_TRY(first_rows.alloc(size_t(R) * 4 + 16, s));
+    k::first_rows(L, st.order_ptr, st.out_pos.as<uint32_t>(), st.d_r, R, first_rows.as<uint32_t>());
+    rep_rows = first_rows.as<uint32_t>();
+  }
   for (size_t i = 0; i < out_cols.size() && R > 0; i++) {
     DecodedCol& dc = st.cols[out_cols[i]];
     HostColumn& hcx = data->cols[i];
+    if (dc.type == T_BINARY) {
+      // Binary: Arrow offsets by an exclusive scan of the byte lengths, then one warp per value copies the bytes.
+      //   Overwrite: one value per output row (its run's last row).   Append (BytesMergeOperator, operator.rs:75-95): the values of
+      //   ALL rows of a run concatenated in merged order = every surviving row's bytes laid out in merged order, offsets taken at
+      //   the runs' first rows; the result is never NULL.
+      const uint32_t cnt_cap = append ? N : R;                     // elements scanned (device counts: M resp. R)
+      const uint32_t* src_rows = append ? st.order_ptr : st.out_rows.as<uint32_t>();
+      const uint32_t* d_cnt = append ? st.d_m : st.d_r;
+      DevBuf lens_scan, offs_dev, d_total;
+      CU_TRY(lens_scan.alloc((size_t(cnt_cap) + 1) * 4 + 16, s));
+      CU_TRY(d_total.alloc(16, s));
+      k::gather_lens(L, dc.view(), src_rows, d_cnt, cnt_cap + 1, lens_scan.as<uint32_t>());
+      k::exclusive_scan_u32(L, lens_scan.as<uint32_t>(), cnt_cap + 1, d_total.as<uint32_t>());
+      uint32_t total = 0;
+      CU_TRY(cudaMemcpyAsync(&total, d_total.p, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      if (total >= 0x7fffffffu) return set_error(HG_ERR_UNSUPPORTED, "Binary column larger than 2 GiB in one call (Arrow int32 offsets)");
+      CU_TRY(gv[i].alloc(size_t(total) + 16, s));
+      k::copy_var(L, dc.view(), src_rows, d_cnt, cnt_cap, lens_scan.as<uint32_t>(), gv[i].as<uint8_t>());
+      const uint32_t* offs_src = lens_scan.as<uint32_t>();
+      if (append) {
+        CU_TRY(offs_dev.alloc((size_t(R) + 1) * 4 + 16, s));
+        k::run_offsets(L, lens_scan.as<uint32_t>(), st.out_pos.as<uint32_t>(), st.d_r, st.d_m, R, offs_dev.as<uint32_t>());
+        offs_src = offs_dev.as<uint32_t>();
+      }
+      hcx.vals = pinned_pool().alloc(size_t(total) + 16);
+      hcx.offsets = static_cast<int32_t*>(pinned_pool().alloc((size_t(R) + 1) * 4 + 16));
+      if (!hcx.vals || !hcx.offsets) return set_error(HG_ERR_OOM, "pinned host memory");
+      if (total) CU_TRY(cudaMemcpyAsync(hcx.vals, gv[i].p, total, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaMemcpyAsync(hcx.offsets, offs_src, (size_t(R) + 1) * 4, cudaMemcpyDeviceToHost, s));
+      d2h += size_t(total) + (size_t(R) + 1) * 4;
+      if (!append) {                                                // validity of the representative rows
+        CU_TRY(gb[i].alloc(size_t(R) + 16, s));
+        CU_TRY(gm[i].alloc((size_t(R) + 7) / 8 + 16, s));
+        DevBuf scratch_ptrs;
+        CU_TRY(scratch_ptrs.alloc(size_t(R) * 8 + 16, s));
+        k::gather_column(L, dc.view(), st.out_rows.as<uint32_t>(), st.d_r, R, scratch_ptrs.p, gb[i].as<uint8_t>());
+        k::pack_validity(L, gb[i].as<uint8_t>(), R, gm[i].as<uint8_t>(), d_null.as<unsigned long long>() + i);
+        hcx.bitmap = static_cast<uint8_t*>(pinned_pool().alloc((size_t(R) + 7) / 8 + 16));
+        if (!hcx.bitmap) return set_error(HG_ERR_OOM, "pinned host memory");
+        CU_TRY(cudaMemcpyAsync(hcx.bitmap, gm[i].p, (size_t(R) + 7) / 8, cudaMemcpyDeviceToHost, s));
+        d2h += (size_t(R) + 7) / 8;
+        CU_TRY(cudaStreamSynchronize(s));                            // the temporaries above are popped off the arena on scope exit
+      } else CU_TRY(cudaStreamSynchronize(s));
+      continue;
+    }
     CU_TRY(gv[i].alloc(size_t(R) * dc.width + 16, s));
     bool nulls = dc.valid.p != nullptr;
     if (nulls) { CU_TRY(gb[i].alloc(size_t(R) + 16, s)); CU_TRY(gm[i].alloc((size_t(R) + 7) / 8 + 16, s)); }
-    k::gather_column(L, dc.view(), st.out_rows.as<uint32_t>(), st.d_r, R, gv[i].p, gb[i].as<uint8_t>());
+    k::gather_column(L, dc.view(), rep_rows, st.d_r, R, gv[i].p, gb[i].as<uint8_t>());
     hcx.vals = pinned_pool().alloc(size_t(R) * dc.width + 16);
     if (!hcx.vals) return set_error(HG_ERR_OOM, "pinned host memory");
     CU_TRY(cudaMemcpyAsync(hcx.vals, gv[i].p, size_t(R) * dc.width, cudaMemcpyDeviceToHost, s));
@@ -1654,6 +1728,9 @@ int hg_compact_to_sst(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   if (!e || !props || !out_path || !out || (n_shard_preds && !shard_preds)) return set_error(HG_ERR_INVALID, "null argument");
   for (size_t i = 0; i < n_shard_preds; i++)
     if (shard_preds[i].column != 0) return set_error(HG_ERR_INVALID, "compaction shards are ranges of the first primary-key column");
+  if (schema && schema->types)
+    for (uint32_t c = 0; c < schema->num_columns; c++)
+      if (schema->types[c] == T_BINARY) return set_error(HG_ERR_UNSUPPORTED, "GPU SST writer: Binary columns are not implemented (use hg_compact_open + the host writer)");
   {
     int vrc = validate_schema(schema);
     if (vrc) return vrc;
@@ -1732,6 +1809,8 @@ int hg_write_batch(hg_engine* e, const hg_schema_desc* schema, const struct Arro
   int rc = validate_schema(schema);
   if (rc) return rc;
   const uint32_t ncols = schema->num_columns, user = ncols - 2, npk = schema->num_primary_keys;
+  for (uint32_t c = 0; c < ncols; c++)
+    if (schema->types[c] == T_BINARY) return set_error(HG_ERR_UNSUPPORTED, "GPU SST writer: Binary columns are not implemented");
   if (batch->n_children != int64_t(user)) return set_error(HG_ERR_INVALID, "batch must hold the user columns of the schema");
   if (batch->length < 0 || batch->length >= 0xfffffff0ll) return set_error(HG_ERR_UNSUPPORTED, "batch larger than 2^32 rows");
   if (batch->null_count > 0) return set_error(HG_ERR_UNSUPPORTED, "NULL rows (struct-level validity) are not supported");
@@ -1772,7 +1851,7 @@ int hg_write_batch(hg_engine* e, const hg_schema_desc* schema, const struct Arro
       bm.release();                          // arena memory: stays valid until the next call
       h2d += nbytes;
     }
-    views[c] = ColView{vals[c].p, has_nulls ? valid[c].as<uint8_t>() : nullptr, schema->types[c], w};
+    views[c] = ColView{vals[c].p, has_nulls ? valid[c].as<uint8_t>() : nullptr, schema->types[c], w, nullptr};
   }
   // ---- sort by (pk0, .., pkN-1): LSD over the key columns, last key first; every pass is a stable radix sort
   DevBuf perm, perm2, keys, keys2, counts, d_n;
@@ -1856,6 +1935,9 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
   if (n == 0) { ab->G = 0; return HG_OK; }
 
   if (agg->mode > HG_AGG_HASH) return set_error(HG_ERR_INVALID, "aggregation mode");
+  if (schema->update_mode != HG_UPDATE_OVERWRITE) return set_error(HG_ERR_UNSUPPORTED, "aggregation over an Append-mode (BytesMergeOperator) table");
+  for (int32_t c : {agg->group_col, agg->ts_col, agg->value_col})
+    if (c >= 0 && schema->types[c] == T_BINARY) return set_error(HG_ERR_INVALID, "Binary columns cannot be grouped or aggregated");
   // HASH mode only differs from RUNS when the key is not a prefix of the sort order (pk0 [, bucket of pk1]) / not global
   const bool prefix_key = (agg->group_col < 0 && !has_ts) || (agg->group_col == 0 && (!has_ts || agg->ts_col == 1));
   const bool hash_sort = agg->mode == HG_AGG_HASH && !prefix_key;

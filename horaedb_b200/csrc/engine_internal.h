@@ -41,11 +41,12 @@ inline int expected_phys(uint32_t t) {
     case T_U64: case T_I64: return PT_INT64;
     case T_F32: return PT_FLOAT;
     case T_F64: return PT_DOUBLE;
+    case T_BINARY: return PT_BYTE_ARRAY;
     default: return PT_INT32;
   }
 }
 inline const char* arrow_format(uint32_t t) {
-  static const char* f[] = {"C", "c", "S", "s", "I", "i", "L", "l", "f", "g"};
+  static const char* f[] = {"C", "c", "S", "s", "I", "i", "L", "l", "f", "g", "z"};
   return f[t];
 }
 

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
   const ChunkDev* chunks = sst.chunks + size_t(rs.rg) * sst.ncols;
   ColSel cs = cols[ci];
   ChunkDev ch = chunks[cs.col];
-  const uint32_t pw = (ch.phys == 1 || ch.phys == 4) ? 4u : 8u;   // INT32/FLOAT : INT64/DOUBLE
+  const uint32_t pw = (ch.phys == 1 || ch.phys == 4) ? 4u : 8u;   // INT32/FLOAT : INT64/DOUBLE (BYTE_ARRAY: variable, handled apart)
   uint8_t* sc = scratch + (ch.scratch_bytes ? chunk_scratch_off(rs, chunks, cols, ci) : 0);
   const uint8_t* dict = sst.bytes + ch.dict_payload_off;             // dictionary values (PLAIN): in place, or decompressed first in the scratch
   if (ch.dict_uncomp && ch.codec == 1) { dict = sc; sc += page_scratch(ch.dict_uncomp); }
@@ -537,7 +537,29 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
         __syncthreads();
       }
     }
-    if (all_valid && nv > max_vals) {
+    if (ch.phys == 6) {
+      // BYTE_ARRAY, PLAIN: [u32 length][bytes] per non-null value — a serial walk (a value's position depends on every length
+      // before it); Binary values of this engine's tables are few and large (batched payloads), one thread does it.  Rows point
+      // at their bytes in place (page payload or decompression scratch): nothing is copied here.
+      const uint8_t** optr = reinterpret_cast<const uint8_t**>(cs.out_vals);
+      if (tid == 0) {
+        const uint8_t* p = val_ptr;
+        bool bad = p > page_end;
+        for (uint32_t j = 0; j < nv && !bad; j++) {
+          const bool v = all_valid || cs.out_valid[row + j] != 0;
+          if (v) {
+            if (p + 4 > page_end) { bad = true; break; }
+            const uint32_t len = ld32_any(p);
+            if (len > uint32_t(page_end - p - 4)) { bad = true; break; }
+            optr[row + j] = p + 4;
+            cs.out_lens[row + j] = len;
+            p += 4 + size_t(len);
+          } else { optr[row + j] = nullptr; cs.out_lens[row + j] = 0; }
+        }
+        if (bad) s_bad = 6;
+      }
+      if (all_valid && cs.out_valid) for (uint32_t j = tid; j < nv; j += kThreads) cs.out_valid[row + j] = 1;
+    } else if (all_valid && nv > max_vals) {
       if (tid == 0) s_bad = 3;
     } else if (all_valid) {
       if (pw == 8) {
@@ -995,6 +1017,49 @@ __global__ void pack_agg_kernel(AggOut in, uint32_t gwidth, uint64_t g, uint64_t
   }
 }
 
+// ------------------------------------------------------------------------------------------- Binary columns: export
+// byte length of the i-th output row (0 for NULL and beyond the count), for an exclusive scan -> Arrow offsets
+__global__ void __launch_bounds__(kThreads) gather_lens_kernel(ColView col, const uint32_t* __restrict__ rows, const uint32_t* d_n, uint32_t cap,
+                                                              uint32_t* __restrict__ out) {
+  const uint32_t n = *d_n;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < cap; i += gridDim.x * kThreads) {
+    uint32_t len = 0;
+    if (i < n) { const uint32_t row = rows ? rows[i] : i; if (col.valid == nullptr || col.valid[row]) len = col.lens[row]; }
+    out[i] = len;
+  }
+}
+// one warp per row: bytes of row rows[i] -> dst + offs[i]
+__global__ void __launch_bounds__(kThreads) copy_var_kernel(ColView col, const uint32_t* __restrict__ rows, const uint32_t* d_n,
+                                                           const uint32_t* __restrict__ offs, uint8_t* __restrict__ dst) {
+  const uint32_t n = *d_n;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nwarps = gridDim.x * (kThreads / 32);
+  for (uint32_t i = (blockIdx.x * kThreads + threadIdx.x) >> 5; i < n; i += nwarps) {
+    const uint32_t row = rows ? rows[i] : i;
+    if (col.valid && !col.valid[row]) continue;
+    const uint8_t* src = reinterpret_cast<const uint8_t* const*>(col.vals)[row];
+    const uint32_t len = col.lens[row];
+    uint8_t* d = dst + offs[i];
+    for (uint32_t b = lane; b < len; b += 32) d[b] = src[b];
+  }
+}
+// Append mode: first row of the j-th primary-key run in merged order (the run ends at merged position out_pos[j])
+__global__ void __launch_bounds__(kThreads) first_rows_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ out_pos, const uint32_t* d_r,
+                                                             uint32_t* __restrict__ out) {
+  const uint32_t r = *d_r;
+  for (uint32_t j = blockIdx.x * kThreads + threadIdx.x; j < r; j += gridDim.x * kThreads) {
+    const uint32_t pos = j ? out_pos[j - 1] + 1 : 0;
+    out[j] = order ? order[pos] : pos;
+  }
+}
+// Append mode: Arrow offsets of the concatenated values = the running byte count sampled at the runs' first rows (+ the total)
+__global__ void __launch_bounds__(kThreads) run_offsets_kernel(const uint32_t* __restrict__ cum, const uint32_t* __restrict__ out_pos, const uint32_t* d_r,
+                                                              const uint32_t* d_m, uint32_t* __restrict__ out) {
+  const uint32_t r = *d_r, m = *d_m;
+  for (uint32_t j = blockIdx.x * kThreads + threadIdx.x; j <= r; j += gridDim.x * kThreads)
+    out[j] = j == r ? cum[m] : cum[j ? out_pos[j - 1] + 1 : 0];
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
@@ -1134,6 +1199,29 @@ void reduce_groups(const Launch& L, const AggSpecDev& spec, const uint32_t* rows
 void pack_agg(const Launch& L, AggOut in, uint32_t gwidth, uint64_t g, uint64_t cap, long long* dst) {
   if (!cap) return;
   pack_agg_kernel<<<grid_for(cap), kThreads, 0, L.stream>>>(in, gwidth, g, cap, dst);
+  L.tick();
+}
+void gather_lens(const Launch& L, ColView col, const uint32_t* rows, const uint32_t* d_n, uint32_t cap, uint32_t* out) {
+  if (!cap) return;
+  gather_lens_kernel<<<grid_for(cap), kThreads, 0, L.stream>>>(col, rows, d_n, cap, out);
+  L.tick();
+}
+void copy_var(const Launch& L, ColView col, const uint32_t* rows, const uint32_t* d_n, uint32_t cap, const uint32_t* offs, uint8_t* dst) {
+  if (!cap) return;
+  copy_var_kernel<<<grid_for(uint64_t(cap) * 32), kThreads, 0, L.stream>>>(col, rows, d_n, offs, dst);
+  L.tick();
+}
+void first_rows(const Launch& L, const uint32_t* order, const uint32_t* out_pos, const uint32_t* d_r, uint32_t cap, uint32_t* out) {
+  if (!cap) return;
+  first_rows_kernel<<<grid_for(cap), kThreads, 0, L.stream>>>(order, out_pos, d_r, out);
+  L.tick();
+}
+void run_offsets(const Launch& L, const uint32_t* cum, const uint32_t* out_pos, const uint32_t* d_r, const uint32_t* d_m, uint32_t cap, uint32_t* out) {
+  run_offsets_kernel<<<grid_for(uint64_t(cap) + 1), kThreads, 0, L.stream>>>(cum, out_pos, d_r, d_m, out);
+  L.tick();
+}
+void exclusive_scan_u32(const Launch& L, uint32_t* data, uint32_t n, uint32_t* d_total) {
+  compact_scan_sums_kernel<<<1, 1024, 0, L.stream>>>(data, n, d_total);
   L.tick();
 }
 void fill_u32(const Launch& L, uint32_t* p, uint32_t v, uint32_t n) {

@@ -120,6 +120,14 @@ int radix_sort_pairs(const Launch& L, uint64_t* keys, uint32_t* vals, uint64_t* 
 // order-preserving sort keys of the rows `rows[0..*d_r)`: gk = group value, bk = bucket start (either may be null); vals = rows
 void group_sort_keys(const Launch& L, const AggSpecDev& spec, const uint32_t* rows, const uint32_t* d_r, uint32_t cap, uint64_t* gk, uint64_t* bk,
                      uint32_t* vals);
+// Binary (variable-width) columns: export helpers.  gather_lens: byte length per output row (0 beyond *d_n / for NULL);
+// exclusive_scan_u32: single-block in-place exclusive scan of n words (*d_total = sum); copy_var: bytes of row rows[i] -> dst + offs[i];
+// first_rows / run_offsets: Append mode (BytesMergeOperator): the runs' first rows, the offsets of the concatenated values.
+void gather_lens(const Launch& L, ColView col, const uint32_t* rows, const uint32_t* d_n, uint32_t cap, uint32_t* out);
+void copy_var(const Launch& L, ColView col, const uint32_t* rows, const uint32_t* d_n, uint32_t cap, const uint32_t* offs, uint8_t* dst);
+void first_rows(const Launch& L, const uint32_t* order, const uint32_t* out_pos, const uint32_t* d_r, uint32_t cap, uint32_t* out);
+void run_offsets(const Launch& L, const uint32_t* cum, const uint32_t* out_pos, const uint32_t* d_r, const uint32_t* d_m, uint32_t cap, uint32_t* out);
+void exclusive_scan_u32(const Launch& L, uint32_t* data, uint32_t n, uint32_t* d_total);
 // write path helpers (radix_agg.cu)
 void column_sort_keys(const Launch& L, ColView col, const uint32_t* perm, uint32_t n, uint64_t* keys);
 void iota_u32(const Launch& L, uint32_t* p, uint32_t n);

@@ -25,6 +25,7 @@ namespace k {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMergeThreads = 512;        // merge CTA: 512 threads x 2 CTAs/SM (64 KB of shared memory each): shorter per-thread merge runs
 constexpr int kChunk = 4096;              // keys per round in shared memory (two buffers of 32 KB)
 constexpr int kIdxBits = 12;              // log2(kChunk): slot of a key inside its round
 constexpr int kSamples = 8192;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) kway_bounds_kernel(const uint64_t* _
 // one level of the shared-memory merge tree: lists of `step` streams each are merged pairwise, src -> dst, same offsets
 __device__ __forceinline__ void merge_level(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, const uint32_t* offs, int k, int step,
                                             uint32_t n, int tid) {
-  const uint32_t vt = (n + kThreads - 1) / kThreads;
+  const uint32_t vt = (n + kMergeThreads - 1) / kMergeThreads;
   uint32_t pos = uint32_t(tid) * vt;
   const uint32_t end = pos + vt < n ? pos + vt : n;
   const int npairs = (k + 2 * step - 1) / (2 * step);
@@ -147,7 +148,7 @@ __device__ __forceinline__ void merge_level(const uint64_t* __restrict__ src, ui
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) kway_merge_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ surv,
+__global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ surv,
                                                                 const uint32_t* __restrict__ run_start, int k, const uint32_t* __restrict__ bounds,
                                                                 uint32_t R, uint32_t pk_shift, unsigned int* ticket,
                                                                 uint32_t* __restrict__ order, uint8_t* __restrict__ keep) {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 3) kway_merge_kernel(const uint64_t*
   const uint32_t B = uint32_t(kChunk) / uint32_t(k);
   int levels = 0;
   while ((1 << levels) < k) levels++;
-  for (int i = tid; i <= k; i += kThreads) s_rs[i] = run_start[i];
+  for (int i = tid; i <= k; i += kMergeThreads) s_rs[i] = run_start[i];
   for (;;) {
     __syncthreads();
     if (tid == 0) s_range = atomicAdd(ticket, 1u);
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 3) kway_merge_kernel(const uint64_t*
       }
       __syncthreads();
       if (!s_any) break;
-      for (uint32_t i = tid; i < uint32_t(k) * B; i += kThreads) {
+      for (uint32_t i = tid; i < uint32_t(k) * B; i += kMergeThreads) {
         const uint32_t f = i / B, j = i % B;
         s_a[i] = j < s_take[f] ? keys[s_rs[f] + s_cur[f] + j] : kInf;
       }
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 3) kway_merge_kernel(const uint64_t*
       if (tid == 0) { uint32_t o = 0; for (int f = 0; f < k; f++) { s_offs[f] = o; o += s_n[f]; } s_offs[k] = o; }
       __syncthreads();
       const uint32_t n = s_offs[k];
-      for (uint32_t i = tid; i < uint32_t(k) * B; i += kThreads) {
+      for (uint32_t i = tid; i < uint32_t(k) * B; i += kMergeThreads) {
         const uint32_t f = i / B, j = i % B;
         if (j < s_n[f]) s_b[s_offs[f] + j] = (s_a[i] << kIdxBits) | i;
       }
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 3) kway_merge_kernel(const uint64_t*
       const uint32_t out0 = s_out;
       const uint32_t sh = pk_shift + kIdxBits;
       if (tid == 0 && s_has_carry && n) keep[out0 - 1] = (s_carry >> sh) != (src[0] >> sh);
-      for (uint32_t j = tid; j < n; j += kThreads) {
+      for (uint32_t j = tid; j < n; j += kMergeThreads) {
         const uint64_t w = src[j];
         const uint32_t slot = uint32_t(w) & (kChunk - 1);
         const uint32_t f = slot / B, i = slot % B;
@@ -270,7 +271,7 @@ void kway_merge(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* s
   L.tick();
   kway_bounds_kernel<<<int(((R + 1) * uint64_t(k) + kThreads - 1) / kThreads), kThreads, 0, L.stream>>>(keys, run_start, k, splitters, R, bounds);
   L.tick();
-  kway_merge_kernel<<<int(R < 148u * 3 ? R : 148u * 3), kThreads, 2 * kChunk * 8, L.stream>>>(keys, surv, run_start, k, bounds, R, kp.pk_shift, ticket, order, keep);
+  kway_merge_kernel<<<int(R < 148u * 2 ? R : 148u * 2), kMergeThreads, 2 * kChunk * 8, L.stream>>>(keys, surv, run_start, k, bounds, R, kp.pk_shift, ticket, order, keep);
   L.tick();
 }
 

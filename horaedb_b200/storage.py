@@ -131,6 +131,7 @@ class ObjectBasedStorage:
         fpath = self.sst_path_gen.generate(file_id)
         w = self.config.write
         gpu_writer = (hasattr(self.engine, "write_batch") and w.encoding == "PLAIN" and not w.enable_dict and not w.column_options
+                      and not any(pa.types.is_binary(f.type) for f in self.schema_.arrow_schema)
                       and str(w.compression).lower() in ("snappy", "uncompressed", "none")
                       and all(req.batch.column(i).null_count == 0 for i in range(self.schema_.num_primary_keys)))
         if gpu_writer:
@@ -195,7 +196,8 @@ class ObjectBasedStorage:
                 time_range.merge(f.meta().time_range)
             file_id = allocate_id()
             w = self.config.write
-            if w.encoding == "PLAIN" and not w.enable_dict and not w.column_options and str(w.compression).lower() in ("snappy", "uncompressed", "none"):
+            if (w.encoding == "PLAIN" and not w.enable_dict and not w.column_options and str(w.compression).lower() in ("snappy", "uncompressed", "none")
+                    and not any(pa.types.is_binary(f.type) for f in self.schema_.arrow_schema)):
                 # the whole of do_compaction on the GPU: merge + dedup (keep_builtin = true) AND the Parquet encode (hg_compact_to_sst)
                 meta = self.engine.compact_to_sst(self.handle, self._inputs(task.inputs), self.sst_path_gen.generate(file_id),
                                                   max_row_group_size=w.max_row_group_size, compression=str(w.compression),

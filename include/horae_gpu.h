@@ -53,7 +53,8 @@ typedef enum {
 
 /* Arrow primitive types the reference's primary_key_eq / value columns use (read.rs:269-286) */
 typedef enum {
-  HG_U8 = 0, HG_I8 = 1, HG_U16 = 2, HG_I16 = 3, HG_U32 = 4, HG_I32 = 5, HG_U64 = 6, HG_I64 = 7, HG_F32 = 8, HG_F64 = 9
+  HG_U8 = 0, HG_I8 = 1, HG_U16 = 2, HG_I16 = 3, HG_U32 = 4, HG_I32 = 5, HG_U64 = 6, HG_I64 = 7, HG_F32 = 8, HG_F64 = 9,
+  HG_BINARY = 10   /* Arrow Binary / Parquet BYTE_ARRAY: value columns only (what BytesMergeOperator concatenates, operator.rs:47-111) */
 } hg_type;
 
 typedef enum { HG_UPDATE_OVERWRITE = 0, HG_UPDATE_APPEND = 1 } hg_update_mode; /* config.rs:166-172 */
@@ -65,7 +66,9 @@ typedef enum { HG_OP_EQ = 0, HG_OP_NE = 1, HG_OP_LT = 2, HG_OP_LE = 3, HG_OP_GT 
 typedef struct {
   uint32_t num_columns;       /* including the two builtin columns */
   uint32_t num_primary_keys;
-  uint32_t update_mode;       /* hg_update_mode; only OVERWRITE (LastValueOperator, operator.rs:37-44) is implemented */
+  uint32_t update_mode;       /* hg_update_mode: OVERWRITE = LastValueOperator (operator.rs:37-44); APPEND = BytesMergeOperator
+                                 (operator.rs:47-111: every value column must be HG_BINARY; the run's values are concatenated in
+                                 (pk, seq) order, the other columns come from the run's FIRST row) */
   uint32_t _pad;
   const uint32_t* types;      /* hg_type per column */
   const char* const* names;   /* column names (for the exported Arrow schema) */
