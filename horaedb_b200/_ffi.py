@@ -199,6 +199,8 @@ def _make_preds(arrow_schema: pa.Schema, preds: Sequence[tuple]):
             # (DataFusion would coerce the comparison to a wider type; this ABI compares in the column's own domain)
             if isinstance(lit, float) and not lit.is_integer():
                 raise HgError(1, f"predicate literal {lit!r} is not integral for column {arrow_schema.field(idx).name}")
+            if not pa.types.is_integer(t):
+                raise HgError(2, f"predicates on {t} column {arrow_schema.field(idx).name} are not implemented on the GPU path")
             iv = int(lit)
             bits = t.bit_width
             lo, hi = (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if pa.types.is_signed_integer(t) else (0, (1 << bits) - 1)

@@ -951,7 +951,9 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
     k::decode_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
                      int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());
     CU_TRY(cudaEventRecord(e->evk1, s));
-    st->d_scratch.reset();
+    bool rows_point_into_scratch = false;                   // Binary rows are pointers to their bytes in place (page or decompression scratch)
+    for (uint32_t c : need_cols) if (schema->types[c] == T_BINARY) rows_point_into_scratch = true;
+    if (!rows_point_into_scratch) st->d_scratch.reset();
     if (trace) fprintf(stderr, "[general] col alloc+upload %.0f us, scratch alloc (%.1f MB) + decode launches %.0f us\n", us(tp0, tp1), plan.scratch_bytes / 1e6, us(tp1, now()));
   }
 
@@ -1126,6 +1128,7 @@ static int check_device_error(hg_engine* e, PipelineState* st) {
   int herr = 0;
   CU_TRY(cudaMemcpyAsync(&herr, st->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(cudaStreamSynchronize(e->stream));
+  if (herr == 130) return set_error(HG_ERR_INVALID, "failed to construct RecordBatch in BytesMergeOperator (a run of several rows whose Binary values are all empty)");
   if (herr) return set_error(HG_ERR_FORMAT, "device decode error code " + std::to_string(herr));
   return HG_OK;
 }
@@ -1593,19 +1596,22 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
       if (total) CU_TRY(cudaMemcpyAsync(hcx.vals, gv[i].p, total, cudaMemcpyDeviceToHost, s));
       CU_TRY(cudaMemcpyAsync(hcx.offsets, offs_src, (size_t(R) + 1) * 4, cudaMemcpyDeviceToHost, s));
       d2h += size_t(total) + (size_t(R) + 1) * 4;
-      if (!append) {                                                // validity of the representative rows
-        CU_TRY(gb[i].alloc(size_t(R) + 16, s));
-        CU_TRY(gm[i].alloc((size_t(R) + 7) / 8 + 16, s));
-        DevBuf scratch_ptrs;
+      // validity: Overwrite = the representative row's; Append = valid unless the run is ONE row whose value is NULL (a run with no
+      // bytes returns its column unchanged, operator.rs:80-92; more than one such row is the reference's RecordBatch error)
+      CU_TRY(gb[i].alloc(size_t(R) + 16, s));
+      CU_TRY(gm[i].alloc((size_t(R) + 7) / 8 + 16, s));
+      DevBuf scratch_ptrs;
+      if (append) k::append_validity(L, dc.view(), st.order_ptr, st.out_pos.as<uint32_t>(), st.d_r, offs_src, R, gb[i].as<uint8_t>(), st.d_err.as<int>());
+      else {
         CU_TRY(scratch_ptrs.alloc(size_t(R) * 8 + 16, s));
         k::gather_column(L, dc.view(), st.out_rows.as<uint32_t>(), st.d_r, R, scratch_ptrs.p, gb[i].as<uint8_t>());
-        k::pack_validity(L, gb[i].as<uint8_t>(), R, gm[i].as<uint8_t>(), d_null.as<unsigned long long>() + i);
-        hcx.bitmap = static_cast<uint8_t*>(pinned_pool().alloc((size_t(R) + 7) / 8 + 16));
-        if (!hcx.bitmap) return set_error(HG_ERR_OOM, "pinned host memory");
-        CU_TRY(cudaMemcpyAsync(hcx.bitmap, gm[i].p, (size_t(R) + 7) / 8, cudaMemcpyDeviceToHost, s));
-        d2h += (size_t(R) + 7) / 8;
-        CU_TRY(cudaStreamSynchronize(s));                            // the temporaries above are popped off the arena on scope exit
-      } else CU_TRY(cudaStreamSynchronize(s));
+      }
+      k::pack_validity(L, gb[i].as<uint8_t>(), R, gm[i].as<uint8_t>(), d_null.as<unsigned long long>() + i);
+      hcx.bitmap = static_cast<uint8_t*>(pinned_pool().alloc((size_t(R) + 7) / 8 + 16));
+      if (!hcx.bitmap) return set_error(HG_ERR_OOM, "pinned host memory");
+      CU_TRY(cudaMemcpyAsync(hcx.bitmap, gm[i].p, (size_t(R) + 7) / 8, cudaMemcpyDeviceToHost, s));
+      d2h += (size_t(R) + 7) / 8;
+      CU_TRY(cudaStreamSynchronize(s));                              // the temporaries above are popped off the arena on scope exit
       continue;
     }
     CU_TRY(gv[i].alloc(size_t(R) * dc.width + 16, s));
@@ -1627,6 +1633,7 @@ static int scan_impl(hg_engine* e, const hg_schema_desc* schema, const hg_sst_de
   std::vector<uint32_t> bound(st.nchunks);
   if (st.nchunks && N > 0) CU_TRY(cudaMemcpyAsync(bound.data(), st.bound.p, st.nchunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaEventRecord(e->ev1, s));
+  if (append) { rc = check_device_error(e, &st); if (rc) return rc; }       // BytesMergeOperator's own failure mode (see append_validity)
   CU_TRY(cudaStreamSynchronize(s));
   // MergeStream batch boundaries (read.rs:289-343, 349-384): batch c = outputs [bound[c-1], bound[c]); final flush = the rest
   uint32_t prev = 0;

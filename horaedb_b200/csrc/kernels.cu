@@ -1060,6 +1060,20 @@ __global__ void __launch_bounds__(kThreads) run_offsets_kernel(const uint32_t* _
     out[j] = j == r ? cum[m] : cum[j ? out_pos[j - 1] + 1 : 0];
 }
 
+__global__ void __launch_bounds__(kThreads) append_validity_kernel(ColView col, const uint32_t* __restrict__ order, const uint32_t* __restrict__ out_pos,
+                                                                  const uint32_t* d_r, const uint32_t* __restrict__ run_offs, uint8_t* __restrict__ valid, int* err) {
+  const uint32_t r = *d_r;
+  for (uint32_t j = blockIdx.x * kThreads + threadIdx.x; j < r; j += gridDim.x * kThreads) {
+    uint8_t v = 1;
+    if (run_offs[j + 1] == run_offs[j]) {
+      const uint32_t first = j ? out_pos[j - 1] + 1 : 0, last = out_pos[j];
+      if (first == last) { const uint32_t row = order ? order[first] : first; v = (col.valid == nullptr || col.valid[row]) ? 1 : 0; }
+      else atomicExch(err, 130);
+    }
+    valid[j] = v;
+  }
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
@@ -1218,6 +1232,12 @@ void first_rows(const Launch& L, const uint32_t* order, const uint32_t* out_pos,
 }
 void run_offsets(const Launch& L, const uint32_t* cum, const uint32_t* out_pos, const uint32_t* d_r, const uint32_t* d_m, uint32_t cap, uint32_t* out) {
   run_offsets_kernel<<<grid_for(uint64_t(cap) + 1), kThreads, 0, L.stream>>>(cum, out_pos, d_r, d_m, out);
+  L.tick();
+}
+void append_validity(const Launch& L, ColView col, const uint32_t* order, const uint32_t* out_pos, const uint32_t* d_r, const uint32_t* run_offs,
+                     uint32_t cap, uint8_t* valid, int* err) {
+  if (!cap) return;
+  append_validity_kernel<<<grid_for(cap), kThreads, 0, L.stream>>>(col, order, out_pos, d_r, run_offs, valid, err);
   L.tick();
 }
 void exclusive_scan_u32(const Launch& L, uint32_t* data, uint32_t n, uint32_t* d_total) {

@@ -127,6 +127,10 @@ void gather_lens(const Launch& L, ColView col, const uint32_t* rows, const uint3
 void copy_var(const Launch& L, ColView col, const uint32_t* rows, const uint32_t* d_n, uint32_t cap, const uint32_t* offs, uint8_t* dst);
 void first_rows(const Launch& L, const uint32_t* order, const uint32_t* out_pos, const uint32_t* d_r, uint32_t cap, uint32_t* out);
 void run_offsets(const Launch& L, const uint32_t* cum, const uint32_t* out_pos, const uint32_t* d_r, const uint32_t* d_m, uint32_t cap, uint32_t* out);
+// validity of a run's concatenated value (operator.rs:80-92: a run whose bytes are empty returns its column UNCHANGED — one row keeps
+// its own validity; several rows cannot be assembled into the one-row batch, which the reference reports as an error: *err = 130)
+void append_validity(const Launch& L, ColView col, const uint32_t* order, const uint32_t* out_pos, const uint32_t* d_r, const uint32_t* run_offs,
+                     uint32_t cap, uint8_t* valid, int* err);
 void exclusive_scan_u32(const Launch& L, uint32_t* data, uint32_t n, uint32_t* d_total);
 // write path helpers (radix_agg.cu)
 void column_sort_keys(const Launch& L, ColView col, const uint32_t* perm, uint32_t n, uint64_t* keys);

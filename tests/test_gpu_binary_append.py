@@ -54,7 +54,10 @@ def _check(got, exp):
     for a, e in zip(got, exp):
         assert a.schema.names == e.schema.names and a.num_rows == e.num_rows
         for c in range(a.num_columns):
-            assert arrays_equal(a.column(c), e.column(c)), a.schema.names[c]
+            if not arrays_equal(a.column(c), e.column(c)):
+                ga, ea = a.column(c).to_pylist(), e.column(c).to_pylist()
+                bad = [i for i in range(len(ea)) if ga[i] != ea[i]]
+                raise AssertionError(f"column {a.schema.names[c]}: {len(bad)} of {len(ea)} rows differ, first {[(i, ga[i], ea[i]) for i in bad[:4]]}")
 
 
 def test_reference_merge_stream_vectors_through_ssts(golden):
@@ -79,7 +82,7 @@ def test_binary_columns_overwrite_and_append_match_merge_stream(codec):
     rng = np.random.default_rng(31)
     user = arrow_schema([("pk1", "uint64"), ("pk2", "int32"), ("blob", "binary"), ("idx", "binary")])
 
-    def make(nrows, seq, keyspace):
+    def make(nrows, seq, keyspace, f=0, min_len=0):
         pk1 = np.sort(rng.integers(0, keyspace, nrows))
         pk2 = rng.integers(-2, 3, nrows)
         order = np.lexsort((pk2, pk1))
@@ -88,7 +91,9 @@ def test_binary_columns_overwrite_and_append_match_merge_stream(codec):
         keep[1:] = (pk1[1:] != pk1[:-1]) | (pk2[1:] != pk2[:-1])          # no duplicate PKs inside a file
         pk1, pk2 = pk1[keep], pk2[keep]
         n = len(pk1)
-        blob = [None if rng.random() < 0.1 else rng.bytes(int(rng.integers(0, 40))) for _ in range(n)]
+        # a key is NULL in at most one file ((pk1 + f) % 7): a run of SEVERAL rows never has zero bytes in Append mode, which the
+        # reference cannot assemble (operator.rs:80-92, tested apart in test_append_mode_rules); one-row NULL runs do occur
+        blob = [None if (int(k) + f) % 7 == 0 else rng.bytes(int(rng.integers(min_len, 40))) for k in pk1]
         idx = [bytes([seq % 251]) * int(rng.integers(1, 5)) for _ in range(n)]
         return record_batch(user, {"pk1": pk1.tolist(), "pk2": pk2.tolist(), "blob": blob, "idx": idx})
 
@@ -97,9 +102,10 @@ def test_binary_columns_overwrite_and_append_match_merge_stream(codec):
         mode = UpdateMode.Append if append else UpdateMode.Overwrite
         schema = StorageSchema.try_new(user, 2, mode)
         handle = SchemaHandle(schema.arrow_schema, 2, mode)
-        cases = [[make(3000, 5, 400)],                                                   # one file, several row groups
-                 [make(2500, 10 + f, 300) for f in range(5)],                             # overlapping files: real merge + runs
-                 [make(9000, 20 + f, 2000) for f in range(3)] + [make(0, 30, 10)]]        # > 8192 merged rows: MergeStream carry; an empty file
+        ml = 1 if append else 0                                                          # Overwrite also sees empty (non-NULL) values
+        cases = [[make(3000, 5, 400, 0, 0)],                                                      # one file, several row groups
+                 [make(2500, 10 + f, 300, f, ml) for f in range(5)],                              # overlapping files: real merge + runs
+                 [make(9000, 20 + f, 2000, f, ml) for f in range(3)] + [make(0, 30, 10)]]         # > 8192 merged rows: MergeStream carry; an empty file
         for batches in cases:
             datas = [sstgen.write_sst(schema, b, seq=100 + i, cfg=WriteConfig(compression=codec, max_row_group_size=1000), presorted=True)
                      for i, b in enumerate(batches)]
@@ -144,4 +150,17 @@ def test_append_mode_rules():
         eng.scan_aggregate(hb, [SstInput(id=next(_ids), data=db)], [], group_col=0, value_col=1)
     with pytest.raises(HgError):
         eng.compact_to_sst(hb, [SstInput(id=next(_ids), data=db)], "/tmp/never_written.sst")
+    # operator.rs:80-92: a run without bytes returns its column unchanged — one row keeps its validity, several rows cannot form the
+    # one-row batch: the reference fails with "failed to construct RecordBatch in BytesMergeOperator", and so does this path
+    sa = StorageSchema.try_new(ub, 1, UpdateMode.Append)
+    ha = SchemaHandle(sa.arrow_schema, 1, UpdateMode.Append)
+    one = [sstgen.write_sst(sa, record_batch(ub, {"pk1": [1, 2, 3], "b": [None, b"", b"q"]}), seq=1)]
+    assert pa.Table.from_batches(list(eng.scan(ha, [SstInput(id=next(_ids), data=one[0])])))["b"].to_pylist() == [None, b"", b"q"]
+    assert [r for b in _reference_scan(sa, one, True, False) for r in b.column(1).to_pylist()] == [None, b"", b"q"]
+    two = one + [sstgen.write_sst(sa, record_batch(ub, {"pk1": [1, 3], "b": [b"", b"r"]}), seq=2)]
+    with pytest.raises(HgError) as ei:
+        list(eng.scan(ha, [SstInput(id=next(_ids), data=d) for d in two]))
+    assert ei.value.code == 1 and "failed to construct RecordBatch in BytesMergeOperator" in str(ei.value)
+    with pytest.raises(Exception):
+        _reference_scan(sa, two, True, False)
     eng.close()
