@@ -607,7 +607,14 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
         ranges.back().bytes = std::max<uint64_t>(b0 + ranges.back().bytes, hi) - b0;
       } else ranges.push_back(CopyRange{datas[j] + lo, r.d_bytes + lo, hi - lo});
     };
+    // the ranges leave in slices: the gather kernel of one slice crosses PCIe while the host builds the next slice's ranges
+    const size_t slice_rgs = kept.size() > 4096 ? (kept.size() + 7) / 8 : kept.size();
     for (size_t i = 0; i < kept.size(); i++) {
+      if (i && i % slice_rgs == 0) {
+        int rc = move_ranges(ranges);
+        if (rc) return rc;
+        ranges.clear();
+      }
       const KeptRg& kr = kept[i];
       SstResident& r = *rs[kr.j];
       for (uint32_t c : need_cols) {
@@ -617,19 +624,19 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
         const bool by_row = !gate_out.empty() && c >= schema->num_primary_keys && rc.single_page && rc.null_none &&
                             (cd.codec == CODEC_UNCOMPRESSED || cd.stored);
         if (!by_row) { add_range(ranges, kr.j, kr.g, c); continue; }
-        // rows [first, last] of a page whose values can be addressed by row
+        // a page whose values can be addressed by row: only the blocks of rows that hold a passing row (GateOut::mask), cut to
+        // [first, last]; adjacent blocks travel as one interval
         const PageDev& pg = pages[kr.j][cd.first_page];
         const uint32_t w = (cd.phys == PT_INT32 || cd.phys == PT_FLOAT) ? 4u : 8u;
-        const uint64_t first = gate_out[i].first, last = gate_out[i].last;
         const uint8_t* base = datas[kr.j];
-        uint64_t body = pg.payload_off;
+        const uint64_t body = pg.payload_off;
+        // layout: PLAIN page = [prefix][values]; stored page (classify_stored) = [varint][literal 0 = prefix + n0 values][literal 1 = the rest]
+        uint64_t v0 = body, v1 = 0, n0 = ~0ull, prefix = 0;                  // v0 / v1: file offsets of value 0 and of value n0
         if (cd.codec == CODEC_UNCOMPRESSED) {
-          uint64_t prefix = 0;
           if (cd.optional) { uint32_t dl; std::memcpy(&dl, base + body, 4); prefix = 4 + uint64_t(dl); }
           add_bytes(kr.j, body, body + prefix);
-          add_bytes(kr.j, body + prefix + first * w, body + prefix + (last + 1) * w);
+          v0 = body + prefix;
         } else {
-          // stored page (classify_stored): [varint][literal 0 = level prefix + n0 values][literal 1 = the remaining values]
           uint64_t p = body;
           while (base[p] & 0x80) p++;
           p++;
@@ -641,16 +648,27 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
           };
           uint64_t len0 = 0, len1 = 0;
           const uint64_t lit0 = p + lit(p, &len0);
-          uint64_t prefix = 0;
           if (cd.optional) { uint32_t dl; std::memcpy(&dl, base + lit0, 4); prefix = 4 + uint64_t(dl); }
-          const uint64_t n0 = (len0 - prefix) / w;
+          n0 = (len0 - prefix) / w;
           add_bytes(kr.j, body, lit0 + prefix);
-          if (first < n0) add_bytes(kr.j, lit0 + prefix + first * w, lit0 + prefix + (std::min<uint64_t>(last, n0 - 1) + 1) * w);
+          v0 = lit0 + prefix;
           if (lit0 + len0 < body + pg.comp_size) {
-            const uint64_t lit1 = lit0 + len0 + lit(lit0 + len0, &len1);
-            add_bytes(kr.j, lit0 + len0, lit1);
-            if (last >= n0) add_bytes(kr.j, lit1 + (std::max<uint64_t>(first, n0) - n0) * w, lit1 + (last - n0 + 1) * w);
+            v1 = lit0 + len0 + lit(lit0 + len0, &len1);
+            add_bytes(kr.j, lit0 + len0, v1);
           }
+        }
+        const uint32_t brows = fused::gate_block_rows(r.rg_rows[kr.g]);
+        const uint32_t mask = gate_out[i].mask;
+        for (uint32_t b = 0; b < 32u;) {
+          if (!((mask >> b) & 1u)) { b++; continue; }
+          uint32_t e2 = b;
+          while (e2 + 1 < 32u && ((mask >> (e2 + 1)) & 1u)) e2++;
+          const uint64_t first = std::max<uint64_t>(gate_out[i].first, uint64_t(b) * brows);
+          const uint64_t last = std::min<uint64_t>(gate_out[i].last, uint64_t(e2 + 1) * brows - 1);
+          b = e2 + 1;
+          if (first > last) continue;
+          if (first < n0) add_bytes(kr.j, v0 + first * w, v0 + (std::min<uint64_t>(last, n0 - 1) + 1) * w);
+          if (v1 && last >= n0) add_bytes(kr.j, v1 + (std::max<uint64_t>(first, n0) - n0) * w, v1 + (last - n0 + 1) * w);
         }
       }
     }

@@ -1042,23 +1042,24 @@ bool is_int_type(uint32_t t) { return t != T_F32 && t != T_F64; }
 struct GatePreds { int n; uint32_t kind, cls, _pad; uint32_t op[MAX_PREDS]; uint64_t lit[MAX_PREDS]; };
 __global__ void __launch_bounds__(256) gate_rgs_kernel(const GateRg* __restrict__ rgs, uint32_t n, const __grid_constant__ GatePreds gp,
                                                        GateOut* __restrict__ out) {
-  __shared__ uint32_t s_first, s_last;
+  __shared__ uint32_t s_first, s_last, s_mask;
   for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
     const GateRg g = rgs[r];
     const uint8_t* vals = g.vals;
     if (g.prefixed) vals += 4 + ld32u(vals);
-    if (threadIdx.x == 0) { s_first = 0xffffffffu; s_last = 0; }
+    if (threadIdx.x == 0) { s_first = 0xffffffffu; s_last = 0; s_mask = 0; }
     __syncthreads();
-    uint32_t first = 0xffffffffu, last = 0;             // last = 1 + index
+    const uint32_t brows = gate_block_rows(g.nrows);
+    uint32_t first = 0xffffffffu, last = 0, mask = 0;   // last = 1 + index
     for (uint32_t i = threadIdx.x; i < g.nrows; i += 256) {
       const uint64_t v = load_kind(vals, gp.kind, i);
       bool ok = true;
       for (int p = 0; p < gp.n; p++) ok = ok && pred_ok(v, gp.lit[p], gp.cls, gp.op[p]);
-      if (ok) { first = first < i ? first : i; last = i + 1; }
+      if (ok) { first = first < i ? first : i; last = i + 1; mask |= 1u << (i / brows); }
     }
-    if (last) { atomicMin(&s_first, first); atomicMax(&s_last, last); }
+    if (last) { atomicMin(&s_first, first); atomicMax(&s_last, last); atomicOr(&s_mask, mask); }
     __syncthreads();
-    if (threadIdx.x == 0) out[r] = s_last ? GateOut{s_first, s_last - 1} : GateOut{1u, 0u};
+    if (threadIdx.x == 0) out[r] = s_last ? GateOut{s_first, s_last - 1, s_mask} : GateOut{1u, 0u, 0u};
     __syncthreads();
   }
 }

@@ -18,8 +18,10 @@ struct GateRg {
   const uint8_t* vals;       // PLAIN values of the gate column — or, with `prefixed`, the page body [u32 len][levels][values]
   uint32_t nrows, prefixed;  //   (a Snappy page decompressed on the device: the level length is only known there)
 };
-// first / last = the first and the last row (0-based) that pass; first > last: no row passes
-struct GateOut { uint32_t first, last; };
+// first / last = the first and the last row (0-based) that pass; first > last: no row passes.  mask: bit b set = a row of
+// block b passes, blocks of gate_block_rows(nrows) consecutive rows (32 blocks cover the row group)
+struct GateOut { uint32_t first, last, mask; };
+inline __host__ __device__ uint32_t gate_block_rows(uint32_t nrows) { const uint32_t b = (nrows + 31u) / 32u; return b < 32u ? 32u : b; }
 int gate_row_groups(hg_engine* e, const GateRg* d_rgs, uint32_t n, uint32_t type, const hg_predicate* preds, size_t np, GateOut* d_out);
 }  // namespace fused
 }  // namespace horae

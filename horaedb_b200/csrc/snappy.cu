@@ -122,8 +122,9 @@ __device__ __forceinline__ uint32_t flush_words(const WarpSmem& sm, uint8_t* dst
 }
 
 // stop_at: the consumer only needs the first stop_at bytes of the page (>= ulen: all of it).  Decoding may overshoot by one batch.
+// csz: CTA-shared table, compressed size of an element by its tag byte (elem_csize)
 __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, uint32_t stop_at,
-                            WarpSmem& sm, int lane, int* err) {
+                            WarpSmem& sm, const uint8_t* __restrict__ csz, int lane, int* err) {
   uint32_t pos = 0, ulen = 0;
   for (int sh = 0; pos < n && sh < 35; sh += 7) {
     uint32_t b = __ldg(src + pos++);
@@ -164,31 +165,37 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       fl = o & ~31u;
       continue;
     }
-    // ---- stage the window and build the jump tables.  Lane l owns positions l, l+32, ..: conflict-free table rows.
+    // ---- stage the window and build the jump tables.  Lane l owns the 8 positions [8l, 8l+8): their tag bytes are the window word it
+    //      just loaded, a table row is one 64-bit store per lane and level.  J[lv][p] = start of the 2^lv-th element after the one at
+    //      p, kExit when that leaves the window; position kWin-1 can never start an element with a staged successor, so
+    //      J[lv][kExit] == kExit on every level and the lookups need no test for kExit.
     __syncwarp();
+    uint32_t jlo = 0, jhi = 0;
     {
-      uint64_t w = (uint32_t(lane) * 8 < avail + 8) ? ld8_any(src + pos + lane * 8) : 0ull;
+      const uint64_t w = (uint32_t(lane) * 8 < avail + 8) ? ld8_any(src + pos + lane * 8) : 0ull;
       reinterpret_cast<uint64_t*>(sm.win)[lane] = w;
       if (lane < kWinPad / 8) reinterpret_cast<uint64_t*>(sm.win)[32 + lane] = (uint32_t(kWin + lane * 8) < avail + 8) ? ld8_any(src + pos + kWin + lane * 8) : 0ull;
-    }
-    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < kWin / 32; j++) {
-      const uint32_t p = j * 32 + lane;
-      const uint32_t sz = elem_csize(sm.win[p]);
-      const uint32_t nx = p + sz;
-      // the NEXT element must start inside the stream and have its (<= 5 byte) header inside the window
-      sm.J[0][p] = (sz == 0 || p >= avail || nx + 5 > uint32_t(kWin) || nx >= avail) ? uint8_t(kExit) : uint8_t(nx);
+      for (int i = 0; i < 8; i++) {
+        const uint32_t sz = csz[uint32_t(w >> (8 * i)) & 0xffu];
+        const uint32_t nx = uint32_t(lane) * 8 + i + sz;
+        // the NEXT element must start inside the stream and have its (<= 5 byte) header inside the window
+        const uint32_t v = (sz == 0 || nx + 5 > uint32_t(kWin) || nx >= avail) ? kExit : nx;
+        if (i < 4) jlo |= v << (8 * i); else jhi |= v << (8 * (i - 4));
+      }
+      reinterpret_cast<uint2*>(sm.J[0])[lane] = make_uint2(jlo, jhi);
     }
     __syncwarp();
 #pragma unroll
     for (int lv = 1; lv < kLevels; lv++) {
+      uint32_t nlo = 0, nhi = 0;
 #pragma unroll
-      for (int j = 0; j < kWin / 32; j++) {
-        const uint32_t p = j * 32 + lane;
-        const uint32_t a = sm.J[lv - 1][p];
-        sm.J[lv][p] = a == kExit ? uint8_t(kExit) : sm.J[lv - 1][a];
+      for (int i = 0; i < 4; i++) {
+        nlo |= uint32_t(sm.J[lv - 1][(jlo >> (8 * i)) & 0xffu]) << (8 * i);
+        nhi |= uint32_t(sm.J[lv - 1][(jhi >> (8 * i)) & 0xffu]) << (8 * i);
       }
+      jlo = nlo; jhi = nhi;
+      reinterpret_cast<uint2*>(sm.J[lv])[lane] = make_uint2(jlo, jhi);
       __syncwarp();
     }
     uint32_t qs = 0;                                   // window-relative start of the next batch
@@ -197,7 +204,7 @@ __device__ void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t
       uint32_t q = qs;
 #pragma unroll
       for (int lv = 0; lv < 5; lv++)
-        if ((lane >> lv) & 1) q = q == kExit ? kExit : sm.J[lv][q];
+        if ((lane >> lv) & 1) q = sm.J[lv][q];
       bool valid = q != kExit;
       uint32_t len = 0, off = 0, hdr = 0, csz = 0;
       bool is_lit = false;
@@ -380,6 +387,9 @@ __device__ __forceinline__ uint64_t chunk_scratch_off2(const RgSel& rs, const Ch
 // and the short ones fill the tail.
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(const __grid_constant__ SnappyJob J) {
   __shared__ WarpSmem s_w[kWarpsPerCta];
+  __shared__ uint8_t s_csz[256];
+  for (uint32_t t = threadIdx.x; t < 256; t += kWarpsPerCta * 32) s_csz[t] = uint8_t(elem_csize(t));
+  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpSmem& sm = s_w[wid];
   const uint32_t nsel = J.d_nsel ? *J.d_nsel : J.nsel;
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
                                                : chunk_scratch_off2(rs, chunks, J.cols, ci));
     if (ch.dict_uncomp) {                                        // compressed dictionary page: first in the chunk's scratch
       const uint8_t* dsrc = sst.bytes + ch.dict_payload_off;
-      snappy_page(dsrc, ch.dict_comp, dst, ch.dict_uncomp, 0xffffffffu, sm, lane, J.err);
+      snappy_page(dsrc, ch.dict_comp, dst, ch.dict_uncomp, 0xffffffffu, sm, s_csz, lane, J.err);
       dst += page_scratch2(ch.dict_uncomp);
     }
     for (uint32_t p = 0; p < ch.num_pages; p++) {
@@ -421,7 +431,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
         const uint32_t w = (ch.phys == 1 || ch.phys == 4) ? 4u : 8u;
         stop_at = 16u + (rs.num_rows + 7u) / 8u + 8u + rs.out_row * w;
       }
-      if (compressed) snappy_page(src, n, dst, ulen, stop_at, sm, lane, J.err);
+      if (compressed) snappy_page(src, n, dst, ulen, stop_at, sm, s_csz, lane, J.err);
       dst += page_scratch2(pg.uncomp_size);
       if (pg.encoding == 5 || pg.encoding == 8 || pg.encoding == 2) dst += page_scratch2(pg.num_values * 8u);   // PLAIN image of a DELTA / dictionary page (decode_chunks)
     }
@@ -431,6 +441,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
 // pages given by pointer (transient loads decompress the gate column before the SST's tables exist on the device)
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_raw_kernel(const RawPage* __restrict__ pages, uint32_t n, unsigned int* ticket, int* err) {
   __shared__ WarpSmem s_w[kWarpsPerCta];
+  __shared__ uint8_t s_csz[256];
+  for (uint32_t t = threadIdx.x; t < 256; t += kWarpsPerCta * 32) s_csz[t] = uint8_t(elem_csize(t));
+  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (;;) {
     uint32_t c = 0;
@@ -438,7 +451,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_raw_kernel(const 
     c = __shfl_sync(0xffffffffu, c, 0);
     if (c >= n) return;
     const RawPage pg = pages[c];
-    snappy_page(pg.src, pg.comp_size, pg.dst, pg.uncomp_size, 0xffffffffu, s_w[wid], lane, err);
+    snappy_page(pg.src, pg.comp_size, pg.dst, pg.uncomp_size, 0xffffffffu, s_w[wid], s_csz, lane, err);
   }
 }
 
