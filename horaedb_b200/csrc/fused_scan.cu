@@ -319,10 +319,15 @@ __global__ void __launch_bounds__(256) gate_sel_kernel(const __grid_constant__ F
   }
 }
 
-// one block: stable compaction of the selected row groups by flag (RgSel carries its scratch offset along)
+// one block: stable compaction of the selected row groups by flag (RgSel carries its scratch offset along).
+// lpt (optional): the compacted row groups' indices ordered by descending out_row = descending decompression work of the
+// partially decoded pages.  One warp decodes one page and a page is serial, so the decompression stage ends when the warp with
+// the longest total finishes: handing out the longest pages first (LPT) lets the short ones fill the tail.
 __global__ void __launch_bounds__(1024) compact_sel_kernel(const RgSel* __restrict__ in, const uint8_t* __restrict__ flags, uint32_t* d_nsel,
-                                                           RgSel* __restrict__ out) {
+                                                           RgSel* __restrict__ out, uint32_t* __restrict__ lpt) {
   __shared__ uint32_t s_w[33];
+  __shared__ uint32_t s_bin[1024];
+  __shared__ uint32_t s_max;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t n = *d_nsel;
   const uint32_t per = (n + 1023u) / 1024u;
@@ -334,6 +339,8 @@ __global__ void __launch_bounds__(1024) compact_sel_kernel(const RgSel* __restri
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
   if (lane == 31) s_w[w] = inc;
+  s_bin[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_max = 0;
   __syncthreads();
   if (w == 0) {
     uint32_t x = s_w[lane], xi = x;
@@ -344,9 +351,40 @@ __global__ void __launch_bounds__(1024) compact_sel_kernel(const RgSel* __restri
   }
   __syncthreads();
   uint32_t pos = s_w[w] + inc - cnt;
-  for (uint32_t i = lo; i < hi; i++) if (flags[i]) out[pos++] = in[i];
+  uint32_t mx = 0;
+  for (uint32_t i = lo; i < hi; i++)
+    if (flags[i]) { out[pos++] = in[i]; mx = in[i].out_row > mx ? in[i].out_row : mx; }
+  const uint32_t m = s_w[32];
+  if (lpt) {
+    // counting sort of the compacted list by out_row, descending (1024 bins over [0, max]; order inside a bin is arbitrary)
+    if (mx) atomicMax(&s_max, mx);
+    __syncthreads();
+    int shift = 0;
+    while ((s_max >> shift) > 1023u) shift++;
+    const uint32_t per2 = (m + 1023u) / 1024u;
+    const uint32_t lo2 = threadIdx.x * per2, hi2 = lo2 + per2 < m ? lo2 + per2 : m;
+    for (uint32_t i = lo2; i < hi2; i++) atomicAdd(&s_bin[1023u - (out[i].out_row >> shift)], 1u);
+    __syncthreads();
+    const uint32_t c = s_bin[threadIdx.x];
+    uint32_t ci = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ci, d); if (lane >= d) ci += t; }
+    __syncthreads();
+    if (lane == 31) s_w[w] = ci;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t x = s_w[lane], xi = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+      s_w[lane] = xi - x;
+    }
+    __syncthreads();
+    s_bin[threadIdx.x] = s_w[w] + ci - c;                       // exclusive start of this bin
+    __syncthreads();
+    for (uint32_t i = lo2; i < hi2; i++) lpt[atomicAdd(&s_bin[1023u - (out[i].out_row >> shift)], 1u)] = i;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) *d_nsel = s_w[32];
+  if (threadIdx.x == 0) *d_nsel = m;
 }
 
 // phase 1: one thread per row group, all blocks in parallel: keep flag (0/1) + rows
@@ -1230,7 +1268,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   static const int items_per_warp = getenv("HORAE_ITEMS_PER_WARP") ? atoi(getenv("HORAE_ITEMS_PER_WARP")) : 4;
   while (split < 8 && uint64_t(total_rgs) * split < 148ull * 32 * uint64_t(items_per_warp)) split *= 2;
   const uint32_t nitems = total_rgs * split;      // upper bound: pruning only removes items
-  DevBuf d_ssts, d_files, d_sel, d_sel2, d_rec, d_item, d_work, d_adj, d_keep, d_bsum, d_bases, d_vseg, d_gflags, d_scratch;
+  DevBuf d_ssts, d_files, d_sel, d_sel2, d_rec, d_item, d_work, d_adj, d_keep, d_bsum, d_bases, d_vseg, d_gflags, d_scratch, d_lpt;
   // ticket / slot counters, row counters and the error word share one zeroed block (one memset node per call)
   CU_TRY(d_work.alloc(256, s));
   CU_TRY(cudaMemsetAsync(d_work.p, 0, 256, s));
@@ -1249,6 +1287,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   if (need_snappy) {
     CU_TRY(d_sel2.alloc(size_t(total_rgs + 1) * sizeof(RgSel), s));
     CU_TRY(d_gflags.alloc(size_t(total_rgs) + 16, s));
+    CU_TRY(d_lpt.alloc(size_t(total_rgs + 1) * sizeof(uint32_t), s));
     CU_TRY(d_scratch.alloc(size_t(total_rgs) * size_t(nregions) * scratch_stride + 256, s));
   }
   if ((uint64_t(nitems) + 1023) / 1024 > 1024) return NOT_APPLICABLE;   // two-level item scan covers 1 M work items
@@ -1401,7 +1440,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
         if (w4) gate_sel_kernel<true><<<148 * 8, 256, 0, s>>>(P, d_sel.as<RgSel>(), gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
         else gate_sel_kernel<false><<<148 * 8, 256, 0, s>>>(P, d_sel.as<RgSel>(), gate_slot, P.hot_flip[nhot - 1], P.hot_lo[nhot - 1], P.hot_span[nhot - 1], d_gflags.as<uint8_t>());
         L.tick();
-        compact_sel_kernel<<<1, 1024, 0, s>>>(d_sel.as<RgSel>(), d_gflags.as<uint8_t>(), d_work.as<uint32_t>() + 3, d_sel2.as<RgSel>());
+        compact_sel_kernel<<<1, 1024, 0, s>>>(d_sel.as<RgSel>(), d_gflags.as<uint8_t>(), d_work.as<uint32_t>() + 3, d_sel2.as<RgSel>(), d_lpt.as<uint32_t>());
         L.tick();
         P.sel = d_sel2.as<RgSel>();
       }
@@ -1411,6 +1450,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
         // non-gate columns — except pk0, which the work-item boundaries probe anywhere (and pk1 when groups are time buckets)
         if (!first.empty() && !has_ts)
           for (size_t i = 0; i < rest.size(); i++) J2.partial[i] = rest[i] != 0 ? 1 : 0;
+        if (!first.empty()) { J2.sel = P.sel; J2.lpt = d_lpt.as<uint32_t>(); }       // longest pages first (compact_sel_kernel)
         k::snappy_pages(L, J2, total_rgs * uint32_t(rest.size()));
       }
     }

@@ -29,6 +29,7 @@ struct SnappyJob {
   const SstDev* ssts;
   const RgSel* sel;
   const uint32_t* d_nsel;     // device-side count of row groups, or nullptr: use nsel
+  const uint32_t* lpt;        // optional: row-group indices in the order the tickets hand them out (longest pages first)
   uint32_t nsel;
   int ncols;                  // columns to decompress per row group
   uint32_t col[kSnappyMaxCols];        // schema column of entry i
