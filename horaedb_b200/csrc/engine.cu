@@ -211,7 +211,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
     const uint32_t t0 = schema->types[0];
     for (int c = 0; c < m.ncols && c < MAX_COLS; c++) {
       r->col_all_simple[c] = true; r->col_null_none[c] = true; r->col_has_minmax[c] = true;
-      r->col_all_single[c] = true; r->col_any_snappy[c] = false; r->col_snappy_all_stored[c] = true;
+      r->col_all_single[c] = true; r->col_any_snappy[c] = false; r->col_snappy_all_stored[c] = true; r->col_snappy_any_stored[c] = false;
     }
     bool first = true;
     r->pk0_range_ok = true;
@@ -223,7 +223,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       for (int c = 0; c < m.ncols && c < MAX_COLS; c++) {
         if (!rc[c].simple_page) r->col_all_simple[c] = false;
         if (!rc[c].single_page) r->col_all_single[c] = false;
-        if (rc[c].snappy) { r->col_any_snappy[c] = true; if (!rc[c].stored) r->col_snappy_all_stored[c] = false; }
+        if (rc[c].snappy) { r->col_any_snappy[c] = true; if (!rc[c].stored) r->col_snappy_all_stored[c] = false; else r->col_snappy_any_stored[c] = true; }
         r->col_max_scratch[c] = std::max(r->col_max_scratch[c], rc[c].scratch);
         r->col_comp_bytes[c] += uint64_t(m.rgs[g].cols[c].total_compressed);
         if (!rc[c].null_none) r->col_null_none[c] = false;

@@ -126,6 +126,7 @@ struct SstResident {
   bool col_all_single[MAX_COLS] = {false};       // every chunk: one V1 PLAIN page (any supported codec)
   bool col_any_snappy[MAX_COLS] = {false};
   bool col_snappy_all_stored[MAX_COLS] = {false};  // every Snappy chunk of the column is a stored (literal-only) page
+  bool col_snappy_any_stored[MAX_COLS] = {false};  // some Snappy chunk of the column is one
   uint32_t col_max_scratch[MAX_COLS] = {0};      // largest decompression scratch of one chunk of the column
   uint64_t col_comp_bytes[MAX_COLS] = {0};       // compressed bytes of the column (work estimate for the decompressor)
   uint64_t pk0_min = 0, pk0_max = 0;

@@ -1214,13 +1214,19 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   bool slot_snappy[MAXC] = {false};
   uint64_t slot_comp[MAXC] = {0};
   uint64_t scratch_stride = 0;
-  bool value_stored = value_slot >= 0;
+  // The value column's stored (literal-only) Snappy pages are read in place through a per-row-group segment table (VSeg); its other
+  // pages — a random f64 column still yields the odd page with a copy element — are decompressed like any column and the table
+  // points at the scratch.  value_stored = that table is in use; value_all_stored = no page of the column needs scratch at all.
+  bool value_stored = false, value_all_stored = true;
   for (size_t i = 0; i < slots.size(); i++)
     for (SstResident* f : files) {
       const uint32_t c = slots[i];
       if (f->col_any_snappy[c]) { slot_snappy[i] = true; scratch_stride = std::max<uint64_t>(scratch_stride, f->col_max_scratch[c]); }
       slot_comp[i] += f->col_comp_bytes[c];
-      if (int(i) == value_slot && !f->col_snappy_all_stored[c]) value_stored = false;
+      if (int(i) == value_slot) {
+        if (f->col_snappy_any_stored[c]) value_stored = true;
+        if (f->col_any_snappy[c] && !f->col_snappy_all_stored[c]) value_all_stored = false;
+      }
     }
   if (value_slot >= 0) {
     if (!slot_snappy[value_slot]) value_stored = false;
@@ -1230,7 +1236,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
   scratch_stride = (scratch_stride + 255) & ~uint64_t(255);
   int region[MAXC];
   int nregions = 0;
-  for (size_t i = 0; i < slots.size(); i++) region[i] = (slot_snappy[i] && !(value_stored && int(i) == value_slot)) ? nregions++ : -1;
+  for (size_t i = 0; i < slots.size(); i++) region[i] = (slot_snappy[i] && !(value_stored && value_all_stored && int(i) == value_slot)) ? nregions++ : -1;
   const bool need_snappy = nregions > 0;
   auto t1 = now();
 
@@ -1418,7 +1424,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
           J.col[i] = slots[job_slots[i]];
           J.region[i] = uint32_t(region[job_slots[i]]);
           J.order[i] = uint8_t(ord[i]);
-          J.skip_stored[i] = 0;
+          J.skip_stored[i] = (value_stored && job_slots[i] == value_slot) ? 1 : 0;   // stored pages of the value column stay where they are
         }
         J.fixed_stride = scratch_stride; J.scratch = d_scratch.as<uint8_t>(); J.ticket = ticket; J.err = err_p;
         return J;

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
   init_tag_tables(s_csz, s_lut);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpSmem& sm = s_w[wid];
+  bulk_init(sm, lane);
+  uint32_t phase = 0;
   const uint32_t nsel = J.d_nsel ? *J.d_nsel : J.nsel;
   const uint32_t nchunks = nsel * uint32_t(J.ncols);
   for (;;) {
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
         advance = page_scratch2(pg.uncomp_size);
         if (pg.encoding == 5 || pg.encoding == 8 || pg.encoding == 2) advance += page_scratch2(pg.num_values * 8u);   // PLAIN image of a DELTA / dictionary page (decode_chunks)
       }
-      if (compressed) snappy_page(src, n, dst, ulen, stop_at, sm, s_csz, s_lut, lane, J.err);
+      if (compressed) snappy_page(src, n, dst, ulen, stop_at, sm, phase, s_csz, s_lut, lane, J.err);
       dst += advance;
     }
   }
@@ -120,13 +122,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_raw_kernel(const 
   __shared__ uint8_t s_csz[256];
   init_tag_tables(s_csz, s_lut);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  bulk_init(s_w[wid], lane);
+  uint32_t phase = 0;
   for (;;) {
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(ticket, 1u);
     c = __shfl_sync(0xffffffffu, c, 0);
     if (c >= n) return;
     const RawPage pg = pages[c];
-    snappy_page(pg.src, pg.comp_size, pg.dst, pg.uncomp_size, 0xffffffffu, s_w[wid], s_csz, s_lut, lane, err);
+    snappy_page(pg.src, pg.comp_size, pg.dst, pg.uncomp_size, 0xffffffffu, s_w[wid], phase, s_csz, s_lut, lane, err);
   }
 }
 

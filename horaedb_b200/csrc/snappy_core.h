@@ -25,6 +25,7 @@
 //                 page's earlier output, or from an earlier element of the same batch (parent links collapsed with five
 //                 register shuffles) — and drops them into a shared-memory ring.  An element whose source straddles
 //                 two elements of the batch simply ends the prefix: it starts the next batch, where its source is old.
+//   staging  the compressed bytes travel global -> shared by cp.async.bulk + mbarrier, one region ahead of the parser.
 //     run mode    a long element, or a run of copies with one offset (RLE-like columns: 64-byte copies at offset 4/8):
 //                 out[x] = out[x - off] over the union, i.e. one periodic pattern; for off in {1,2,4,8} that is a single
 //                 64-bit word stored to every aligned word of the run.
@@ -52,18 +53,32 @@ constexpr uint64_t kFill = 0xfcfcfcfcfcfcfcfcull;   // tag of a long literal: wh
 
 // 256-byte aligned, every jump table on a 256-byte boundary: a table address is the block's base with the index as its low
 // byte, i.e. ONE byte-permute (index extraction and address formation together) in front of the load.
+constexpr int kStage = 448;        // bytes per staging buffer of the compressed stream (multiple of 16: bulk-copy granularity)
+constexpr uint32_t kAhead = kRestage;      // the next window starts more than this many bytes behind the current one
 struct alignas(256) WarpSmem {
   uint64_t ring64[kRing / 8];      // output byte at absolute position x lives at byte x & (kRing-1)
   uint8_t J[kLevels][kWin];
-  uint8_t win[kWin + kWinPad];     // same block as the ring: one base pointer + byte offset addresses both
-  uint8_t pad_[256 - kWinPad];
+  // The compressed stream reaches shared memory by asynchronous bulk copies (cp.async.bulk + mbarrier: one instruction moves the
+  // whole region, no registers, no per-lane address arithmetic), double-buffered: while the batches of one window execute, the
+  // region the next window must lie in is already on its way.  A window is a byte offset into one of the two buffers.
+  alignas(16) uint8_t stage[2][kStage];
+  uint64_t bar[2];                 // one mbarrier per buffer
 };
 constexpr uint32_t kJOff = kRing;                          // byte offsets inside WarpSmem
-constexpr uint32_t kWinOff = kRing + kLevels * kWin;
+constexpr uint32_t kStageOff = kRing + kLevels * kWin;
+constexpr uint32_t kBarOff = kStageOff + 2 * kStage;
+// where the staging buffers stand: which one holds the current window, what the other one was asked to fetch, barrier phases
+struct StageState {
+  uint32_t phase;                  // bit b = parity the next wait on bar[b] uses
+  int cur;                         // buffer of the current window
+  bool pf;                         // a copy into buffer cur ^ 1 was issued and not yet waited for
+  int pf_start;                    // stream position (relative to the page's first byte, may be < 0) of that buffer's byte 0
+  uint32_t pf_bytes;
+};
 
 // Tag-byte tables (256 entries each, shared by the CTA).
 //   csz : compressed size of the element, 255 = literal with a multi-byte length field (never part of a batch)
-//   lut : len (bits 0-6) | hdr << 8 (3 bits) | offset high bits of a 1-byte-offset copy << 12 (3 bits) | is_lit << 16 | long_lit << 17 |
+//   lut : len (bits 0-6) | offset bits 8-10 of a 1-byte-offset copy, in place (bits 8-10) | is_lit << 16 | long_lit << 17 |
 //         (32 - 8 * offset bytes) << 18 (5 bits) | csz << 24
 SNP_FN uint32_t elem_csize(uint32_t t) {
   const uint32_t kind = t & 3;
@@ -81,7 +96,7 @@ SNP_FN uint32_t elem_lut(uint32_t t) {
   else if (kind == 2) { len = (t >> 2) + 1; hdr = 3; msh = 16; }
   else { len = (t >> 2) + 1; hdr = 5; msh = 0; }
   const uint32_t csz = long_lit ? 0u : hdr + (is_lit ? len : 0u);
-  return len | (hdr << 8) | (offhi << 12) | (is_lit << 16) | (long_lit << 17) | (msh << 18) | (csz << 24);
+  return len | (offhi << 8) | (is_lit << 16) | (long_lit << 17) | (msh << 18) | (csz << 24);
 }
 
 SNP_FN uint64_t page_scratch2(uint32_t uncomp) { return (uint64_t(uncomp) + 15u) / 16u * 16u + 32u; }
@@ -151,6 +166,51 @@ SNP_FN void store_elem(WarpSmem& sm, uint32_t, uint32_t rb, uint64_t w, uint32_t
   for (uint32_t i = 0; i < len; i++) reinterpret_cast<uint8_t*>(sm.ring64)[rb + i] = uint8_t(w >> (8 * i));
 }
 #endif
+// bulk_init: once per warp (lane 0 initialises both barriers);  bulk_issue: lane 0 starts the copy of `bytes` (multiple of 16) from the
+// 16-byte aligned global address g into buffer b;  bulk_wait: every lane blocks until the copy into buffer b has landed.
+#ifdef __CUDACC__
+SNP_FN void bulk_init(WarpSmem& sm, int lane) {
+  if (lane == 0) {
+    const uint32_t a = sm_base(sm) + kBarOff;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  snp_syncwarp();
+}
+SNP_FN void bulk_issue(WarpSmem& sm, int b, const uint8_t* g, uint32_t bytes, int lane) {
+  if (lane == 0) {
+    const uint32_t bar = sm_base(sm) + kBarOff + 8u * uint32_t(b), dst = sm_base(sm) + kStageOff + uint32_t(kStage) * uint32_t(b);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the lanes' earlier reads of this buffer are done (syncwarp before)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g), "r"(bytes), "r"(bar) : "memory");
+  }
+}
+SNP_FN void bulk_wait(WarpSmem& sm, int b, uint32_t parity) {
+  const uint32_t bar = sm_base(sm) + kBarOff + 8u * uint32_t(b);
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+#else
+SNP_FN void bulk_init(WarpSmem&, int) {}
+SNP_FN void bulk_issue(WarpSmem& sm, int b, const uint8_t* g, uint32_t bytes, int lane) {
+  if (lane == 0) for (uint32_t i = 0; i < bytes; i++) sm.stage[b][i] = g[i];
+}
+SNP_FN void bulk_wait(WarpSmem&, int, uint32_t) { snp_syncwarp(); }
+#endif
+// start fetching the region that holds stream positions [from, from + kStage) (clamped to the stream's end n) into buffer b
+SNP_FN void stage_fetch(WarpSmem& sm, StageState& st, int b, const uint8_t* src, uint32_t n, uint32_t from, int lane) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src + from) & ~uintptr_t(15);
+  const uintptr_t end = (reinterpret_cast<uintptr_t>(src + n) + 15) & ~uintptr_t(15);
+  uint32_t bytes = uint32_t(end - a);
+  if (bytes > uint32_t(kStage)) bytes = uint32_t(kStage);
+  st.pf_start = int(intptr_t(a) - intptr_t(reinterpret_cast<uintptr_t>(src)));
+  st.pf_bytes = bytes;
+  bulk_issue(sm, b, reinterpret_cast<const uint8_t*>(a), bytes, lane);
+}
+
 template <int LV> SNP_FN void jt_level(WarpSmem& sm, uint32_t smbase, uint32_t& jlo, uint32_t& jhi, int lane) {
   uint32_t nlo = 0, nhi = 0;
   nlo = put_byte<0>(nlo, jt_get<0, LV - 1>(sm, smbase, jlo)); nhi = put_byte<0>(nhi, jt_get<0, LV - 1>(sm, smbase, jhi));
@@ -192,8 +252,8 @@ SNP_FN uint32_t flush_words(const WarpSmem& sm, uint8_t* dst, uint32_t fl, uint3
 
 // stop_at: the consumer only needs the first stop_at bytes of the page (>= ulen: all of it).  Decoding may overshoot by one batch.
 // csz / lut: the CTA-shared tag tables (elem_csize / elem_lut)
-SNP_FN void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, uint32_t stop_at,
-                        WarpSmem& sm, const uint8_t* __restrict__ csz, const uint32_t* __restrict__ lut, int lane, int* err) {
+SNP_FN void snappy_page_body(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, uint32_t stop_at,
+                             WarpSmem& sm, StageState& st, const uint8_t* __restrict__ csz, const uint32_t* __restrict__ lut, int lane, int* err) {
   uint32_t pos = 0, ulen = 0;
   for (int sh = 0; pos < n && sh < 35; sh += 7) {
     const uint32_t b = snp_ldg8(src + pos++);
@@ -202,7 +262,8 @@ SNP_FN void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __
   }
   if (ulen != ulen_expected) { if (lane == 0) snp_set_err(err, 101); return; }
   uint8_t* const ring = ring_bytes(sm);
-  const uint32_t* const win32 = reinterpret_cast<const uint32_t*>(sm.win);
+  const uint32_t* const sm32 = reinterpret_cast<const uint32_t*>(&sm);
+  const uint8_t* const sm8 = reinterpret_cast<const uint8_t*>(&sm);
   const uint32_t smbase = sm_base(sm);
   uint32_t o = 0;                 // bytes produced so far
   uint32_t fl = 0;                // output bytes [0, fl) are in global memory (fl is a multiple of 32, fl <= o)
@@ -245,23 +306,36 @@ SNP_FN void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __
     //      every level and the lookups need no test.
     snp_syncwarp();
     SNP_STAT(windows, 1);
+    // the window's bytes: already fetched (or on their way) if the last window's look-ahead covers [pos, pos + need), else fetched now
+    uint32_t wbase;                                    // byte offset of window position 0 inside the warp's shared block
+    {
+      const uint32_t need = avail < uint32_t(kWin + kWinPad) ? avail : uint32_t(kWin + kWinPad);
+      const int nb = st.cur ^ 1;
+      bool hit = false;
+      if (st.pf) {
+        bulk_wait(sm, nb, (st.phase >> nb) & 1u);
+        st.phase ^= 1u << nb;
+        st.pf = false;
+        hit = int(pos) >= st.pf_start && pos + need <= uint32_t(st.pf_start + int(st.pf_bytes));
+        SNP_STAT(stage_hits, hit ? 1 : 0);
+      }
+      if (!hit) {
+        stage_fetch(sm, st, nb, src, n, pos, lane);
+        bulk_wait(sm, nb, (st.phase >> nb) & 1u);
+        st.phase ^= 1u << nb;
+      }
+      wbase = kStageOff + uint32_t(kStage) * uint32_t(nb) + uint32_t(int(pos) - st.pf_start);
+      st.cur = nb;
+      // look ahead: the next window starts in (pos + kAhead, pos + kWin + 61]; its region goes into the buffer just left
+      if (pos + kAhead < n) { stage_fetch(sm, st, nb ^ 1, src, n, pos + kAhead, lane); st.pf = true; }
+    }
     uint32_t jlo, jhi;
     {
       uint64_t w = kFill;
       const int nv = int(avail) - lane * 8;                       // stream bytes in this lane's word
       if (nv > 0) {
-        w = ld8_any(src + pos + lane * 8);
+        w = sm_ld8(sm, wbase + uint32_t(lane) * 8);
         if (nv < 8) w = (w & ((1ull << (8 * nv)) - 1)) | (kFill << (8 * nv));
-      }
-      reinterpret_cast<uint64_t*>(sm.win)[lane] = w;
-      if (lane < kWinPad / 8) {
-        uint64_t wp = kFill;
-        const int nvp = int(avail) - (kWin + lane * 8);
-        if (nvp > 0) {
-          wp = ld8_any(src + pos + kWin + lane * 8);
-          if (nvp < 8) wp = (wp & ((1ull << (8 * nvp)) - 1)) | (kFill << (8 * nvp));
-        }
-        reinterpret_cast<uint64_t*>(sm.win)[32 + lane] = wp;
       }
       const uint32_t wl = uint32_t(w), wh = uint32_t(w >> 32), p0 = uint32_t(lane) * 8;
       uint32_t a;
@@ -289,15 +363,15 @@ SNP_FN void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __
       for (int lv = 0; lv < 5; lv++)
         if ((lane >> lv) & 1) q = sm.J[lv][q];
       // ---- decode the element at q (branch-free: tag table + the 4 bytes behind the tag)
-      const uint32_t e = lut[sm.win[q]];
+      const uint32_t e = lut[sm8[wbase + q]];
       uint32_t len = e & 0x7fu;
       uint32_t ecsz = e >> 24;
       bool is_lit = (e >> 16) & 1u;
       uint32_t off;
       {
-        const uint32_t p1 = q + 1;
-        const uint32_t raw = snp_funnel_r(win32[p1 >> 2], win32[(p1 >> 2) + 1], (p1 & 3) * 8);
-        off = is_lit ? 0u : ((raw & (0xffffffffu >> ((e >> 18) & 31u))) | (((e >> 12) & 7u) << 8));
+        const uint32_t p1 = wbase + q + 1;
+        const uint32_t raw = snp_funnel_r(sm32[p1 >> 2], sm32[(p1 >> 2) + 1], (p1 & 3) * 8);
+        off = is_lit ? 0u : ((raw & (0xffffffffu >> ((e >> 18) & 31u))) | (e & 0x700u));
       }
       // a long literal ends the batch (straight-copy path); a truncated element is caught by m == 0 / the final size check
       const bool valid = q != kExit && !((e >> 17) & 1u) && q + ecsz <= avail;
@@ -343,7 +417,7 @@ SNP_FN void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __
           const uint32_t r = spos & (kRing - 1);
           if (skind == 1 && o - spos > uint32_t(kHist)) w = ld8_out(dst + spos);
           else if (skind == 1 && r > uint32_t(kRing) - 8) w = ring_ld8(sm, spos);
-          else w = sm_ld8(sm, skind == 0 ? kWinOff + q + 1 : r);
+          else w = sm_ld8(sm, skind == 0 ? wbase + q + 1 : r);
           if (skind == 1 && off < len) {                           // periodic: repeat the first `off` bytes
             w &= (off >= 8) ? ~0ull : ((1ull << (8 * off)) - 1);
             for (uint32_t f = off; f < 8; f <<= 1) w |= w << (8 * f);
@@ -459,6 +533,21 @@ SNP_FN void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __
   fl = flush_words(sm, dst, fl, o, lane);
   if (fl + lane < o) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];
   if (o != ulen && stop_at >= ulen) { if (lane == 0) snp_set_err(err, 104); }
+}
+
+// One page.  st.phase carries the barriers' phases from page to page; no copy is in flight on return.
+SNP_FN void snappy_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t ulen_expected, uint32_t stop_at,
+                        WarpSmem& sm, uint32_t& phase, const uint8_t* __restrict__ csz, const uint32_t* __restrict__ lut, int lane, int* err) {
+  StageState st;
+  st.phase = phase; st.cur = 0; st.pf = false; st.pf_start = 0; st.pf_bytes = 0;
+  snappy_page_body(src, n, dst, ulen_expected, stop_at, sm, st, csz, lut, lane, err);
+  snp_syncwarp();
+  if (st.pf) {                                         // drain the look-ahead nobody came to use
+    const int nb = st.cur ^ 1;
+    bulk_wait(sm, nb, (st.phase >> nb) & 1u);
+    st.phase ^= 1u << nb;
+  }
+  phase = st.phase;
 }
 
 }  // namespace snp

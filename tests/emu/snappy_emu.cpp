@@ -1,4 +1,4 @@
-// snappy_emu.cpp — TEST INFRASTRUCTURE.  Runs the product's warp-level Snappy decoder (horaedb_b200/csrc/snappy_core.h, the very text
+// snappy_emu.cpp — TEST INFRASTRUCTURE.  Runs the product's warp-level Snappy decoder (horaedb_b2../../horaedb_b200/csrc/snappy_core.h, the very text
 // nvcc compiles for sm_100a) on the CPU: the 32 lanes of the warp are 32 coroutines (ucontext), every warp collective
 // (shuffle / ballot / any / syncwarp) is a rendezvous.  Lanes run one after another between collectives, so the emulation checks the
 // lane-level LOGIC (tables, source classification, parent links, ring arithmetic, flush positions), not instruction timing.
@@ -48,7 +48,7 @@ struct uint2 { uint32_t x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 
 // dynamic counters of the decoder's loop (lane 0 counts): windows, steps, elements, word_steps, bytes, parent_searches
-struct EmuStats { long windows, steps, elements, word_steps, bytes, parent_searches; };
+struct EmuStats { long windows, steps, elements, word_steps, bytes, parent_searches, stage_hits; };
 static EmuStats g_stats;
 #define SNP_STAT(counter, amount) do { if (emu::lane_id() == 0) g_stats.counter += long(amount); } while (0)
 #define SNP_FN static inline
@@ -75,7 +75,9 @@ struct Job {
 Job g_job;
 void lane_main() {
   const int lane = emu::W->cur;
-  horae::snp::snappy_page(g_job.src, g_job.n, g_job.dst, g_job.ulen, g_job.stop_at, *g_job.sm, g_job.csz, g_job.lut, lane, g_job.err);
+  uint32_t phase = 0;
+  horae::snp::bulk_init(*g_job.sm, lane);
+  horae::snp::snappy_page(g_job.src, g_job.n, g_job.dst, g_job.ulen, g_job.stop_at, *g_job.sm, phase, g_job.csz, g_job.lut, lane, g_job.err);
   emu::W->done[lane] = true;
   swapcontext(&emu::W->lane_ctx[lane], &emu::W->sched);
 }
@@ -83,7 +85,7 @@ void lane_main() {
 
 // Decode one raw Snappy stream.  dst must have ulen + 64 bytes of room (the decoder may overshoot stop_at by one batch and reads
 // whole words).  Returns the decoder's error word (0 = ok); *collectives = warp collectives executed (a proxy for steps).
-extern "C" void emu_stats(long* out6) { std::memcpy(out6, &g_stats, sizeof(g_stats)); std::memset(&g_stats, 0, sizeof(g_stats)); }
+extern "C" void emu_stats(long* out7) { std::memcpy(out7, &g_stats, sizeof(g_stats)); std::memset(&g_stats, 0, sizeof(g_stats)); }
 extern "C" int emu_snappy_page(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t ulen, uint32_t stop_at, long* collectives) {
   using namespace horae::snp;
   static uint8_t csz[256];

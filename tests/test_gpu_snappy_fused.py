@@ -76,8 +76,12 @@ def test_snappy_fused_value_column_variants():
     sid = np.repeat(np.arange(30), 1000)
     ts = sstgen.T0_MS + np.tile(np.arange(1000) * 1000, 30)
     tag = (sid % 4).astype(np.uint32)
+    # "mixed": random values with one compressible stretch, so one file holds stored pages (read in place) next to pages with copy
+    # elements (decompressed into scratch) — what a large random f64 column looks like in practice (the odd 4-byte match)
+    mixed = rng.random(n)
+    mixed[9000:15000] = 0.25
     for name, value, rg in (("random", rng.random(n), 8192), ("runs", np.repeat(rng.random(n // 100), 100), 8192), ("ragged", rng.random(n), 5000),
-                            ("big-rg", rng.random(n), 20_000)):
+                            ("big-rg", rng.random(n), 20_000), ("mixed", mixed, 4096), ("mixed-ragged", mixed, 5000)):
         data = sstgen.write_sst(schema, _metric_batch(sid, ts, value, tag), seq=300,
                                 cfg=WriteConfig(compression=ParquetCompression.Snappy, max_row_group_size=rg), presorted=True)
         for preds in ([], [("tag", "eq", 1)], [("tag", "eq", 1), ("ts", "lt", sstgen.T0_MS + 400_000)]):

@@ -3,7 +3,8 @@
 ncu's CSV source page lists SASS without file:line; `nvdisasm -g` of the shipped cubin lists the same SASS with line info.
 The two listings are matched instruction by instruction (the opcode sequence must agree), then summed per source line.
 
-Usage: ncu_hot_lines.py <report.ncu-rep> <cubin name inside libhorae_gpu.so, e.g. fused_scan> <substring of the mangled kernel name> [top=25]
+Usage: ncu_hot_lines.py <report.ncu-rep> <cubin name inside libhorae_gpu.so, e.g. fused_scan> <substring of the mangled kernel name> [top=25] [launch=-1]
+(launch = index of the captured launch inside the report, default the last one)
 Needs the CUDA toolkit (ncu, cuobjdump, nvdisasm) and a library built with -lineinfo (the Makefile's default)."""
 import collections
 import csv
@@ -20,6 +21,7 @@ LIB = os.path.join(ROOT, "horaedb_b200", "csrc", "libhorae_gpu.so")
 def main():
     rep, cubin, kernel = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+    which = int(sys.argv[5]) if len(sys.argv) > 5 else -1
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=td, check=True, stdout=subprocess.DEVNULL)
         path = [f for f in os.listdir(td) if f.startswith(cubin + ".")][0]
@@ -37,7 +39,10 @@ def main():
             ins.append((cur, m.group(2)))
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, data = rows[1], rows[2:]
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]     # one block per captured launch
+    b0 = starts[which if which >= 0 else len(starts) - 2]
+    b1 = starts[starts.index(b0) + 1]
+    hdr, data = rows[b0 + 1], rows[b0 + 2:b1]
     isrc, ismp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     if len(ins) != len(data) or any(a[1].split()[:1] != b[isrc].split()[:1] for a, b in zip(ins, data)):
         sys.exit(f"SASS of the library ({len(ins)} instructions) does not match the capture ({len(data)}): rebuild the commit that was profiled")
