@@ -623,7 +623,29 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
         const RgCol& rc = r.rgcol[size_t(kr.g) * size_t(r.meta.ncols) + c];
         const bool by_row = !gate_out.empty() && c >= schema->num_primary_keys && rc.single_page && rc.null_none &&
                             (cd.codec == CODEC_UNCOMPRESSED || cd.stored);
-        if (!by_row) { add_range(ranges, kr.j, kr.g, c); continue; }
+        if (!by_row) {
+          // A Snappy page the device will decode only up to the last gate-passing row (fused scan, partial decode) travels as a
+          // PREFIX of its compressed stream: the share of the stream that the needed share of the output takes, plus a margin.  The
+          // page table tells the decoder where the prefix ends; a stream that turns out lopsided ends early, the decoder reports
+          // it, and the entry point repeats the call without prefixes (e->trunc_used) — never a wrong result.
+          if (!gate_out.empty() && gate_col == e->trunc_gate && c < 32 && ((e->trunc_mask >> c) & 1u) && cd.codec == CODEC_SNAPPY && rc.single_page && !cd.stored) {
+            const PageDev& pg = pages[kr.j][cd.first_page];
+            const uint32_t w = (cd.phys == PT_INT32 || cd.phys == PT_FLOAT) ? 4u : 8u;
+            const uint64_t rows = r.rg_rows[kr.g];
+            const uint64_t out_row = std::min<uint64_t>(uint64_t(gate_out[i].last) + 2, rows);            // gate_sel_kernel's RgSel::out_row
+            const uint64_t need_uncomp = 16 + (rows + 7) / 8 + 8 + out_row * w + 2304;                    // stop_at + one batch of overshoot
+            const uint64_t est = uint64_t(double(pg.comp_size) * double(need_uncomp) / double(std::max<uint32_t>(pg.uncomp_size, 1)) * 1.08) + 1024;
+            if (est + 4096 < pg.comp_size) {
+              const ChunkMeta& cm = r.meta.rgs[kr.g].cols[c];
+              add_bytes(kr.j, uint64_t(cm.data_page_offset), pg.payload_off + est);
+              pages[kr.j][cd.first_page].comp_size = uint32_t(est);
+              e->trunc_used = true;
+              continue;
+            }
+          }
+          add_range(ranges, kr.j, kr.g, c);
+          continue;
+        }
         // a page whose values can be addressed by row: only the blocks of rows that hold a passing row (GateOut::mask), cut to
         // [first, last]; adjacent blocks travel as one interval
         const PageDev& pg = pages[kr.j][cd.first_page];
@@ -1486,7 +1508,7 @@ struct CallGuard { hg_engine* e; ~CallGuard() { end_call(e); } };
 
 // need_cols: the columns this call can touch (only used to select the byte ranges of non-resident SSTs)
 static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n, const hg_predicate* preds, size_t np,
-                      std::vector<uint32_t> need_cols, bool seq_if_overlap) {
+                      std::vector<uint32_t> need_cols, bool seq_if_overlap, uint32_t trunc_mask = 0, int trunc_gate = -1) {
   int rc = validate_schema(schema);
   if (rc) return rc;
   rc = validate_preds(schema, preds, np);
@@ -1497,6 +1519,9 @@ static int begin_call(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   e->launches = 0;
   e->stage_cursor = 0;
   e->last_agg = hg_agg_device{};
+  e->trunc_mask = trunc_mask;
+  e->trunc_gate = trunc_gate;
+  e->trunc_used = false;
   e->arena.reset();
   g_arena = &e->arena;
   CU_TRY(cudaEventRecord(e->ev0, e->stream));
@@ -2051,14 +2076,35 @@ static int aggregate_core(hg_engine* e, const hg_schema_desc* schema, const hg_s
   return HG_OK;
 }
 
-int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
-                             const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg, hg_agg_device* out) {
-  HG_GUARD_BEGIN
-  if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> g(e->mu);
+
+// Which columns may a transient load ship as compressed prefixes for this aggregate?  Only when the call has the fused scan's shape
+// with late materialisation and no time buckets: that kernel reads every column but pk0 only up to the row group's last row passing
+// the gate column (fused_scan.cu: gate_sel_kernel, SnappyJob::partial).  *gate = the column that will be its gate.
+static uint32_t aggregate_trunc_mask(const hg_engine* e, const hg_schema_desc* schema, const hg_predicate* preds, size_t np, const hg_agg_spec* agg, int* gate) {
+  *gate = -1;
+  if (!schema || !agg || np == 0 || schema->num_primary_keys < 2) return 0;
+  if (e->flags & (HG_FLAG_NO_FUSED | HG_FLAG_NO_LATE_MATERIALIZATION | HG_FLAG_NO_PRUNING)) return 0;
+  if (agg->ts_col >= 0 && agg->window_ms > 0) return 0;
+  if (!(agg->group_col == 0 || (agg->group_col < 0 && agg->value_col < 0))) return 0;
+  int extra = -1;
+  bool on_pk1 = false;
+  for (size_t i = 0; i < np; i++) {
+    const uint32_t c = preds[i].column;
+    if (c >= schema->num_columns || c >= 32) return 0;
+    if (type_is_float(schema->types[c]) || preds[i].op == HG_OP_NE || preds[i].op == HG_OP_IN) return 0;
+    if (c == 1) on_pk1 = true;
+    if (c >= 2) { if (extra >= 0 && extra != int(c)) return 0; extra = int(c); }
+  }
+  *gate = extra >= 0 ? extra : (on_pk1 ? 1 : -1);
+  if (*gate < 0) return 0;
+  return ~1u;                                        // everything but pk0
+}
+
+static int aggregate_device_once(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
+                                 size_t n_preds, const hg_agg_spec* agg, uint32_t trunc_mask, int trunc_gate, hg_agg_device* out) {
   std::vector<uint32_t> touch;
   if (agg) for (int32_t c : {agg->group_col, agg->ts_col, agg->value_col}) if (c >= 0 && uint32_t(c) < (schema ? schema->num_columns : 0)) touch.push_back(uint32_t(c));
-  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds, touch, true);
+  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds, touch, true, trunc_mask, trunc_gate);
   if (rc) return rc;
   CallGuard guard{e};
   AggBuffers ab;
@@ -2082,17 +2128,33 @@ int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const h
   e->last_gtype = ab.gtype;
   for (DevBuf* b : {&ab.gkey, &ab.bucket, &ab.count, &ab.sum, &ab.mn, &ab.mx}) b->release();   // arena memory: valid until the next call
   return HG_OK;
-  HG_GUARD_END
 }
 
-int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
-                      size_t n_preds, const hg_agg_spec* agg, struct ArrowArrayStream* out) {
+int hg_scan_aggregate_device(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts,
+                             const hg_predicate* preds, size_t n_preds, const hg_agg_spec* agg, hg_agg_device* out) {
   HG_GUARD_BEGIN
   if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> g(e->mu);
+  int gate = -1;
+  const uint32_t mask = aggregate_trunc_mask(e, schema, preds, n_preds, agg, &gate);
+  int rc = aggregate_device_once(e, schema, ssts, n_ssts, preds, n_preds, agg, mask, gate, out);
+  if (rc && e->trunc_used) {                          // a compressed prefix ran out (lopsided page): repeat with whole pages
+    static const bool trace = getenv("HORAE_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[transient] a compressed prefix ended before the last needed row: repeating the call with whole pages\n");
+    const uint64_t wasted = e->stats.bytes_h2d;
+    rc = aggregate_device_once(e, schema, ssts, n_ssts, preds, n_preds, agg, 0, -1, out);
+    e->stats.bytes_h2d += wasted;
+    e->stats.path |= 2u;
+  }
+  return rc;
+  HG_GUARD_END
+}
+
+static int aggregate_host_once(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
+                               size_t n_preds, const hg_agg_spec* agg, uint32_t trunc_mask, int trunc_gate, struct ArrowArrayStream* out) {
   std::vector<uint32_t> touch;
   if (agg) for (int32_t c : {agg->group_col, agg->ts_col, agg->value_col}) if (c >= 0 && uint32_t(c) < (schema ? schema->num_columns : 0)) touch.push_back(uint32_t(c));
-  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds, touch, true);
+  int rc = begin_call(e, schema, ssts, n_ssts, preds, n_preds, touch, true, trunc_mask, trunc_gate);
   if (rc) return rc;
   CallGuard guard{e};
   cudaStream_t s = e->stream;
@@ -2138,6 +2200,25 @@ int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_d
   if (G) data->batch_start.push_back(G);
   make_stream(out, data);
   return HG_OK;
+}
+
+int hg_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, size_t n_ssts, const hg_predicate* preds,
+                      size_t n_preds, const hg_agg_spec* agg, struct ArrowArrayStream* out) {
+  HG_GUARD_BEGIN
+  if (!e || !out) return set_error(HG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  int gate = -1;
+  const uint32_t mask = aggregate_trunc_mask(e, schema, preds, n_preds, agg, &gate);
+  int rc = aggregate_host_once(e, schema, ssts, n_ssts, preds, n_preds, agg, mask, gate, out);
+  if (rc && e->trunc_used) {                          // a compressed prefix ran out (lopsided page): repeat with whole pages
+    static const bool trace = getenv("HORAE_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[transient] a compressed prefix ended before the last needed row: repeating the call with whole pages\n");
+    const uint64_t wasted = e->stats.bytes_h2d;
+    rc = aggregate_host_once(e, schema, ssts, n_ssts, preds, n_preds, agg, 0, -1, out);
+    e->stats.bytes_h2d += wasted;
+    e->stats.path |= 2u;
+  }
+  return rc;
   HG_GUARD_END
 }
 

@@ -241,6 +241,9 @@ struct hg_engine {
   uint32_t last_gwidth = 8, last_gtype = T_U64;
   struct hg_comm* comm = nullptr;  // NCCL communicator + combine stream (comm.cu)
   std::vector<uint64_t> transient_ids;   // SSTs loaded only for the running call
+  uint32_t trunc_mask = 0;               // bit c: the running call reads column c of a row group only up to its last gate-passing row
+  int trunc_gate = -1;                    // ... and the column whose predicates define that row (the device's gate column)
+  bool trunc_used = false;               // the transient load shipped a compressed PREFIX of some page (see load_transient)
   Launch L() { return Launch{stream, &launches}; }
 };
 

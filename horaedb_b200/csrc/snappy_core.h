@@ -269,41 +269,7 @@ SNP_FN void snappy_page_body(const uint8_t* __restrict__ src, uint32_t n, uint8_
   uint32_t fl = 0;                // output bytes [0, fl) are in global memory (fl is a multiple of 32, fl <= o)
   while (pos < n && o < stop_at) {
     const uint32_t avail = n - pos;
-    const uint32_t tag0 = snp_ldg8(src + pos);
-    // ---- literal with an explicit length field: straight copy
-    if ((tag0 & 3) == 0 && (tag0 >> 2) >= 60) {
-      const uint32_t nb = (tag0 >> 2) - 59;
-      uint32_t len = 0;
-      for (uint32_t i = 0; i < nb && i + 1 < avail; i++) len |= uint32_t(snp_ldg8(src + pos + 1 + i)) << (8 * i);
-      len += 1;
-      if (1 + nb + len > avail || o + len > ulen || len < 1) { if (lane == 0) snp_set_err(err, 102); return; }
-      const uint8_t* lsrc = src + pos + 1 + nb;
-      snp_syncwarp();
-      fl = flush_words(sm, dst, fl, o, lane);
-      if (uint32_t(lane) < o - fl) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];     // pending partial sector (< 32 bytes)
-      warp_copy_in(dst + o, lsrc, len, lane);
-      // the ring keeps the tail of the literal (whole words where possible)
-      const uint32_t keep = len < uint32_t(kHist) ? len : uint32_t(kHist);
-      const uint32_t k0 = o + len - keep, k1 = o + len;
-      const uint32_t a0 = (k0 + 7) & ~7u, a1 = k1 & ~7u;
-      if (a0 < a1) {
-        for (uint32_t w = (a0 >> 3) + lane; w < (a1 >> 3); w += 32) sm.ring64[w & (kRing / 8 - 1)] = ld8_any(lsrc + ((w << 3) - o));
-        if (k0 + lane < a0) ring[(k0 + lane) & (kRing - 1)] = snp_ldg8(lsrc + (k0 + lane - o));
-        if (a1 + lane < k1) ring[(a1 + lane) & (kRing - 1)] = snp_ldg8(lsrc + (a1 + lane - o));
-      } else {
-        for (uint32_t i = k0 + lane; i < k1; i += 32) ring[i & (kRing - 1)] = snp_ldg8(lsrc + (i - o));
-      }
-      snp_syncwarp();
-      pos += 1 + nb + len;
-      o += len;
-      fl = o & ~31u;
-      continue;
-    }
-    // ---- stage the window and build the jump tables.  Lane l owns the 8 positions [8l, 8l+8): their tag bytes are the window word it
-    //      just loaded.  J[lv][p] = start of the 2^lv-th element after the one at p, kExit when that leaves the window.  Positions
-    //      behind the end of the stream are staged as long-literal tags (csz 255): every chain ends there, and a lookup that lands
-    //      on one finds an element that can never be part of a batch.  csz[...] + p saturates at kExit, so J[lv][kExit] == kExit on
-    //      every level and the lookups need no test.
+    // ---- stage the window (every look at the compressed stream goes through the staged bytes, never a dependent global load)
     snp_syncwarp();
     SNP_STAT(windows, 1);
     // the window's bytes: already fetched (or on their way) if the last window's look-ahead covers [pos, pos + need), else fetched now
@@ -329,6 +295,47 @@ SNP_FN void snappy_page_body(const uint8_t* __restrict__ src, uint32_t n, uint8_
       // look ahead: the next window starts in (pos + kAhead, pos + kWin + 61]; its region goes into the buffer just left
       if (pos + kAhead < n) { stage_fetch(sm, st, nb ^ 1, src, n, pos + kAhead, lane); st.pf = true; }
     }
+    const uint32_t tag0 = sm8[wbase];
+    // ---- literal with an explicit length field: straight copy
+    if ((tag0 & 3) == 0 && (tag0 >> 2) >= 60) {
+      const uint32_t nb = (tag0 >> 2) - 59;
+      uint32_t len = 0;
+      for (uint32_t i = 0; i < nb && i + 1 < avail; i++) len |= uint32_t(sm8[wbase + 1 + i]) << (8 * i);
+      len += 1;
+      if (1 + nb > avail || o + len > ulen || len < 1) { if (lane == 0) snp_set_err(err, 102); return; }
+      if (len > avail - 1 - nb) {
+        // the literal runs past the end of the stream: an error, unless the stream is a compressed PREFIX (transient loads ship only
+        // what a partial decode needs) and the bytes that are there reach the position the consumer stops at
+        if (o + (avail - 1 - nb) < stop_at) { if (lane == 0) snp_set_err(err, 102); return; }
+        len = avail - 1 - nb;
+      }
+      const uint8_t* lsrc = src + pos + 1 + nb;
+      snp_syncwarp();
+      fl = flush_words(sm, dst, fl, o, lane);
+      if (uint32_t(lane) < o - fl) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];     // pending partial sector (< 32 bytes)
+      warp_copy_in(dst + o, lsrc, len, lane);
+      // the ring keeps the tail of the literal (whole words where possible)
+      const uint32_t keep = len < uint32_t(kHist) ? len : uint32_t(kHist);
+      const uint32_t k0 = o + len - keep, k1 = o + len;
+      const uint32_t a0 = (k0 + 7) & ~7u, a1 = k1 & ~7u;
+      if (a0 < a1) {
+        for (uint32_t w = (a0 >> 3) + lane; w < (a1 >> 3); w += 32) sm.ring64[w & (kRing / 8 - 1)] = ld8_any(lsrc + ((w << 3) - o));
+        if (k0 + lane < a0) ring[(k0 + lane) & (kRing - 1)] = snp_ldg8(lsrc + (k0 + lane - o));
+        if (a1 + lane < k1) ring[(a1 + lane) & (kRing - 1)] = snp_ldg8(lsrc + (a1 + lane - o));
+      } else {
+        for (uint32_t i = k0 + lane; i < k1; i += 32) ring[i & (kRing - 1)] = snp_ldg8(lsrc + (i - o));
+      }
+      snp_syncwarp();
+      pos += 1 + nb + len;
+      o += len;
+      fl = o & ~31u;
+      continue;
+    }
+    // ---- build the jump tables.  Lane l owns the 8 positions [8l, 8l+8): their tag bytes are the window word it
+    //      just loaded.  J[lv][p] = start of the 2^lv-th element after the one at p, kExit when that leaves the window.  Positions
+    //      behind the end of the stream are staged as long-literal tags (csz 255): every chain ends there, and a lookup that lands
+    //      on one finds an element that can never be part of a batch.  csz[...] + p saturates at kExit, so J[lv][kExit] == kExit on
+    //      every level and the lookups need no test.
     uint32_t jlo, jhi;
     {
       uint64_t w = kFill;
@@ -532,7 +539,7 @@ SNP_FN void snappy_page_body(const uint8_t* __restrict__ src, uint32_t n, uint8_
   snp_syncwarp();
   fl = flush_words(sm, dst, fl, o, lane);
   if (fl + lane < o) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];
-  if (o != ulen && stop_at >= ulen) { if (lane == 0) snp_set_err(err, 104); }
+  if (o != ulen && o < stop_at) { if (lane == 0) snp_set_err(err, 104); }      // the stream ended before the bytes the consumer needs
 }
 
 // One page.  st.phase carries the barriers' phases from page to page; no copy is in flight on return.

@@ -131,7 +131,8 @@ typedef struct {
   uint64_t groups_out;
   uint64_t bytes_h2d, bytes_d2h;
   uint32_t kernel_launches;   /* kernels launched by the last call */
-  uint32_t path;              /* 0 = general pipeline, 1 = fused fast path */
+  uint32_t path;              /* bit 0: 0 = general pipeline, 1 = fused fast path;  bit 1: the call ran twice (a transient load's
+                                 compressed page prefix ended before the last needed row: repeated with whole pages) */
   float gpu_ms;               /* device time of the last call, first kernel to last (CUDA events on the engine stream) */
   float kernel_ms;            /* device time of the call's dominant kernel alone (fused scan / page decode) */
   float merge_ms;             /* device time of S4-S6 (sort records, merge passes, dedup, compaction of survivors) */

@@ -124,6 +124,33 @@ def test_snappy_fused_duplicates_and_gate_dropped_row_groups():
     eng.close()
 
 
+def test_snappy_transient_prefix_transfer_and_retry():
+    """Host-buffer SSTs (transient loads): pages the fused scan decodes only up to the last gate-passing row cross PCIe as a
+    PREFIX of their compressed stream, sized by the share of the output that is needed.  A lopsided page (incompressible first
+    half, constant second half) makes that estimate too short: the decoder must notice the stream ending early and the call must
+    repeat with whole pages — same result as the oracle either way."""
+    rng = np.random.default_rng(21)
+    schema = sstgen.metric_storage_schema()
+    handle = SchemaHandle(schema.arrow_schema, 2)
+    eng = Engine(device=0)
+    n = 40_000
+    sid = np.repeat(np.arange(40), 1000)
+    ts = sstgen.T0_MS + np.tile(np.arange(1000) * 1000 + rng.integers(0, 400, 1000), 40)
+    for name, tag, value in (
+            # the passing rows sit in the first half of every 8192-row group; the value page is lopsided (random, then constant)
+            ("lopsided", np.where((np.arange(n) % 8192) < 3500, 3, 5), np.where((np.arange(n) % 8192) < 4000, rng.random(n), 0.5)),
+            # evenly compressible columns: the prefix estimate holds
+            ("even", np.where((np.arange(n) % 8192) < 3500, 3, 5), np.round(rng.random(n), 2))):
+        data = sstgen.write_sst(schema, _metric_batch(sid, ts, value, tag.astype(np.uint32)), seq=450,
+                                cfg=WriteConfig(compression=ParquetCompression.Snappy), presorted=True)
+        for preds in ([("tag", "eq", 3)], [("tag", "eq", 3), ("ts", "ge", sstgen.T0_MS + 200_000)]):
+            kw = KWS[0]
+            got = _agg(eng, handle, [data], preds, **kw)
+            assert eng.stats()["path"] == (3 if name == "lopsided" else 1), name      # bit 1: the call had to be repeated
+            _check(got, oracle.scan_aggregate([data], schema.arrow_schema, 2, preds, **kw), False)
+    eng.close()
+
+
 def test_snappy_general_pipeline_still_agrees():
     """HG_FLAG_NO_FUSED: the materialising pipeline (decompress -> decode -> filter -> dedup -> reduce) on the same files."""
     schema = sstgen.metric_storage_schema()

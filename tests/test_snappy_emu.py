@@ -93,6 +93,18 @@ def test_emulated_partial_decode(emu, name, stop_at):
     check(emu, CASES[name], stop_at)
 
 
+def test_emulated_prefix_of_a_long_literal(emu):
+    """A compressed PREFIX (transient loads) may end inside a long literal: fine when the bytes present reach stop_at, an error otherwise."""
+    raw = CASES["random"]                                       # one 64 KiB literal
+    comp = CODEC.compress(raw, asbytes=True)
+    err, out = decode(emu, comp[:20_000], len(raw), stop_at=15_000)
+    assert err == 0 and bytes(out[:15_000]) == raw[:15_000]
+    err, _ = decode(emu, comp[:20_000], len(raw), stop_at=30_000)
+    assert err != 0
+    err, _ = decode(emu, comp[:20_000], len(raw))
+    assert err != 0
+
+
 def test_emulated_decoder_rejects_malformed(emu):
     raw = CASES["jitter_ts"]
     comp = CODEC.compress(raw, asbytes=True)
