@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--files", type=int, default=FILES_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-variant", action="store_true", help="skip the secondary codec measurement")
+    ap.add_argument("--no-compaction", action="store_true", help="skip the merge-compaction variant (N=1 only, own process)")
     args = ap.parse_args()
 
     # stdout carries exactly ONE JSON line: route everything else (NCCL banners, library chatter) to stderr
@@ -517,6 +518,24 @@ def main():
                              "e2e_rows_per_s": r["rows"] * world / r["e2e_s"], "sst_bytes_per_gpu": r["file_bytes"],
                              "launches": r["launches"], "scan_kernel": scan_kernel_block(r)} for c, r in res.items() if c != args.codec},
         }
+        if world == 1 and not args.no_compaction:
+            # BASELINE config 5's shape at a size that keeps the default run short: 16 overlapping Snappy SSTs (32 M rows in) -> one sorted,
+            # deduplicated run (hg_compact_open) and the same through the GPU SST writer (hg_compact_to_sst).  Its own process (own engine);
+            # config 5 at full size (64 SSTs, 250 M rows): tools/bench_compaction.py 64 15625 1000 0.25 snappy 32 -> profiles/.
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_compaction.py"), "16", "4000", "1000", "0.5", "snappy", "16"],
+                                     capture_output=True, text=True, timeout=300)
+                cj = json.loads(out.stdout.strip().splitlines()[-1])
+                line["variants"]["compaction"] = {
+                    "workload": cj["workload"], "rows_in": cj["rows_in"], "rows_out": cj["rows_out"],
+                    "merge_rows_per_s": cj["merge_rows_per_s"], "merge_ms": cj["merge_ms"], "decode_ms": cj["decode_ms"], "call_gpu_ms": cj["call_gpu_ms"],
+                    "roofline": {"bound": "hbm", "kernel": "kway_merge_kernel (+ build_keys64, splitters, bounds, survivor compaction): S4-S6",
+                                 "achieved": cj["roofline_merge"]["achieved_GBps"], "peak": cj["roofline_merge"]["peak_GBps"], "unit": "GB/s",
+                                 "frac": cj["roofline_merge"]["frac"], "alg_bytes_per_launch": cj["roofline_merge"]["alg_bytes"],
+                                 "bytes_model": cj["roofline_merge"]["bytes_model"]},
+                    "pairwise_passes_merge_ms": cj["pairwise_passes"]["merge_ms"], "compact_to_sst": cj["compact_to_sst"]}
+            except Exception as ex:      # the main line stands on its own
+                line["variants"]["compaction"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         emit(line)
     ok_all = all(r["parity"]["resident"] and r["parity"]["e2e"] and r["parity"]["combined"] is not False for r in res.values())
     if world > 1:

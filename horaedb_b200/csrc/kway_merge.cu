@@ -51,6 +51,9 @@ __device__ __forceinline__ uint64_t pk_norm(const ColView& c, uint32_t row) {
   }
 }
 
+constexpr uint32_t kKeyChunk = 2048;      // survivors per CTA trip of build_keys64_kernel (8 per thread, coalesced)
+// WIDE: every primary-key column and __seq__ are 8-byte integers without a validity vector (the metric schema): no per-row dispatch
+template <bool WIDE>
 __global__ void __launch_bounds__(kThreads) build_keys64_kernel(PkSet pk, ColView seq, const uint32_t* __restrict__ surv, const uint32_t* d_m,
                                                                const uint32_t* __restrict__ run_start, int k, KeyPack kp,
                                                                uint64_t* __restrict__ keys, int* err) {
@@ -59,21 +62,33 @@ __global__ void __launch_bounds__(kThreads) build_keys64_kernel(PkSet pk, ColVie
   __syncthreads();
   const uint32_t m = *d_m;
   bool bad = false;
-  for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < m; s += gridDim.x * kThreads) {
-    const uint32_t row = surv ? surv[s] : s;
-    int lo = 0, hi = k;                       // stream of survivor s: last f with run_start[f] <= s
+  uint64_t flip[MAX_PK];
+#pragma unroll
+  for (int c = 0; c < MAX_PK; c++) flip[c] = (c < pk.n && pk.c[c].type == T_I64) ? (1ull << 63) : 0ull;
+  for (uint64_t base = uint64_t(blockIdx.x) * kKeyChunk; base < m; base += uint64_t(gridDim.x) * kKeyChunk) {
+    uint32_t s = uint32_t(base) + threadIdx.x;
+    int lo = 0, hi = k;                       // stream of survivor s: last f with run_start[f] <= s (searched once, then advanced)
     while (lo + 1 < hi) { int mid = (lo + hi) >> 1; if (s_rs[mid] <= s) lo = mid; else hi = mid; }
-    uint64_t key = uint64_t(lo);
-    for (int c = 0; c < pk.n; c++) {
-      const uint64_t v = pk_norm(pk.c[c], row);
-      if (v < kp.mn[c] || v - kp.mn[c] > kp.span[c]) bad = true;     // outside the chunk statistics: the packed key would be wrong
-      key |= (v - kp.mn[c]) << kp.shift[c];
+#pragma unroll
+    for (uint32_t t = 0; t < kKeyChunk / kThreads; t++, s += kThreads) {
+      if (s >= m) break;
+      while (lo + 1 < k && s_rs[lo + 1] <= s) lo++;
+      const uint32_t row = surv ? surv[s] : s;
+      uint64_t key = uint64_t(lo);
+#pragma unroll
+      for (int c = 0; c < MAX_PK; c++) {
+        if (c >= pk.n) break;
+        const uint64_t v = WIDE ? (reinterpret_cast<const uint64_t*>(pk.c[c].vals)[row] ^ flip[c]) : pk_norm(pk.c[c], row);
+        if (v < kp.mn[c] || v - kp.mn[c] > kp.span[c]) bad = true;     // outside the chunk statistics: the packed key would be wrong
+        key |= (v - kp.mn[c]) << kp.shift[c];
+      }
+      uint64_t q;                                                       // ASC NULLS FIRST: null sorts before every value
+      if (WIDE) q = reinterpret_cast<const uint64_t*>(seq.vals)[row] + 1;
+      else { const bool sv = seq.valid == nullptr || seq.valid[row] != 0; q = sv ? raw_at(seq, row) + 1 : 0; }
+      if (q < kp.seq_min || q - kp.seq_min > kp.seq_span) bad = true;
+      key |= (q - kp.seq_min) << kp.seq_shift;
+      keys[s] = key;
     }
-    const bool sv = seq.valid == nullptr || seq.valid[row] != 0;
-    const uint64_t q = sv ? raw_at(seq, row) + 1 : 0;                 // ASC NULLS FIRST: null sorts before every value
-    if (q < kp.seq_min || q - kp.seq_min > kp.seq_span) bad = true;
-    key |= (q - kp.seq_min) << kp.seq_shift;
-    keys[s] = key;
   }
   if (bad) atomicExch(err, 120);
 }
@@ -159,7 +174,10 @@ __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint
   __shared__ uint64_t s_thr, s_carry;
   __shared__ uint32_t s_range, s_out, s_any, s_has_carry;
   const int tid = threadIdx.x;
-  const uint32_t B = uint32_t(kChunk) / uint32_t(k);
+  // keys per stream and round: the largest power of two with k * B <= kChunk (slot -> stream / position by shift and mask)
+  uint32_t logB = 0;
+  while ((2u << logB) * uint32_t(k) <= uint32_t(kChunk)) logB++;
+  const uint32_t B = 1u << logB;
   int levels = 0;
   while ((1 << levels) < k) levels++;
   for (int i = tid; i <= k; i += kMergeThreads) s_rs[i] = run_start[i];
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint
       __syncthreads();
       if (!s_any) break;
       for (uint32_t i = tid; i < uint32_t(k) * B; i += kMergeThreads) {
-        const uint32_t f = i / B, j = i % B;
+        const uint32_t f = i >> logB, j = i & (B - 1);
         s_a[i] = j < s_take[f] ? keys[s_rs[f] + s_cur[f] + j] : kInf;
       }
       __syncthreads();
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint
       __syncthreads();
       const uint32_t n = s_offs[k];
       for (uint32_t i = tid; i < uint32_t(k) * B; i += kMergeThreads) {
-        const uint32_t f = i / B, j = i % B;
+        const uint32_t f = i >> logB, j = i & (B - 1);
         if (j < s_n[f]) s_b[s_offs[f] + j] = (s_a[i] << kIdxBits) | i;
       }
       __syncthreads();
@@ -222,7 +240,7 @@ __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint
       for (uint32_t j = tid; j < n; j += kMergeThreads) {
         const uint64_t w = src[j];
         const uint32_t slot = uint32_t(w) & (kChunk - 1);
-        const uint32_t f = slot / B, i = slot % B;
+        const uint32_t f = slot >> logB, i = slot & (B - 1);
         const uint32_t s = s_rs[f] + s_cur[f] + i;
         order[out0 + j] = surv ? surv[s] : s;
         if (j + 1 < n) keep[out0 + j] = (w >> sh) != (src[j + 1] >> sh);
@@ -263,7 +281,11 @@ void kway_merge(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* s
   uint64_t* splitters = keys + cap + 2;
   uint32_t* bounds = reinterpret_cast<uint32_t*>(splitters + R);
   uint64_t nb = (uint64_t(cap) + kThreads - 1) / kThreads;
-  build_keys64_kernel<<<int(nb > 148 * 16 ? 148 * 16 : nb), kThreads, 0, L.stream>>>(pk, seq, surv, d_m, run_start, k, kp, keys, err);
+  nb = (uint64_t(cap) + kKeyChunk - 1) / kKeyChunk;
+  bool wide = seq.width == 8 && seq.valid == nullptr;
+  for (int c = 0; c < pk.n; c++) wide = wide && pk.c[c].width == 8 && (pk.c[c].type == T_U64 || pk.c[c].type == T_I64);
+  if (wide) build_keys64_kernel<true><<<int(nb > 148 * 16 ? 148 * 16 : nb), kThreads, 0, L.stream>>>(pk, seq, surv, d_m, run_start, k, kp, keys, err);
+  else build_keys64_kernel<false><<<int(nb > 148 * 16 ? 148 * 16 : nb), kThreads, 0, L.stream>>>(pk, seq, surv, d_m, run_start, k, kp, keys, err);
   L.tick();
   cudaFuncSetAttribute(kway_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSamples * 8);      // per device
   cudaFuncSetAttribute(kway_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kChunk * 8);
