@@ -301,30 +301,33 @@ def main():
             inputs_host.append(SstInput(id=sid, ptr=t.data_ptr(), size=len(data), num_rows=n))
         resident = [SstInput(id=sid, num_rows=n) for sid, _, n in ssts]
         # ---- e2e: host buffers in, host result out, every step (SSTs are evicted between steps)
-        e2e_t = []
         d2h = 0
         h2d = 0
-        for it in range(e2e_steps + 1):
+
+        def e2e_step():
             for sid, _, _ in ssts:
                 try:
                     eng.unload_sst(sid)
                 except Exception:
                     pass
-            barrier()
-            t0 = time.perf_counter()
-            tbl = eng.scan_aggregate(handle, inputs_host, P, group_col=0, ts_col=-1, window_ms=0, value_col=2)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            d2h = eng.stats()["bytes_d2h"]
-            h2d = eng.stats()["bytes_h2d"]
-            if it > 0:
-                e2e_t.append(dt)
+            return eng.scan_aggregate(handle, inputs_host, P, group_col=0, ts_col=-1, window_ms=0, value_col=2)
+
+        # two untimed calls: the first sizes the engine's arena and pinned staging, the second runs on the consolidated arena
+        for _ in range(2):
+            tbl = e2e_step()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for it in range(e2e_steps):          # each call returns the host result: H2D, kernels and D2H are inside it
+            tbl = e2e_step()
+        torch.cuda.synchronize()
+        e2e_dt = (time.perf_counter() - t0) / max(e2e_steps, 1)
+        d2h = eng.stats()["bytes_d2h"]
+        h2d = eng.stats()["bytes_h2d"]
         if world > 1:
-            tt = torch.tensor([max(e2e_t)], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_dt = float(tt.item())
-        else:
-            e2e_dt = float(np.median(e2e_t))
         groups_local = tbl.num_rows
         parity_e2e = check_parity(tbl, expected)
         # ---- HBM-resident steps: make the SSTs resident once (untimed), then every step is one scan call

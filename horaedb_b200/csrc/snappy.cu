@@ -2,6 +2,7 @@
 // window, word mode / run mode execution, ring -> global flushes) lives in snappy_core.h, which the CPU test-suite compiles too.
 #include "kernels.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #define SNP_FN __device__ __forceinline__
@@ -136,10 +137,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_raw_kernel(const 
 
 }  // namespace
 
+// Resident CTAs per SM the decompression kernels ask for.  8 fill an SM's shared memory (8 x (26.9 + 1) KB of 228 KB): right for a GPU that
+// only scans.  With a communicator attached (hg_comm_init) the library's own NCCL all-gather of the previous step's partials has to
+// find room NEXT to the decompression of the current step — its CTAs need shared memory too — so 7 are used and 28 KB per SM stay free.
+static int g_ctas_per_sm = 0;
+void snappy_set_ctas_per_sm(int n) { g_ctas_per_sm = n; }
+static uint32_t snappy_max_ctas() {
+  static const int env = getenv("HORAE_SNAPPY_CTAS_PER_SM") ? atoi(getenv("HORAE_SNAPPY_CTAS_PER_SM")) : 0;
+  int n = env > 0 ? env : (g_ctas_per_sm > 0 ? g_ctas_per_sm : 8);
+  if (n > 8) n = 8;
+  return 148u * uint32_t(n);
+}
+
 void snappy_raw_pages(const Launch& L, const RawPage* d_pages, uint32_t n, unsigned int* ticket, int* err) {
   if (!n) return;
   uint32_t ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (ctas > 148u * 8) ctas = 148u * 8;
+  if (ctas > snappy_max_ctas()) ctas = snappy_max_ctas();
   snappy_raw_kernel<<<ctas, kWarpsPerCta * 32, 0, L.stream>>>(d_pages, n, ticket, err);
   L.tick();
 }
@@ -147,7 +160,7 @@ void snappy_raw_pages(const Launch& L, const RawPage* d_pages, uint32_t n, unsig
 void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks) {
   if (!max_chunks) return;
   uint32_t ctas = (max_chunks + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (ctas > 148u * 8) ctas = 148u * 8;
+  if (ctas > snappy_max_ctas()) ctas = snappy_max_ctas();
   snappy_pages_kernel<<<ctas, kWarpsPerCta * 32, 0, L.stream>>>(job);
   L.tick();
 }
