@@ -45,7 +45,7 @@ struct SnappyJob {
   int* err;
 };
 void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks);
-void snappy_set_ctas_per_sm(int n);   // 0 = default (8: the whole SM); hg_comm_init asks for 7 so that NCCL's kernels fit beside
+void snappy_set_ctas_per_sm(int n);   // resident CTAs per SM of the decompression kernels (0 = default 7, see snappy.cu)
 // raw Snappy streams by pointer: dst must be 16-byte aligned with uncomp_size + 48 bytes of room; ticket = zeroed device counter
 struct RawPage { const uint8_t* src; uint8_t* dst; uint32_t comp_size, uncomp_size; };
 void snappy_raw_pages(const Launch& L, const RawPage* d_pages, uint32_t n, unsigned int* ticket, int* err);

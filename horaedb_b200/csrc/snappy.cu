@@ -137,14 +137,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_raw_kernel(const 
 
 }  // namespace
 
-// Resident CTAs per SM the decompression kernels ask for.  8 fill an SM's shared memory (8 x (26.9 + 1) KB of 228 KB): right for a GPU that
-// only scans.  With a communicator attached (hg_comm_init) the library's own NCCL all-gather of the previous step's partials has to
-// find room NEXT to the decompression of the current step — its CTAs need shared memory too — so 7 are used and 28 KB per SM stay free.
+// Resident CTAs per SM the decompression kernels ask for.  8 would fill an SM's shared memory (8 x (26.9 + 1) KB of 228 KB); 7 measured
+// 2.6 % faster on the bench (config 2: 8 -> 1.997, 7 -> 1.944, 6 -> 1.983, 5 -> 2.141 ms per step: the stage is bound by instruction
+// issue and shared-memory traffic, not by the number of warps; compiling for 7 with 72 registers was no faster than 64), and 28 KB per
+// SM stay free for the library's own NCCL all-gather of the previous step's partials, which runs NEXT to the decompression of the
+// current step (hg_agg_combine).  Also measured without effect: a persisting-L2 carve-out (32 / 64 MB) with evict_last stores of the
+// word-mode output, meant to keep a page's far-copy sources in L2.
 static int g_ctas_per_sm = 0;
 void snappy_set_ctas_per_sm(int n) { g_ctas_per_sm = n; }
 static uint32_t snappy_max_ctas() {
   static const int env = getenv("HORAE_SNAPPY_CTAS_PER_SM") ? atoi(getenv("HORAE_SNAPPY_CTAS_PER_SM")) : 0;
-  int n = env > 0 ? env : (g_ctas_per_sm > 0 ? g_ctas_per_sm : 8);
+  int n = env > 0 ? env : (g_ctas_per_sm > 0 ? g_ctas_per_sm : 7);
   if (n > 8) n = 8;
   return 148u * uint32_t(n);
 }
