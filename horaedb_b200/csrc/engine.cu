@@ -125,8 +125,8 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
   for (size_t g = 0; g < m.rgs.size(); g++)
     for (int c = 0; c < m.ncols; c++) {
       const ChunkMeta& cm = m.rgs[g].cols[c];
-      if (cm.codec != CODEC_UNCOMPRESSED && cm.codec != CODEC_SNAPPY)
-        return fail(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED and SNAPPY are implemented)");
+      if (cm.codec != CODEC_UNCOMPRESSED && cm.codec != CODEC_SNAPPY && cm.codec != CODEC_ZSTD)
+        return fail(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (UNCOMPRESSED, SNAPPY and ZSTD are implemented)");
       if (cm.scratch_bytes > 0xffffffffull) return fail(HG_ERR_UNSUPPORTED, "column chunk larger than 4 GiB");
       // every kernel indexes a chunk by the ROW GROUP's row count: the chunk must hold exactly that many values, and an
       // uncompressed page must really contain the bytes the decoders will read (compressed pages are bounded by their
@@ -211,7 +211,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
     const uint32_t t0 = schema->types[0];
     for (int c = 0; c < m.ncols && c < MAX_COLS; c++) {
       r->col_all_simple[c] = true; r->col_null_none[c] = true; r->col_has_minmax[c] = true;
-      r->col_all_single[c] = true; r->col_any_snappy[c] = false; r->col_snappy_all_stored[c] = true; r->col_snappy_any_stored[c] = false;
+      r->col_all_single[c] = true; r->col_any_snappy[c] = false; r->col_snappy_all_stored[c] = true; r->col_snappy_any_stored[c] = false; r->col_any_zstd[c] = false;
     }
     bool first = true;
     r->pk0_range_ok = true;
@@ -223,6 +223,7 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       for (int c = 0; c < m.ncols && c < MAX_COLS; c++) {
         if (!rc[c].simple_page) r->col_all_simple[c] = false;
         if (!rc[c].single_page) r->col_all_single[c] = false;
+        if (m.rgs[g].cols[c].codec == CODEC_ZSTD) { r->col_any_zstd[c] = true; r->any_zstd = true; }
         if (rc[c].snappy) { r->col_any_snappy[c] = true; if (!rc[c].stored) r->col_snappy_all_stored[c] = false; else r->col_snappy_any_stored[c] = true; }
         r->col_max_scratch[c] = std::max(r->col_max_scratch[c], rc[c].scratch);
         r->col_comp_bytes[c] += uint64_t(m.rgs[g].cols[c].total_compressed);
@@ -513,7 +514,7 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
       for (size_t i2 = 0; i2 < np; i2++) if (preds[i2].column == c && preds[i2].op == HG_OP_IN) ok = false;   // the gate kernel tests intervals
       uint64_t bytes = 0;
       for (size_t j = 0; j < k && ok; j++) {
-        ok = rs[j]->rows_total == 0 || (rs[j]->col_all_single[c] && rs[j]->col_null_none[c]);
+        ok = rs[j]->rows_total == 0 || (rs[j]->col_all_single[c] && rs[j]->col_null_none[c] && !rs[j]->col_any_zstd[c]);
         bytes += rs[j]->col_comp_bytes[c];
       }
       if (ok && bytes < best_bytes) { best_bytes = bytes; gate_col = int(c); }
@@ -987,6 +988,11 @@ static int run_pipeline(hg_engine* e, const hg_schema_desc* schema, const hg_sst
       else
         k::snappy_chunks_v2(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
                             int(colsel.size()), st->d_scratch.as<uint8_t>(), st->counters() + 4, st->d_err.as<int>());
+      bool any_zstd = false;
+      for (const SstResident* f : plan.files) any_zstd = any_zstd || f->any_zstd;
+      if (any_zstd)                                          // ParquetCompression::Zstd (config.rs:78-94): its own kernel, same scratch layout
+        k::zstd_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
+                       int(colsel.size()), st->d_scratch.as<uint8_t>(), st->counters() + 6, st->d_err.as<int>());
     }
     k::decode_chunks(L, st->d_ssts.as<SstDev>(), st->d_sel.as<RgSel>(), uint32_t(plan.sel.size()), st->d_colsel.as<ColSel>(),
                      int(colsel.size()), st->d_scratch.as<uint8_t>(), st->d_err.as<int>());

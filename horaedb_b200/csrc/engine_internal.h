@@ -127,6 +127,8 @@ struct SstResident {
   bool col_any_snappy[MAX_COLS] = {false};
   bool col_snappy_all_stored[MAX_COLS] = {false};  // every Snappy chunk of the column is a stored (literal-only) page
   bool col_snappy_any_stored[MAX_COLS] = {false};  // some Snappy chunk of the column is one
+  bool col_any_zstd[MAX_COLS] = {false};           // some chunk of the column is Zstandard-compressed (general pipeline only)
+  bool any_zstd = false;
   uint32_t col_max_scratch[MAX_COLS] = {0};      // largest decompression scratch of one chunk of the column
   uint64_t col_comp_bytes[MAX_COLS] = {0};       // compressed bytes of the column (work estimate for the decompressor)
   uint64_t pk0_min = 0, pk0_max = 0;

@@ -1197,7 +1197,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     rows_in_files += f->rows_total;
     if (f->rows_total == 0) continue;
     for (uint32_t c : slots)
-      if (!f->col_all_single[c] || !f->col_null_none[c]) return NOT_APPLICABLE;
+      if (!f->col_all_single[c] || !f->col_null_none[c] || f->col_any_zstd[c]) return NOT_APPLICABLE;   // (Zstandard pages: general pipeline)
     if (!global_mode && (!f->col_has_minmax[0] || (has_ts && !f->col_has_minmax[1]))) return NOT_APPLICABLE;
     files.push_back(f);
   }

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
   const uint32_t pw = (ch.phys == 1 || ch.phys == 4) ? 4u : 8u;   // INT32/FLOAT : INT64/DOUBLE (BYTE_ARRAY: variable, handled apart)
   uint8_t* sc = scratch + (ch.scratch_bytes ? chunk_scratch_off(rs, chunks, cols, ci) : 0);
   const uint8_t* dict = sst.bytes + ch.dict_payload_off;             // dictionary values (PLAIN): in place, or decompressed first in the scratch
-  if (ch.dict_uncomp && ch.codec == 1) { dict = sc; sc += page_scratch(ch.dict_uncomp); }
+  if (ch.dict_uncomp && ch.codec != 0) { dict = sc; sc += page_scratch(ch.dict_uncomp); }
   const uint32_t dict_n = ch.dict_uncomp / pw;
   uint32_t row = rs.out_row;
   if (tid == 0) s_bad = 0;
@@ -459,9 +459,9 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
     if (pg.page_type == 3) {            // V2: levels uncompressed in front, values optionally compressed
       lv_ptr = payload + pg.v2_rep_len;
       lv_len = pg.v2_def_len;
-      val_ptr = (ch.codec == 1 && pg.v2_compressed) ? sc : payload + pg.v2_rep_len + pg.v2_def_len;
+      val_ptr = (ch.codec != 0 && pg.v2_compressed) ? sc : payload + pg.v2_rep_len + pg.v2_def_len;
     } else {                            // V1: [u32 len][levels][values], compressed as a whole
-      const uint8_t* body = ch.codec == 1 ? sc : payload;
+      const uint8_t* body = ch.codec != 0 ? sc : payload;        // 1 Snappy, 6 Zstandard: decompressed into the scratch before this kernel
       if (ch.optional) {
         lv_len = ld32_any(body);
         lv_ptr = body + 4;
@@ -469,10 +469,10 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
       } else val_ptr = body;
     }
     // values available in this page (malformed pages must not make the decoder read past the page: ABI = HG_ERR_FORMAT)
-    const uint8_t* page_end = (ch.codec == 1 && !(pg.page_type == 3 && !pg.v2_compressed)) ? sc + (pg.page_type == 3 ? pg.uncomp_size - pg.v2_def_len - pg.v2_rep_len : pg.uncomp_size)
+    const uint8_t* page_end = (ch.codec != 0 && !(pg.page_type == 3 && !pg.v2_compressed)) ? sc + (pg.page_type == 3 ? pg.uncomp_size - pg.v2_def_len - pg.v2_rep_len : pg.uncomp_size)
                                                                                        : payload + pg.comp_size;
     uint32_t max_vals = val_ptr <= page_end ? uint32_t(size_t(page_end - val_ptr) / pw) : 0u;
-    if (ch.codec == 1) sc += page_scratch(pg.uncomp_size);
+    if (ch.codec != 0) sc += page_scratch(pg.uncomp_size);
     if (pg.encoding == 5) {
       // DELTA_BINARY_PACKED: expand the values into the page's PLAIN image in scratch, then decode that like any PLAIN page
       uint8_t* img = sc;

@@ -45,6 +45,9 @@ struct SnappyJob {
   int* err;
 };
 void snappy_pages(const Launch& L, const SnappyJob& job, uint32_t max_chunks);
+// Zstandard pages of the selected chunks -> scratch (zstd.cu); `ticket` is a zeroed device counter
+void zstd_chunks(const Launch& L, const SstDev* ssts, const RgSel* sel, uint32_t nsel, const ColSel* cols, int ncolsel, uint8_t* scratch,
+                 unsigned int* ticket, int* err);
 void snappy_set_ctas_per_sm(int n);   // resident CTAs per SM of the decompression kernels (0 = default 7, see snappy.cu)
 // raw Snappy streams by pointer: dst must be 16-byte aligned with uncomp_size + 48 bytes of room; ticket = zeroed device counter
 struct RawPage { const uint8_t* src; uint8_t* dst; uint32_t comp_size, uncomp_size; };

@@ -277,6 +277,13 @@ bool parse_parquet(const uint8_t* data, size_t len, FileMetaData* out, std::stri
       }
       if (seen != cm.num_values) return bad("page value counts do not add up to the chunk");
       cm.num_pages = uint32_t(out->pages.size()) - cm.first_page;
+      if (cm.codec == CODEC_ZSTD) {
+        // Zstandard: the block's Huffman-decoded literals need a buffer of their own: min(largest page of the chunk, 128 KiB), at the
+        // END of the chunk's scratch (zstd.cu computes the same size from the page table)
+        uint32_t big = cm.has_dict_page ? cm.dict_uncomp_size : 0;
+        for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++) big = std::max(big, out->pages[pi].uncomp_size);
+        cm.scratch_bytes += page_scratch_bytes(std::min<uint32_t>(big, 128u << 10));
+      }
     }
   }
   return true;

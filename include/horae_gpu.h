@@ -136,7 +136,7 @@ typedef struct {
   float gpu_ms;               /* device time of the last call, first kernel to last (CUDA events on the engine stream) */
   float kernel_ms;            /* device time of the call's dominant kernel alone (fused scan / page decode) */
   float merge_ms;             /* device time of S4-S6 (sort records, merge passes, dedup, compaction of survivors) */
-  float decomp_ms;            /* device time of the page-decompression stage (Snappy), when one ran */
+  float decomp_ms;            /* device time of the page-decompression stage (Snappy; fused path), when one ran */
   uint64_t rows_materialized; /* fused path: rows whose non-gate columns were read (== rows_decoded without the gate);
                                  general pipeline: rows_decoded */
 } hg_scan_stats;
@@ -175,7 +175,8 @@ int hg_compact_open(hg_engine* e, const hg_schema_desc* schema, const hg_sst_des
  * PLAIN values, RLE definition levels, dictionary off, bloom filters off, chunk statistics on, one DataPage V1 per chunk. */
 typedef struct {
   uint32_t max_row_group_size;      /* 0 = 8192 (WriteConfig::default) */
-  uint32_t compression;             /* Parquet codec id: 0 UNCOMPRESSED, 1 SNAPPY (the default) */
+  uint32_t compression;             /* Parquet codec id the WRITER applies: 0 UNCOMPRESSED, 1 SNAPPY (the default).  Readers also take 6 = ZSTD
+                                       (config.rs:78-94: Uncompressed / Snappy / Zstd); Zstd SSTs run on the general pipeline */
   uint32_t enable_sorting_columns;  /* sorting_columns = primary keys, ascending, nulls first */
   uint32_t _pad;
 } hg_write_props;
@@ -263,7 +264,7 @@ typedef struct {
   uint64_t sum_page_values;          /* sum of num_values over all data pages */
   uint64_t sum_uncompressed_bytes;   /* sum of uncompressed page payload sizes (page headers excluded) */
   uint64_t sum_compressed_bytes;     /* the same, as stored */
-  uint32_t codec_mask;               /* bit c set: some column chunk uses Parquet codec id c (0 uncompressed, 1 Snappy) */
+  uint32_t codec_mask;               /* bit c set: some column chunk uses Parquet codec id c (0 uncompressed, 1 Snappy, 6 Zstd) */
   uint32_t max_pages_per_chunk;
 } hg_parquet_summary;
 

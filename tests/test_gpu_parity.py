@@ -396,7 +396,7 @@ def test_empty_inputs(eng):
 def test_unsupported_is_an_error_not_a_fallback(eng):
     schema = sstgen.metric_storage_schema()
     handle = SchemaHandle(schema.arrow_schema, 2)
-    data, _ = sstgen.synth_sst(0, 4, 10, 1000, seq=2, compression="zstd")
+    data, _ = sstgen.synth_sst(0, 4, 10, 1000, seq=2, compression="gzip")          # not a codec the reference can configure (config.rs:78-94)
     with pytest.raises(HgError) as ei:
         eng.scan(handle, _inputs([data]), [])
     assert ei.value.code == 2
