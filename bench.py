@@ -304,12 +304,13 @@ def main():
         d2h = 0
         h2d = 0
 
-        def e2e_step():
-            for sid, _, _ in ssts:
-                try:
-                    eng.unload_sst(sid)
-                except Exception:
-                    pass
+        for sid, _, _ in ssts:                       # nothing of these files may be resident: every e2e call moves its bytes itself
+            try:
+                eng.unload_sst(sid)
+            except Exception:
+                pass
+
+        def e2e_step():                              # (SSTs given as host buffers are transient: gone from HBM when the call returns)
             return eng.scan_aggregate(handle, inputs_host, P, group_col=0, ts_col=-1, window_ms=0, value_col=2)
 
         # two untimed calls: the first sizes the engine's arena and pinned staging, the second runs on the consolidated arena

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -377,6 +379,76 @@ __global__ void __launch_bounds__(256) gather_ranges_kernel(const CopyRange* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------- host worker pool
+// A transient load parses footers / page headers and builds tens of thousands of byte ranges per call on the host while PCIe waits:
+// per-file work, run on a small persistent pool (threads created per call cost as much as the work they would do).
+namespace {
+class WorkPool {
+ public:
+  explicit WorkPool(unsigned n) { for (unsigned i = 0; i < n; i++) th_.emplace_back([this] { loop(); }); }
+  ~WorkPool() {
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // fn(i) for every i in [0, n), on the workers and on the caller; returns when all have finished
+  void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+    if (n == 0) return;
+    if (n == 1 || th_.empty()) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::lock_guard<std::mutex> serial(call_mu_);           // one parallel_for at a time
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      fn_ = &fn; n_ = n; next_.store(0); done_ = 0; gen_++;
+    }
+    cv_.notify_all();
+    run();
+    std::unique_lock<std::mutex> g(mu_);
+    cv_done_.wait(g, [&] { return done_ == n_; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run() {
+    size_t mine = 0;
+    for (;;) {
+      const size_t i = next_.fetch_add(1);
+      if (i >= n_) break;
+      (*fn_)(i);
+      mine++;
+    }
+    if (mine) {
+      std::lock_guard<std::mutex> g(mu_);
+      done_ += mine;
+      if (done_ == n_) cv_done_.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      run();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, cv_done_;
+  const std::function<void(size_t)>* fn_ = nullptr;
+  size_t n_ = 0, done_ = 0;
+  std::atomic<size_t> next_{0};
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+WorkPool& work_pool() {
+  static WorkPool* p = new WorkPool(std::min(15u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // + the caller = 16
+  return *p;
+}
+}  // namespace
+
 static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_sst_desc* ssts, const std::vector<size_t>& pending,
                           const hg_predicate* preds, size_t np, std::vector<uint32_t> need_cols, bool seq_if_overlap,
                           const std::vector<size_t>& resident_idx) {
@@ -408,21 +480,9 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
   // ---- parse in parallel
   std::vector<int> codes(k, 0);
   std::vector<std::string> errs(k);
-  {
-    const unsigned nthreads = unsigned(std::min<size_t>(k, 16));
-    std::atomic<size_t> next{0};
-    auto work = [&] {
-      for (;;) {
-        size_t j = next.fetch_add(1);
-        if (j >= k) break;
-        codes[j] = prepare_sst(schema, ssts[pending[j]].id, datas[j], sizes[j], rs[j].get(), &pages[j], &chunks[j], &errs[j]);
-      }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
-  }
+  work_pool().parallel_for(k, [&](size_t j) {
+    codes[j] = prepare_sst(schema, ssts[pending[j]].id, datas[j], sizes[j], rs[j].get(), &pages[j], &chunks[j], &errs[j]);
+  });
   for (size_t j = 0; j < k; j++) if (codes[j]) return set_error(codes[j], errs[j]);
   const auto tt1 = now();
   // ---- __seq__ is only needed when the inputs are not provably PK-disjoint (a real merge will run)
@@ -525,38 +585,63 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
   }
   std::vector<fused::GateOut> gate_out;
   if (gate_col >= 0) {
-    std::vector<CopyRange> ranges;
     std::vector<fused::GateRg> descs(kept.size());
     std::vector<k::RawPage> raw;
     const uint32_t gw = type_width_host(schema->types[gate_col]) <= 4 ? 4u : 8u;
+    // per file on the worker pool: the gate column's byte ranges, the pages to decompress and the gate descriptors.  Scratch addresses
+    // are offsets into the file's share until the (serial) arena allocation below
+    std::vector<std::vector<CopyRange>> franges(k);
+    std::vector<std::vector<k::RawPage>> fraw(k);
+    std::vector<uint64_t> fneed(k, 0);
+    std::vector<int> ferr(k, 0);
+    std::vector<std::pair<size_t, size_t>> gseg(k, {0, 0});             // kept[] is ordered by file: [begin, end) per file
     for (size_t i = 0; i < kept.size(); i++) {
-      const size_t j = kept[i].j;
-      const uint32_t g = kept[i].g;
-      SstResident& r = *rs[j];
-      add_range(ranges, j, g, uint32_t(gate_col));
-      const ChunkDev& cd = chunks[j][size_t(g) * size_t(r.meta.ncols) + size_t(gate_col)];
-      const PageDev& pg = pages[j][cd.first_page];
-      uint64_t off = pg.payload_off;
-      if (cd.codec == CODEC_SNAPPY) {
-        // decompressed on the device into arena scratch; the level prefix is skipped there
-        uint8_t* dst = static_cast<uint8_t*>(g_arena->alloc(page_scratch_bytes(pg.uncomp_size) + 16));
-        if (!dst) return set_error(HG_ERR_OOM, "out of device memory");
-        raw.push_back(k::RawPage{r.d_bytes + off, dst, pg.comp_size, pg.uncomp_size});
-        if (uint64_t(pg.uncomp_size) < uint64_t(r.rg_rows[g]) * gw) return set_error(HG_ERR_FORMAT, "column chunk smaller than its values");
-        descs[i] = fused::GateRg{dst, r.rg_rows[g], cd.optional ? 1u : 0u};
-      } else {
-        if (cd.optional) {                                  // [u32 len][RLE def levels] in front of the values (all valid here)
-          uint32_t len = 0;
-          if (off + 4 > r.size) return set_error(HG_ERR_FORMAT, "page payload out of bounds");
-          std::memcpy(&len, datas[j] + off, 4);
-          off += 4 + uint64_t(len);
-        }
-        if (off + uint64_t(r.rg_rows[g]) * gw > r.size) return set_error(HG_ERR_FORMAT, "column chunk out of bounds");
-        descs[i] = fused::GateRg{r.d_bytes + off, r.rg_rows[g], 0};
-      }
+      if (gseg[kept[i].j].second == 0) gseg[kept[i].j].first = i;
+      gseg[kept[i].j].second = i + 1;
     }
-    int rc = move_ranges(ranges);
-    if (rc) return rc;
+    work_pool().parallel_for(k, [&](size_t j) {
+      SstResident& r = *rs[j];
+      for (size_t i = gseg[j].first; i < gseg[j].second; i++) {
+        const uint32_t g = kept[i].g;
+        add_range(franges[j], j, g, uint32_t(gate_col));
+        const ChunkDev& cd = chunks[j][size_t(g) * size_t(r.meta.ncols) + size_t(gate_col)];
+        const PageDev& pg = pages[j][cd.first_page];
+        uint64_t off = pg.payload_off;
+        if (cd.codec == CODEC_SNAPPY) {
+          // decompressed on the device into arena scratch; the level prefix is skipped there
+          uint8_t* rel = reinterpret_cast<uint8_t*>(uintptr_t(fneed[j]));
+          fneed[j] += (page_scratch_bytes(pg.uncomp_size) + 16 + 255) & ~uint64_t(255);
+          fraw[j].push_back(k::RawPage{r.d_bytes + off, rel, pg.comp_size, pg.uncomp_size});
+          if (uint64_t(pg.uncomp_size) < uint64_t(r.rg_rows[g]) * gw) { ferr[j] = 1; return; }
+          descs[i] = fused::GateRg{rel, r.rg_rows[g], (cd.optional ? 1u : 0u) | 0x80000000u};      // bit 31: vals is still an offset
+        } else {
+          if (cd.optional) {                                  // [u32 len][RLE def levels] in front of the values (all valid here)
+            uint32_t len = 0;
+            if (off + 4 > r.size) { ferr[j] = 2; return; }
+            std::memcpy(&len, datas[j] + off, 4);
+            off += 4 + uint64_t(len);
+          }
+          if (off + uint64_t(r.rg_rows[g]) * gw > r.size) { ferr[j] = 3; return; }
+          descs[i] = fused::GateRg{r.d_bytes + off, r.rg_rows[g], 0};
+        }
+      }
+    });
+    for (size_t j = 0; j < k; j++) {
+      if (ferr[j] == 1) return set_error(HG_ERR_FORMAT, "column chunk smaller than its values");
+      if (ferr[j] == 2) return set_error(HG_ERR_FORMAT, "page payload out of bounds");
+      if (ferr[j] == 3) return set_error(HG_ERR_FORMAT, "column chunk out of bounds");
+      uint8_t* base = nullptr;
+      if (fneed[j]) {
+        base = static_cast<uint8_t*>(g_arena->alloc(fneed[j]));
+        if (!base) return set_error(HG_ERR_OOM, "out of device memory");
+      }
+      for (auto& rp : fraw[j]) { rp.dst = base + uintptr_t(rp.dst); raw.push_back(rp); }
+      for (size_t i = gseg[j].first; i < gseg[j].second; i++)
+        if (descs[i].prefixed & 0x80000000u) { descs[i].vals = base + uintptr_t(descs[i].vals); descs[i].prefixed &= 1u; }
+      int rc = move_ranges(franges[j]);
+      if (rc) return rc;
+    }
+    int rc = 0;
     fused::GateRg* d_descs = static_cast<fused::GateRg*>(g_arena->alloc(descs.size() * sizeof(fused::GateRg)));
     fused::GateOut* d_out = static_cast<fused::GateOut*>(g_arena->alloc(kept.size() * sizeof(fused::GateOut) + 16));
     uint32_t* d_tick = static_cast<uint32_t*>(g_arena->alloc(64));
@@ -595,27 +680,29 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
     gate_out.swap(alive_out);
   }
   const auto tt1b = now();
-  // ---- the remaining columns of the row groups still in play
+  // ---- the remaining columns of the row groups still in play: one task per file on the worker pool (a file's ranges only touch
+  //      that file's tables), the files' range lists leave in file order
   {
-    std::vector<CopyRange> ranges;
-    auto add_bytes = [&](size_t j, uint64_t lo, uint64_t hi) {           // file byte range [lo, hi) (+ slack for the unaligned loads)
-      SstResident& r = *rs[j];
-      hi = std::min<uint64_t>(r.size, hi + 16);
-      if (lo >= hi) return;
-      if (!ranges.empty() && ranges.back().src + ranges.back().bytes >= datas[j] + lo && ranges.back().src <= datas[j] + lo &&
-          ranges.back().dst == r.d_bytes + (ranges.back().src - datas[j])) {
-        const uint64_t b0 = uint64_t(ranges.back().src - datas[j]);
-        ranges.back().bytes = std::max<uint64_t>(b0 + ranges.back().bytes, hi) - b0;
-      } else ranges.push_back(CopyRange{datas[j] + lo, r.d_bytes + lo, hi - lo});
-    };
-    // the ranges leave in slices: the gather kernel of one slice crosses PCIe while the host builds the next slice's ranges
-    const size_t slice_rgs = kept.size() > 4096 ? (kept.size() + 7) / 8 : kept.size();
+    std::vector<std::vector<CopyRange>> file_ranges(k);
+    std::vector<std::pair<size_t, size_t>> seg(k, {0, 0});              // kept[] is ordered by file: [begin, end) per file
     for (size_t i = 0; i < kept.size(); i++) {
-      if (i && i % slice_rgs == 0) {
-        int rc = move_ranges(ranges);
-        if (rc) return rc;
-        ranges.clear();
-      }
+      if (seg[kept[i].j].second == 0) seg[kept[i].j].first = i;
+      seg[kept[i].j].second = i + 1;
+    }
+    std::vector<uint8_t> file_trunc(k, 0);
+    work_pool().parallel_for(k, [&](size_t fj) {
+      std::vector<CopyRange>& ranges = file_ranges[fj];
+      auto add_bytes = [&](size_t j, uint64_t lo, uint64_t hi) {           // file byte range [lo, hi) (+ slack for the unaligned loads)
+        SstResident& r = *rs[j];
+        hi = std::min<uint64_t>(r.size, hi + 16);
+        if (lo >= hi) return;
+        if (!ranges.empty() && ranges.back().src + ranges.back().bytes >= datas[j] + lo && ranges.back().src <= datas[j] + lo &&
+            ranges.back().dst == r.d_bytes + (ranges.back().src - datas[j])) {
+          const uint64_t b0 = uint64_t(ranges.back().src - datas[j]);
+          ranges.back().bytes = std::max<uint64_t>(b0 + ranges.back().bytes, hi) - b0;
+        } else ranges.push_back(CopyRange{datas[j] + lo, r.d_bytes + lo, hi - lo});
+      };
+      for (size_t i = seg[fj].first; i < seg[fj].second; i++) {
       const KeptRg& kr = kept[i];
       SstResident& r = *rs[kr.j];
       for (uint32_t c : need_cols) {
@@ -640,7 +727,7 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
               const ChunkMeta& cm = r.meta.rgs[kr.g].cols[c];
               add_bytes(kr.j, uint64_t(cm.data_page_offset), pg.payload_off + est);
               pages[kr.j][cd.first_page].comp_size = uint32_t(est);
-              e->trunc_used = true;
+              file_trunc[fj] = 1;
               continue;
             }
           }
@@ -694,9 +781,13 @@ static int load_transient(hg_engine* e, const hg_schema_desc* schema, const hg_s
           if (v1 && last >= n0) add_bytes(kr.j, v1 + (std::max<uint64_t>(first, n0) - n0) * w, v1 + (last - n0 + 1) * w);
         }
       }
+      }
+    });
+    for (size_t j = 0; j < k; j++) {
+      if (file_trunc[j]) e->trunc_used = true;
+      int rc = move_ranges(file_ranges[j]);
+      if (rc) return rc;
     }
-    int rc = move_ranges(ranges);
-    if (rc) return rc;
   }
   const auto tt1c = now();
   // ---- planning tables (device copies: dead row groups have zero rows => pruned by every device-side planner)
