@@ -26,6 +26,7 @@ constexpr int kMaxLL = 36, kMaxML = 53, kMaxOF = 32;       // symbols of the thr
 constexpr int kLLLog = 9, kMLLog = 9, kOFLog = 8;          // maximum accuracy logs
 constexpr int kHufLog = 11;                                // maximum Huffman code length
 constexpr uint32_t kBlockMax = 128u << 10;
+constexpr uint32_t kRingZ = 4096;      // output history kept in shared memory: a match that starts within it never waits for L2
 
 struct alignas(16) WarpSmem {
   uint32_t ll[1 << kLLLog], ml[1 << kMLLog], of[1 << kOFLog];   // FSE cells: symbol | nbits << 8 | new-state base << 16
@@ -36,6 +37,8 @@ struct alignas(16) WarpSmem {
   uint32_t ll_log, ml_log, of_log, huf_log;                    // accuracy logs of the current tables (they persist across blocks)
   uint32_t rep[3];                                             // repeat offsets (persist across the blocks of a frame)
   uint32_t huf_ok;
+  uint8_t per[32];                                             // the period of a short-offset match
+  uint8_t ring[kRingZ];                                        // the most recent output bytes (byte at output position x: x & (kRingZ-1))
   uint32_t wt[128];                                            // FSE table of a compressed Huffman tree description
   uint32_t xfer[2];                                            // lane 0 -> warp: bytes consumed by a table description
 };
@@ -91,27 +94,37 @@ SNP_FN uint32_t fwd_read(FwdBits& b, int n) {                  // n <= 24
 
 // ---- backward bit reader (Huffman and FSE streams): the stream is read from its last byte down; `off` = bits not yet consumed, may go
 //      negative (reads below the stream's start deliver zero bits, RFC 8878 4.1 / 4.2.1)
-struct BwdBits { const uint8_t* p; const uint8_t* end; int64_t off; };
+struct BwdBits { const uint8_t* p; const uint8_t* end; int64_t off; uint64_t cache; int64_t cache_bit; };
 SNP_FN bool bwd_init(BwdBits& b, const uint8_t* p, uint32_t len) {
-  b.p = p; b.end = p + len; b.off = 0;
+  b.p = p; b.end = p + len; b.off = 0; b.cache = 0; b.cache_bit = int64_t(1) << 40;      // (empty cache)
   if (len == 0) return false;
   const uint32_t last = snp_ldg8(p + len - 1);
   if (last == 0) return false;                                 // the final byte carries the end mark
   b.off = int64_t(len) * 8 - (8 - highbit(last));
   return true;
 }
+// The reader keeps the 8 stream bytes that END at the current position in a register: reads walk down through them, one load serves
+// ~50 bits (two sequences' worth), and the dependent chain of a sequence no longer contains a memory access per field.
 SNP_FN uint32_t bwd_read(BwdBits& b, int n) {                  // n <= 32
   if (n == 0) return 0;
   b.off -= n;
-  int64_t o = b.off;
-  int bits = n;
-  if (o < 0) { bits += int(o); o = 0; }
+  if (b.off >= b.cache_bit && b.off + n <= b.cache_bit + 64) return uint32_t(b.cache >> (b.off - b.cache_bit)) & uint32_t((1ull << n) - 1ull);
+  if (b.off >= 0) {
+    int64_t byte = ((b.off + n + 7) >> 3) - 8;                 // the word ends at the byte holding the top bit of this read
+    if (byte < 0) byte = 0;
+    b.cache = ld_le(b.p + byte, b.end);
+    b.cache_bit = byte * 8;
+    return uint32_t(b.cache >> (b.off - b.cache_bit)) & uint32_t((1ull << n) - 1ull);
+  }
+  // below the start of the stream: the missing low bits read as zero
+  int64_t o = 0;
+  int bits = n + int(b.off);
   uint64_t v = 0;
   if (bits > 0) {
     v = ld_le(b.p + (o >> 3), b.end) >> (o & 7);
-    v &= (bits >= 64) ? ~0ull : ((1ull << bits) - 1ull);
+    v &= (1ull << bits) - 1ull;
   }
-  if (b.off < 0) v = (-b.off >= 32) ? 0 : (v << (-b.off));
+  v = (-b.off >= 32) ? 0 : (v << (-b.off));
   return uint32_t(v);
 }
 
@@ -264,24 +277,47 @@ SNP_FN bool huf_stream(const WarpSmem& sm, const uint8_t* p, uint32_t len, uint8
   return b.off == -int64_t(mb);                                // the stream is consumed exactly
 }
 
-// warp copies.  in: read-only input;  out_fill / match: the page's own output
-SNP_FN void copy_in(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) { for (uint32_t i = lane; i < n; i += 32) dst[i] = snp_ldg8(src + i); }
-SNP_FN void copy_buf(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) { for (uint32_t i = lane; i < n; i += 32) dst[i] = snp_ldcg8(src + i); }
-SNP_FN void fill(uint8_t* dst, uint8_t v, uint32_t n, int lane) { for (uint32_t i = lane; i < n; i += 32) dst[i] = v; }
+// warp copies to output position `pos` (every output byte also lands in the ring).  in: read-only input; buf: the literal buffer
+SNP_FN void copy_in(WarpSmem& sm, uint8_t* out, uint32_t pos, const uint8_t* src, uint32_t n, int lane) {
+  for (uint32_t i = lane; i < n; i += 32) { const uint8_t v = snp_ldg8(src + i); out[pos + i] = v; if (n - i <= kRingZ) sm.ring[(pos + i) & (kRingZ - 1)] = v; }
+}
+SNP_FN void copy_buf(WarpSmem& sm, uint8_t* out, uint32_t pos, const uint8_t* src, uint32_t n, int lane) {
+  for (uint32_t i = lane; i < n; i += 32) { const uint8_t v = snp_ldcg8(src + i); out[pos + i] = v; if (n - i <= kRingZ) sm.ring[(pos + i) & (kRingZ - 1)] = v; }
+}
+SNP_FN void fill(WarpSmem& sm, uint8_t* out, uint32_t pos, uint8_t v, uint32_t n, int lane) {
+  for (uint32_t i = lane; i < n; i += 32) { out[pos + i] = v; if (n - i <= kRingZ) sm.ring[(pos + i) & (kRingZ - 1)] = v; }
+}
+// byte at output position x < `written`: from the ring if it is among the last kRingZ / 2 bytes (a pass writes at most kRingZ / 2 new
+// bytes, so those slots are not overwritten while it reads), else from global memory (coherent load)
+SNP_FN uint8_t out_byte(const WarpSmem& sm, const uint8_t* out, uint32_t written, uint32_t x) {
+  return (written - x <= kRingZ / 2) ? sm.ring[x & (kRingZ - 1)] : snp_ldcg8(out + x);
+}
 // out[pos + i] = out[pos + i - off] for i < n, overlapping allowed: byte i comes from the period out[pos - off .. pos)
-SNP_FN void copy_match(uint8_t* out, uint32_t pos, uint32_t off, uint32_t n, int lane) {
+SNP_FN void copy_match(WarpSmem& sm, uint8_t* out, uint32_t pos, uint32_t off, uint32_t n, int lane) {
   if (off >= n || off >= 32) {
-    // passes of min(off, 32..) bytes never read what the same pass writes
+    // passes of at most `off` bytes (a multiple of 32) never read what the same pass writes
     const uint32_t chunk = off < n ? (off / 32u) * 32u : n;      // off >= 32 here when off < n
     uint32_t done = 0;
     while (done < n) {
-      const uint32_t m = n - done < chunk ? n - done : chunk;
-      for (uint32_t i = lane; i < m; i += 32) out[pos + done + i] = snp_ldcg8(out + pos + done + i - off);
+      uint32_t m = n - done < chunk ? n - done : chunk;
+      if (m > kRingZ / 2) m = kRingZ / 2;                        // a pass must not overwrite ring bytes it still has to read
+      for (uint32_t i = lane; i < m; i += 32) {
+        const uint8_t v = out_byte(sm, out, pos + done, pos + done + i - off);
+        out[pos + done + i] = v;
+        sm.ring[(pos + done + i) & (kRingZ - 1)] = v;
+      }
       done += m;
       snp_syncwarp();
     }
   } else {
-    for (uint32_t i = lane; i < n; i += 32) out[pos + i] = snp_ldcg8(out + pos - off + (i % off));
+    // short period: every byte of the match is a byte of out[pos - off .. pos): park the period, then spread it
+    if (uint32_t(lane) < off) sm.per[lane] = out_byte(sm, out, pos, pos - off + uint32_t(lane));
+    snp_syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint8_t v = sm.per[i % off];
+      out[pos + i] = v;
+      if (n - i <= kRingZ) sm.ring[(pos + i) & (kRingZ - 1)] = v;
+    }
   }
 }
 
@@ -322,11 +358,11 @@ SNP_FN void zstd_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __re
       const uint32_t last = bh & 1u, type = (bh >> 1) & 3u, bsize = bh >> 3;
       if (type == 0) {                                         // raw
         if (p + bsize > end || o + bsize > ulen) ZFAIL(206);
-        copy_in(dst + o, p, bsize, lane);
+        copy_in(sm, dst, o, p, bsize, lane);
         p += bsize; o += bsize;
       } else if (type == 1) {                                  // RLE
         if (p + 1 > end || o + bsize > ulen) ZFAIL(206);
-        fill(dst + o, snp_ldg8(p), bsize, lane);
+        fill(sm, dst, o, snp_ldg8(p), bsize, lane);
         p += 1; o += bsize;
       } else if (type == 2) {
         if (bsize > kBlockMax || p + bsize > end || bsize < 2) ZFAIL(207);
@@ -356,7 +392,7 @@ SNP_FN void zstd_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __re
           p = lp + regen;
         } else if (ltype == 1) {
           if (lp + 1 > bend) ZFAIL(208);
-          fill(lit, snp_ldg8(lp), regen, lane);
+          for (uint32_t i = lane; i < regen; i += 32) lit[i] = snp_ldg8(lp);
           lits = lit;
           p = lp + 1;
         } else {
@@ -478,10 +514,10 @@ SNP_FN void zstd_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __re
               }
             }
             if (lpos + llen > regen || o + llen + mlen > ulen || off == 0 || off > o + llen) ZFAIL(219);
-            if (lits_in_input) copy_in(dst + o, lits + lpos, llen, lane); else copy_buf(dst + o, lits + lpos, llen, lane);
+            if (lits_in_input) copy_in(sm, dst, o, lits + lpos, llen, lane); else copy_buf(sm, dst, o, lits + lpos, llen, lane);
             lpos += llen; o += llen;
             snp_syncwarp();
-            copy_match(dst, o, off, mlen, lane);
+            copy_match(sm, dst, o, off, mlen, lane);
             o += mlen;
             snp_syncwarp();
           }
@@ -493,7 +529,7 @@ SNP_FN void zstd_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __re
         {
           const uint32_t rest = regen - lpos;
           if (o + rest > ulen) ZFAIL(221);
-          if (lits_in_input) copy_in(dst + o, lits + lpos, rest, lane); else copy_buf(dst + o, lits + lpos, rest, lane);
+          if (lits_in_input) copy_in(sm, dst, o, lits + lpos, rest, lane); else copy_buf(sm, dst, o, lits + lpos, rest, lane);
           o += rest;
         }
         p = bend;
