@@ -8,6 +8,7 @@
 #include <cstring>
 
 #define SNP_FN __device__ __forceinline__
+#define SNP_CONST __constant__ const
 #define snp_any(p) __any_sync(0xffffffffu, (p))
 #define snp_syncwarp() __syncwarp()
 #define snp_ldg8(p) __ldg(p)

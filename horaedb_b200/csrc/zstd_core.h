@@ -4,7 +4,7 @@
 // Like snappy_core.h this header is ONE source: zstd.cu compiles it for sm_100a, tests/emu/zstd_emu.cpp compiles the same text with the
 // 32 lanes as coroutines, so the CPU test-suite runs the device decoder on real libzstd streams.  The includer provides the same
 // primitives as for snappy_core.h: SNP_FN, snp_syncwarp(), snp_any(pred), snp_ldg8(p), snp_ldg64u(p) (8 input bytes at any alignment),
-// snp_ldcg8(p), snp_set_err(err, code).  Input buffers carry >= 8 readable bytes behind their last byte (SST bytes: +64, transient ranges: +16).
+// snp_ldcg8(p), snp_set_err(err, code), and SNP_CONST (qualifier of a namespace-scope constant table).  Input buffers carry >= 8 readable bytes behind their last byte (SST bytes: +64, transient ranges: +16).
 //
 // One warp owns one page (= one frame).  Zstandard is two serial entropy decoders per block — Huffman literals, then FSE-coded
 // (literal length, match length, offset) sequences whose copies may overlap their own output — so the warp splits the work by
@@ -38,44 +38,32 @@ struct alignas(16) WarpSmem {
   uint32_t rep[3];                                             // repeat offsets (persist across the blocks of a frame)
   uint32_t huf_ok;
   uint8_t per[32];                                             // the period of a short-offset match
-  uint8_t ring[kRingZ];                                        // the most recent output bytes (byte at output position x: x & (kRingZ-1))
+  alignas(8) uint8_t ring[kRingZ];                                        // the most recent output bytes (byte at output position x: x & (kRingZ-1))
   uint32_t wt[128];                                            // FSE table of a compressed Huffman tree description
   uint32_t xfer[2];                                            // lane 0 -> warp: bytes consumed by a table description
 };
 
+// Constant tables live at namespace scope (SNP_CONST: __constant__ memory on the device — every lane reads the same entry, a broadcast):
+// as function-local arrays the compiler rebuilt them on the thread's stack at every call.
 // literal length / match length codes -> (baseline, extra bits)
-SNP_FN uint32_t ll_base(uint32_t c) {
-  const uint32_t t[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
-  return t[c];
-}
-SNP_FN uint32_t ll_bits(uint32_t c) {
-  const uint8_t t[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-  return t[c];
-}
-SNP_FN uint32_t ml_base(uint32_t c) {
-  const uint32_t t[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34,
-                          35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
-  return t[c];
-}
-SNP_FN uint32_t ml_bits(uint32_t c) {
-  const uint8_t t[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-                         1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-  return t[c];
-}
+SNP_CONST uint32_t kLLBase[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
+SNP_CONST uint8_t kLLBits[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+SNP_CONST uint32_t kMLBase[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34,
+                                  35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
+SNP_CONST uint8_t kMLBits[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
 // predefined distributions (RFC 8878 section 3.1.1.3.2.2)
-SNP_FN int ll_default(int s) {
-  const int8_t t[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
-  return t[s];
-}
-SNP_FN int ml_default(int s) {
-  const int8_t t[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
-                        1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
-  return t[s];
-}
-SNP_FN int of_default(int s) {
-  const int8_t t[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
-  return t[s];
-}
+SNP_CONST int8_t kLLDefault[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
+SNP_CONST int8_t kMLDefault[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                   1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+SNP_CONST int8_t kOFDefault[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+SNP_FN uint32_t ll_base(uint32_t c) { return kLLBase[c]; }
+SNP_FN uint32_t ll_bits(uint32_t c) { return kLLBits[c]; }
+SNP_FN uint32_t ml_base(uint32_t c) { return kMLBase[c]; }
+SNP_FN uint32_t ml_bits(uint32_t c) { return kMLBits[c]; }
+SNP_FN int ll_default(int s) { return kLLDefault[s]; }
+SNP_FN int ml_default(int s) { return kMLDefault[s]; }
+SNP_FN int of_default(int s) { return kOFDefault[s]; }
 
 SNP_FN int highbit(uint32_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }      // index of the highest set bit, -1 for 0
 
@@ -279,7 +267,22 @@ SNP_FN bool huf_stream(const WarpSmem& sm, const uint8_t* p, uint32_t len, uint8
 
 // warp copies to output position `pos` (every output byte also lands in the ring).  in: read-only input; buf: the literal buffer
 SNP_FN void copy_in(WarpSmem& sm, uint8_t* out, uint32_t pos, const uint8_t* src, uint32_t n, int lane) {
-  for (uint32_t i = lane; i < n; i += 32) { const uint8_t v = snp_ldg8(src + i); out[pos + i] = v; if (n - i <= kRingZ) sm.ring[(pos + i) & (kRingZ - 1)] = v; }
+  uint32_t done = 0;
+  if (n >= 256 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {          // (output position and address share their alignment)
+    // long runs (raw blocks, raw literal sections of incompressible columns): bytes up to the first 8-aligned output address, then 8 bytes per lane
+    const uint32_t head = uint32_t((8 - (reinterpret_cast<uintptr_t>(out + pos) & 7)) & 7);
+    if (uint32_t(lane) < head) { const uint8_t v = snp_ldg8(src + lane); out[pos + lane] = v; if (n - uint32_t(lane) <= kRingZ) sm.ring[(pos + lane) & (kRingZ - 1)] = v; }
+    const uint32_t nwords = (n - head) >> 3;
+    uint64_t* d8 = reinterpret_cast<uint64_t*>(out + pos + head);
+    for (uint32_t w = lane; w < nwords; w += 32) {
+      const uint64_t v = snp_ldg64u(src + head + (size_t(w) << 3));
+      d8[w] = v;
+      const uint32_t at = head + (w << 3);
+      if (n - at <= kRingZ) *reinterpret_cast<uint64_t*>(&sm.ring[(pos + at) & (kRingZ - 1)]) = v;       // (pos + at is 8-aligned, like the ring)
+    }
+    done = head + (nwords << 3);
+  }
+  for (uint32_t i = done + lane; i < n; i += 32) { const uint8_t v = snp_ldg8(src + i); out[pos + i] = v; if (n - i <= kRingZ) sm.ring[(pos + i) & (kRingZ - 1)] = v; }
 }
 SNP_FN void copy_buf(WarpSmem& sm, uint8_t* out, uint32_t pos, const uint8_t* src, uint32_t n, int lane) {
   for (uint32_t i = lane; i < n; i += 32) { const uint8_t v = snp_ldcg8(src + i); out[pos + i] = v; if (n - i <= kRingZ) sm.ring[(pos + i) & (kRingZ - 1)] = v; }

@@ -9,6 +9,7 @@
 #include <vector>
 
 #define SNP_FN static inline
+#define SNP_CONST static const
 #define snp_any(p) (emu::ballot(bool(p)) != 0)
 #define snp_syncwarp() ((void)emu::rendezvous(0))
 #define snp_ldg8(p) (*(p))
