@@ -108,8 +108,10 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
   pages.assign(m.pages.size(), PageDev());
   for (size_t i = 0; i < pages.size(); i++) {
     const PageMeta& pm = m.pages[i];
-    if (pm.encoding != ENC_PLAIN && pm.encoding != ENC_DELTA_BINARY_PACKED && pm.encoding != ENC_RLE_DICT && pm.encoding != ENC_PLAIN_DICT)
-      return fail(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) + " (PLAIN, DELTA_BINARY_PACKED and RLE_DICTIONARY are implemented)");
+    if (pm.encoding != ENC_PLAIN && pm.encoding != ENC_DELTA_BINARY_PACKED && pm.encoding != ENC_DELTA_LENGTH_BYTE_ARRAY && pm.encoding != ENC_RLE_DICT &&
+        pm.encoding != ENC_PLAIN_DICT)
+      return fail(HG_ERR_UNSUPPORTED, "page encoding " + std::to_string(pm.encoding) +
+                                      " (PLAIN, DELTA_BINARY_PACKED, DELTA_LENGTH_BYTE_ARRAY and RLE_DICTIONARY are implemented)");
     PageDev& pd = pages[i];
     pd.payload_off = pm.payload_off;
     pd.comp_size = pm.comp_size;
@@ -171,11 +173,14 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       cd.stored = 0;
       if (cm.phys_type == PT_BYTE_ARRAY)
         for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++)
-          if (m.pages[pi].encoding != ENC_PLAIN) return fail(HG_ERR_UNSUPPORTED, "byte-array column: only PLAIN pages are implemented");
+          if (m.pages[pi].encoding != ENC_PLAIN && m.pages[pi].encoding != ENC_DELTA_LENGTH_BYTE_ARRAY)
+            return fail(HG_ERR_UNSUPPORTED, "byte-array column: PLAIN and DELTA_LENGTH_BYTE_ARRAY pages are implemented");
       cd.dict_payload_off = cm.has_dict_page ? cm.dict_payload_off : 0;
       cd.dict_comp = cm.has_dict_page ? cm.dict_comp_size : 0;
       cd.dict_uncomp = cm.has_dict_page ? cm.dict_uncomp_size : 0;
       for (uint32_t pi = cm.first_page; pi < cm.first_page + cm.num_pages; pi++) {
+        if (m.pages[pi].encoding == ENC_DELTA_LENGTH_BYTE_ARRAY && cm.phys_type != PT_BYTE_ARRAY)
+          return fail(HG_ERR_FORMAT, "DELTA_LENGTH_BYTE_ARRAY on a fixed-width column");
         if (m.pages[pi].encoding == ENC_DELTA_BINARY_PACKED && cm.phys_type != PT_INT32 && cm.phys_type != PT_INT64)
           return fail(HG_ERR_FORMAT, "DELTA_BINARY_PACKED on a non-integer column");
         if ((m.pages[pi].encoding == ENC_RLE_DICT || m.pages[pi].encoding == ENC_PLAIN_DICT) && !cm.has_dict_page)

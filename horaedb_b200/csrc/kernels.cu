@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(32) snappy_chunks_kernel(const SstDev* __restr
     }
     if (compressed) snappy_warp(src, n, dst, ulen, lane, err);
     dst += page_scratch(pg.uncomp_size);
-    if (pg.encoding == 5 || pg.encoding == 8 || pg.encoding == 2) dst += page_scratch(pg.num_values * 8u);
+    if (pg.encoding == 5 || pg.encoding == 6 || pg.encoding == 8 || pg.encoding == 2) dst += page_scratch(pg.num_values * 8u);
   }
 }
 
@@ -267,7 +267,9 @@ __device__ __forceinline__ uint64_t block_incl_scan64(uint64_t v, uint64_t* tota
   return r;
 }
 
-__device__ bool delta_decode_page(const uint8_t* p, const uint8_t* end, uint32_t pw, uint32_t max_out, uint8_t* out, uint32_t* count_out) {
+// *end_pos (optional): bytes of [p, end) the encoded values occupy (what follows is the caller's: DELTA_LENGTH_BYTE_ARRAY data)
+__device__ bool delta_decode_page(const uint8_t* p, const uint8_t* end, uint32_t pw, uint32_t max_out, uint8_t* out, uint32_t* count_out,
+                                  uint32_t* end_pos = nullptr) {
   __shared__ uint64_t s_w64[9];
   __shared__ uint64_t s_min, s_cur;
   __shared__ uint32_t s_block, s_nmini, s_total, s_pos, s_ok;
@@ -352,6 +354,7 @@ __device__ bool delta_decode_page(const uint8_t* p, const uint8_t* end, uint32_t
     }
     done += nvals;
   }
+  if (end_pos) *end_pos = s_pos;
   return true;
 }
 
@@ -431,6 +434,7 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
                                                                 const ColSel* __restrict__ cols, int ncolsel,
                                                                 uint8_t* __restrict__ scratch, int* err) {
   __shared__ uint32_t s_warp[9];
+  __shared__ uint64_t s_w64b[9];
   __shared__ uint32_t s_kind, s_count, s_val, s_bad;
   __shared__ const uint8_t* s_ptr;
   const int tid = threadIdx.x;
@@ -537,7 +541,41 @@ __global__ void __launch_bounds__(kThreads) decode_chunks_kernel(const SstDev* _
         __syncthreads();
       }
     }
-    if (ch.phys == 6) {
+    if (ch.phys == 6 && pg.encoding == 6) {
+      // BYTE_ARRAY, DELTA_LENGTH_BYTE_ARRAY (config.rs:54-75): [DELTA_BINARY_PACKED lengths of the non-null values][their bytes, back to
+      // back].  The lengths expand into the page's scratch image, an exclusive scan turns them into offsets, and every row points at
+      // its bytes in place.
+      const uint8_t** optr = reinterpret_cast<const uint8_t**>(cs.out_vals);
+      uint32_t* lens = reinterpret_cast<uint32_t*>(sc);
+      sc += page_scratch(nv * 8u);
+      uint32_t cnt = 0, used = 0;
+      bool ok = val_ptr <= page_end && delta_decode_page(val_ptr, page_end, 4, nv, reinterpret_cast<uint8_t*>(lens), &cnt, &used);
+      __syncthreads();
+      const uint8_t* data = val_ptr + used;
+      const uint64_t room = ok && data <= page_end ? uint64_t(page_end - data) : 0;
+      if (!ok || data > page_end) { if (tid == 0) s_bad = 7; cnt = 0; }
+      if (all_valid && cs.out_valid) for (uint32_t j = tid; j < nv; j += kThreads) cs.out_valid[row + j] = 1;
+      uint32_t run_vals = 0;                                  // non-null values before the current tile
+      uint64_t run_off = 0;                                   // ... and their bytes
+      for (uint32_t base = 0; base < nv; base += kThreads) {
+        const uint32_t j = base + tid;
+        const uint32_t v = (j < nv) ? (all_valid ? 1u : uint32_t(cs.out_valid[row + j] != 0)) : 0u;
+        uint32_t tile_vals;
+        const uint32_t kidx = run_vals + block_excl_scan(v, &tile_vals, s_warp);
+        const uint64_t len = (v && kidx < cnt) ? lens[kidx] : 0;
+        uint64_t tile_bytes;
+        const uint64_t incl = block_incl_scan64(len, &tile_bytes, s_w64b);
+        if (j < nv) {
+          const uint64_t off = run_off + incl - len;
+          if (v && (kidx >= cnt || off + len > room)) { s_bad = 7; optr[row + j] = nullptr; cs.out_lens[row + j] = 0; }
+          else if (v) { optr[row + j] = data + off; cs.out_lens[row + j] = uint32_t(len); }
+          else { optr[row + j] = nullptr; cs.out_lens[row + j] = 0; }
+        }
+        run_vals += tile_vals;
+        run_off += tile_bytes;
+        __syncthreads();
+      }
+    } else if (ch.phys == 6) {
       // BYTE_ARRAY, PLAIN: [u32 length][bytes] per non-null value — a serial walk (a value's position depends on every length
       // before it); Binary values of this engine's tables are few and large (batched payloads), one thread does it.  Rows point
       // at their bytes in place (page payload or decompression scratch): nothing is copied here.

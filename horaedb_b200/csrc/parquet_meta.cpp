@@ -271,7 +271,7 @@ bool parse_parquet(const uint8_t* data, size_t len, FileMetaData* out, std::stri
         out->pages.push_back(pm);
         // device scratch of the page: the decompressed payload (compressed chunks) + the PLAIN image of a DELTA_BINARY_PACKED page
         if (cm.codec != CODEC_UNCOMPRESSED) cm.scratch_bytes += page_scratch_bytes(pm.uncomp_size);
-        if (pm.encoding == ENC_DELTA_BINARY_PACKED || pm.encoding == ENC_RLE_DICT || pm.encoding == ENC_PLAIN_DICT) cm.scratch_bytes += page_scratch_bytes(uint32_t(std::min<uint64_t>(uint64_t(pm.num_values) * 8, 0xfffffff0ull)));
+        if (pm.encoding == ENC_DELTA_BINARY_PACKED || pm.encoding == ENC_DELTA_LENGTH_BYTE_ARRAY || pm.encoding == ENC_RLE_DICT || pm.encoding == ENC_PLAIN_DICT) cm.scratch_bytes += page_scratch_bytes(uint32_t(std::min<uint64_t>(uint64_t(pm.num_values) * 8, 0xfffffff0ull)));
         seen += h.num_values;
         if (h.num_values <= 0) return bad("page with no values");
       }

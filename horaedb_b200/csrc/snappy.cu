@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) snappy_pages_kernel(cons
           stop_at = 16u + (rs.num_rows + 7u) / 8u + 8u + rs.out_row * w;
         }
         advance = page_scratch2(pg.uncomp_size);
-        if (pg.encoding == 5 || pg.encoding == 8 || pg.encoding == 2) advance += page_scratch2(pg.num_values * 8u);   // PLAIN image of a DELTA / dictionary page (decode_chunks)
+        if (pg.encoding == 5 || pg.encoding == 6 || pg.encoding == 8 || pg.encoding == 2) advance += page_scratch2(pg.num_values * 8u);   // PLAIN image of a DELTA / dictionary page (decode_chunks)
       }
       if (compressed) snappy_page(src, n, dst, ulen, stop_at, sm, phase, s_csz, s_lut, lane, J.err);
       dst += advance;

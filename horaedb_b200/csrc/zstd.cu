@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) zstd_chunks_kernel(const Ss
           compressed = pg.v2_compressed != 0;
         }
         advance = page_scratch_z(pg.uncomp_size);
-        if (pg.encoding == 5 || pg.encoding == 8 || pg.encoding == 2) advance += page_scratch_z(pg.num_values * 8u);
+        if (pg.encoding == 5 || pg.encoding == 6 || pg.encoding == 8 || pg.encoding == 2) advance += page_scratch_z(pg.num_values * 8u);
       }
       if (compressed) zst::zstd_page(src, n, dst, ulen, lit, sm, lane, err);
       __syncwarp();

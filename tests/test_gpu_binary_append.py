@@ -129,6 +129,43 @@ def test_binary_columns_overwrite_and_append_match_merge_stream(codec):
     eng.close()
 
 
+@pytest.mark.parametrize("codec", [ParquetCompression.Snappy, ParquetCompression.Uncompressed, ParquetCompression.Zstd])
+def test_delta_length_byte_array_binary_columns(codec):
+    """ParquetEncoding::DeltaLengthByteArray on the Binary value columns (config.rs:54-75): the lengths are a DELTA_BINARY_PACKED run in
+    front of the concatenated bytes.  Same data, same expectation as the PLAIN case (pyarrow decodes the reference stream)."""
+    from horaedb_b200.config import ColumnOptions
+    rng = np.random.default_rng(47)
+    user = arrow_schema([("pk1", "uint64"), ("pk2", "int32"), ("blob", "binary"), ("idx", "binary")])
+
+    def make(nrows, seq, keyspace, f):
+        pk1 = np.sort(rng.integers(0, keyspace, nrows))
+        pk2 = rng.integers(-2, 3, nrows)
+        order = np.lexsort((pk2, pk1))
+        pk1, pk2 = pk1[order], pk2[order]
+        keep = np.ones(nrows, bool)
+        keep[1:] = (pk1[1:] != pk1[:-1]) | (pk2[1:] != pk2[:-1])
+        pk1, pk2 = pk1[keep], pk2[keep]
+        blob = [None if (int(k) + f) % 7 == 0 else rng.bytes(int(rng.integers(1, 60))) for k in pk1]
+        idx = [bytes([seq % 251]) * int(rng.integers(1, 5)) for _ in range(len(pk1))]
+        return record_batch(user, {"pk1": pk1.tolist(), "pk2": pk2.tolist(), "blob": blob, "idx": idx})
+
+    opts = {"blob": ColumnOptions(encoding="DELTA_LENGTH_BYTE_ARRAY"), "idx": ColumnOptions(encoding="DELTA_LENGTH_BYTE_ARRAY")}
+    eng = Engine(device=0)
+    for append in (False, True):
+        mode = UpdateMode.Append if append else UpdateMode.Overwrite
+        schema = StorageSchema.try_new(user, 2, mode)
+        handle = SchemaHandle(schema.arrow_schema, 2, mode)
+        for batches, rg in (([make(3000, 5, 400, 0)], 1000), ([make(2500, 10 + f, 300, f) for f in range(4)], 700)):
+            datas = [sstgen.write_sst(schema, b, seq=100 + i, cfg=WriteConfig(compression=codec, max_row_group_size=rg, column_options=opts), presorted=True)
+                     for i, b in enumerate(batches)]
+            md = pq.ParquetFile(io.BytesIO(datas[0])).metadata
+            assert "DELTA_LENGTH_BYTE_ARRAY" in md.row_group(0).column(2).encodings
+            for keep_builtin in (False, True):
+                got = list(eng.scan(handle, [SstInput(id=next(_ids), data=d) for d in datas], (), None, keep_builtin))
+                _check(got, _reference_scan(schema, datas, append, keep_builtin))
+    eng.close()
+
+
 def test_append_mode_rules():
     """read.rs:485-490 + operator.rs:66-73: Append merges EVERY value column, which must be Binary; Binary keys, predicates on
     Binary columns, aggregation and the GPU writer refuse Binary / Append (error codes, no fallback)."""
