@@ -47,7 +47,7 @@ constexpr int kRing = 4096;        // ring buffer of the most recent output (pow
 constexpr int kHist = 2048;        // bytes before the current batch that are guaranteed to still be in the ring
 constexpr int kLevels = 5;         // J1, J2, J4, J8, J16 (the next batch starts right after the last executed element)
 constexpr uint32_t kExit = 0xff;   // "leaves the window"; window positions are one byte per table entry
-constexpr uint32_t kRestage = kWin - 96;   // start a new window when a batch would begin beyond this position
+constexpr uint32_t kRestage = kWin - 80;   // start a new window when a batch would begin beyond this position (176: 14 % fewer windows than 160 on ts pages, same number of steps)
 constexpr uint32_t kFlushAt = 256;         // ring -> global once this many bytes are pending (one 8-byte word per lane)
 constexpr uint64_t kFill = 0xfcfcfcfcfcfcfcfcull;   // tag of a long literal: what positions behind the stream's end are staged as
 
