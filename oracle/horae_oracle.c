@@ -12,7 +12,9 @@
  *          and WriteConfig::default (config.rs:120-133).  The arithmetic lives in the un-vendored crates
  *          parquet 53.2.0 / snap 1.1.1 (Cargo.lock:2454, 3145); restated here from the published Apache Parquet
  *          format spec (Thrift compact footer + page headers, RLE/bit-packed hybrid levels, PLAIN values) and the
- *          Snappy raw-block format.  Pinned in tests against pyarrow 24 (independent C++ implementation).
+ *          Snappy raw-block format; Zstandard pages (ParquetCompression::Zstd, config.rs:78-94; zstd 0.13.2, Cargo.lock:3893) through
+ *          zstd_oracle.h, a sequential restatement of RFC 8878.  Pinned in tests against pyarrow 24 (independent C++ implementation;
+ *          its codecs are libsnappy / libzstd themselves).
  *   S2     row-group pruning = DataFusion PruningPredicate as pinned by the plan text at read.rs:613
  *          ("CASE WHEN null_count = row_count THEN false ELSE min <= lit AND lit <= max").
  *   S3     FilterExec(conjunction(predicates)) BEFORE the merge (read.rs:459-470); NULL => false.
@@ -318,6 +320,18 @@ static int snappy_decompress(const uint8_t *src, int64_t n, uint8_t *dst, int64_
     return 0;
 }
 
+/* -------------------------------------------------------------------------------- Zstandard (RFC 8878) */
+#include "zstd_oracle.h"
+
+/* page payload -> uncompressed bytes by Parquet codec id (1 Snappy, 6 Zstandard: ParquetCompression, config.rs:78-94) */
+static int page_decompress(int codec, const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap) {
+    if (codec == 1) return snappy_decompress(src, n, dst, cap);
+    if (codec == 6) return zstd_decompress(src, n, dst, cap);
+    FAIL("oracle: unsupported codec %d", codec);
+}
+/* test hook: one raw codec stream (tests pin the restatement on libsnappy / libzstd streams from pyarrow) */
+int orc_decompress(int codec, const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap) { return page_decompress(codec, src, n, dst, cap); }
+
 /* ------------------------------------------------------------------- RLE / bit-packed hybrid (def levels) */
 static int decode_levels_bw1(const uint8_t *p, int64_t nbytes, int n, uint8_t *out) {
     const uint8_t *end = p + nbytes;
@@ -438,7 +452,7 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
                         int64_t num_rows, uint64_t *vals, uint8_t *valid) {
     int w = phys_width(cm->phys_type);
     if (!w) FAIL("oracle: unsupported physical type %d", cm->phys_type);
-    if (cm->codec != 0 && cm->codec != 1) FAIL("oracle: unsupported codec %d", cm->codec);
+    if (cm->codec != 0 && cm->codec != 1 && cm->codec != 6) FAIL("oracle: unsupported codec %d", cm->codec);
     int64_t pos = cm->data_page_offset, row = 0;
     if (cm->dict_page_offset > 0 && cm->dict_page_offset < cm->data_page_offset) pos = cm->dict_page_offset;   /* dictionary page first */
     uint8_t *buf = NULL; int64_t bufcap = 0;
@@ -454,7 +468,7 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
         if (h.type == 2) {                        /* dictionary page: PLAIN values, compressed like a data page */
             free(dict);
             dict = malloc((size_t)(h.uncomp > 0 ? h.uncomp : 1));
-            if (cm->codec == 1) { if (snappy_decompress(payload, h.comp, dict, h.uncomp)) { rc = -1; break; } }
+            if (cm->codec != 0) { if (page_decompress(cm->codec, payload, h.comp, dict, h.uncomp)) { rc = -1; break; } }
             else memcpy(dict, payload, (size_t)h.comp);
             dict_n = h.uncomp / w;
             continue;
@@ -468,9 +482,9 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
         const uint8_t *body; int64_t body_len;
         const uint8_t *levels = NULL; int64_t levels_len = 0;
         if (h.type == 0) { /* V1: whole payload compressed */
-            if (cm->codec == 1) {
+            if (cm->codec != 0) {
                 if (h.uncomp > bufcap) { bufcap = h.uncomp + 64; buf = realloc(buf, bufcap); }
-                if (snappy_decompress(payload, h.comp, buf, h.uncomp)) { rc = -1; break; }
+                if (page_decompress(cm->codec, payload, h.comp, buf, h.uncomp)) { rc = -1; break; }
                 body = buf; body_len = h.uncomp;
             } else { body = payload; body_len = h.comp; }
             if (optional) {
@@ -481,9 +495,9 @@ static int decode_chunk(const uint8_t *data, uint64_t len, const col_meta *cm, i
             levels = payload + h.v2_rep_len; levels_len = h.v2_def_len;
             const uint8_t *vsrc = payload + h.v2_rep_len + h.v2_def_len;
             int64_t vcomp = h.comp - h.v2_rep_len - h.v2_def_len, vun = h.uncomp - h.v2_rep_len - h.v2_def_len;
-            if (cm->codec == 1 && h.v2_is_compressed) {
+            if (cm->codec != 0 && h.v2_is_compressed) {
                 if (vun > bufcap) { bufcap = vun + 64; buf = realloc(buf, bufcap); }
-                if (snappy_decompress(vsrc, vcomp, buf, vun)) { rc = -1; break; }
+                if (page_decompress(cm->codec, vsrc, vcomp, buf, vun)) { rc = -1; break; }
                 body = buf; body_len = vun;
             } else { body = vsrc; body_len = vcomp; }
         }

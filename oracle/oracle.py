@@ -37,8 +37,8 @@ class OrcPred(C.Structure):
 
 
 def build() -> str:
-    src = os.path.join(_HERE, "horae_oracle.c")
-    if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "horae_oracle.c"), os.path.join(_HERE, "zstd_oracle.h")]
+    if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
     return _LIB
 

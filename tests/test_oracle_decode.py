@@ -32,7 +32,7 @@ def _random_batch(rng, n, null_frac):
     return sch, pa.RecordBatch.from_arrays(cols, schema=sch)
 
 
-@pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed])
+@pytest.mark.parametrize("compression", [ParquetCompression.Snappy, ParquetCompression.Uncompressed, ParquetCompression.Zstd])
 @pytest.mark.parametrize("n,null_frac,rg", [(0, 0.0, 8192), (1, 0.0, 8192), (5, 0.5, 2), (1000, 0.0, 8192), (20000, 0.3, 8192),
                                             (20000, 1.0, 8192), (70000, 0.01, 8192), (9000, 0.9, 100)])
 def test_decode_matches_pyarrow(compression, n, null_frac, rg):
@@ -54,7 +54,7 @@ def test_decode_small_pages_and_v2():
     schema = StorageSchema.try_new(user, 2)
     full = schema.fill_builtin_columns(batch, 5)
     for version in ("1.0", "2.0"):
-        for comp in ("snappy", "none"):
+        for comp in ("snappy", "none", "zstd"):
             sink = io.BytesIO()
             pq.write_table(pa.Table.from_batches([full]), sink, row_group_size=8192, compression=comp, use_dictionary=False,
                            data_page_size=3000, data_page_version=version)
@@ -203,3 +203,62 @@ def test_dictionary_encoded_columns_match_pyarrow():
             for c in ref.schema.names:
                 assert got[c].combine_chunks().equals(ref[c].combine_chunks()), (comp, rg, c)
             assert parquet_inspect(data)["num_rows"] == n
+
+
+@pytest.mark.parametrize("level", [1, 3, 9])
+def test_zstd_restatement_matches_libzstd(level):
+    """oracle/zstd_oracle.h (sequential restatement of RFC 8878) against libzstd itself (pyarrow's codec): frames of every shape the
+    device decoder is tested on — raw / RLE / Huffman literals in one and four streams, predefined / RLE / described / repeated
+    sequence tables, repeat offsets, overlapping matches, several blocks."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_decompress.argtypes = [C.c_int, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]
+    L.orc_decompress.restype = C.c_int
+    rng = np.random.default_rng(5)
+    n = 8192
+    ts = (1_700_000_000_000 + np.tile(np.arange(1000), 9)[:n].astype(np.int64) * 1000 + rng.integers(0, 500, n)).astype(np.int64)
+    cases = {
+        "empty": b"", "three_bytes": b"abc", "short_run": b"a" * 70,
+        "jitter_ts": b"\x02\x00\x00\x00\x03\x10" + ts.tobytes(),
+        "series_id": np.repeat(np.arange(9, dtype=np.uint64) + 77, 1000)[:n].tobytes(),
+        "random": rng.integers(0, 2**63, n, dtype=np.uint64).tobytes(),
+        "sawtooth": ((np.arange(n, dtype=np.uint64) % 1000) * 37).tobytes(),
+        "slow_counter": (np.arange(n, dtype=np.uint64) // 3).tobytes(),
+        "few_values": rng.choice(rng.integers(0, 2**60, 5, dtype=np.uint64), n).tobytes(),
+        "small_u32": rng.integers(0, 16, n).astype(np.uint32).tobytes(),
+        "text": (b"the quick brown fox jumps over the lazy dog. " * 500)[:20000],
+        "f64_round": np.round(rng.random(n), 2).tobytes(),
+        "skewed_bytes_300k": rng.integers(0, 50, 300_000).astype(np.uint8).tobytes(),
+    }
+    for name, raw in cases.items():
+        comp = pa.Codec("zstd", compression_level=level).compress(raw, asbytes=True)
+        out = np.zeros(len(raw) + 8, dtype=np.uint8)
+        rc = L.orc_decompress(6, comp, len(comp), out.ctypes.data, len(raw))
+        assert rc == 0, (name, L.orc_last_error())
+        assert bytes(out[:len(raw)]) == raw, name
+    comp = pa.Codec("zstd").compress(cases["jitter_ts"], asbytes=True)
+    out = np.zeros(len(cases["jitter_ts"]) + 8, dtype=np.uint8)
+    assert L.orc_decompress(6, comp[: len(comp) // 2], len(comp) // 2, out.ctypes.data, len(cases["jitter_ts"])) != 0       # truncated frame
+
+
+def test_oracle_reads_zstd_ssts_like_their_snappy_twins():
+    """The GPU parity tests of Zstd SSTs (tests/test_gpu_zstd.py) compare against the oracle's result on a Snappy TWIN of every file;
+    here the oracle itself reads the Zstd files: scan (merge + dedup over overlapping files, batch boundaries) and aggregates are
+    identical to the twins'."""
+    rng = np.random.default_rng(3)
+    schema = sstgen.metric_storage_schema()
+    zs, ss = [], []
+    for f in range(3):
+        sid = np.repeat(np.arange(20 * f, 20 * f + 40), 600)
+        ts = sstgen.T0_MS + np.tile(np.arange(600) * 1000 + rng.integers(0, 300, 600), 40)
+        b = pa.RecordBatch.from_arrays([pa.array(sid.astype(np.uint64)), pa.array(ts.astype(np.int64)), pa.array(rng.random(len(sid))),
+                                        pa.array((sid % 16).astype(np.uint32))], schema=sstgen.METRIC_SCHEMA)
+        zs.append(sstgen.write_sst(schema, b, seq=700 + f, cfg=WriteConfig(compression=ParquetCompression.Zstd), presorted=True))
+        ss.append(sstgen.write_sst(schema, b, seq=700 + f, cfg=WriteConfig(compression=ParquetCompression.Snappy), presorted=True))
+    for preds in ([], [("tag", "eq", 3)], [("ts", "ge", sstgen.T0_MS + 100_000), ("ts", "lt", sstgen.T0_MS + 400_000)]):
+        a = oracle.scan(zs, schema.arrow_schema, 2, preds).batches
+        b = oracle.scan(ss, schema.arrow_schema, 2, preds).batches
+        assert len(a) == len(b) and all(x.equals(y) for x, y in zip(a, b))
+        kw = dict(group_col=0, ts_col=1, window_ms=60_000, value_col=2)
+        x, y = oracle.scan_aggregate(zs, schema.arrow_schema, 2, preds, **kw), oracle.scan_aggregate(ss, schema.arrow_schema, 2, preds, **kw)
+        assert x.gkey.tolist() == y.gkey.tolist() and x.count.tolist() == y.count.tolist() and np.array_equal(x.sum, y.sum)
