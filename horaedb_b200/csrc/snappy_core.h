@@ -314,6 +314,7 @@ SNP_FN void snappy_page_body(const uint8_t* __restrict__ src, uint32_t n, uint8_
       fl = flush_words(sm, dst, fl, o, lane);
       if (uint32_t(lane) < o - fl) dst[fl + lane] = ring[(fl + lane) & (kRing - 1)];     // pending partial sector (< 32 bytes)
       warp_copy_in(dst + o, lsrc, len, lane);
+      snp_syncwarp();                                  // every lane has read its pending ring words before the tail below overwrites them
       // the ring keeps the tail of the literal (whole words where possible)
       const uint32_t keep = len < uint32_t(kHist) ? len : uint32_t(kHist);
       const uint32_t k0 = o + len - keep, k1 = o + len;

@@ -384,7 +384,7 @@ SNP_FN void zstd_page(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __re
           else if (sf == 2) { regen = uint32_t(h >> 4) & 0x3fffu; csize = uint32_t(h >> 18) & 0x3fffu; hdr = 4; nstreams = 4; }
           else { regen = uint32_t(h >> 4) & 0x3ffffu; csize = uint32_t(h >> 22) & 0x3ffffu; hdr = 5; nstreams = 4; }
         }
-        if (regen > kBlockMax) ZFAIL(208);
+        if (regen > kBlockMax || regen > ulen - o) ZFAIL(208);   // literals all end up in the output; also bounds the literal buffer (min(page, 128 KB))
         const uint8_t* lp = p + hdr;                           // literal payload
         const uint8_t* lits;                                   // where the block's literals are read from
         bool lits_in_input = false;

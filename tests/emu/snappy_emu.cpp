@@ -45,6 +45,7 @@ void lane_main() {
 
 // Decode one raw Snappy stream.  dst must have ulen + 64 bytes of room (the decoder may overshoot stop_at by one batch and reads
 // whole words).  Returns the decoder's error word (0 = ok); *collectives = warp collectives executed (a proxy for steps).
+extern "C" void emu_set_order(int order) { emu::g_order = order; }
 extern "C" void emu_stats(long* out7) { std::memcpy(out7, &g_stats, sizeof(g_stats)); std::memset(&g_stats, 0, sizeof(g_stats)); }
 extern "C" int emu_snappy_page(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t ulen, uint32_t stop_at, long* collectives) {
   using namespace horae::snp;

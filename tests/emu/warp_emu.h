@@ -1,7 +1,10 @@
 // warp_emu.h — TEST INFRASTRUCTURE shared by snappy_emu.cpp / zstd_emu.cpp: a 32-lane "warp" on the CPU.  Lanes are coroutines (ucontext),
 // every warp collective (shuffle / ballot / any / syncwarp) is a rendezvous; lanes run one after another between collectives, so the
 // emulation checks lane-level LOGIC, not instruction timing.  run_warp() returns 9001 / 9002 when lanes fall out of step (a collective
-// reached by some lanes only: undefined on the GPU too).
+// reached by some lanes only: undefined on the GPU too).  Between two collectives the hardware may run the lanes in ANY order (independent
+// thread scheduling), so the order is a knob: g_order 0 ascending, 1 descending, >= 2 a fresh pseudo-random permutation per interval
+// (seeded by the value).  A read-after-write or write-after-read between lanes that lacks a __syncwarp() shows up as a wrong result under
+// one of them.
 #pragma once
 #include <ucontext.h>
 
@@ -23,6 +26,7 @@ struct Warp {
   long collectives = 0;
 };
 static Warp* W;
+static int g_order = 0;
 static inline int lane_id() { return W->cur; }
 // publish v, wait for everyone, return the buffer all lanes published into
 static inline const uint32_t* rendezvous(uint32_t v) {
@@ -51,6 +55,7 @@ static inline int run_warp(void (*lane_main)(), long* collectives) {
   Warp warp;
   W = &warp;      // (valid until run_warp returns: nothing runs on the lanes afterwards)
   int err = 0;
+  uint64_t rng = uint64_t(g_order) * 0x9e3779b97f4a7c15ull + 1;
   for (int l = 0; l < kLanes; l++) {
     warp.stacks[l].resize(512 * 1024);
     warp.done[l] = false;
@@ -63,7 +68,16 @@ static inline int run_warp(void (*lane_main)(), long* collectives) {
   }
   for (;;) {
     int live = 0;
-    for (int l = 0; l < kLanes; l++) {
+    int perm[kLanes];
+    for (int i = 0; i < kLanes; i++) perm[i] = g_order == 1 ? kLanes - 1 - i : i;
+    if (g_order >= 2)
+      for (int i = kLanes - 1; i > 0; i--) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        const int j = int((rng >> 33) % uint64_t(i + 1));
+        const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+      }
+    for (int i = 0; i < kLanes; i++) {
+      const int l = perm[i];
       if (warp.done[l]) continue;
       warp.cur = l;
       swapcontext(&warp.sched, &warp.lane_ctx[l]);

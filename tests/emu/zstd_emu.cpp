@@ -28,6 +28,7 @@ void lane_main() {
 }  // namespace
 
 // Decode the Zstandard frame(s) in src to dst (ulen bytes expected, ulen + 64 bytes of room).  Returns the decoder's error word.
+extern "C" void emu_set_order(int order) { emu::g_order = order; }
 extern "C" int emu_zstd_page(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t ulen, long* collectives) {
   std::vector<uint8_t> in(size_t(n) + 128, 0xA5);
   std::memcpy(in.data() + 32, src, n);
@@ -38,6 +39,8 @@ extern "C" int emu_zstd_page(const uint8_t* src, uint32_t n, uint8_t* dst, uint3
   g_job = Job{in.data() + 32, n, dst, ulen, lit.data(), sm, &err};
   const int werr = emu::run_warp(lane_main, collectives);
   if (werr) err = werr;
+  // the literal buffer holds min(page, 128 KB) bytes (+ the slack every scratch region has): nothing may be written behind it
+  for (size_t i = lit.size() - 32; i < lit.size(); i++) if (lit[i] != 0xEE) err = 9003;
   free(sm);
   return err;
 }

@@ -21,11 +21,12 @@ OUT = os.path.join(HERE, "emu", "_build", "libsnappy_emu.so")
 @pytest.fixture(scope="module")
 def emu():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(os.path.join(HERE, "emu", "warp_emu.h"))):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", OUT, SRC])
     lib = C.CDLL(OUT)
     lib.emu_snappy_page.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_long)]
     lib.emu_snappy_page.restype = C.c_int
+    lib.emu_set_order.argtypes = [C.c_int]
     return lib
 
 
