@@ -159,3 +159,44 @@ def test_zstd_cases_under_other_lane_orders(zstd_emu, order):  # noqa: F811
             assert err == 0 and got == raw, name
     finally:
         zstd_emu.emu_set_order(0)
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_partial_decodes_of_damaged_and_cut_snappy_streams(snappy_emu, order):  # noqa: F811
+    """stop_at (the consumer needs only the first rows of a page) with damage behind or before the stop position, and compressed PREFIXES
+    (transient loads ship only the bytes a partial decode is expected to need): the first stop_at bytes are right, or the call reports an
+    error (the engine then repeats the load with whole streams) — never wrong bytes, never a write outside the page's scratch."""
+    snappy_emu.emu_set_order(order)
+    try:
+        codec = pa.Codec("snappy")
+        rng = np.random.default_rng(300 + order)
+        names = ["jitter_ts", "mixed", "sawtooth", "tag_u32", "period3", "few_values", "random", "f64_cumsum"]
+        delivered = short = 0
+        for it in range(360):
+            raw = S.CASES[names[it % len(names)]]
+            full = codec.compress(raw, asbytes=True)
+            stop_at = int(rng.integers(1, len(raw)))
+            if it % 3 == 1:
+                comp = full[: int(rng.integers(1, len(full)))]
+                err, got = _snappy(snappy_emu, comp, len(raw), stop_at)
+                if err == 0:
+                    assert got[:stop_at] == raw[:stop_at], it
+                    delivered += 1
+                else:
+                    short += 1
+                continue
+            comp = bytearray(full)
+            if it % 3 == 0:
+                for _ in range(int(rng.integers(1, 3))):
+                    comp[int(rng.integers(0, len(comp)))] ^= 1 << int(rng.integers(0, 8))
+            comp = bytes(comp)
+            try:
+                want = codec.decompress(comp, len(raw), asbytes=True)
+            except Exception:
+                want = None
+            err, got = _snappy(snappy_emu, comp, len(raw), stop_at)
+            if want is not None:
+                assert err == 0 and got[:stop_at] == want[:stop_at], it
+        assert delivered > 20 and short > 20
+    finally:
+        snappy_emu.emu_set_order(0)
