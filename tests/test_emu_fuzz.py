@@ -36,6 +36,16 @@ def _damage(rng, comp, lo=0):
     return bytes(comp)
 
 
+def _stream_length(comp):
+    v = sh = 0
+    for x in comp[:5]:
+        v |= (x & 0x7F) << sh
+        sh += 7
+        if not x & 0x80:
+            return v
+    return -1
+
+
 def _snappy(lib, comp, ulen, stop_at=0xFFFFFFFF):
     out = np.full(ulen + 320, GUARD, dtype=np.uint8)
     n = C.c_long(0)
@@ -67,6 +77,8 @@ def test_damaged_snappy_streams_agree_with_libsnappy(snappy_emu, order):  # noqa
                 want = codec.decompress(comp, len(raw), asbytes=True)
             except Exception:
                 want = None
+            if _stream_length(comp) != len(raw):
+                want = None                                       # (pyarrow does not compare the stream's length prefix with the size it was given)
             err, got = _snappy(snappy_emu, comp, len(raw))
             assert (err == 0) == (want is not None), (it, err)
             if want is not None:
