@@ -1,0 +1,48 @@
+"""The GPU parity tests, run WITHOUT a GPU against the emulated build of the library (tests/emu/cuda_emu.h + build_engine_emu.py: the
+product's own kernels and host code compiled by g++, every CUDA thread a coroutine, every barrier / warp collective a rendezvous,
+cudaMalloc'ed memory filled with 0xCD).  What this adds to the `-m gpu` run on a B200:
+
+* the kernels' LOGIC is checked on every `pytest -m "not gpu"` run, here and on the driver's CPU box;
+* threads run in a chosen order between two barriers (HORAE_EMU_ORDER): a missing __syncthreads() / __syncwarp() that the hardware's
+  scheduling hides becomes a wrong result or a scheduler error (lanes meeting in different collectives, a collective naming an exited
+  lane, a barrier that cannot complete);
+* an out-of-bounds access is a segfault with the kernel, block and thread named; uninitialised device memory is 0xCD…, not the zeros a
+  fresh cudaMalloc usually returns (that is how the unbounded level-length read of the fused path was found).
+
+The emulated library is test infrastructure: nothing in horaedb_b200/ loads it, and these tests say nothing about speed.  Runs in
+subprocesses (pytest + the emu_plugin) so that this process keeps using libhorae_gpu.so for the host-only tests.
+
+The whole GPU suite minus the tests that need a device pointer in torch / NCCL / 100 M rows passes this way (81 of 87; the config-shape
+file alone takes 8 minutes): `PYTHONPATH=tests/emu python -m pytest -p emu_plugin tests/test_gpu_*.py -m gpu`.  The CPU suite runs the
+quick files."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+QUICK = ["tests/test_gpu_snappy_fused.py", "tests/test_gpu_fused_edges.py", "tests/test_gpu_sst_writer.py", "tests/test_gpu_binary_append.py",
+         "tests/test_gpu_zstd.py", "tests/test_gpu_parity.py"]
+
+
+def _run(order, files, extra=()):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_engine_emu
+    build_engine_emu.build()                                     # once, here: the xdist workers below only find it up to date
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(ROOT, "tests", "emu") + os.pathsep + env.get("PYTHONPATH", "")
+    env["HORAE_EMU_ORDER"] = str(order)
+    env["HORAE_EMU_CRASH_REPORT"] = "1"
+    cmd = [sys.executable, "-m", "pytest", "-p", "emu_plugin", "-n", "4", "-m", "gpu", "-q", "-p", "no:cacheprovider", *extra, *files]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
+    assert r.returncode == 0, tail
+    return tail
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_gpu_parity_tests_on_the_emulated_library(order):
+    # order 0: threads 0..n-1 in turn; 2: a fresh random permutation of the runnable threads in every scheduling pass (1 = descending)
+    tail = _run(order, QUICK)
+    assert " passed" in tail and "failed" not in tail
