@@ -154,12 +154,21 @@ struct SstResident {
 // of the next call (results handed out as device pointers stay valid until then).  Steady state = no cudaMalloc at all.
 struct Arena {
   struct Chunk { char* base; size_t cap, used; };
+#ifdef HORAE_EMULATED_BUILD
+  static bool chunk_per_alloc() { static const bool on = getenv("HORAE_EMU_GUARD") != nullptr; return on; }
+#endif
   std::vector<Chunk> chunks;
   size_t high_water = 0, in_call = 0;
   void* alloc(size_t bytes) {
+#ifdef HORAE_EMULATED_BUILD
+    const size_t exact = (bytes + 15) & ~size_t(15);
+#endif
     bytes = (bytes + 255) & ~size_t(255);
     if (chunks.empty() || chunks.back().used + bytes > chunks.back().cap) {
       size_t cap = std::max<size_t>(bytes, chunks.empty() ? (size_t(64) << 20) : chunks.back().cap * 2);
+#ifdef HORAE_EMULATED_BUILD          // the test-suite's CPU emulation (tests/emu): with HORAE_EMU_GUARD every allocation is its own
+      if (chunk_per_alloc()) cap = bytes = exact;   // guarded mapping (16-byte granularity): an overrun between arena neighbours is a fault
+#endif
       void* p = nullptr;
       if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
       chunks.push_back(Chunk{static_cast<char*>(p), cap, 0});
@@ -180,6 +189,9 @@ struct Arena {
   // start of a call (stream idle): one chunk big enough for everything seen so far
   void reset() {
     in_call = 0;
+#ifdef HORAE_EMULATED_BUILD
+    if (chunk_per_alloc()) { destroy(); return; }
+#endif
     if (chunks.size() > 1) {
       size_t total = 0;
       for (auto& c : chunks) { total += c.cap; cudaFree(c.base); }

@@ -109,7 +109,7 @@ def build(force=False):
     with open(os.path.join(shim, "cuda_runtime.h"), "w") as f:
         f.write('#pragma once\n#include "%s"\n' % os.path.join(HERE, "cuda_emu.h"))
     objs, procs = [], []
-    flags = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-w", "-D__grid_constant__=", "-I", shim, "-I", CSRC, "-I", os.path.join(ROOT, "include")]
+    flags = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-w", "-D__grid_constant__=", "-DHORAE_EMULATED_BUILD", "-I", shim, "-I", CSRC, "-I", os.path.join(ROOT, "include")]
     for name in CU:
         src = os.path.join(BUILD, name.replace(".cu", "_emu.cpp"))
         with open(os.path.join(CSRC, name)) as f:

@@ -332,18 +332,27 @@ static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { std::memset(p, 0, sizeof(*p)); std::strcpy(p->name, "emulated"); p->multiProcessorCount = 148; p->totalGlobalMem = size_t(8) << 30; p->major = 10; p->sharedMemPerBlockOptin = 227 * 1024; return cudaSuccess; }
+// HORAE_EMU_GUARD=1: every allocation ends (up to 16-byte alignment) right before an inaccessible page, so a read or write past the end
+// of a cudaMalloc'ed buffer is a segfault (reported with kernel / block / thread by engine_emu_glue.cpp) instead of a silent neighbour access
+namespace emu {
+void* guarded_alloc(size_t n);
+bool guarded_free(void* p);
+}  // namespace emu
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) {
   void* q = nullptr;
-  if (posix_memalign(&q, 512, n ? (n + 511) / 512 * 512 : 512) != 0) return cudaErrorMemoryAllocation;
+  static const bool guard = getenv("HORAE_EMU_GUARD") != nullptr;
+  if (guard) q = emu::guarded_alloc(n ? n : 1);
+  else if (posix_memalign(&q, 512, n ? (n + 511) / 512 * 512 : 512) != 0) q = nullptr;
+  if (!q) return cudaErrorMemoryAllocation;
   std::memset(q, 0xCD, n);
   *p = static_cast<T*>(q);
   if (getenv("HORAE_EMU_TRACE_ALLOC")) fprintf(stderr, "[emu] alloc %p .. %p (%zu bytes)\n", q, static_cast<void*>(static_cast<char*>(q) + n), n);
   return cudaSuccess;
 }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) { if (p && !emu::guarded_free(p)) free(p); return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n, unsigned = 0) { return cudaMalloc(p, n); }
 template <class T> static inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { if (n) std::memset(d, v, n); return cudaSuccess; }

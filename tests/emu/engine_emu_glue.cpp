@@ -3,7 +3,11 @@
 
 #include <execinfo.h>
 #include <signal.h>
+#include <sys/mman.h>
 #include <unistd.h>
+
+#include <map>
+#include <mutex>
 
 extern "C" void emu_set_order(int order) { emu::G().order = order; emu::G().rng = uint64_t(order) * 0x9e3779b97f4a7c15ull + 1; }
 // first scheduling error since the last call (0 = none): 9001 lanes met in different collectives, 9002 a collective names an exited lane,
@@ -62,3 +66,28 @@ struct Install {
   }
 } install;
 }  // namespace
+
+namespace emu {
+namespace {
+std::mutex g_guard_mu;
+std::map<void*, std::pair<void*, size_t>> g_guarded;          // user pointer -> (mapping, length)
+}  // namespace
+void* guarded_alloc(size_t n) {
+  const size_t page = 4096, body = (n + 15) / 16 * 16, len = (body + page - 1) / page * page + page;
+  char* base = static_cast<char*>(mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+  if (base == MAP_FAILED) return nullptr;
+  mprotect(base + len - page, page, PROT_NONE);
+  void* user = base + len - page - body;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  g_guarded[user] = {base, len};
+  return user;
+}
+bool guarded_free(void* p) {
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  auto it = g_guarded.find(p);
+  if (it == g_guarded.end()) return false;
+  munmap(it->second.first, it->second.second);
+  g_guarded.erase(it);
+  return true;
+}
+}  // namespace emu

@@ -6,8 +6,9 @@ cudaMalloc'ed memory filled with 0xCD).  What this adds to the `-m gpu` run on a
 * threads run in a chosen order between two barriers (HORAE_EMU_ORDER): a missing __syncthreads() / __syncwarp() that the hardware's
   scheduling hides becomes a wrong result or a scheduler error (lanes meeting in different collectives, a collective naming an exited
   lane, a barrier that cannot complete);
-* an out-of-bounds access is a segfault with the kernel, block and thread named; uninitialised device memory is 0xCD…, not the zeros a
-  fresh cudaMalloc usually returns (that is how the unbounded level-length read of the fused path was found).
+* an out-of-bounds access is a segfault with the kernel, block and thread named (with HORAE_EMU_GUARD every allocation, arena
+  sub-allocations included, ends at an inaccessible page); uninitialised device memory is 0xCD…, not the zeros a fresh cudaMalloc usually
+  returns (that is how the unbounded level-length read of the fused path was found).
 
 The emulated library is test infrastructure: nothing in horaedb_b200/ loads it, and these tests say nothing about speed.  Runs in
 subprocesses (pytest + the emu_plugin) so that this process keeps using libhorae_gpu.so for the host-only tests.
@@ -26,7 +27,7 @@ QUICK = ["tests/test_gpu_snappy_fused.py", "tests/test_gpu_fused_edges.py", "tes
          "tests/test_gpu_zstd.py", "tests/test_gpu_parity.py"]
 
 
-def _run(order, files, extra=()):
+def _run(order, files, extra=(), guard=False):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_engine_emu
     build_engine_emu.build()                                     # once, here: the xdist workers below only find it up to date
@@ -34,6 +35,8 @@ def _run(order, files, extra=()):
     env["PYTHONPATH"] = os.path.join(ROOT, "tests", "emu") + os.pathsep + env.get("PYTHONPATH", "")
     env["HORAE_EMU_ORDER"] = str(order)
     env["HORAE_EMU_CRASH_REPORT"] = "1"
+    if guard:
+        env["HORAE_EMU_GUARD"] = "1"
     cmd = [sys.executable, "-m", "pytest", "-p", "emu_plugin", "-n", "4", "-m", "gpu", "-q", "-p", "no:cacheprovider", *extra, *files]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
@@ -41,8 +44,9 @@ def _run(order, files, extra=()):
     return tail
 
 
-@pytest.mark.parametrize("order", [0, 2])
-def test_gpu_parity_tests_on_the_emulated_library(order):
-    # order 0: threads 0..n-1 in turn; 2: a fresh random permutation of the runnable threads in every scheduling pass (1 = descending)
-    tail = _run(order, QUICK)
+@pytest.mark.parametrize("order,guard", [(0, True), (2, False)])
+def test_gpu_parity_tests_on_the_emulated_library(order, guard):
+    # order 0: threads 0..n-1 in turn; 2: a fresh random permutation of the runnable threads in every scheduling pass (1 = descending).
+    # guard: every device allocation — every arena sub-allocation too — ends (to 16 bytes) at an inaccessible page
+    tail = _run(order, QUICK, guard=guard)
     assert " passed" in tail and "failed" not in tail
