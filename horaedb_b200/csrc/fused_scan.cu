@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(1024) item_scan_kernel(uint32_t* cnt, const ui
 
 __global__ void __launch_bounds__(256) scatter_records_kernel(const FRec* __restrict__ rec, const unsigned int* nrec, const uint32_t* __restrict__ item_off,
                                                               const uint32_t* __restrict__ bsum, uint32_t nblocks, uint32_t* d_total, uint32_t gwidth,
-                                                              AggOut out) {
+                                                              AggOut out, uint32_t out_cap, uint32_t rec_cap, int* err) {
   __shared__ uint32_t s_boff[1024];
   // exclusive prefix of the block sums (nblocks <= 1024), computed redundantly by every CTA
   for (uint32_t b = threadIdx.x; b < 1024; b += blockDim.x) s_boff[b] = b < nblocks ? bsum[b] : 0;
@@ -1056,10 +1056,14 @@ __global__ void __launch_bounds__(256) scatter_records_kernel(const FRec* __rest
   }
   __syncthreads();
   uint32_t n = *nrec;
+  if (n > rec_cap) n = rec_cap;                     // slots reserved beyond the buffer were never written (emit() flagged 201)
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     FRec x = rec[r];
     if (x.item == 0xffffffffu) continue;          // unused tail of a warp's slot reservation
     uint32_t pos = s_boff[x.item >> 10] + item_off[x.item] + x.local;
+    // the output is sized by the group bound the chunk statistics give: rows that contradict their statistics (a damaged file) can make
+    // more groups than that — an error, never a write behind the arrays
+    if (pos >= out_cap) { atomicExch(err, 203); continue; }
     switch (gwidth) {
       case 1: reinterpret_cast<uint8_t*>(out.gkey)[pos] = uint8_t(x.gkey); break;
       case 4: reinterpret_cast<uint32_t*>(out.gkey)[pos] = uint32_t(x.gkey); break;
@@ -1492,7 +1496,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
       item_scan_kernel<<<sblocks, 1024, 0, s>>>(d_item.as<uint32_t>(), d_work.as<uint32_t>() + 3, split, d_bsum.as<uint32_t>());
       L.tick();
       scatter_records_kernel<<<148 * 4, 256, 0, s>>>(d_rec.as<FRec>(), d_work.as<unsigned int>() + 1, d_item.as<uint32_t>(), d_bsum.as<uint32_t>(),
-                                                     sblocks, d_work.as<uint32_t>() + 2, out->gwidth, ao);
+                                                     sblocks, d_work.as<uint32_t>() + 2, out->gwidth, ao, uint32_t(std::min<uint64_t>(bound, 0xffffffffu)), uint32_t(std::min<uint64_t>(rec_cap, 0xffffffffu)), err_p);
       L.tick();
     }
     auto t3 = now();
@@ -1508,6 +1512,7 @@ int try_scan_aggregate(hg_engine* e, const hg_schema_desc* schema, const hg_sst_
     }
     auto t4 = now();
     if (trace) fprintf(stderr, "[fused] plan %.0f us, bound+alloc %.0f us, upload+launch %.0f us, wait %.0f us (row groups %u, max items %u)\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), total_rgs, nitems);
+    if (herr >= 201 && herr <= 203) return set_error(HG_ERR_FORMAT, "fused scan: rows contradict their chunk statistics or a page is damaged (device error " + std::to_string(herr) + ")");
     if (herr) return set_error(HG_ERR_INTERNAL, "fused scan: device error " + std::to_string(herr));
     float kms = 0;
     cudaEventElapsedTime(&kms, e->evk0, e->evk1);

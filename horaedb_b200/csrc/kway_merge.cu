@@ -166,7 +166,7 @@ __device__ __forceinline__ void merge_level(const uint64_t* __restrict__ src, ui
 __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ surv,
                                                                 const uint32_t* __restrict__ run_start, int k, const uint32_t* __restrict__ bounds,
                                                                 uint32_t R, uint32_t pk_shift, unsigned int* ticket,
-                                                                uint32_t* __restrict__ order, uint8_t* __restrict__ keep) {
+                                                                uint32_t* __restrict__ order, uint8_t* __restrict__ keep, int* err) {
   extern __shared__ uint64_t s_dyn[];          // two key buffers of kChunk words (64 KB: beyond the static limit)
   uint64_t* const s_a = s_dyn;
   uint64_t* const s_b = s_dyn + kChunk;
@@ -187,7 +187,11 @@ __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint
     __syncthreads();
     const uint32_t r = s_range;
     if (r >= R) return;
-    if (tid < k) { s_cur[tid] = bounds[r * k + tid]; s_end[tid] = bounds[(r + 1) * k + tid]; }
+    if (tid < k) {
+      s_cur[tid] = bounds[r * k + tid]; s_end[tid] = bounds[(r + 1) * k + tid];
+      // a stream that is not sorted (a damaged file: the reader trusts the writer's order, read.rs:412-427) can give cuts that go backwards
+      if (s_end[tid] < s_cur[tid]) { s_end[tid] = s_cur[tid]; atomicExch(err, 121); }
+    }
     if (tid == 0) { s_has_carry = 0; s_out = 0; }
     __syncthreads();
     if (tid == 0) { uint32_t o = 0; for (int f = 0; f < k; f++) o += s_cur[f]; s_out = o; }
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint
       if (tid == 0) { uint32_t o = 0; for (int f = 0; f < k; f++) { s_offs[f] = o; o += s_n[f]; } s_offs[k] = o; }
       __syncthreads();
       const uint32_t n = s_offs[k];
+      // sorted streams always advance (the stream that set the threshold gives all B keys); an unsorted one may not: an error, not a hang
+      if (n == 0) { if (tid == 0) atomicExch(err, 121); break; }
       for (uint32_t i = tid; i < uint32_t(k) * B; i += kMergeThreads) {
         const uint32_t f = i >> logB, j = i & (B - 1);
         if (j < s_n[f]) s_b[s_offs[f] + j] = (s_a[i] << kIdxBits) | i;
@@ -293,7 +299,7 @@ void kway_merge(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* s
   L.tick();
   kway_bounds_kernel<<<int(((R + 1) * uint64_t(k) + kThreads - 1) / kThreads), kThreads, 0, L.stream>>>(keys, run_start, k, splitters, R, bounds);
   L.tick();
-  kway_merge_kernel<<<int(R < 148u * 2 ? R : 148u * 2), kMergeThreads, 2 * kChunk * 8, L.stream>>>(keys, surv, run_start, k, bounds, R, kp.pk_shift, ticket, order, keep);
+  kway_merge_kernel<<<int(R < 148u * 2 ? R : 148u * 2), kMergeThreads, 2 * kChunk * 8, L.stream>>>(keys, surv, run_start, k, bounds, R, kp.pk_shift, ticket, order, keep, err);
   L.tick();
 }
 
