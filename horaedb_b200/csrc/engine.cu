@@ -132,6 +132,9 @@ static int prepare_sst(const hg_schema_desc* schema, uint64_t id, const uint8_t*
       if (cm.codec != CODEC_UNCOMPRESSED && cm.codec != CODEC_SNAPPY && cm.codec != CODEC_ZSTD)
         return fail(HG_ERR_UNSUPPORTED, "codec " + std::to_string(cm.codec) + " (UNCOMPRESSED, SNAPPY and ZSTD are implemented)");
       if (cm.scratch_bytes > 0xffffffffull) return fail(HG_ERR_UNSUPPORTED, "column chunk larger than 4 GiB");
+      // the kernels decode by the CHUNK's physical type; the output buffers are laid out by the schema's
+      if (cm.phys_type != m.phys_types[c])
+        return fail(HG_ERR_FORMAT, "sst " + std::to_string(id) + ": column chunk type differs from the schema element's type");
       // every kernel indexes a chunk by the ROW GROUP's row count: the chunk must hold exactly that many values, and an
       // uncompressed page must really contain the bytes the decoders will read (compressed pages are bounded by their
       // scratch size on the device)
