@@ -50,3 +50,19 @@ def test_gpu_parity_tests_on_the_emulated_library(order, guard):
     # guard: every device allocation — every arena sub-allocation too — ends (to 16 bytes) at an inaccessible page
     tail = _run(order, QUICK, guard=guard)
     assert " passed" in tail and "failed" not in tail
+
+
+def test_damaged_ssts_through_the_emulated_library():
+    """tests/emu/fuzz_engine.py: damaged footers, page headers and page bytes (rows that contradict their statistics and their sort order,
+    levels / dictionary indices / delta headers / compressed streams that lie) through aggregate (fused and general), scan, compaction
+    and the device SST writer — with guard pages behind every device allocation.  Every call returns a result or an error; a crash or a
+    kernel that never ends fails the test.  (What a longer run of this tool found is listed in DESIGN.md.)"""
+    env = dict(os.environ)
+    env["HORAE_EMU_GUARD"] = "1"
+    env["HORAE_EMU_CRASH_REPORT"] = "1"
+    r = subprocess.run(["timeout", "-s", "SEGV", "600", sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_engine.py"), "5", "40"],
+                       cwd=ROOT, env=env, capture_output=True, text=True)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0, tail
+    last = r.stdout.strip().splitlines()[-1].split()
+    assert last[0] == "accepted" and int(last[1]) > 50 and int(last[3]) > 50, tail
