@@ -3,7 +3,7 @@ allocation (HORAE_EMU_GUARD) and cudaMalloc'ed memory filled with 0xCD.  Every c
 reads or writes outside its buffers because a footer, a page header or page bytes lie is a segfault here (reported with kernel, block and
 thread) — on the GPU it would be silent corruption or a sticky illegal-address error.
 
-    python tests/emu/fuzz_engine.py SEED ITERATIONS [KIND ...]      KIND: metric-snappy metric-none metric-zstd dict delta nulls
+    python tests/emu/fuzz_engine.py SEED ITERATIONS [KIND ...]      KIND: metric-snappy metric-none metric-zstd dict delta nulls binary binary-append
 
 Damage: 1-3 bytes overwritten / bits flipped, 40 % of them in the footer (statistics, sizes, offsets, encodings), the rest anywhere in the
 page area (page headers, level runs, compressed streams, dictionary indices, delta headers, values -> rows that contradict their chunk
@@ -71,6 +71,23 @@ def make_case(kind, rng):
                 _nulls(rng, rng.random(n).tolist(), 0.05, pa.float64())]
         cfg = [WriteConfig(compression=c, max_row_group_size=700) for c in ("snappy", "zstd")]
         preds, kw = [("a", "gt", 0)], dict(group_col=0, ts_col=1, window_ms=5000, value_col=4)
+    elif kind in ("binary", "binary-append"):
+        # Binary value columns (BYTE_ARRAY PLAIN / DELTA_LENGTH_BYTE_ARRAY), LastValue or BytesMerge (operator.rs:47-111)
+        from horaedb_b200.types import UpdateMode
+        mode = UpdateMode.Append if kind == "binary-append" else UpdateMode.Overwrite
+        user = pa.schema([pa.field("pk1", pa.uint64()), pa.field("pk2", pa.int32()), pa.field("blob", pa.binary()), pa.field("idx", pa.binary())])
+        n = 1500
+        files = []
+        for i, (codec, enc) in enumerate((("snappy", None), ("none", "DELTA_LENGTH_BYTE_ARRAY"), ("zstd", None))):
+            pk1 = np.unique(rng.integers(0, 4000, n))
+            cols = [pa.array(pk1.astype(np.uint64)), pa.array((pk1 % 5 - 2).astype(np.int32)),
+                    pa.array([None if (int(k) + i) % 7 == 0 else rng.bytes(int(rng.integers(1, 40))) for k in pk1], pa.binary()),
+                    pa.array([bytes([i + 1]) * int(rng.integers(1, 5)) for _ in pk1], pa.binary())]
+            opts = {c: ColumnOptions(encoding=enc) for c in ("blob", "idx")} if enc else {}
+            sch = StorageSchema.try_new(user, 2, mode)
+            files.append(sstgen.write_sst(sch, pa.RecordBatch.from_arrays(cols, schema=user), 30 + i,
+                                          WriteConfig(compression=codec, max_row_group_size=600, column_options=opts), presorted=True))
+        return SchemaHandle(sch.arrow_schema, 2, mode), files, [("pk2", "ge", 0)], None
     else:
         raise SystemExit("unknown kind " + kind)
     schema = StorageSchema.try_new(user, 2)
@@ -93,21 +110,22 @@ def damage(rng, data):
 
 def main():
     seed, iters = int(sys.argv[1]), int(sys.argv[2])
-    kinds = sys.argv[3:] or ["metric-snappy", "metric-none", "metric-zstd", "dict", "delta", "nulls"]
+    kinds = sys.argv[3:] or ["metric-snappy", "metric-none", "metric-zstd", "dict", "delta", "nulls", "binary", "binary-append"]
     rng = np.random.default_rng(seed)
     eng = Engine(device=0)
     tmp = tempfile.mkdtemp(prefix="horae_fuzz_")
     accepted = rejected = 0
     for kind in kinds:
         handle, files, preds, kw = make_case(kind, rng)
-        nrows = [0, 0]
         for it in range(iters):
             which = it % len(files)
             bad = damage(rng, files[which])
             with open(os.path.join(tmp, "current.sst"), "wb") as f:          # the input of a crash stays on disk
                 f.write(bad)
-            ins = [SstInput(id=10_000 + it, data=bad, num_rows=nrows[which]), SstInput(id=5, data=files[1 - which], num_rows=nrows[1 - which])]
+            ins = [SstInput(id=10_000 + it, data=bad), SstInput(id=5, data=files[(which + 1) % len(files)])]
             op = it % 6
+            if kw is None and op in (0, 1, 5):                   # Binary tables: no aggregation; the device writer takes fixed-width columns
+                op = 2 + it % 3
             try:
                 eng.set_flags(HG_FLAG_NO_FUSED if op == 1 else 0)
                 if op in (0, 1):
