@@ -132,6 +132,20 @@ __global__ void __launch_bounds__(kThreads) kway_bounds_kernel(const uint64_t* _
   bounds[idx] = lo;
 }
 
+// Cuts of a stream never go backwards from one range to the next.  They cannot for a sorted stream; for an unsorted one (a damaged
+// file) the binary searches above may disagree, and ranges that overlap or leave holes would leave `order` partly unwritten.
+__global__ void kway_bounds_monotone_kernel(int k, uint32_t R, uint32_t* __restrict__ bounds, int* err) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= k) return;
+  uint32_t prev = 0;
+  bool bad = false;
+  for (uint32_t r = 0; r <= R; r++) {
+    const uint32_t b = bounds[r * k + f];
+    if (b < prev) { bounds[r * k + f] = prev; bad = true; } else prev = b;
+  }
+  if (bad) atomicExch(err, 121);
+}
+
 // one level of the shared-memory merge tree: lists of `step` streams each are merged pairwise, src -> dst, same offsets
 __device__ __forceinline__ void merge_level(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, const uint32_t* offs, int k, int step,
                                             uint32_t n, int tid) {
@@ -226,7 +240,28 @@ __global__ void __launch_bounds__(kMergeThreads, 2) kway_merge_kernel(const uint
       __syncthreads();
       const uint32_t n = s_offs[k];
       // sorted streams always advance (the stream that set the threshold gives all B keys); an unsorted one may not: an error, not a hang
-      if (n == 0) { if (tid == 0) atomicExch(err, 121); break; }
+      if (n == 0) {
+        // the call fails, but what follows the merge in the stream indexes by `order`: hand out the rest of the range unmerged, so
+        // that `order` stays a permutation of the survivors
+        if (tid == 0) {
+          atomicExch(err, 121);
+          uint32_t o = 0;
+          for (int f = 0; f < k; f++) { s_offs[f] = o; o += s_end[f] - s_cur[f]; }
+          if (s_has_carry) keep[s_out - 1] = 1;
+          s_has_carry = 0;
+        }
+        __syncthreads();
+        const uint32_t out0 = s_out;
+        for (int f = 0; f < k; f++) {
+          const uint32_t rem = s_end[f] - s_cur[f];
+          for (uint32_t j = tid; j < rem; j += kMergeThreads) {
+            const uint32_t sidx = s_rs[f] + s_cur[f] + j;
+            order[out0 + s_offs[f] + j] = surv ? surv[sidx] : sidx;
+            keep[out0 + s_offs[f] + j] = 1;
+          }
+        }
+        break;
+      }
       for (uint32_t i = tid; i < uint32_t(k) * B; i += kMergeThreads) {
         const uint32_t f = i >> logB, j = i & (B - 1);
         if (j < s_n[f]) s_b[s_offs[f] + j] = (s_a[i] << kIdxBits) | i;
@@ -298,6 +333,8 @@ void kway_merge(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* s
   kway_splitters_kernel<<<1, 1024, kSamples * 8, L.stream>>>(keys, d_m, R, splitters);
   L.tick();
   kway_bounds_kernel<<<int(((R + 1) * uint64_t(k) + kThreads - 1) / kThreads), kThreads, 0, L.stream>>>(keys, run_start, k, splitters, R, bounds);
+  L.tick();
+  kway_bounds_monotone_kernel<<<(k + 63) / 64, 64, 0, L.stream>>>(k, R, bounds, err);
   L.tick();
   kway_merge_kernel<<<int(R < 148u * 2 ? R : 148u * 2), kMergeThreads, 2 * kChunk * 8, L.stream>>>(keys, surv, run_start, k, bounds, R, kp.pk_shift, ticket, order, keep, err);
   L.tick();
