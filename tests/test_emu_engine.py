@@ -66,3 +66,16 @@ def test_damaged_ssts_through_the_emulated_library():
     assert r.returncode == 0, tail
     last = r.stdout.strip().splitlines()[-1].split()
     assert last[0] == "accepted" and int(last[1]) > 50 and int(last[3]) > 50, tail
+
+
+def test_random_tables_against_the_oracle_on_the_emulated_library():
+    """tests/emu/diff_engine.py: random schemas / NULL rates / key densities / duplicates, 1-4 overlapping files written with random codecs,
+    row-group sizes, dictionaries and DELTA_BINARY_PACKED, random predicates and engine flags — scan (batch boundaries, builtin columns),
+    aggregate (bit-exact f64 sums) and compaction against the CPU oracle."""
+    env = dict(os.environ)
+    env["HORAE_EMU_GUARD"] = "1"
+    env["HORAE_EMU_CRASH_REPORT"] = "1"
+    r = subprocess.run(["timeout", "-s", "SEGV", "900", sys.executable, os.path.join(ROOT, "tests", "emu", "diff_engine.py"), "7", "40"],
+                       cwd=ROOT, env=env, capture_output=True, text=True)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0 and "40 cases ok" in r.stdout, tail
