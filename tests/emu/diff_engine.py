@@ -6,8 +6,10 @@ boundaries, builtin columns, group keys, counts, f64 sums bit for bit.
     python tests/emu/diff_engine.py SEED CASES
 
 The fixed GPU tests pick their shapes by hand; this walks the combinations nobody picked."""
+import io
 import os
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
@@ -19,6 +21,7 @@ os.environ.setdefault("HORAE_EMU_CRASH_REPORT", "1")
 
 import numpy as np  # noqa: E402
 import pyarrow as pa  # noqa: E402
+import pyarrow.parquet as pq  # noqa: E402
 
 import build_engine_emu  # noqa: E402
 from horaedb_b200 import _ffi  # noqa: E402
@@ -28,7 +31,7 @@ _ffi._lib = None
 
 from helpers import check_stream  # noqa: E402
 from horaedb_b200 import sstgen  # noqa: E402
-from horaedb_b200._ffi import HG_FLAG_NO_FUSED, HG_FLAG_NO_LATE_MATERIALIZATION, HG_FLAG_PAIRWISE_MERGE, Engine, SchemaHandle, SstInput  # noqa: E402
+from horaedb_b200._ffi import HG_AGG_HASH, HG_FLAG_NO_FUSED, HG_FLAG_NO_LATE_MATERIALIZATION, HG_FLAG_PAIRWISE_MERGE, Engine, SchemaHandle, SstInput  # noqa: E402
 from horaedb_b200.config import ColumnOptions, WriteConfig  # noqa: E402
 from horaedb_b200.types import StorageSchema  # noqa: E402
 from oracle import oracle  # noqa: E402
@@ -83,7 +86,7 @@ def make_case(rng):
     for _ in range(int(rng.integers(0, 3))):
         c = int(rng.integers(0, 2 + nval))
         name = user.names[c]
-        op = str(rng.choice(["eq", "ne", "lt", "le", "gt", "ge"]))
+        op = str(rng.choice(["eq", "ne", "lt", "le", "gt", "ge", "in"]))
         t = user.field(c).type
         if pa.types.is_floating(t):
             lit = float(rng.choice([0.0, 0.5, -1.0, 2.25, 50.0]))
@@ -93,11 +96,22 @@ def make_case(rng):
             lit = int(rng.integers(0, keyspace)) - (keyspace // 2 if pk0_t in (pa.int64(), pa.int32()) else 0)
         else:
             lit = int(rng.integers(-3, 10)) if pa.types.is_signed_integer(t) else int(rng.integers(0, 10))
+        if op == "in":
+            lit = [lit, lit + 1, lit + 3] if not isinstance(lit, float) else [lit, 0.25, -1.0]
         preds.append((name, op, lit))
     return schema, files, preds, nval, t_step
 
 
+def _nan_equal(a, b):
+    x, y = a.combine_chunks(), b.combine_chunks()
+    if not pa.types.is_floating(x.type) or x.null_count != y.null_count:
+        return False
+    xv, yv = x.to_numpy(zero_copy_only=False), y.to_numpy(zero_copy_only=False)
+    return np.array_equal(np.isnan(xv), np.isnan(yv)) and np.array_equal(xv[~np.isnan(xv)], yv[~np.isnan(yv)])
+
+
 def main():
+    tmpdir = tempfile.mkdtemp(prefix="horae_diff_")
     seed, cases = int(sys.argv[1]), int(sys.argv[2])
     rng = np.random.default_rng(seed)
     eng = Engine(device=0)
@@ -135,10 +149,33 @@ def main():
             assert [int(x) & 0xffffffffffffffff for x in a[a.schema.names[0]].to_pylist()] == [int(x) for x in b.gkey.tolist()]
             assert np.array_equal(a["sum"].to_numpy().view(np.uint64), b.sum.view(np.uint64))
             assert np.array_equal(a["min"].to_numpy().view(np.uint64), b.min.view(np.uint64)) and np.array_equal(a["max"].to_numpy().view(np.uint64), b.max.view(np.uint64))
+            # GROUP BY a value column (not a prefix of the sort order): radix-partitioned aggregation, groups sorted by (key, bucket)
+            gcol = 2 + int(rng.integers(0, nval))
+            if not pa.types.is_floating(schema.arrow_schema.field(gcol).type) or rng.random() < 0.5:
+                kwh = dict(group_col=gcol, ts_col=1 if with_ts else -1, window_ms=kw["window_ms"], value_col=vc)
+                a = eng.scan_aggregate(handle, ins(), preds, mode=HG_AGG_HASH, **kwh)
+                b = oracle.scan_aggregate(files, schema.arrow_schema, 2, preds, mode=1, **kwh)
+                assert a.num_rows == len(b.count), (a.num_rows, len(b.count))
+                assert a["count"].to_numpy().tolist() == b.count.tolist()
+                assert np.array_equal(a["sum"].to_numpy().view(np.uint64), b.sum.view(np.uint64))
             # compaction = scan without predicates, builtin columns kept
             got = list(eng.compact(handle, ins()))
             exp = oracle.scan(files, schema.arrow_schema, 2, (), True, 8192).batches
             check_stream(got, exp)
+            # ... and written as an SST on the device: pyarrow and the oracle read back the same rows
+            if exp and rng.random() < 0.5:
+                path = os.path.join(tmpdir, "out.sst")
+                eng.compact_to_sst(handle, ins(), path, max_row_group_size=int(rng.choice([8192, 500])), compression=str(rng.choice(["snappy", "none"])))
+                with open(path, "rb") as f:
+                    written = f.read()
+                want = pa.Table.from_batches(exp)
+                back = pq.read_table(io.BytesIO(written))
+                assert back.num_rows == want.num_rows
+                for c in range(want.num_columns):
+                    assert back.column(c).combine_chunks().equals(want.column(c).combine_chunks()) or \
+                        back.column(c).to_pylist() == want.column(c).to_pylist() or _nan_equal(back.column(c), want.column(c)), (c, "device-written SST differs")
+                again = pa.Table.from_batches(oracle.scan([written], schema.arrow_schema, 2, (), True, 8192).batches)     # (batch boundaries follow the new row groups)
+                check_stream([again.combine_chunks().to_batches()[0]], [want.combine_chunks().to_batches()[0]])
         except Exception:
             print("FAILED", tag, flush=True)
             for i, d in enumerate(files):
