@@ -120,16 +120,29 @@ def main():
         schema, files, preds, nval, t_step = make_case(rng)
         handle = SchemaHandle(schema.arrow_schema, 2)
 
+        # half of the cases keep (some of) their files RESIDENT in device memory (hg_sst_load: the SST cache keyed by file id) and pass
+        # them by id; the others hand host bytes to every call (transient loads: only the needed column chunks travel)
+        resident = {}
+        if rng.random() < 0.5:
+            for i, d in enumerate(files):
+                if rng.random() < 0.7:
+                    resident[i] = next_id[0]
+                    eng.load_sst(handle, SstInput(id=next_id[0], data=d))
+                    next_id[0] += 1
+
         def ins():
             out = []
-            for d in files:
-                out.append(SstInput(id=next_id[0], data=d))
-                next_id[0] += 1
+            for i, d in enumerate(files):
+                if i in resident:
+                    out.append(SstInput(id=resident[i]))
+                else:
+                    out.append(SstInput(id=next_id[0], data=d))
+                    next_id[0] += 1
             return out
 
         flags = int(rng.choice([0, 0, HG_FLAG_NO_FUSED, HG_FLAG_NO_LATE_MATERIALIZATION, HG_FLAG_PAIRWISE_MERGE]))
         eng.set_flags(flags)
-        tag = f"case {case} (seed {seed}): {len(files)} files, preds {preds}, flags {flags}"
+        tag = f"case {case} (seed {seed}): {len(files)} files ({len(resident)} resident), preds {preds}, flags {flags}"
         try:
             # scan: rows, batch boundaries, builtin columns
             keep = bool(rng.random() < 0.5)
@@ -176,6 +189,8 @@ def main():
                         back.column(c).to_pylist() == want.column(c).to_pylist() or _nan_equal(back.column(c), want.column(c)), (c, "device-written SST differs")
                 again = pa.Table.from_batches(oracle.scan([written], schema.arrow_schema, 2, (), True, 8192).batches)     # (batch boundaries follow the new row groups)
                 check_stream([again.combine_chunks().to_batches()[0]], [want.combine_chunks().to_batches()[0]])
+            for rid in resident.values():
+                eng.unload_sst(rid)
         except Exception:
             print("FAILED", tag, flush=True)
             for i, d in enumerate(files):
