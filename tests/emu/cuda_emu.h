@@ -371,7 +371,8 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
-static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = nullptr; return cudaSuccess; }
+// HORAE_EMU_PINNED=1: every host buffer counts as pinned, so transient loads take the zero-copy gather kernel instead of one memcpy per range
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { static const bool pinned = getenv("HORAE_EMU_PINNED") != nullptr; a->type = pinned ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 

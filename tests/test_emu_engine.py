@@ -27,7 +27,7 @@ QUICK = ["tests/test_gpu_snappy_fused.py", "tests/test_gpu_fused_edges.py", "tes
          "tests/test_gpu_zstd.py", "tests/test_gpu_parity.py"]
 
 
-def _run(order, files, extra=(), guard=False):
+def _run(order, files, extra=(), guard=False, pinned=False):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_engine_emu
     build_engine_emu.build()                                     # once, here: the xdist workers below only find it up to date
@@ -37,6 +37,8 @@ def _run(order, files, extra=(), guard=False):
     env["HORAE_EMU_CRASH_REPORT"] = "1"
     if guard:
         env["HORAE_EMU_GUARD"] = "1"
+    if pinned:
+        env["HORAE_EMU_PINNED"] = "1"
     cmd = [sys.executable, "-m", "pytest", "-p", "emu_plugin", "-n", "4", "-m", "gpu", "-q", "-p", "no:cacheprovider", *extra, *files]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
@@ -44,11 +46,12 @@ def _run(order, files, extra=(), guard=False):
     return tail
 
 
-@pytest.mark.parametrize("order,guard", [(0, True), (2, False)])
-def test_gpu_parity_tests_on_the_emulated_library(order, guard):
+@pytest.mark.parametrize("order,guard,pinned", [(0, True, False), (2, False, True)])
+def test_gpu_parity_tests_on_the_emulated_library(order, guard, pinned):
     # order 0: threads 0..n-1 in turn; 2: a fresh random permutation of the runnable threads in every scheduling pass (1 = descending).
     # guard: every device allocation — every arena sub-allocation too — ends (to 16 bytes) at an inaccessible page
-    tail = _run(order, QUICK, guard=guard)
+    # pinned: host buffers count as pinned memory, so transient loads take the zero-copy gather kernel instead of one memcpy per range
+    tail = _run(order, QUICK, guard=guard, pinned=pinned)
     assert " passed" in tail and "failed" not in tail
 
 
