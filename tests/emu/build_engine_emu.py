@@ -7,6 +7,7 @@ The sources are used as they are except for what g++ cannot parse:
   * inline PTX outside `#ifdef __CUDACC__` (L2 prefetches, `ld.global.cg`) -> nothing / a plain load
   * the literal SM count 148 -> 4 (grids of `148 * k` blocks would only repeat the same code on empty work; 4 * k blocks still exercise
     tickets, look-backs and "last block" patterns)
+  * comm.cu's `dlopen("libnccl.so.2")` -> tests/emu/nccl_emu.cpp (ranks = threads of the test process)
 snappy_core.h / zstd_core.h select their host variants by `#ifdef __CUDACC__`, exactly as for tests/emu/snappy_emu.cpp.
 Nothing in horaedb_b200/ knows this library exists."""
 import os
@@ -18,6 +19,7 @@ ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "horaedb_b200", "csrc")
 BUILD = os.path.join(HERE, "_build", "engine")
 OUT = os.path.join(HERE, "_build", "libhorae_emu.so")
+NCCL_OUT = os.path.join(HERE, "_build", "libnccl_emu.so")
 CU = ["engine.cu", "kernels.cu", "fused_scan.cu", "snappy.cu", "zstd.cu", "kway_merge.cu", "radix_agg.cu", "comm.cu", "sst_writer.cu"]
 CPP = ["parquet_meta.cpp", "inspect.cpp"]
 
@@ -95,13 +97,14 @@ def transform(text):
     text = re.sub(r'asm volatile\("prefetch\.global\.L2 \[%0\];"[^;]*;', "(void)0;", text)
     text = re.sub(r'asm volatile\("ld\.global\.cg\.u(?:8|16|32|64) %0, \[%1\];" : "=[rl]"\((\w+)\) : "l"\((\w+)\)\);', r"\1 = *\2;", text)
     text = re.sub(r"\b148(u|ull|ULL)?\b", r"4\1", text)
+    text = text.replace('"libnccl.so.2", "libnccl.so"', '"%s"' % NCCL_OUT)       # comm.cu binds NCCL with dlopen: the test's stand-in
     return text
 
 
 def build(force=False):
     os.makedirs(BUILD, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp", ".h", ".hpp"))]
-    deps += [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "engine_emu_glue.cpp"), os.path.abspath(__file__), os.path.join(ROOT, "include", "horae_gpu.h")]
+    deps += [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "engine_emu_glue.cpp"), os.path.join(HERE, "nccl_emu.cpp"), os.path.abspath(__file__), os.path.join(ROOT, "include", "horae_gpu.h")]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     shim = os.path.join(BUILD, "shim")
@@ -127,6 +130,7 @@ def build(force=False):
     failed = [n for p, n in procs if p.wait() != 0]
     if failed:
         raise RuntimeError("emulated build failed: " + ", ".join(failed))
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-o", NCCL_OUT, os.path.join(HERE, "nccl_emu.cpp"), "-lpthread"])
     subprocess.check_call(["g++", "-shared", "-o", OUT] + objs + ["-ldl", "-lpthread"])
     return OUT
 

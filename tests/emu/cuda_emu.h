@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -210,8 +211,11 @@ inline void run_block(int nthreads) {
   }
 }
 
+// kernels of different host threads (ranks of an emulated multi-GPU run) take turns: the scheduler's state is global
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem, F&& body) {
+  std::lock_guard<std::mutex> turn(launch_mutex());
   Globals& g = G();
   g.launches++;
   if (smem > g.dyn_cap) { free(g.dyn_smem); g.dyn_smem = static_cast<unsigned char*>(aligned_alloc(256, (smem + 255) / 256 * 256)); g.dyn_cap = smem; }

@@ -82,3 +82,15 @@ def test_random_tables_against_the_oracle_on_the_emulated_library():
                        cwd=ROOT, env=env, capture_output=True, text=True)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0 and "40 cases ok" in r.stdout, tail
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_combine_with_ranks_as_threads(world):
+    """tests/emu/combine_check.py: hg_comm_init / hg_agg_combine (csrc/comm.cu: all-gather of per-rank partials, GATHER for disjoint keys,
+    REDUCE — sort by key, rank-ordered f64 adds — for keys that cross ranks) with `world` engines of the emulated build in threads and
+    tests/emu/nccl_emu.cpp behind comm.cu's dlopen; every rank's result against the oracle's multi-shard definition.  (The same checks run
+    on real GPUs in tools/nccl_combine_check.py: world 1 and 2 there, up to 8 here.)"""
+    r = subprocess.run(["timeout", "-s", "SEGV", "600", sys.executable, os.path.join(ROOT, "tests", "emu", "combine_check.py"), str(world)],
+                       cwd=ROOT, capture_output=True, text=True)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0 and f"world {world}: ok" in r.stdout, tail
