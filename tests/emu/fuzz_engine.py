@@ -3,7 +3,7 @@ allocation (HORAE_EMU_GUARD) and cudaMalloc'ed memory filled with 0xCD.  Every c
 reads or writes outside its buffers because a footer, a page header or page bytes lie is a segfault here (reported with kernel, block and
 thread) — on the GPU it would be silent corruption or a sticky illegal-address error.
 
-    python tests/emu/fuzz_engine.py SEED ITERATIONS [KIND ...]      KIND: metric-snappy metric-none metric-zstd dict delta nulls binary binary-append
+    python tests/emu/fuzz_engine.py SEED ITERATIONS [KIND ...]      KIND: metric-snappy metric-none metric-zstd dict delta nulls pages binary binary-append
 
 Damage: 1-3 bytes overwritten / bits flipped, 40 % of them in the footer (statistics, sizes, offsets, encodings), the rest anywhere in the
 page area (page headers, level runs, compressed streams, dictionary indices, delta headers, values -> rows that contradict their chunk
@@ -71,6 +71,21 @@ def make_case(kind, rng):
                 _nulls(rng, rng.random(n).tolist(), 0.05, pa.float64())]
         cfg = [WriteConfig(compression=c, max_row_group_size=700) for c in ("snappy", "zstd")]
         preds, kw = [("a", "gt", 0)], dict(group_col=0, ts_col=1, window_ms=5000, value_col=4)
+    elif kind == "pages":
+        # many small data pages per chunk, page versions 1.0 and 2.0 (levels outside the compressed part), NULLs: written with pyarrow directly
+        import io
+        import pyarrow.parquet as pq
+        user = pa.schema([pa.field("k", pa.uint64()), pa.field("t", pa.int64()), pa.field("a", pa.int32()), pa.field("c", pa.float64())])
+        schema = StorageSchema.try_new(user, 2)
+        cols = [pa.array(np.arange(n, dtype=np.uint64) // 6), pa.array(np.arange(n, dtype=np.int64) * 100),
+                _nulls(rng, [int(x) for x in rng.integers(-50, 50, n)], 0.2, pa.int32()), _nulls(rng, rng.random(n).tolist(), 0.1, pa.float64())]
+        files = []
+        for i, (ver, comp) in enumerate((("2.0", "snappy"), ("1.0", "none"), ("2.0", "zstd"))):
+            full = schema.fill_builtin_columns(pa.RecordBatch.from_arrays(cols, schema=user), 40 + i)
+            sink = io.BytesIO()
+            pq.write_table(pa.Table.from_batches([full]), sink, row_group_size=1500, compression=comp, use_dictionary=False, data_page_size=700, data_page_version=ver)
+            files.append(sink.getvalue())
+        return SchemaHandle(schema.arrow_schema, 2), files, [("a", "ge", 0)], dict(group_col=0, ts_col=1, window_ms=5000, value_col=3)
     elif kind in ("binary", "binary-append"):
         # Binary value columns (BYTE_ARRAY PLAIN / DELTA_LENGTH_BYTE_ARRAY), LastValue or BytesMerge (operator.rs:47-111)
         from horaedb_b200.types import UpdateMode
@@ -110,7 +125,7 @@ def damage(rng, data):
 
 def main():
     seed, iters = int(sys.argv[1]), int(sys.argv[2])
-    kinds = sys.argv[3:] or ["metric-snappy", "metric-none", "metric-zstd", "dict", "delta", "nulls", "binary", "binary-append"]
+    kinds = sys.argv[3:] or ["metric-snappy", "metric-none", "metric-zstd", "dict", "delta", "nulls", "pages", "binary", "binary-append"]
     rng = np.random.default_rng(seed)
     eng = Engine(device=0)
     tmp = tempfile.mkdtemp(prefix="horae_fuzz_")
