@@ -5,7 +5,7 @@ thread) — on the GPU it would be silent corruption or a sticky illegal-address
 
     python tests/emu/fuzz_engine.py SEED ITERATIONS [KIND ...]      KIND: metric-snappy metric-none metric-zstd dict delta nulls pages binary binary-append
 
-Damage: 1-3 bytes overwritten / bits flipped, 40 % of them in the footer (statistics, sizes, offsets, encodings), the rest anywhere in the
+Damage: 1-3 places with a byte overwritten / a bit flipped / a short range zeroed, set to 0xff or copied from elsewhere, 40 % of them in the footer (statistics, sizes, offsets, encodings), the rest anywhere in the
 page area (page headers, level runs, compressed streams, dictionary indices, delta headers, values -> rows that contradict their chunk
 statistics and the sort order).  Operations: aggregate on the fused path, aggregate on the general pipeline, scan, scan with predicates,
 merge-compaction to a stream and to an SST written on the device."""
@@ -116,10 +116,20 @@ def damage(rng, data):
     flen = int.from_bytes(data[-8:-4], "little")
     for _ in range(int(rng.integers(1, 4))):
         p = len(b) - 8 - flen + int(rng.integers(0, flen)) if rng.random() < 0.4 else int(rng.integers(4, len(b) - 8 - flen))
-        if rng.random() < 0.5:
+        how = rng.random()
+        if how < 0.4:
             b[p] = int(rng.integers(0, 256))
-        else:
+        elif how < 0.8:
             b[p] ^= 1 << int(rng.integers(0, 8))
+        else:
+            # a short range: zeroed, set to 0xff (huge varints / lengths / offsets), or overwritten with bytes from elsewhere in the file
+            n = min(int(rng.integers(2, 48)), len(b) - 8 - p)
+            kind = int(rng.integers(0, 3))
+            if kind == 2:
+                q = int(rng.integers(4, len(b) - 8 - n))
+                b[p:p + n] = b[q:q + n]
+            else:
+                b[p:p + n] = bytes([0x00 if kind == 0 else 0xFF]) * n
     return bytes(b)
 
 
