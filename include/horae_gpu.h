@@ -45,7 +45,8 @@ typedef enum {
   HG_ERR_INVALID = 1,      /* bad argument / schema mismatch                       (ensure!, macros.rs:36-52) */
   HG_ERR_UNSUPPORTED = 2,  /* encoding / codec / type / expression not implemented on the GPU path (never a CPU fallback) */
   HG_ERR_CUDA = 3,
-  HG_ERR_FORMAT = 4,       /* malformed Parquet */
+  HG_ERR_FORMAT = 4,       /* malformed Parquet: footer / page headers, or page contents found inconsistent on the device (levels, dictionary
+                              indices, compressed streams, rows that contradict their chunk statistics or the file's sort order) */
   HG_ERR_OOM = 5,          /* HBM admission control (the analogue of Executor::pre_check, executor.rs:93-114) */
   HG_ERR_NOT_FOUND = 6,
   HG_ERR_INTERNAL = 7
