@@ -94,3 +94,21 @@ def test_multi_gpu_combine_with_ranks_as_threads(world):
                        cwd=ROOT, capture_output=True, text=True)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0 and f"world {world}: ok" in r.stdout, tail
+
+
+def test_plain_c_binding_on_the_emulated_library(tmp_path):
+    """tests/c/c_abi_smoke.c — the header bound from plain C, as the Rust FFI would — linked against the emulated build: the full call
+    sequence (engine, schema, predicates, aggregate over an Arrow C stream, scan, error paths) runs to "ok" without a GPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_engine_emu
+    lib = build_engine_emu.build()
+    sys.path.insert(0, ROOT)
+    from horaedb_b200 import sstgen
+    data, _ = sstgen.synth_sst(0, 64, 300, 1000, seq=5, compression="snappy")
+    sst = tmp_path / "5.sst"
+    sst.write_bytes(data)
+    exe = str(tmp_path / "c_abi_smoke_emu")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "c_abi_smoke.c"),
+                           "-o", exe, lib, f"-Wl,-rpath,{os.path.dirname(lib)}", "-lstdc++"])
+    p = subprocess.run([exe, str(sst)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "c_abi_smoke: ok" in p.stdout, p.stdout + p.stderr
