@@ -17,8 +17,12 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "horaedb_b200", "csrc")
-BUILD = os.path.join(HERE, "_build", "engine")
-OUT = os.path.join(HERE, "_build", "libhorae_emu.so")
+# HORAE_EMU_DROP_BARRIER=file.cu:N builds a MUTANT without the N-th __syncthreads() of that file, into its own directory: how the
+# sensitivity of the emulated runs is measured (a mutant that passes every test under every thread order is a barrier the tests do not need)
+MUTANT = os.environ.get("HORAE_EMU_DROP_BARRIER", "")
+_TAG = ("_mut_" + MUTANT.replace(".", "_").replace(":", "_")) if MUTANT else ""
+BUILD = os.path.join(HERE, "_build", "engine" + _TAG)
+OUT = os.path.join(HERE, "_build", "libhorae_emu%s.so" % _TAG)
 NCCL_OUT = os.path.join(HERE, "_build", "libnccl_emu.so")
 CU = ["engine.cu", "kernels.cu", "fused_scan.cu", "snappy.cu", "zstd.cu", "kway_merge.cu", "radix_agg.cu", "comm.cu", "sst_writer.cu"]
 CPP = ["parquet_meta.cpp", "inspect.cpp"]
@@ -91,7 +95,14 @@ def rewrite_launches(s):
         pos = e
 
 
-def transform(text):
+def transform(text, name=""):
+    if MUTANT and MUTANT.split(":")[0] == name:
+        n, pos = int(MUTANT.split(":")[1]), -1
+        for _ in range(n + 1):
+            pos = text.find("__syncthreads();", pos + 1)
+            if pos < 0:
+                raise SystemExit("no such barrier: " + MUTANT)
+        text = text[:pos] + "/* dropped */     " + text[pos + len("__syncthreads();"):]
     text = rewrite_launches(text)
     text = re.sub(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;", r"EMU_DYN_SMEM(\1, \2);", text)
     text = re.sub(r'asm volatile\("prefetch\.global\.L2 \[%0\];"[^;]*;', "(void)0;", text)
@@ -116,7 +127,7 @@ def build(force=False):
     for name in CU:
         src = os.path.join(BUILD, name.replace(".cu", "_emu.cpp"))
         with open(os.path.join(CSRC, name)) as f:
-            text = transform(f.read())
+            text = transform(f.read(), name)
         with open(src, "w") as f:
             f.write('#include "cuda_runtime.h"\n#line 1 "%s"\n' % os.path.join(CSRC, name) + text)
         obj = src[:-4] + ".o"
