@@ -11,6 +11,10 @@
 //               random permutation per scheduling pass) makes a missing barrier show up as a wrong result
 //   memory      cudaMalloc = malloc filled with 0xCD, "device" pointers are host pointers, copies are memcpy, streams and events are
 //               no-ops (launches run synchronously)
+//   knobs       HORAE_EMU_ORDER (thread order), HORAE_EMU_GUARD (an inaccessible page right behind every allocation), HORAE_EMU_PINNED (host
+//               buffers count as pinned: the zero-copy gather path of transient loads), HORAE_EMU_CRASH_REPORT (kernel / block / thread of a
+//               fault), HORAE_EMU_TRACE_ALLOC; HORAE_EMU_DROP_BARRIER at build time (mutants, build_engine_emu.py)
+//   ranks       engines of several host threads take turns kernel by kernel (launch_mutex); tests/emu/nccl_emu.cpp is the all-gather between them
 //   not modelled: timing, caches, memory-model effects beyond "a write is visible after the next rendezvous or kernel end"
 #pragma once
 #include <algorithm>
