@@ -63,6 +63,7 @@ struct Install {
     sigaltstack(&ss, nullptr);
     struct sigaction sa; memset(&sa, 0, sizeof sa); sa.sa_sigaction = on_segv; sa.sa_flags = SA_ONSTACK | SA_SIGINFO;
     if (getenv("HORAE_EMU_CRASH_REPORT")) { sigaction(SIGSEGV, &sa, nullptr); sigaction(SIGBUS, &sa, nullptr); }
+    if (const char* o = getenv("HORAE_EMU_ORDER")) emu_set_order(atoi(o));      // (the pytest plugin sets it too; the tools rely on this)
   }
 } install;
 }  // namespace
