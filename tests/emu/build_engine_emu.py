@@ -17,7 +17,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "horaedb_b200", "csrc")
-# HORAE_EMU_DROP_BARRIER=file.cu:N builds a MUTANT without the N-th __syncthreads() of that file, into its own directory: how the
+# HORAE_EMU_DROP_BARRIER=file.cu:N[:warp] builds a MUTANT without the N-th __syncthreads() (or __syncwarp()) of that file, into its own directory: how the
 # sensitivity of the emulated runs is measured (a mutant that passes every test under every thread order is a barrier the tests do not need)
 MUTANT = os.environ.get("HORAE_EMU_DROP_BARRIER", "")
 _TAG = ("_mut_" + MUTANT.replace(".", "_").replace(":", "_")) if MUTANT else ""
@@ -97,12 +97,13 @@ def rewrite_launches(s):
 
 def transform(text, name=""):
     if MUTANT and MUTANT.split(":")[0] == name:
-        n, pos = int(MUTANT.split(":")[1]), -1
+        parts = MUTANT.split(":")
+        n, pos, tok = int(parts[1]), -1, ("__syncwarp();" if len(parts) > 2 and parts[2] == "warp" else "__syncthreads();")
         for _ in range(n + 1):
-            pos = text.find("__syncthreads();", pos + 1)
+            pos = text.find(tok, pos + 1)
             if pos < 0:
                 raise SystemExit("no such barrier: " + MUTANT)
-        text = text[:pos] + "/* dropped */     " + text[pos + len("__syncthreads();"):]
+        text = text[:pos] + "/* dropped */" + " " * (len(tok) - 13) + text[pos + len(tok):]
     text = rewrite_launches(text)
     text = re.sub(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;", r"EMU_DYN_SMEM(\1, \2);", text)
     text = re.sub(r'asm volatile\("prefetch\.global\.L2 \[%0\];"[^;]*;', "(void)0;", text)
