@@ -117,24 +117,30 @@ __global__ void __launch_bounds__(1024) kway_splitters_kernel(const uint64_t* __
 
 // bounds[r * k + f] = number of keys of stream f that precede range r (r = 0..R)
 __global__ void __launch_bounds__(kThreads) kway_bounds_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ run_start, int k,
-                                                              const uint64_t* __restrict__ splitters, uint32_t R, uint32_t* __restrict__ bounds) {
+                                                              const uint64_t* __restrict__ splitters, uint32_t R, uint32_t* __restrict__ bounds, int* err) {
   const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
   if (idx >= (R + 1) * uint32_t(k)) return;
   const uint32_t r = idx / k, f = idx % k;
   const uint32_t base = run_start[f], n = run_start[f + 1] - base;
+  auto lower_bound = [&](uint64_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[base + mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
   uint32_t lo = 0;
   if (r == R) lo = n;
-  else if (r > 0) {
-    const uint64_t key = splitters[r - 1];
-    uint32_t hi = n;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[base + mid] < key) lo = mid + 1; else hi = mid; }
-  }
+  else if (r > 0) lo = lower_bound(splitters[r - 1]);
+  // the cut of the range before this one, searched again: for a sorted stream it can never lie behind this cut (splitters ascend).  For
+  // an unsorted one (a damaged file) it can; the flag sends kway_bounds_monotone_kernel to work
+  if (r > 1 && r < R && lower_bound(splitters[r - 2]) > lo) atomicExch(err, 121);
   bounds[idx] = lo;
 }
 
 // Cuts of a stream never go backwards from one range to the next.  They cannot for a sorted stream; for an unsorted one (a damaged
 // file) the binary searches above may disagree, and ranges that overlap or leave holes would leave `order` partly unwritten.
+// Error path only: one thread per stream walks its R + 1 cuts (a well-formed call returns at the first line).
 __global__ void kway_bounds_monotone_kernel(int k, uint32_t R, uint32_t* __restrict__ bounds, int* err) {
+  if (*err == 0) return;                       // (set by kway_bounds_kernel when a cut goes backwards; any earlier error: the call fails anyway)
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= k) return;
   uint32_t prev = 0;
@@ -332,7 +338,7 @@ void kway_merge(const Launch& L, const PkSet& pk, ColView seq, const uint32_t* s
   cudaFuncSetAttribute(kway_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kChunk * 8);
   kway_splitters_kernel<<<1, 1024, kSamples * 8, L.stream>>>(keys, d_m, R, splitters);
   L.tick();
-  kway_bounds_kernel<<<int(((R + 1) * uint64_t(k) + kThreads - 1) / kThreads), kThreads, 0, L.stream>>>(keys, run_start, k, splitters, R, bounds);
+  kway_bounds_kernel<<<int(((R + 1) * uint64_t(k) + kThreads - 1) / kThreads), kThreads, 0, L.stream>>>(keys, run_start, k, splitters, R, bounds, err);
   L.tick();
   kway_bounds_monotone_kernel<<<(k + 63) / 64, 64, 0, L.stream>>>(k, R, bounds, err);
   L.tick();
