@@ -122,17 +122,24 @@ __global__ void __launch_bounds__(kThreads) kway_bounds_kernel(const uint64_t* _
   if (idx >= (R + 1) * uint32_t(k)) return;
   const uint32_t r = idx / k, f = idx % k;
   const uint32_t base = run_start[f], n = run_start[f + 1] - base;
-  auto lower_bound = [&](uint64_t key) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[base + mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
-  };
-  uint32_t lo = 0;
+  // this range's cut and, for the check below, the cut of the range before it: two binary searches advanced in the same loop, so that
+  // their (dependent) loads overlap instead of doubling the kernel's latency
+  uint32_t lo = 0, hi = 0, lo2 = 0, hi2 = 0;
+  uint64_t key = 0, key2 = 0;
   if (r == R) lo = n;
-  else if (r > 0) lo = lower_bound(splitters[r - 1]);
-  // the cut of the range before this one, searched again: for a sorted stream it can never lie behind this cut (splitters ascend).  For
-  // an unsorted one (a damaged file) it can; the flag sends kway_bounds_monotone_kernel to work
-  if (r > 1 && r < R && lower_bound(splitters[r - 2]) > lo) atomicExch(err, 121);
+  else if (r > 0) { hi = n; key = splitters[r - 1]; }
+  const bool check = r > 1 && r < R;
+  if (check) { hi2 = n; key2 = splitters[r - 2]; }
+  while (lo < hi || lo2 < hi2) {
+    const bool a1 = lo < hi, a2 = lo2 < hi2;
+    const uint32_t m1 = (lo + hi) >> 1, m2 = (lo2 + hi2) >> 1;
+    const uint64_t k1 = a1 ? keys[base + m1] : 0, k2 = a2 ? keys[base + m2] : 0;
+    if (a1) { if (k1 < key) lo = m1 + 1; else hi = m1; }
+    if (a2) { if (k2 < key2) lo2 = m2 + 1; else hi2 = m2; }
+  }
+  // for a sorted stream the earlier cut can never lie behind this one (splitters ascend).  For an unsorted one (a damaged file) it can;
+  // the flag sends kway_bounds_monotone_kernel to work
+  if (check && lo2 > lo) atomicExch(err, 121);
   bounds[idx] = lo;
 }
 
